@@ -1,0 +1,170 @@
+/*
+ * kmap_b200.h -- C ABI of libkmap_b200.so: the sm_100a CUDA implementation of KMAP's scan_motif counting path.
+ *
+ * The reference (chengl7-lab/kmap v0.0.7) has no FFI of its own: its hot path is a set of Python functions that
+ * call Taichi kernels on NumPy arrays.  Each entry point below names the reference function / kernel it replaces
+ * (paths relative to the reference's src/kmap/).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive cudaError_t value or a negative KMAP_ERR_* otherwise;
+ *     kmap_last_error() gives a message for the calling thread.  Nothing throws.
+ *   - all array pointers are DEVICE pointers owned by the caller (the Python side allocates them as torch
+ *     tensors) unless the parameter name ends in _host.  `stream` is a cudaStream_t passed as void*.
+ *     Calls are asynchronous on that stream except where a *_host output forces a synchronisation (documented).
+ *   - the library keeps no global state.
+ *   - hashes are the reference's: 2 bits per base (A0 C1 G2 T3), first base most significant
+ *     (taichi_core.py:9-19); uint32 for k < 16, uint64 for 16 <= k < 32 (kmer_count.py:359-365);
+ *     the invalid hash is all-ones (kmer_count.py:369-370).
+ *
+ * Packed sequence format (produced by kmap_pack2bit, consumed by the fused kernels)
+ *   packed : uint32[kmap_packed_words(n)]  16 bases per word, base p in word p>>4 at bits [31-2(p&15), 30-2(p&15)]
+ *            (first base in the most significant bits, so a funnel shift yields the reference hash directly);
+ *            positions holding 255 are stored as 0.
+ *   valid  : uint32[kmap_valid_words(n)]   1 bit per position, position p = bit (p&31) of word p>>5; 0 for 255
+ *            (N, read separators, masked bases) and for the zero padding after position n-1.
+ */
+#ifndef KMAP_B200_H
+#define KMAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMAP_OK 0
+#define KMAP_ERR_BAD_ARG (-1)
+#define KMAP_ERR_CAPACITY (-2)      /* output buffer too small; the required size was written to the *_host out-param */
+#define KMAP_ERR_NEED_SCRATCH (-3)  /* a read longer than the on-chip paths needs the caller-provided bitmap scratch */
+
+const char* kmap_last_error(void);
+int kmap_version(void);
+
+/* sizes of the packed representation for n positions (includes the zero padding the kernels rely on) */
+int64_t kmap_packed_words(int64_t n);
+int64_t kmap_valid_words(int64_t n);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 1:1 primitives: drop-in for the ten integer Taichi kernels (taichi_core.py:3-224)
+ * ---------------------------------------------------------------------------------------------------------- */
+/* kmer2hash_kernel_uint32/64 (taichi_core.py:25-61) behind comp_kmer_hash_taichi (kmer_count.py:449-473):
+ * one hash per position of seq (uint8, 255 = missing); invalid if the window leaves the array or touches 255. */
+int kmap_kmer2hash_u32(const uint8_t* seq, int64_t n, int k, uint32_t* hash_out, void* stream);
+int kmap_kmer2hash_u64(const uint8_t* seq, int64_t n, int k, uint64_t* hash_out, void* stream);
+/* cal_ham_dist_kernel_uint32/64 (taichi_core.py:75-104) behind cal_hamming_dist (kmer_count.py:494-515) */
+int kmap_ham_dist_u32(const uint32_t* kh, int64_t n, uint32_t target, int k, uint8_t* dist_out, void* stream);
+int kmap_ham_dist_u64(const uint64_t* kh, int64_t n, uint64_t target, int k, uint8_t* dist_out, void* stream);
+/* cal_partial_ham_dist_head/tail kernels (taichi_core.py:108-177) behind cal_hamming_dist_head/_tail
+ * (kmer_count.py:518-577) */
+int kmap_ham_dist_head_u32(const uint32_t* kh, int64_t n, uint32_t target, int k, int conseq_len, uint8_t* dist_out, void* stream);
+int kmap_ham_dist_head_u64(const uint64_t* kh, int64_t n, uint64_t target, int k, int conseq_len, uint8_t* dist_out, void* stream);
+int kmap_ham_dist_tail_u32(const uint32_t* kh, int64_t n, uint32_t target, int k, int conseq_len, uint8_t* dist_out, void* stream);
+int kmap_ham_dist_tail_u64(const uint64_t* kh, int64_t n, uint64_t target, int k, int conseq_len, uint8_t* dist_out, void* stream);
+/* revcom_hash_kernel_uint32/64 (taichi_core.py:181-224) behind get_revcom_hash_arr (kmer_count.py:613-623) */
+int kmap_revcom_u32(const uint32_t* in, int64_t n, int k, uint32_t* out, void* stream);
+int kmap_revcom_u64(const uint64_t* in, int64_t n, int k, uint64_t* out, void* stream);
+/* remove_duplicate_hash_per_seq (kmer_count.py:743-760): in place on a hash array; borders = int64[n_seq][2]
+ * ([start, end) per read).  Keeps the FIRST occurrence of every hash inside a read. */
+int kmap_dedup_hash_per_read_u32(uint32_t* hash, int64_t n, const int64_t* borders, int64_t n_seq, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * fused hot path on the packed representation
+ * ---------------------------------------------------------------------------------------------------------- */
+/* input.bin bytes (kmer_count.py:244-263, 326-347) -> packed + valid */
+int kmap_pack2bit(const uint8_t* seq, int64_t n, uint32_t* packed, uint32_t* valid, void* stream);
+/* write the masking state back: seq[i] = 255 wherever valid bit i is 0 (what mask_input leaves in seq_np_arr,
+ * kmer_count.py:599-602) */
+int kmap_apply_valid_to_seq(uint8_t* seq, int64_t n, const uint32_t* valid, void* stream);
+
+/* comp_kmer_hash_taichi + count_uniq_hash (kmer_count.py:449-491) fused: table[h] += 1 for every valid window.
+ * table = uint32[4^k], k <= 15.  The caller zeroes the table (kmap_fill_u32) when it wants a fresh count. */
+int kmap_count_dense(const uint32_t* packed, const uint32_t* valid, int64_t n, int k, uint32_t* table, void* stream);
+/* the same with remove_duplicate_hash_per_seq (kmer_count.py:743-760) fused in: every distinct k-mer of a read
+ * counts once.  borders = int64[n_seq][2] as in input.seqboarder.bin.pkl.
+ * work : uint32[kmap_dedup_work_words(n_seq)] scratch; bitmap : uint32[4^k/32] scratch or NULL (only needed when
+ * a read has more than KMAP_DEDUP_BLOCK_MAX windows; KMAP_ERR_NEED_SCRATCH is returned if it is NULL then).
+ * Synchronises the stream once (reads two counters back). */
+int kmap_count_dense_dedup(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders,
+                           int64_t n_seq, int k, uint32_t* table, uint32_t* work, uint32_t* bitmap, void* stream);
+int64_t kmap_dedup_work_words(int64_t n_seq);
+
+int kmap_fill_u32(uint32_t* p, int64_t n_words, uint32_t value, void* stream);
+
+/* count_uniq_hash (kmer_count.py:476-491) for callers that hold a materialised hash array: table[h] += 1 for every
+ * h < 4^k (the invalid hash is skipped) */
+int kmap_count_hashes_u32(const uint32_t* hash, int64_t n, int k, uint32_t* table, void* stream);
+/* rebuild a dense table from a (unique hash, count) list: table[kh[i]] += cnt[i]; used by merge_revcom when it is
+ * called on lists (kmer_count.py:643) */
+int kmap_scatter_counts(const uint32_t* kh, const int32_t* cnt, int64_t n, int k, uint32_t* table, void* stream);
+/* the side effect of merge_revcom on its count argument (kmer_count.py:661): cnt[i] += table[rc(kh[i])] */
+int kmap_list_add_rc_counts(const uint32_t* kh, int32_t* cnt, int64_t n, int k, const uint32_t* table, void* stream);
+
+/* count_uniq_hash + merge_revcom (kmer_count.py:476-491, 643-685) from the dense forward table, in the
+ * reference's exact output order (ascending forward hash of the surviving entries; value = min(h, rc h) when
+ * revcom; palindromes doubled).  scratch = uint64[kmap_compact_scratch_words(k)].
+ * Two-step: call with capacity 0 (out pointers may be NULL) to get *n_out_host, then with buffers.
+ * Synchronises the stream. */
+int kmap_compact_merge(const uint32_t* table, int k, int revcom, uint64_t* scratch, uint32_t* kh_out,
+                       int32_t* cnt_out, int64_t capacity, int64_t* n_out_host, void* stream);
+int64_t kmap_compact_scratch_words(int k);
+
+/* Hamming-ball count of find_motif (motif_discovery.py:666-673) for m candidate consensus hashes, evaluated by
+ * neighbour enumeration over the dense forward table: sums[i] = sum of merged counts within distance d of
+ * cand[i] (or of its reverse complement when revcom).  sums = uint64[m] (overwritten). */
+int kmap_hamball_sum(const uint32_t* table, int k, const uint32_t* cand, int m, int d, int revcom, uint64_t* sums,
+                     void* stream);
+/* the same quantity computed the reference's way, as a scan of the merged (kh, cnt) list: used for lists that
+ * did not come from a dense table (a loaded k{k}.pkl) */
+int kmap_hamball_sum_list(const uint32_t* kh, const int32_t* cnt, int64_t n, int k, const uint32_t* cand, int m,
+                          int d, int revcom, uint64_t* sums, void* stream);
+
+/* mask_input (kmer_count.py:580-610) on the packed representation: for each of the m (<= 16) consensus hashes flag
+ * the positions whose PRE-MASK window (validity taken from valid_pre) is within d[i] (invalid windows compare as
+ * T..T) and clear bits [i, min(i+k, n)) of valid.  valid_pre may alias valid; callers with more than 16 consensus
+ * hashes pass a snapshot as valid_pre on every call.  flag_scratch = uint32[kmap_valid_words(n)]; cons/d are
+ * device arrays. */
+int kmap_mask(const uint32_t* packed, const uint32_t* valid_pre, uint32_t* valid, int64_t n, int k, const uint32_t* cons,
+              const int32_t* d, int m, uint32_t* flag_scratch, void* stream);
+
+/* ex_hamball_kh_arr (motif_discovery.py:959-975) on a merged (kh, cnt) list + cal_cnt_mat
+ * (motif_discovery.py:978-986).  Ball members keep list order; members strictly closer to rc(conseq) are
+ * reverse-complemented.  cnt_mat = int64[4*k] row-major [base][pos] (overwritten).
+ * scratch = uint64[kmap_list_scratch_words(n)].  Two-step like kmap_compact_merge.  Synchronises the stream. */
+int kmap_hamball_extract(const uint32_t* kh, const int32_t* cnt, int64_t n, int k, uint32_t conseq, int d,
+                         int revcom, uint64_t* scratch, uint32_t* kh_out, int32_t* cnt_out, int64_t capacity,
+                         int64_t* n_out_host, int64_t* cnt_mat, void* stream);
+int64_t kmap_list_scratch_words(int64_t n);
+
+/* get_motif_occurence (motif_discovery.py:1441-1465) for all reads at once.  Per read r: positions whose
+ * min(fwd, rc) distance to conseq is <= d and equal to the read's minimum such distance.
+ * step 1: min_dist[r] (255 = no hit) and n_hit[r];  step 2 (after the caller's exclusive scan of n_hit into
+ * offsets, int64[n_seq]): pos_out[offsets[r] ...] = hit positions ascending. */
+int kmap_occurrence_count(const uint32_t* packed, const uint32_t* valid, const int64_t* borders, int64_t n_seq,
+                          int k, uint32_t conseq, int d, int revcom, uint8_t* min_dist, uint32_t* n_hit, void* stream);
+int kmap_occurrence_fill(const uint32_t* packed, const uint32_t* valid, const int64_t* borders, int64_t n_seq,
+                         int k, uint32_t conseq, int d, int revcom, const uint8_t* min_dist, const int64_t* offsets,
+                         int32_t* pos_out, void* stream);
+
+/* cal_samp_kmer_hamdist_mat (motif_discovery.py:777-803): rows [row0, row1) of the n x n distance matrix of
+ * kh[] at k bases; pairs whose labels are equal and have head_len[label] < k use only the first head_len bases.
+ * head_len = int32[n_labels] (k for labels without override).  out = uint8[(row1-row0) * n] row-major. */
+int kmap_hamdist_matrix_u32(const uint32_t* kh, const int32_t* labels, int64_t n, int k, const int32_t* head_len,
+                            int n_labels, int64_t row0, int64_t row1, uint8_t* out, void* stream);
+int kmap_hamdist_matrix_u64(const uint64_t* kh, const int32_t* labels, int64_t n, int k, const int32_t* head_len,
+                            int n_labels, int64_t row0, int64_t row1, uint8_t* out, void* stream);
+
+/* exclusive prefix sum of uint32 counts into int64 offsets (out[n] = total); scratch = uint64[kmap_list_scratch_words(n)] */
+int kmap_exclusive_scan_u32(const uint32_t* in, int64_t n, int64_t* out, uint64_t* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * synthetic reads (bench / tests): counter-based generator, identical to kmap_b200/synth.py
+ * seq = uint8[n_reads*(L+1)] in the input.bin layout, borders = int64[n_reads][2] (may be NULL)
+ * ---------------------------------------------------------------------------------------------------------- */
+int kmap_synth_reads(uint64_t seed, int64_t read0, int64_t n_reads, int L, const uint8_t* motifs, const int32_t* motif_len,
+                     const float* motif_cum_frac, int n_motifs, float mut_rate, float n_rate, int64_t pos0,
+                     uint8_t* seq, int64_t* borders, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMAP_B200_H */

@@ -1,0 +1,180 @@
+// mask_input (kmer_count.py:580-610) and get_motif_occurence (motif_discovery.py:1422-1477) on the packed
+// representation.  Both compare every window of the sequence with a consensus hash; neither materialises the
+// hash or distance arrays of the reference.
+#include "common.cuh"
+
+namespace {
+
+constexpr int MK_BLOCK = 256;
+constexpr int MK_MAXM = 16;
+
+// ---- mask: pass 1, flag word per 32 positions ----------------------------------------------------------------
+// flag bit i <=> some consensus j has dist(window_i, cons[j]) <= d[j], where an invalid window (touches 255 or
+// leaves the array) compares like the all-ones hash, i.e. like T..T (kmer_count.py:592-598).
+__global__ void __launch_bounds__(MK_BLOCK) mask_flag_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
+                                                             int64_t n, int64_t n_words, int k, const uint32_t* __restrict__ cons,
+                                                             const int32_t* __restrict__ dmax, int m, uint32_t* __restrict__ flags) {
+    __shared__ uint32_t sc[MK_MAXM];
+    __shared__ int sd[MK_MAXM];
+    __shared__ int inv_hit;                    // does an invalid window fall inside some ball?
+    const uint32_t low = lowmask32(k);
+    if (threadIdx.x == 0) {
+        int hit = 0;
+        for (int j = 0; j < m; ++j) {
+            sc[j] = cons[j] & low; sd[j] = dmax[j];
+            hit |= (int)nz_groups32(0xFFFFFFFFu ^ sc[j], low) <= sd[j];
+        }
+        inv_hit = hit;
+    }
+    __syncthreads();
+    const int64_t t = (int64_t)blockIdx.x * MK_BLOCK + threadIdx.x;
+    if (t >= n_words) return;
+    const uint32_t v0 = __ldg(valid + t), v1 = __ldg(valid + t + 1);
+    const uint2 w01 = __ldg(reinterpret_cast<const uint2*>(packed + 2 * t));
+    const uint32_t w2 = __ldg(packed + 2 * t + 2);
+    const uint32_t km = (1u << k) - 1u;
+    const int sh = 32 - 2 * k;
+    uint32_t f = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const uint32_t vb = __funnelshift_r(v0, v1, i);
+        bool hit;
+        if ((vb & km) == km) {
+            const uint32_t x = (i < 16) ? __funnelshift_l(w01.y, w01.x, 2 * i) : __funnelshift_l(w2, w01.y, 2 * (i - 16));
+            const uint32_t h = x >> sh;
+            hit = false;
+            for (int j = 0; j < m; ++j) hit |= (int)nz_groups32(h ^ sc[j], low) <= sd[j];
+        } else {
+            hit = inv_hit;
+        }
+        f |= (uint32_t)hit << i;
+    }
+    // positions >= n do not exist
+    const int64_t p0 = t * 32;
+    if (p0 + 32 > n) f &= (p0 >= n) ? 0u : ((1u << (n - p0)) - 1u);
+    flags[t] = f;
+}
+
+// ---- mask: pass 2, dilate the flags by k to the right and clear those validity bits ---------------------------
+__global__ void __launch_bounds__(MK_BLOCK) mask_dilate_kernel(const uint32_t* __restrict__ flags, int64_t n_words, int k,
+                                                               uint32_t* __restrict__ valid) {
+    const int64_t t = (int64_t)blockIdx.x * MK_BLOCK + threadIdx.x;
+    if (t >= n_words) return;
+    const uint64_t cur = flags[t];
+    const uint64_t prev = t > 0 ? flags[t - 1] : 0;
+    uint64_t x = (cur << 32) | prev;           // bit 32+i = position 32t+i, bit i = position 32(t-1)+i
+    // OR of x << s for s = 0 .. k-1  (k <= 32), by doubling
+    int covered = 1;
+    while (covered * 2 <= k) { x |= x << covered; covered *= 2; }
+    x |= x << (k - covered);
+    const uint32_t kill = (uint32_t)(x >> 32);
+    if (kill) valid[t] &= ~kill;
+}
+
+// ---- per-read occurrence scan -----------------------------------------------------------------------------------
+// One warp per read.  Window positions 0 .. n_pos-1 where n_pos = L-k+1, or -- reproducing the reference's negative
+// slice hash_arr[0:L-k+1] for reads shorter than k (motif_discovery.py:1447) -- max(0, 2L-k+1) all-invalid windows.
+__device__ __forceinline__ int64_t occurrence_n_pos(int64_t L, int k) {
+    const int64_t m = L - k + 1;
+    if (m > 0) return m;
+    if (m == 0) return 0;
+    return L + m > 0 ? L + m : 0;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(MK_BLOCK) occurrence_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
+                                                              const int64_t* __restrict__ borders, int64_t n_seq, int k, uint32_t conseq,
+                                                              int d, int revcom, uint8_t* __restrict__ min_dist, uint32_t* __restrict__ n_hit,
+                                                              const int64_t* __restrict__ offsets, int32_t* __restrict__ pos_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * MK_BLOCK + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * MK_BLOCK) >> 5;
+    const uint32_t low = lowmask32(k);
+    const uint32_t c = conseq & low, rc = revcom32(c, k);
+    const uint32_t km = (1u << k) - 1u;
+    const int sh = 32 - 2 * k;
+    uint32_t inv_d = nz_groups32(0xFFFFFFFFu ^ c, low);
+    if (revcom) { const uint32_t r = nz_groups32(0xFFFFFFFFu ^ rc, low); inv_d = r < inv_d ? r : inv_d; }
+
+    for (int64_t r = warp0; r < n_seq; r += n_warps) {
+        const int64_t st = __ldg(borders + 2 * r), en = __ldg(borders + 2 * r + 1);
+        const int64_t L = en - st;
+        const int64_t n_pos = occurrence_n_pos(L, k);
+        uint32_t best = 255, hits = 0;
+        if (FILL) { best = min_dist[r]; if (best == 255) continue; }
+        int64_t out = FILL ? offsets[r] : 0;
+        for (int64_t i0 = 0; i0 < n_pos; i0 += 32) {
+            const int64_t i = i0 + lane;
+            uint32_t dist = 255;
+            if (i < n_pos) {
+                const int64_t p = st + i;
+                const bool ok = (L >= k) && ((valid32(valid, p) & km) == km);
+                if (ok) {
+                    const uint32_t h = window16(packed, p) >> sh;
+                    dist = nz_groups32(h ^ c, low);
+                    if (revcom) { const uint32_t rd = nz_groups32(h ^ rc, low); dist = rd < dist ? rd : dist; }
+                } else {
+                    dist = inv_d;
+                }
+                if ((int)dist > d) dist = 255;
+            }
+            if (!FILL) {
+                uint32_t wmin = dist;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, wmin, o); wmin = y < wmin ? y : wmin; }
+                if (wmin < best) { best = wmin; hits = 0; }
+                if (best != 255) hits += __popc(__ballot_sync(0xFFFFFFFFu, dist == best));
+            } else {
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, dist == best);
+                if (dist == best) pos_out[out + __popc(bal & ((1u << lane) - 1u))] = (int32_t)i;
+                out += __popc(bal);
+            }
+        }
+        if (!FILL && lane == 0) { min_dist[r] = (uint8_t)best; n_hit[r] = hits; }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int kmap_mask(const uint32_t* packed, const uint32_t* valid_pre, uint32_t* valid, int64_t n, int k, const uint32_t* cons,
+              const int32_t* d, int m, uint32_t* flag_scratch, void* stream) {
+    KMAP_REQUIRE(n >= 0 && k >= 1 && k <= 15 && m >= 0 && m <= MK_MAXM, "bad argument (k <= 15, m <= 16)");
+    if (n == 0 || m == 0) return KMAP_OK;
+    KMAP_REQUIRE(packed && valid_pre && valid && cons && d && flag_scratch, "null pointer");
+    cudaStream_t s = as_stream(stream);
+    const int64_t n_words = (n + 31) / 32;
+    mask_flag_kernel<<<grid_for(n_words, MK_BLOCK), MK_BLOCK, 0, s>>>(packed, valid_pre, n, n_words, k, cons, d, m, flag_scratch);
+    mask_dilate_kernel<<<grid_for(n_words, MK_BLOCK), MK_BLOCK, 0, s>>>(flag_scratch, n_words, k, valid);
+    return kmap_check_launch("mask");
+}
+
+static unsigned int occurrence_grid(int64_t n_seq) {
+    int64_t blocks = (n_seq * 32 + MK_BLOCK - 1) / MK_BLOCK;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    return (unsigned int)(blocks < 1 ? 1 : blocks);
+}
+
+int kmap_occurrence_count(const uint32_t* packed, const uint32_t* valid, const int64_t* borders, int64_t n_seq, int k,
+                          uint32_t conseq, int d, int revcom, uint8_t* min_dist, uint32_t* n_hit, void* stream) {
+    KMAP_REQUIRE(n_seq >= 0 && k >= 1 && k <= 15, "bad argument");
+    if (n_seq == 0) return KMAP_OK;
+    KMAP_REQUIRE(packed && valid && borders && min_dist && n_hit, "null pointer");
+    occurrence_kernel<false><<<occurrence_grid(n_seq), MK_BLOCK, 0, as_stream(stream)>>>(
+        packed, valid, borders, n_seq, k, conseq, d, revcom, min_dist, n_hit, nullptr, nullptr);
+    return kmap_check_launch("occurrence_count");
+}
+
+int kmap_occurrence_fill(const uint32_t* packed, const uint32_t* valid, const int64_t* borders, int64_t n_seq, int k,
+                         uint32_t conseq, int d, int revcom, const uint8_t* min_dist, const int64_t* offsets, int32_t* pos_out,
+                         void* stream) {
+    KMAP_REQUIRE(n_seq >= 0 && k >= 1 && k <= 15, "bad argument");
+    if (n_seq == 0) return KMAP_OK;
+    KMAP_REQUIRE(packed && valid && borders && min_dist && offsets && pos_out, "null pointer");
+    occurrence_kernel<true><<<occurrence_grid(n_seq), MK_BLOCK, 0, as_stream(stream)>>>(
+        packed, valid, borders, n_seq, k, conseq, d, revcom, const_cast<uint8_t*>(min_dist), nullptr, offsets, pos_out);
+    return kmap_check_launch("occurrence_fill");
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// input.bin bytes (A0 C1 G2 T3, 255 = N / separator; kmer_count.py:244-263) <-> 2-bit packed + validity mask.
+#include "common.cuh"
+
+namespace {
+
+// 4 bytes (each 0..3) held in a little-endian word -> 8 bits, first byte in the two MOST significant bits.
+// y = b0 + b1<<8 + b2<<16 + b3<<24; the multiplier drops b0..b3 at bits 30,28,26,24 with no overlapping terms.
+__device__ __forceinline__ uint32_t squeeze4(uint32_t x) { return ((x & 0x03030303u) * 0x40100401u) >> 24; }
+// 4 bytes -> 4 validity bits (bit i set iff byte i < 4), first byte in bit 0
+__device__ __forceinline__ uint32_t valid4(uint32_t x) {
+    const uint32_t z = x & 0xFCFCFCFCu;
+    const uint32_t nz = (z | ((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu)) & 0x80808080u;  // 0x80 where the byte is non-zero
+    const uint32_t ok = (~nz >> 7) & 0x01010101u;
+    return ((ok * 0x01020408u) >> 24) & 0xFu;
+}
+
+// one thread = 32 positions = one validity word + two packed words; 2 x 128-bit loads when in range
+__global__ void __launch_bounds__(256) pack2bit_kernel(const uint8_t* __restrict__ seq, int64_t n, int64_t n_valid_words,
+                                                       uint32_t* __restrict__ packed, uint32_t* __restrict__ valid) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_valid_words) return;
+    const int64_t p0 = t * 32;
+    uint32_t w[8];
+    if (p0 + 32 <= n && ((reinterpret_cast<uintptr_t>(seq) & 15) == 0)) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(seq + p0));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(seq + p0 + 16));
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int64_t p = p0 + 4 * j + b;
+                const uint32_t v = p < n ? (uint32_t)__ldg(seq + p) : 255u;
+                x |= v << (8 * b);
+            }
+            w[j] = x;
+        }
+    }
+    uint32_t vbits = 0, hi = 0, lo = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t v4 = valid4(w[j]);
+        vbits |= v4 << (4 * j);
+        // zero the 2-bit code of invalid bases so the packed word is canonical
+        uint32_t keep = v4 | (v4 << 7) | (v4 << 14) | (v4 << 21);          // bit 8i <- validity of byte i
+        keep = (keep & 0x01010101u) * 3u;
+        const uint32_t q = squeeze4(w[j] & keep);
+        if (j < 4) hi |= q << (24 - 8 * j); else lo |= q << (24 - 8 * (j - 4));
+    }
+    valid[t] = vbits;
+    packed[2 * t] = hi;
+    packed[2 * t + 1] = lo;
+}
+
+__global__ void __launch_bounds__(256) apply_valid_kernel(uint8_t* __restrict__ seq, int64_t n,
+                                                          const uint32_t* __restrict__ valid) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 positions
+    const int64_t p0 = i * 4;
+    if (p0 >= n) return;
+    const uint32_t v = (__ldg(valid + (p0 >> 5)) >> (p0 & 31)) & 0xFu;
+    if (v == 0xFu) return;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+        if (p0 + b < n && !((v >> b) & 1u)) seq[p0 + b] = 255;
+}
+
+__global__ void fill_u32_kernel(uint32_t* __restrict__ p, int64_t n, uint32_t value) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = value;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t kmap_valid_words(int64_t n) { return (n + 31) / 32 + KMAP_PAD_WORDS; }
+int64_t kmap_packed_words(int64_t n) { return 2 * kmap_valid_words(n); }
+
+int kmap_pack2bit(const uint8_t* seq, int64_t n, uint32_t* packed, uint32_t* valid, void* stream) {
+    KMAP_REQUIRE(n >= 0, "negative size");
+    KMAP_REQUIRE(packed && valid && (seq || n == 0), "null pointer");
+    const int64_t nv = kmap_valid_words(n);
+    pack2bit_kernel<<<grid_for(nv, 256), 256, 0, as_stream(stream)>>>(seq, n, nv, packed, valid);
+    return kmap_check_launch("pack2bit");
+}
+
+int kmap_apply_valid_to_seq(uint8_t* seq, int64_t n, const uint32_t* valid, void* stream) {
+    KMAP_REQUIRE(n >= 0, "negative size");
+    if (n == 0) return KMAP_OK;
+    KMAP_REQUIRE(seq && valid, "null pointer");
+    apply_valid_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(seq, n, valid);
+    return kmap_check_launch("apply_valid_to_seq");
+}
+
+int kmap_fill_u32(uint32_t* p, int64_t n_words, uint32_t value, void* stream) {
+    KMAP_REQUIRE(n_words >= 0, "negative size");
+    if (n_words == 0) return KMAP_OK;
+    KMAP_REQUIRE(p, "null pointer");
+    if (value == 0) {
+        cudaError_t e = cudaMemsetAsync(p, 0, (size_t)n_words * 4, as_stream(stream));
+        if (e != cudaSuccess) { kmap_set_error("kmap_fill_u32: %s", cudaGetErrorString(e)); return (int)e; }
+        return KMAP_OK;
+    }
+    int64_t g = (n_words + 255) / 256;
+    if (g > 148 * 32) g = 148 * 32;
+    fill_u32_kernel<<<(unsigned int)g, 256, 0, as_stream(stream)>>>(p, n_words, value);
+    return kmap_check_launch("fill_u32");
+}
+
+}  // extern "C"

@@ -1,0 +1,258 @@
+"""Device-side engine: torch tensors for the buffers, libkmap_b200 for every kernel.
+
+`SeqOnDevice` is the packed, device-resident form of `input.bin.pkl` + `input.seqboarder.bin.pkl`
+(reference kmer_count.py:326-347) and carries the operations of the scan_motif counting path:
+count (with or without per-read de-duplication), order-exact compaction to the reference's
+`(uniq_kh_arr, uniq_kh_cnt_arr)`, Hamming-ball sums, masking, occurrence scan.
+
+PyTorch is plumbing only (allocation, H2D/D2H, streams, torch.distributed); no torch op computes a result.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from ._lib import KmapError, check, lib
+
+MISSING_VAL = 255
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise KmapError("kmap_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def to_device(a: np.ndarray, dtype=None) -> torch.Tensor:
+    """host ndarray -> device tensor with the same bytes (uint32/uint64 travel as int32/int64 views)."""
+    dev = require_cuda()
+    a = np.ascontiguousarray(a if dtype is None else a.astype(dtype, copy=False))
+    view = {np.dtype(np.uint32): np.int32, np.dtype(np.uint64): np.int64, np.dtype(np.uint16): np.int16}.get(a.dtype)
+    src = a.view(view) if view is not None else a
+    if src.size == 0:
+        return torch.empty(0, dtype=torch.from_numpy(np.empty(0, src.dtype)).dtype, device=dev)
+    return torch.from_numpy(src).to(dev, non_blocking=False)
+
+
+def to_host(t: torch.Tensor, dtype) -> np.ndarray:
+    """device tensor -> host ndarray reinterpreted as `dtype` (same item size)."""
+    a = t.cpu().numpy()
+    return a.view(dtype) if a.dtype != np.dtype(dtype) else a
+
+
+def empty(n: int, dtype: torch.dtype) -> torch.Tensor:
+    return torch.empty(max(int(n), 0), dtype=dtype, device=require_cuda())
+
+
+def zeros(n: int, dtype: torch.dtype) -> torch.Tensor:
+    return torch.zeros(max(int(n), 0), dtype=dtype, device=require_cuda())
+
+
+def check_borders_tile(borders: np.ndarray, n: int):
+    """The fused de-duplicating count walks reads, so every non-separator position must belong to exactly one read:
+    borders must be the layout preproc writes (kmer_count.py:335-343): st_0 = 0, en_i + 1 = st_{i+1}, en_last = n-1."""
+    b = np.asarray(borders)
+    if b.size == 0:
+        if n != 0:
+            raise KmapError("empty border matrix for a non-empty sequence array")
+        return
+    if b.ndim != 2 or b.shape[1] != 2:
+        raise KmapError("boarder_mat must be n_seq x 2")
+    ok = b[0, 0] == 0 and b[-1, 1] == n - 1 and np.all(b[:, 1] >= b[:, 0]) and np.all(b[1:, 0] == b[:-1, 1] + 1)
+    if not ok:
+        raise KmapError("boarder_mat does not tile the sequence array as `kmap preproc` writes it "
+                        "([start, separator index] per read, reads back to back)")
+
+
+class SeqOnDevice:
+    """Packed reads resident in HBM.  packed: 2 bits/base, valid: 1 bit/base, borders: int64[n_seq, 2]."""
+
+    def __init__(self, n: int, packed: torch.Tensor, valid: torch.Tensor, borders: Optional[torch.Tensor], n_seq: int,
+                 seq_u8: Optional[torch.Tensor] = None):
+        self.n, self.packed, self.valid, self.borders, self.n_seq, self.seq_u8 = n, packed, valid, borders, n_seq, seq_u8
+        self._flag_scratch = None
+        self._work = None
+        self._valid0 = None
+
+    # ---- construction ---------------------------------------------------------------------------------------
+    @classmethod
+    def from_device_u8(cls, seq_u8: torch.Tensor, borders: Optional[torch.Tensor], keep_u8: bool = False) -> "SeqOnDevice":
+        L = lib()
+        n = int(seq_u8.numel())
+        packed = empty(L.kmap_packed_words(n), torch.int32)
+        valid = empty(L.kmap_valid_words(n), torch.int32)
+        check(L.kmap_pack2bit(_ptr(seq_u8), n, _ptr(packed), _ptr(valid), _stream_ptr()), "kmap_pack2bit")
+        n_seq = 0 if borders is None else int(borders.shape[0])
+        return cls(n, packed, valid, borders, n_seq, seq_u8 if keep_u8 else None)
+
+    @classmethod
+    def from_numpy(cls, seq_np_arr: np.ndarray, boarder_mat: Optional[np.ndarray] = None, keep_u8: bool = False,
+                   validate: bool = True) -> "SeqOnDevice":
+        seq_np_arr = np.asarray(seq_np_arr)
+        if seq_np_arr.dtype != np.uint8:
+            raise KmapError("seq_np_arr must be uint8 (A0 C1 G2 T3, 255 missing)")
+        borders = None
+        if boarder_mat is not None:
+            b = np.ascontiguousarray(np.asarray(boarder_mat, dtype=np.int64))
+            if validate:
+                check_borders_tile(b, len(seq_np_arr))
+            borders = to_device(b.reshape(-1, 2))
+        return cls.from_device_u8(to_device(seq_np_arr), borders, keep_u8)
+
+    # ---- masking state ----------------------------------------------------------------------------------------
+    def snapshot_valid(self):
+        self._valid0 = self.valid.clone()
+
+    def restore_valid(self):
+        self.valid.copy_(self._valid0)
+
+    # ---- counting ---------------------------------------------------------------------------------------------
+    def count(self, k: int, dedup: bool, table: Optional[torch.Tensor] = None, zero: bool = True) -> torch.Tensor:
+        """dense forward table uint32[4^k] (held as int32 bits).  dedup=True fuses remove_duplicate_hash_per_seq."""
+        L = lib()
+        if not 1 <= k <= 15:
+            raise KmapError(f"dense counting supports 1 <= k <= 15 (got {k}); k >= 16 uses 64-bit hashes "
+                            "(sort path, not built yet)")
+        n_cells = 1 << (2 * k)
+        if table is None:
+            table = zeros(n_cells, torch.int32)
+        elif zero:
+            check(L.kmap_fill_u32(_ptr(table), n_cells, 0, _stream_ptr()), "kmap_fill_u32")
+        if dedup:
+            if self.borders is None:
+                raise KmapError("per-read de-duplication needs the border matrix")
+            need = L.kmap_dedup_work_words(self.n_seq)
+            if self._work is None or self._work.numel() < need:
+                self._work = empty(need, torch.int32)
+            # when accumulating into a caller's table a failed first attempt could not be undone: give the bitmap upfront
+            bitmap = None if zero else zeros(max(n_cells // 32, 1), torch.int32)
+            rc = L.kmap_count_dense_dedup(_ptr(self.packed), _ptr(self.valid), self.n, _ptr(self.borders), self.n_seq, k,
+                                          _ptr(table), _ptr(self._work), _ptr(bitmap), _stream_ptr())
+            if rc == -3:  # KMAP_ERR_NEED_SCRATCH: a very long read; retry the long reads with the bitmap
+                check(L.kmap_fill_u32(_ptr(table), n_cells, 0, _stream_ptr()), "kmap_fill_u32")
+                bitmap = zeros(max(n_cells // 32, 1), torch.int32)
+                rc = L.kmap_count_dense_dedup(_ptr(self.packed), _ptr(self.valid), self.n, _ptr(self.borders), self.n_seq,
+                                              k, _ptr(table), _ptr(self._work), _ptr(bitmap), _stream_ptr())
+            check(rc, "kmap_count_dense_dedup")
+        else:
+            check(L.kmap_count_dense(_ptr(self.packed), _ptr(self.valid), self.n, k, _ptr(table), _stream_ptr()),
+                  "kmap_count_dense")
+        return table
+
+    # ---- masking ----------------------------------------------------------------------------------------------
+    def mask(self, k: int, consensus_kh: Sequence[int], max_dist: Sequence[int]):
+        L = lib()
+        m = len(consensus_kh)
+        if m == 0 or self.n == 0:
+            return
+        cons = to_device(np.asarray([int(c) & 0xFFFFFFFF for c in consensus_kh], dtype=np.uint32))
+        d = to_device(np.asarray([int(x) for x in max_dist], dtype=np.int32))
+        if self._flag_scratch is None:
+            self._flag_scratch = empty(self.valid.numel(), torch.int32)
+        pre = self.valid if m <= 16 else self.valid.clone()   # every consensus is compared on the pre-mask windows
+        for i in range(0, m, 16):
+            mm = min(16, m - i)
+            check(L.kmap_mask(_ptr(self.packed), _ptr(pre), _ptr(self.valid), self.n, k, cons[i:].data_ptr(),
+                              d[i:].data_ptr(), mm, _ptr(self._flag_scratch), _stream_ptr()), "kmap_mask")
+
+    def masked_seq_to_numpy(self, out: np.ndarray):
+        """write the masking state into `out` (the caller's seq_np_arr): 255 wherever a base is no longer valid."""
+        L = lib()
+        if self.n == 0:
+            return out
+        if self.seq_u8 is None:
+            self.seq_u8 = to_device(out)
+        check(L.kmap_apply_valid_to_seq(_ptr(self.seq_u8), self.n, _ptr(self.valid), _stream_ptr()), "kmap_apply_valid_to_seq")
+        out[:] = self.seq_u8.cpu().numpy()
+        return out
+
+
+# ---- table -> reference lists ----------------------------------------------------------------------------------
+_scratch_cache = {}
+
+
+def _scratch(words: int) -> torch.Tensor:
+    dev = torch.cuda.current_device()
+    t = _scratch_cache.get(dev)
+    if t is None or t.numel() < words:
+        t = empty(words, torch.int64)
+        _scratch_cache[dev] = t
+    return t
+
+
+def compact_merge(table: torch.Tensor, k: int, revcom: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(kh uint32-bits, cnt int32) device tensors in the reference's order (kmer_count.py:476-491, 643-685)."""
+    L = lib()
+    scratch = _scratch(L.kmap_compact_scratch_words(k))
+    n_out = ctypes.c_int64(0)
+    check(L.kmap_compact_merge(_ptr(table), k, int(revcom), _ptr(scratch), None, None, 0, ctypes.byref(n_out), _stream_ptr()),
+          "kmap_compact_merge(size)")
+    n = n_out.value
+    kh, cnt = empty(n, torch.int32), empty(n, torch.int32)
+    if n:
+        check(L.kmap_compact_merge(_ptr(table), k, int(revcom), _ptr(scratch), _ptr(kh), _ptr(cnt), n, ctypes.byref(n_out),
+                                   _stream_ptr()), "kmap_compact_merge")
+    return kh, cnt
+
+
+def hamball_sums(table: torch.Tensor, k: int, cand: Sequence[int], d: int, revcom: bool) -> np.ndarray:
+    """int64 ball sums for each candidate hash by neighbour enumeration on the dense table (motif_discovery.py:666-673)."""
+    L = lib()
+    m = len(cand)
+    if m == 0:
+        return np.zeros(0, dtype=np.int64)
+    c = to_device(np.asarray([int(x) for x in cand], dtype=np.uint32))
+    sums = empty(m, torch.int64)
+    check(L.kmap_hamball_sum(_ptr(table), k, _ptr(c), m, int(d), int(revcom), _ptr(sums), _stream_ptr()), "kmap_hamball_sum")
+    return sums.cpu().numpy()
+
+
+def hamball_sums_list(kh: torch.Tensor, cnt: torch.Tensor, k: int, cand: Sequence[int], d: int, revcom: bool) -> np.ndarray:
+    L = lib()
+    out = np.zeros(len(cand), dtype=np.int64)
+    for i in range(0, len(cand), 16):
+        part = list(cand[i:i + 16])
+        c = to_device(np.asarray([int(x) for x in part], dtype=np.uint32))
+        sums = empty(len(part), torch.int64)
+        check(L.kmap_hamball_sum_list(_ptr(kh), _ptr(cnt), int(kh.numel()), k, _ptr(c), len(part), int(d), int(revcom),
+                                      _ptr(sums), _stream_ptr()), "kmap_hamball_sum_list")
+        out[i:i + 16] = sums.cpu().numpy()
+    return out
+
+
+def exclusive_scan_u32(counts: torch.Tensor) -> torch.Tensor:
+    L = lib()
+    n = int(counts.numel())
+    out = empty(n + 1, torch.int64)
+    scratch = _scratch(L.kmap_list_scratch_words(n))
+    check(L.kmap_exclusive_scan_u32(_ptr(counts), n, _ptr(out), _ptr(scratch), _stream_ptr()), "kmap_exclusive_scan_u32")
+    return out
+
+
+def occurrence_scan(seq: SeqOnDevice, k: int, conseq_kh: int, d: int, revcom: bool):
+    """per read: (min_dist uint8[n_seq] (255 = none), offsets int64[n_seq+1], positions int32[total]) on the host."""
+    L = lib()
+    n_seq = seq.n_seq
+    min_dist = empty(n_seq, torch.uint8)
+    n_hit = empty(n_seq, torch.int32)
+    check(L.kmap_occurrence_count(_ptr(seq.packed), _ptr(seq.valid), _ptr(seq.borders), n_seq, k, int(conseq_kh), int(d),
+                                  int(revcom), _ptr(min_dist), _ptr(n_hit), _stream_ptr()), "kmap_occurrence_count")
+    offsets = exclusive_scan_u32(n_hit)
+    total = int(offsets[-1].item()) if n_seq else 0
+    pos = empty(total, torch.int32)
+    if total:
+        check(L.kmap_occurrence_fill(_ptr(seq.packed), _ptr(seq.valid), _ptr(seq.borders), n_seq, k, int(conseq_kh), int(d),
+                                     int(revcom), _ptr(min_dist), _ptr(offsets), _ptr(pos), _stream_ptr()),
+              "kmap_occurrence_fill")
+    return min_dist.cpu().numpy(), offsets.cpu().numpy(), pos.cpu().numpy()

@@ -1,0 +1,622 @@
+"""Drop-in for the counting path of the reference's `kmap/motif_discovery.py` (find_motif, ex_hamball, motif
+occurrence, sampled k-mer distance matrix, the scan_motif / ex_hamball drivers and their file layouts).  Same
+names, signatures and files; integer work runs in libkmap_b200 (sm_100a CUDA) on device-resident packed reads.
+
+Reference line numbers cited below are in /root/reference/src/kmap/motif_discovery.py.  Plotting, KDE position
+densities, co-occurrence networks and consensus alignment are outside this package's scope.
+"""
+from __future__ import annotations
+
+import pickle
+import warnings
+from pathlib import Path
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import engine as E
+from ._lib import KmapError, check, lib
+from .kmer_count import (FileNameDict, MotifDef, cal_hamming_dist, cal_hamming_dist_head, cal_hamming_dist_tail,
+                         dna2arr, fasta_to_arrays, gen_motif_def_dict, get_hash_dtype, get_revcom_hash_arr, hash2kmer,
+                         init_motif_def_dict, kmer2hash, mask_ham_ball, reverse_complement, revcom_hash)
+
+
+def write_lines(str_list: List, outfile):
+    with open(outfile, "w+") as fh:
+        for line in str_list:
+            fh.write(line + "\n")
+
+
+# ======================================================================================================================
+# find_motif (:594-702)
+# ======================================================================================================================
+class _CountState:
+    """Counts of the current (possibly masked) sequence: dense forward table on the device + the reference's merged
+    lists on the host (np.argpartition has to see exactly those arrays)."""
+
+    def __init__(self, k, revcom, table=None, kh_dev=None, cnt_dev=None):
+        self.k, self.revcom, self.table, self.kh_dev, self.cnt_dev = k, revcom, table, kh_dev, cnt_dev
+        self.kh = E.to_host(kh_dev, np.uint32) if kh_dev is not None else None
+        self.cnt = E.to_host(cnt_dev, np.int32) if cnt_dev is not None else None
+
+    @classmethod
+    def from_table(cls, table, k, revcom):
+        kh_dev, cnt_dev = E.compact_merge(table, k, revcom)
+        return cls(k, revcom, table, kh_dev, cnt_dev)
+
+    @classmethod
+    def from_lists(cls, kh, cnt, k, revcom):
+        st = cls(k, revcom)
+        st.kh, st.cnt = np.asarray(kh), np.asarray(cnt)
+        st.kh_dev = E.to_device(st.kh.astype(np.uint32, copy=False))
+        st.cnt_dev = E.to_device(st.cnt.astype(np.int32, copy=False))
+        return st
+
+    def ball_sums(self, cand, d):
+        if self.table is not None:
+            return E.hamball_sums(self.table, self.k, cand, d, self.revcom)
+        return E.hamball_sums_list(self.kh_dev, self.cnt_dev, self.k, cand, d, self.revcom)
+
+
+def find_motif_on_device(dev: E.SeqOnDevice, kmer_len: int, max_ham_dist, p_unif, ratio_mu, ratio_std, ratio_cutoff,
+                         top_k=5, n_trial=10, merge_revcom_mode=True, rep_mode=False, first_lists=None,
+                         first_table: Optional[torch.Tensor] = None, debug=False):
+    """Core of find_motif on a device-resident sequence (mutates dev.valid).  Returns (result dict, (uniq_kh, uniq_cnt)
+    of the first round).  `first_lists` plays the role of a pre-existing k{k}.pkl (:621-624); `first_table` lets a
+    caller that counted every k in one pass hand in the forward table."""
+    from scipy.stats import norm
+    k = kmer_len
+    if first_lists is not None:
+        state = _CountState.from_lists(first_lists[0], first_lists[1], k, merge_revcom_mode)
+    else:
+        table = first_table if first_table is not None else dev.count(k, dedup=not rep_mode)
+        state = _CountState.from_table(table, k, merge_revcom_mode)
+    first = (state.kh, state.cnt)
+    n_total_kmer = int(np.sum(state.cnt, dtype=np.int64))       # exact
+
+    found = {}
+    for i_trial in range(n_trial):
+        if top_k > len(state.cnt):
+            break
+        top_k_inds = np.array(np.argpartition(state.cnt, -top_k)[-top_k:])
+        if len(top_k_inds) == 0:
+            break
+        cand = state.kh[top_k_inds]
+        hamball_cnt_arr = np.zeros(top_k)
+        hamball_cnt_arr[:] = state.ball_sums(cand, max_ham_dist)
+        if debug:
+            print(f"{i_trial= }")
+        best = np.argmax(hamball_cnt_arr)
+        consensus_kh = state.kh[top_k_inds[best]]
+        hamball_proportion = (hamball_cnt_arr[best] + 0.0) / n_total_kmer
+        hamball_ratio = hamball_proportion / p_unif
+        if not hamball_ratio > ratio_cutoff:
+            break
+        found[consensus_kh] = (hamball_proportion, hamball_ratio,
+                               norm.logsf(hamball_ratio, loc=ratio_mu, scale=ratio_std) / np.log(10))
+        cons = [int(consensus_kh)]
+        if merge_revcom_mode:
+            cons.append(int(revcom_hash(consensus_kh, k)))
+        dev.mask(k, cons, [max_ham_dist] * len(cons))
+        table = dev.count(k, dedup=False, table=state.table)          # recounts are never de-duplicated (:695-696)
+        state = _CountState.from_table(table, k, merge_revcom_mode)
+    return found, first
+
+
+def find_motif(seq_np_arr, kmer_len: int, max_ham_dist, p_unif, ratio_mu, ratio_std, ratio_cutoff, top_k=5, n_trial=10,
+               merge_revcom_mode=True, rep_mode=False, save_kmer_cnt_flag=True, kmer_cnt_pkl_file: Path = None,
+               boarder_pkl_file: Path = None, debug=False) -> dict:
+    """:594-702, same signature and side effects: mutates seq_np_arr (masking), reads/writes k{k}.pkl."""
+    if boarder_pkl_file:
+        assert Path(boarder_pkl_file).exists()
+    first_lists = None
+    boarder_mat = None
+    if save_kmer_cnt_flag and kmer_cnt_pkl_file and Path(kmer_cnt_pkl_file).exists():
+        with open(Path(kmer_cnt_pkl_file), "rb") as fh:
+            kmer_len_from_pkl_file, uniq_kh_arr, uniq_kh_cnt_arr = pickle.load(fh)
+            assert kmer_len == kmer_len_from_pkl_file
+        first_lists = (uniq_kh_arr, uniq_kh_cnt_arr)
+    else:
+        with open(boarder_pkl_file, "rb") as fh:
+            boarder_mat = pickle.load(fh)
+    dev = E.SeqOnDevice.from_numpy(seq_np_arr, boarder_mat, keep_u8=True)
+    found, first = find_motif_on_device(dev, kmer_len, max_ham_dist, p_unif, ratio_mu, ratio_std, ratio_cutoff, top_k,
+                                        n_trial, merge_revcom_mode, rep_mode, first_lists, None, debug)
+    if save_kmer_cnt_flag and kmer_cnt_pkl_file and not Path(kmer_cnt_pkl_file).exists():
+        with open(kmer_cnt_pkl_file, "wb") as fh:
+            pickle.dump([kmer_len, first[0], first[1]], fh)
+    if found:
+        dev.masked_seq_to_numpy(seq_np_arr)
+    return found
+
+
+# ======================================================================================================================
+# Hamming ball extraction + count matrix (:489-530, 924-986)
+# ======================================================================================================================
+def _hamball_extract(uniq_kh_arr, uniq_kh_cnt_arr, conseq_kh: int, kmer_len: int, max_ham_dist: int, revcom_mode: bool,
+                     want_list=True):
+    L = lib()
+    n = len(uniq_kh_arr)
+    kh_d = E.to_device(np.asarray(uniq_kh_arr).astype(np.uint32, copy=False))
+    cnt_d = E.to_device(np.asarray(uniq_kh_cnt_arr).astype(np.int32, copy=False))
+    import ctypes
+    scratch = E._scratch(L.kmap_list_scratch_words(n))
+    cnt_mat = E.empty(4 * kmer_len, torch.int64)
+    n_out = ctypes.c_int64(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    # size query = a run without list output (the matrix is complete after it)
+    check(L.kmap_hamball_extract(kh_d.data_ptr(), cnt_d.data_ptr(), n, kmer_len, int(conseq_kh), int(max_ham_dist),
+                                 int(revcom_mode), scratch.data_ptr(), None, None, 0, ctypes.byref(n_out),
+                                 cnt_mat.data_ptr(), stream), "kmap_hamball_extract")
+    mat = cnt_mat.cpu().numpy().reshape(4, kmer_len).astype(int)
+    if not want_list:
+        return None, None, mat
+    m = n_out.value
+    out_kh, out_cnt = E.empty(m, torch.int32), E.empty(m, torch.int32)
+    if m:
+        check(L.kmap_hamball_extract(kh_d.data_ptr(), cnt_d.data_ptr(), n, kmer_len, int(conseq_kh), int(max_ham_dist),
+                                     int(revcom_mode), scratch.data_ptr(), out_kh.data_ptr(), out_cnt.data_ptr(), m,
+                                     ctypes.byref(n_out), cnt_mat.data_ptr(), stream), "kmap_hamball_extract")
+    return E.to_host(out_kh, np.uint32), E.to_host(out_cnt, np.int32), mat
+
+
+def ex_hamball_kh_arr(res_dir: str, conseq: str, max_ham_dist: int = -1, motif_def_file: str = None, revcom_mode=True):
+    """:924-975"""
+    conseq = conseq.upper()
+    assert all([e in ("A", "C", "G", "T") for e in conseq])
+    kmer_len = len(conseq)
+    conseq_kh = kmer2hash(conseq)
+    rc_conseq_kh = revcom_hash(conseq_kh, kmer_len)
+    if revcom_mode:
+        assert conseq_kh <= rc_conseq_kh
+    assert Path(motif_def_file).exists()
+    assert Path(res_dir).exists()
+    kmer_cnt_file = Path(res_dir) / FileNameDict["kmer_count_dir"] / f"k{kmer_len}.pkl"
+    with open(kmer_cnt_file, "rb") as fh:
+        res_list = pickle.load(fh)
+    assert res_list[0] == kmer_len
+    uniq_kh_arr, uniq_kh_cnt_arr = res_list[1], res_list[2]
+    if max_ham_dist == -1:
+        max_ham_dist = init_motif_def_dict(motif_def_file)[kmer_len].max_ham_dist
+    kh, cnt, _ = _hamball_extract(uniq_kh_arr, uniq_kh_cnt_arr, int(conseq_kh), kmer_len, max_ham_dist, revcom_mode)
+    return kh.astype(uniq_kh_arr.dtype, copy=False), cnt.astype(uniq_kh_cnt_arr.dtype, copy=False)
+
+
+def cal_cnt_mat(uniq_kh_arr, uniq_kh_cnt_arr, kmer_len):
+    """:978-986: int64[4, k], row = base code, column = position.  Runs the ball kernel with the ball = everything."""
+    if len(uniq_kh_arr) == 0:
+        return np.zeros((4, kmer_len), dtype=int)
+    _, _, mat = _hamball_extract(uniq_kh_arr, uniq_kh_cnt_arr, 0, kmer_len, kmer_len, False, want_list=False)
+    return mat
+
+
+def _ex_hamball(res_dir: str, conseq: str, return_type: str, output_file: str, max_ham_dist: int = -1):
+    """:489-530"""
+    import tomllib
+    config_file_path = Path(res_dir) / FileNameDict["config_file"]
+    assert config_file_path.exists()
+    with open(config_file_path, "rb") as fh:
+        config_dict = tomllib.load(fh)
+    assert return_type in ("hash", "kmer", "matrix")
+    motif_def_file_path = Path(res_dir) / FileNameDict["motif_def_file"]
+    revcom_mode = config_dict["kmer_count"]["revcom_mode"]
+    uniq_kh_arr, uniq_kh_cnt_arr = ex_hamball_kh_arr(res_dir, conseq, max_ham_dist, motif_def_file_path, revcom_mode)
+    kmer_len = len(conseq)
+    with open(output_file, "w+") as fh:
+        if return_type == "hash":
+            for kh, cnt in zip(uniq_kh_arr, uniq_kh_cnt_arr):
+                fh.write(f"{kh},{cnt}\n")
+        elif return_type == "kmer":
+            for kh, cnt in zip(uniq_kh_arr, uniq_kh_cnt_arr):
+                fh.write(f"{hash2kmer(kh, kmer_len)},{cnt}\n")
+        else:
+            np.savetxt(fh, cal_cnt_mat(uniq_kh_arr, uniq_kh_cnt_arr, kmer_len), delimiter=",", fmt="%d")
+    print(f"Extract Hamming ball [type={return_type}] save in {output_file}.")
+
+
+# ======================================================================================================================
+# motif occurrence (:1345-1477)
+# ======================================================================================================================
+def motif_occurence_table(dev: E.SeqOnDevice, conseq_list: Sequence[str], motif_def_dict: dict, revcom_mode=True):
+    """All reads x all consensus sequences in one device pass per consensus.  Returns a list (per consensus) of
+    (min_dist[n_seq], offsets[n_seq+1], positions[total])."""
+    out = []
+    for conseq in conseq_list:
+        k = len(conseq)
+        out.append(E.occurrence_scan(dev, k, int(kmer2hash(conseq)), motif_def_dict[k].max_ham_dist, revcom_mode))
+    return out
+
+
+def _cells_for_read(per_conseq, r):
+    cells, flag = [], False
+    for min_dist, offsets, pos in per_conseq:
+        lo, hi = offsets[r], offsets[r + 1]
+        if hi == lo:
+            cells.append("")
+            continue
+        locs = pos[lo:hi]
+        if len(locs) > 20:                                   # :1467-1469 (the reference's unseeded random pick)
+            locs = np.sort(locs[np.random.choice(len(locs), 20, replace=False)])
+        flag = True
+        cells.append(",".join(map(str, locs)))
+    return flag, ";".join(cells)
+
+
+def get_motif_occurence(seq_np_arr: np.ndarray, conseq_list: List[str], motif_def_dict: dict, revcom_mode=True):
+    """:1422-1477 for ONE read given without separator.  Returns (motif_flag, 'p,p;..;..')."""
+    arr = np.concatenate([np.asarray(seq_np_arr, dtype=np.uint8), np.array([255], dtype=np.uint8)])
+    dev = E.SeqOnDevice.from_numpy(arr, np.array([[0, len(arr) - 1]], dtype=np.int64))
+    return _cells_for_read(motif_occurence_table(dev, conseq_list, motif_def_dict, revcom_mode), 0)
+
+
+def motif_occurence_lines(dev: E.SeqOnDevice, borders: np.ndarray, conseq_list, motif_def_dict, revcom_mode=True) -> List[str]:
+    """lines of a *.motif_occurence.csv (:1409-1418): header, then one row per read that has at least one hit"""
+    lines = ["seq_ind;" + ";".join(f"motif_{i}_{conseq_list[i]}" for i in range(len(conseq_list))) + ";seq_len"]
+    per_conseq = motif_occurence_table(dev, conseq_list, motif_def_dict, revcom_mode)
+    if not per_conseq:
+        return lines
+    has_hit = np.zeros(dev.n_seq, dtype=bool)
+    for min_dist, offsets, pos in per_conseq:
+        has_hit |= np.diff(offsets) > 0
+    lens = borders[:, 1] - borders[:, 0]
+    for r in np.flatnonzero(has_hit):
+        flag, cells = _cells_for_read(per_conseq, r)
+        lines.append(f"{r};{cells};{lens[r]}")
+    return lines
+
+
+def gen_motif_occurence_file(conseq_list: List[str], motif_def_dict: dict, input_fasta_file: Path, output_file: Path,
+                             revcom_mode=True, _dev_cache=None):
+    """:1396-1419.  The reference re-parses the FASTA file per call; the encoded arrays are identical to input.bin
+    (same upper-casing and code table), so a cached device copy may be passed by the driver."""
+    assert Path(input_fasta_file).exists()
+    if _dev_cache is not None:
+        dev, borders = _dev_cache
+    else:
+        seq, borders = fasta_to_arrays(input_fasta_file)
+        dev = E.SeqOnDevice.from_numpy(seq, borders)
+    write_lines(motif_occurence_lines(dev, borders, conseq_list, motif_def_dict, revcom_mode), output_file)
+
+
+def get_motif_seq_num(occurence_file_path: Path, motif_index: int) -> Tuple[int, int]:
+    """:1345-1393"""
+    lines_with_motif = total_occurrences = 0
+    with open(occurence_file_path, "r") as fh:
+        next(fh)
+        for row in fh:
+            cell = row.rstrip("\n").split(";")[motif_index + 1].strip()
+            if cell == "":
+                continue
+            lines_with_motif += 1
+            total_occurrences += len(cell.split(","))
+    return lines_with_motif, total_occurrences
+
+
+# ======================================================================================================================
+# sampled k-mer distance matrix (:705-808)
+# ======================================================================================================================
+def _convert_to_block_mat(uniq_dist_mat: np.ndarray, block_size_arr: np.ndarray) -> np.ndarray:
+    """:705-730"""
+    assert np.issubdtype(block_size_arr.dtype, np.integer)
+    assert np.all(block_size_arr > 0)
+    return np.repeat(np.repeat(uniq_dist_mat, block_size_arr, axis=0), block_size_arr, axis=1)
+
+
+def _convert_to_block_arr(arr: np.ndarray, block_size_arr: np.ndarray) -> np.ndarray:
+    """:733-757"""
+    assert np.issubdtype(block_size_arr.dtype, np.integer)
+    assert np.all(block_size_arr > 0)
+    assert len(arr) == len(block_size_arr)
+    return np.repeat(arr, block_size_arr)
+
+
+def hamdist_matrix_u8(kh: np.ndarray, labels: np.ndarray, head_len: Sequence[int], kmer_len: int, row0: int = 0,
+                      row1: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """rows [row0,row1) of the pairwise distance matrix as a uint8 device tensor [(row1-row0), n]"""
+    L = lib()
+    n = len(kh)
+    row1 = n if row1 is None else row1
+    hd = get_hash_dtype(kmer_len)
+    kh_d = E.to_device(np.asarray(kh).astype(hd, copy=False))
+    lab_d = E.to_device(np.asarray(labels).astype(np.int32, copy=False))
+    hl_d = E.to_device(np.asarray(list(head_len), dtype=np.int32)) if len(head_len) else None
+    if out is None:
+        out = E.empty((row1 - row0) * n, torch.uint8)
+    fn = L.kmap_hamdist_matrix_u32 if hd == np.uint32 else L.kmap_hamdist_matrix_u64
+    check(fn(kh_d.data_ptr(), lab_d.data_ptr(), n, kmer_len, None if hl_d is None else hl_d.data_ptr(), len(head_len),
+             row0, row1, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "kmap_hamdist_matrix")
+    return out.view(row1 - row0, n)
+
+
+def cal_samp_kmer_hamdist_mat(samp_kh_arr: np.ndarray, samp_cnts: np.ndarray, samp_label_arr: np.ndarray,
+                              conseq_list: List[str], kmer_len: int, uniq_dist_flag=False, dtype=int) -> np.ndarray:
+    """:759-808.  The expansion by samp_cnts is fused: the kernel computes the expanded matrix directly from the
+    repeated key / label arrays.  `dtype=int` reproduces the reference's int64 result; pass np.uint8 to keep the
+    compact device format (1 B per pair) for large samples."""
+    samp_kh_arr = np.asarray(samp_kh_arr)
+    assert len(samp_kh_arr) == len(np.unique(samp_kh_arr))
+    for conseq in conseq_list:
+        assert len(conseq) <= kmer_len
+    head_len = [len(c) for c in conseq_list]
+    labels = np.asarray(samp_label_arr)
+    if uniq_dist_flag:
+        kh, lab = samp_kh_arr, labels
+    else:
+        cnts = np.asarray(samp_cnts)
+        assert np.issubdtype(cnts.dtype, np.integer) and np.all(cnts > 0)
+        kh, lab = np.repeat(samp_kh_arr, cnts), np.repeat(labels, cnts)
+    if len(kh) == 0:
+        return np.zeros((0, 0), dtype=dtype)
+    mat = hamdist_matrix_u8(kh, lab, head_len, kmer_len).cpu().numpy()
+    return mat if np.dtype(dtype) == np.uint8 else mat.astype(dtype)
+
+
+# ======================================================================================================================
+# k-mer sampling for the visualisation (:812-921)
+# ======================================================================================================================
+def sample_disp_kmer(conseq_list: List[str], kmer_len: int, motif_def_dict: dict, kmer_count_dir: Path,
+                     n_total_sample=5000, n_motif_kmer=2500, revcom_mode=True) -> Tuple:
+    conseq_list = [s for s in conseq_list if 2 < len(s) <= kmer_len]
+    assert len(conseq_list) > 0
+    assert all(len(a) >= len(b) for a, b in zip(conseq_list, conseq_list[1:]))
+    with open(Path(kmer_count_dir) / f"k{kmer_len}.pkl", "rb") as fh:
+        res_list = pickle.load(fh)
+    assert res_list[0] == kmer_len
+    uniq_kh_arr, uniq_kh_cnt_arr = res_list[1], res_list[2]
+    total = int(np.sum(uniq_kh_cnt_arr, dtype=np.int64))
+    sampling_flag = True
+    if n_total_sample > total:
+        warnings.warn(f"The number of samples n_sample={n_total_sample} is larger than the original "
+                      f"data n_seq={total}, process and return original data.")
+        sampling_flag = False
+    n_conseq, n_uniq = len(conseq_list), len(uniq_kh_arr)
+    ham_dist_mat = np.zeros((n_conseq, n_uniq), dtype=int)
+    rc_flag_mat = np.zeros((n_conseq, n_uniq), dtype=bool)
+    for i, conseq in enumerate(conseq_list):
+        conseq_kh = kmer2hash(conseq)
+        dist_arr = cal_hamming_dist_head(uniq_kh_arr, conseq_kh, kmer_len, len(conseq))
+        if revcom_mode:
+            rc_conseq_kh = revcom_hash(conseq_kh, len(conseq))
+            assert conseq_kh <= rc_conseq_kh
+            rc_dist_arr = cal_hamming_dist_tail(uniq_kh_arr, rc_conseq_kh, kmer_len, len(conseq))
+            rc_flag_mat[i] = rc_dist_arr < dist_arr
+            dist_arr = np.minimum(dist_arr, rc_dist_arr)
+        ham_dist_mat[i] = dist_arr
+    for i, conseq in enumerate(conseq_list):
+        ham_dist_mat[i][ham_dist_mat[i] > motif_def_dict[len(conseq)].max_ham_dist] = kmer_len
+    min_dist_arr = np.min(ham_dist_mat, axis=0)
+    label_arr = np.argmin(ham_dist_mat, axis=0)
+    label_arr[min_dist_arr > motif_def_dict[kmer_len].max_ham_dist] = n_conseq
+    if revcom_mode:
+        for i in range(n_conseq):
+            idx = np.where((label_arr == i) & rc_flag_mat[i])[0]
+            if len(idx):
+                uniq_kh_arr[idx] = get_revcom_hash_arr(uniq_kh_arr[idx], kmer_len)
+    if not sampling_flag:
+        return uniq_kh_arr, uniq_kh_cnt_arr, label_arr, conseq_list
+    sample_cnt_arr = np.bincount(label_arr, weights=uniq_kh_cnt_arr)
+    motif_weights = sample_cnt_arr[:-1] / sum(sample_cnt_arr[:-1])
+    sample_cnt_arr[:-1] = np.around(n_motif_kmer * motif_weights)
+    sample_cnt_arr[-1] = n_total_sample - sum(sample_cnt_arr[0:-1])
+    sample_cnt_arr = sample_cnt_arr.astype(int)
+    assert len(sample_cnt_arr) == n_conseq + 1
+    samp_inds, samp_cnts = [], []
+    for c in range(n_conseq + 1):
+        c_inds = np.where(label_arr == c)[0]
+        ws = uniq_kh_cnt_arr[c_inds]
+        ws = ws / sum(ws)
+        tmpcnts = np.random.multinomial(sample_cnt_arr[c], ws, size=1).squeeze()
+        samp_inds.append(c_inds[tmpcnts > 0])
+        samp_cnts.append(tmpcnts[tmpcnts > 0])
+    samp_inds = np.concatenate(samp_inds)
+    samp_cnts = np.concatenate(samp_cnts)
+    return uniq_kh_arr[samp_inds], samp_cnts, label_arr[samp_inds], conseq_list
+
+
+# ======================================================================================================================
+# merge candidates of different lengths (:533-591) -- host string logic
+# ======================================================================================================================
+def merge_consensus_seqs(conseq_list: List[str]) -> List[str]:
+    def related(long_kmer, short_kmer):
+        # a (len-1)-substring of short_kmer occurs in long_kmer
+        return short_kmer[:-1] in long_kmer or short_kmer[1:] in long_kmer
+
+    remaining = sorted(conseq_list, key=len, reverse=True)
+    final_conseq_list = []
+    while remaining:
+        cur = remaining[0]
+        rc_cur = reverse_complement(cur)
+
+        def hit(s):
+            return related(cur, s) or related(rc_cur, s)
+
+        one_shorter = next((s for s in remaining if len(s) == len(cur) - 1 and hit(s)), None)
+        two_shorter = next((s for s in remaining if len(s) == len(cur) - 2 and hit(s)), None)
+        if one_shorter and two_shorter:
+            final_conseq_list.append(one_shorter)
+            remaining = [s for s in remaining if not hit(s)]
+        else:
+            remaining = remaining[1:]
+    return final_conseq_list
+
+
+# ======================================================================================================================
+# scan_motif driver (:187-486) -- same files, same resume-by-file-existence behaviour
+# ======================================================================================================================
+def _scan_motif(res_dir: str, debug=False):
+    import tomllib
+    res = Path(res_dir)
+    config_file_path = res / FileNameDict["config_file"]
+    motif_def_file_path = res / FileNameDict["motif_def_file"]
+    proc_fasta_file_path = res / FileNameDict["processed_fasta_file"]
+    assert config_file_path.exists()
+    assert motif_def_file_path.exists()
+    assert proc_fasta_file_path.exists()
+    with open(config_file_path, "rb") as fh:
+        config_dict = tomllib.load(fh)
+    motif_def_dict = gen_motif_def_dict(config_dict, debug=debug)
+    min_k = config_dict["kmer_count"]["min_k"]
+    max_k = config_dict["kmer_count"]["max_k"]
+    revcom_mode = config_dict["kmer_count"]["revcom_mode"]
+    rep_mode = config_dict["general"]["repetitive_mode"]
+    md_cfg = config_dict["motif_discovery"]
+
+    mask_noise_seq_list = []
+    if md_cfg["noise_kmer_file"] != "None":
+        assert Path(md_cfg["noise_kmer_file"]).exists()
+        with open(Path(md_cfg["noise_kmer_file"]), "r") as fh:
+            mask_noise_seq_list = [ln.strip() for ln in fh if ln.strip()]
+    with open(proc_fasta_file_path, "rb") as fh:
+        seq_np_arr = pickle.load(fh)
+    if mask_noise_seq_list:
+        seq_np_arr = mask_ham_ball(seq_np_arr, motif_def_dict, mask_noise_seq_list, [0 for _ in mask_noise_seq_list])
+    boarder_pkl_file = res / FileNameDict["processed_fasta_seqboarder_file"]
+    with open(boarder_pkl_file, "rb") as fh:
+        boarder_mat = pickle.load(fh)
+    n_all_seq = len(boarder_mat)
+
+    top_k, n_trial = md_cfg["top_k"], md_cfg["n_trial"]
+    save_kmer_cnt_flag = md_cfg["save_kmer_cnt_flag"]
+    candidate_conseq_list = []
+    kmer_count_dir = res / FileNameDict["kmer_count_dir"]
+    if save_kmer_cnt_flag:
+        kmer_count_dir.mkdir(exist_ok=True)
+    input_fasta_file = Path(config_dict["general"]["input_fasta_file"])
+
+    # one device copy of the (noise-masked) reads serves every k; the occurrence scans use the unmasked FASTA content
+    dev = E.SeqOnDevice.from_numpy(seq_np_arr, boarder_mat)
+    dev.snapshot_valid()
+    occ_dev = None
+
+    def occurrence_dev():
+        nonlocal occ_dev
+        if occ_dev is None:
+            assert input_fasta_file.exists()
+            fa_seq, fa_borders = fasta_to_arrays(input_fasta_file)
+            occ_dev = (E.SeqOnDevice.from_numpy(fa_seq, fa_borders), fa_borders)
+        return occ_dev
+
+    candidate_conseq_file = res / FileNameDict["candidate_conseq_file"]
+    if candidate_conseq_file.exists():
+        print(f"{candidate_conseq_file} already exist, re-use it.")
+    else:
+        store_flag = md_cfg["store_conseq_occur_info_flag"]
+        header = "kmer_len,conseq_hash,conseq,conseq_rc,hamball_proportion,hamball_ratio,log10_p_value"
+        if store_flag:
+            header += ",n_motif_reads,n_all_reads,motif_reads_prop,motif_occurrence,motif_occurrence_per_motif_read"
+        rows = [header]
+        for kmer_len in range(min_k, max_k + 1):
+            dev.restore_valid()
+            m = motif_def_dict[kmer_len]
+            kmer_cnt_file = kmer_count_dir / f"k{kmer_len}.pkl"
+            first_lists = None
+            if save_kmer_cnt_flag and kmer_cnt_file.exists():
+                with open(kmer_cnt_file, "rb") as fh:
+                    k_from_file, kh0, cnt0 = pickle.load(fh)
+                    assert kmer_len == k_from_file
+                first_lists = (kh0, cnt0)
+            consensus_kh_dict, first = find_motif_on_device(dev, kmer_len, m.max_ham_dist, m.p_uniform, m.ratio_mu,
+                                                            m.ratio_std, m.ratio_cutoff, top_k, n_trial, revcom_mode,
+                                                            rep_mode, first_lists, None, debug)
+            if save_kmer_cnt_flag and not kmer_cnt_file.exists():
+                with open(kmer_cnt_file, "wb") as fh:
+                    pickle.dump([kmer_len, first[0], first[1]], fh)
+            tmp_candidate_conseq_list = [hash2kmer(kh, kmer_len) for kh in consensus_kh_dict]
+            if store_flag:
+                tmp_occurence_file = kmer_count_dir / f"k{kmer_len}.motif_occurence.csv"
+                gen_motif_occurence_file(tmp_candidate_conseq_list, motif_def_dict, input_fasta_file, tmp_occurence_file,
+                                         revcom_mode, _dev_cache=occurrence_dev())
+            for i, kmer_seq in enumerate(tmp_candidate_conseq_list):
+                kh = kmer2hash(kmer_seq)
+                prop, ratio, log10_p_value = consensus_kh_dict[kh]
+                n_motif_seq, n_motif_occurrence = -n_all_seq, -n_all_seq
+                if store_flag:
+                    n_motif_seq, n_motif_occurrence = get_motif_seq_num(tmp_occurence_file, i)
+                motif_seq_prop = float(n_motif_seq) / n_all_seq
+                motif_per_motif_seq = float(n_motif_occurrence) / n_motif_seq
+                row = (f"{kmer_len},{kh},{kmer_seq},{reverse_complement(kmer_seq)},{prop:0.8f},"
+                       f"{ratio:0.4f},{log10_p_value:0.4f}")
+                if store_flag:
+                    row += (f",{n_motif_seq},{n_all_seq},{motif_seq_prop:0.4f},{n_motif_occurrence},"
+                            f"{motif_per_motif_seq:0.2f}")
+                rows.append(row)
+                candidate_conseq_list.append(kmer_seq)
+        print(f"kmer counting finished for k={min_k}...{max_k}. Candidate consensus sequences generated.")
+        write_lines(rows, candidate_conseq_file)
+
+    final_conseq_file = res / FileNameDict["final_conseq_file"]
+    if final_conseq_file.exists():
+        final_conseq_list = final_conseq_file.read_text().splitlines()
+        print(f"{final_conseq_file} already exist, re-use it.")
+    else:
+        final_conseq_list = merge_consensus_seqs(candidate_conseq_list)
+        write_lines(final_conseq_list, final_conseq_file)
+
+    final_conseq_info_file = res / FileNameDict["final_conseq_info_file"]
+    if final_conseq_info_file.exists():
+        print(f"{final_conseq_info_file} already exist, re-use it.")
+    else:
+        final_conseq_list = final_conseq_file.read_text().splitlines()
+        cand_lines = candidate_conseq_file.read_text().splitlines()
+        elements = cand_lines[0].split(",")
+        elements[1] = elements[0]
+        elements[0] = "motif_id"
+        info = [",".join(elements)]
+        motif_ind = 0
+        for conseq in final_conseq_list:
+            for line in cand_lines:
+                if "," + conseq + "," in line:
+                    elements = line.split(",")
+                    elements[1] = elements[0]
+                    elements[0] = str(motif_ind)
+                    motif_ind += 1
+                    info.append(",".join(elements))
+        write_lines(info, final_conseq_info_file)
+        print("Final consensus sequences generated.")
+
+    occurence_file = res / FileNameDict["motif_occurence_file"]
+    gen_motif_occurence_file(final_conseq_list, motif_def_dict, input_fasta_file, occurence_file, revcom_mode,
+                             _dev_cache=occurrence_dev())
+
+    if md_cfg["motif_pos_density_flag"] or md_cfg["motif_co_occurence_flag"]:
+        print("motif position density / co-occurrence plots are produced by the reference package from "
+              f"{occurence_file}; they are outside kmap_b200's scope.")
+
+    if md_cfg["sample_kmer_flag"] and not save_kmer_cnt_flag:
+        print(f"kmers cannot be sampled when {save_kmer_cnt_flag=}, skip kmer sampling!")
+    sample_kmer_pkl_file = res / FileNameDict["sample_kmer_pkl_file"]
+    sample_kmer_txt_file = res / FileNameDict["sample_kmer_txt_file"]
+    if sample_kmer_pkl_file.exists():
+        print(f"sample kmer file {sample_kmer_pkl_file} exists, skip sampling!")
+    elif md_cfg["sample_kmer_flag"] and save_kmer_cnt_flag and final_conseq_list:
+        n_total_sample, n_motif_sample = md_cfg["n_total_sample"], md_cfg["n_motif_sample"]
+        kmer_len = max(len(conseq) for conseq in final_conseq_list)
+        samp_kh_arr, samp_cnts, samp_label_arr, conseq_list = sample_disp_kmer(
+            final_conseq_list, kmer_len, motif_def_dict, kmer_count_dir=kmer_count_dir, n_total_sample=n_total_sample,
+            n_motif_kmer=n_motif_sample, revcom_mode=revcom_mode)
+        with open(sample_kmer_pkl_file, "wb") as fh:
+            pickle.dump([samp_kh_arr, samp_cnts, samp_label_arr, conseq_list], fh)
+        lines = []
+        for kh, cnt, label in zip(samp_kh_arr, samp_cnts, samp_label_arr):
+            lines.extend([f"{hash2kmer(kh, kmer_len)}\t{label}"] * int(cnt))
+        write_lines(lines, sample_kmer_txt_file)
+        print(f"kmers are sampled for visualization. {kmer_len= }, {n_total_sample= }, {n_motif_sample= }")
+        hamdist_mat = cal_samp_kmer_hamdist_mat(samp_kh_arr, samp_cnts, samp_label_arr, conseq_list, kmer_len,
+                                                uniq_dist_flag=False)
+        label_arr = _convert_to_block_arr(samp_label_arr, samp_cnts)
+        with open(res / FileNameDict["sample_kmer_hamdist_mat_file"], "wb") as fh:
+            pickle.dump([kmer_len, hamdist_mat, label_arr], fh)
+        print("Hamming distance matrix of sampled kmers are generated.")
+
+    if md_cfg["gen_hamball_flag"]:
+        out_dir_path = res / FileNameDict["hamball_dir"]
+        out_dir_path.mkdir(exist_ok=True)
+        for i, conseq in enumerate(final_conseq_list):
+            output_cntmat_file = str(out_dir_path / f"cntmat_motif{i}_{conseq}.csv")
+            if Path(output_cntmat_file).exists():
+                print(f"motif matrix file {output_cntmat_file} exist, skip generating.")
+                continue
+            _ex_hamball(res_dir, conseq, "matrix", output_cntmat_file, max_ham_dist=motif_def_dict[len(conseq)].max_ham_dist)
+        print("Motif count matrix extracted (logos are drawn by the reference package's draw_logo).")
+    print("All tasks of scan motif finished.")

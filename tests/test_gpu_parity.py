@@ -1,0 +1,348 @@
+"""Parity of the CUDA path (through the C ABI / the reference-shaped Python API) with the oracle and with the
+golden outputs of the unmodified reference.  Everything here is integer work: the bar is bit-exact.
+Run on the B200 box:  python -m pytest tests -m gpu -x -q
+"""
+import numpy as np
+import pytest
+
+from helpers import assert_occurrence_text_equal
+from oracle import kmap_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import kmap_b200.kmer_count as kc
+    return kc
+
+
+@pytest.fixture(scope="module")
+def MD(K):
+    import kmap_b200.motif_discovery as md
+    return md
+
+
+@pytest.fixture(scope="module")
+def ENG(K):
+    import kmap_b200.engine as E
+    return E
+
+
+def rand_reads(rng, n_reads, lmin, lmax, p_n=0.0, special=()):
+    reads = list(special)
+    for _ in range(n_reads):
+        L = int(rng.integers(lmin, lmax + 1))
+        s = rng.integers(0, 4, L).astype(np.uint8)
+        if p_n > 0:
+            s[rng.random(L) < p_n] = 255
+        reads.append(O.arr2dna(s))
+    arrs = [O.dna2arr(r) for r in reads]
+    seq = np.concatenate(arrs)
+    lens = np.array([len(a) for a in arrs])
+    ends = np.cumsum(lens)
+    borders = np.stack([ends - lens, ends - 1], axis=1).astype(np.int64)
+    return reads, seq, borders
+
+
+def dense_table_from_oracle(seq, borders, k, dedup):
+    h = O.comp_kmer_hash(seq, k)
+    if dedup:
+        h = O.remove_duplicate_hash_per_seq(h, borders, np.uint32(0xFFFFFFFF))
+    u, c = O.count_uniq_hash(h, k)
+    t = np.zeros(4 ** k, dtype=np.uint32)
+    t[u] = c
+    return t
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def test_primitives_match_reference_vectors(K, unit_vectors):
+    for g in unit_vectors["primitives"]:
+        k = g["k"]
+        h = K.comp_kmer_hash_taichi(g["seq"], k)
+        assert h.dtype == g["hash"].dtype and np.array_equal(h, g["hash"]), k
+        assert np.array_equal(K.cal_hamming_dist(g["kh"], g["target"][0], k), g["dist"]), k
+        rc = K.get_revcom_hash_arr(g["revcom_in"], k)
+        assert rc.dtype == g["revcom"].dtype and np.array_equal(rc, g["revcom"]), k
+        assert np.array_equal(np.array([K.revcom_hash(x, k) for x in g["revcom_in"][:20]]), g["revcom_scalar"])
+        for key in g:
+            if key.startswith("head_"):
+                cl = int(key[5:])
+                ct = g[f"ct_{cl}"][0]
+                assert np.array_equal(K.cal_hamming_dist_head(g["kh"], ct, k, cl), g[key]), (k, cl)
+                assert np.array_equal(K.cal_hamming_dist_tail(g["kh"], ct, k, cl), g[f"tail_{cl}"]), (k, cl)
+        if k < 16:
+            dd = K.remove_duplicate_hash_per_seq(g["hash"].copy(), g["borders"], np.uint32(0xFFFFFFFF))
+            assert np.array_equal(dd, g["dedup"]), k
+    assert len(K.cal_hamming_dist(np.zeros(0, dtype=np.uint32), 5, 8)) == 0        # empty input (md:786 last row)
+
+
+def test_primitives_random_vs_oracle(K):
+    rng = np.random.default_rng(5)
+    reads, seq, borders = rand_reads(rng, 300, 0, 90, p_n=0.02, special=["A" * 300, "ACGT" * 700, "", "N"])
+    for k in (1, 2, 7, 12, 15, 16, 23, 31):
+        assert np.array_equal(K.comp_kmer_hash_taichi(seq, k), O.comp_kmer_hash(seq, k)), k
+    for k in (8, 15):
+        h = O.comp_kmer_hash(seq, k)
+        want = O.remove_duplicate_hash_per_seq(h.copy(), borders, np.uint32(0xFFFFFFFF))
+        assert np.array_equal(K.remove_duplicate_hash_per_seq(h.copy(), borders, np.uint32(0xFFFFFFFF)), want), k
+    for k, hd in ((14, np.uint32), (27, np.uint64)):
+        kh = rng.integers(0, 4 ** k, 5000, dtype=np.uint64).astype(hd)
+        t = hd(rng.integers(0, 4 ** k, dtype=np.uint64))
+        assert np.array_equal(K.cal_hamming_dist(kh, t, k), O.cal_hamming_dist(kh, t, k))
+        assert np.array_equal(K.get_revcom_hash_arr(kh, k), O.get_revcom_hash_arr(kh, k))
+
+
+def test_dedup_low_complexity_reads(K, unit_vectors):
+    g = unit_vectors["dedup_lowcomplex"]
+    h = K.comp_kmer_hash_taichi(g["seq"], 8)
+    assert np.array_equal(h, g["hash"])
+    assert np.array_equal(K.remove_duplicate_hash_per_seq(h, g["borders"], np.uint32(0xFFFFFFFF)), g["dedup"])
+
+
+def test_count_k3_known_answer(K, unit_vectors):
+    g = unit_vectors["count_k3"]
+    h = K.comp_kmer_hash_taichi(K.dna2arr(g["seq"]), 3)
+    u, c = K.count_uniq_hash(h, 3)
+    assert np.array_equal(u, g["uniq"]) and np.array_equal(c, g["cnt"]) and c.dtype == g["cnt"].dtype and c.sum() == 96
+
+
+def test_merge_revcom_vectors(K, unit_vectors):
+    for g in unit_vectors["merge_revcom"]:
+        kh, cnt = g["kh"].copy(), g["cnt"].copy()
+        mk, mc = K.merge_revcom(kh, cnt, g["k"])
+        assert np.array_equal(mk, g["out_kh"]) and np.array_equal(mc, g["out_cnt"]), g["k"]
+        assert mk.dtype == g["out_kh"].dtype and mc.dtype == g["out_cnt"].dtype
+        if "mutated_cnt" in g:
+            assert np.array_equal(cnt, g["mutated_cnt"])
+
+
+def test_mask_known_answers(K, unit_vectors, motif_def_file):
+    g = unit_vectors["mask_ham_ball"]
+    mdd = K.init_motif_def_dict(motif_def_file)
+    assert K.arr2dna(K.mask_ham_ball(K.dna2arr(g["s1"])[:-1], mdd, g["c1"], g["d1"])) == g["r1"]
+    assert K.arr2dna(K.mask_ham_ball(K.dna2arr(g["s2"])[:-1], mdd, g["c2"])) == g["r2"]
+    for c in unit_vectors["mask_input"]:
+        k, d = c["k"], c["d"]
+        kh = K.kmer2hash(c["conseq"])
+        a = c["before"].copy()
+        out = K.mask_input(a, k, np.array([kh, K.revcom_hash(kh, k)]), np.array([d, d]))
+        assert out is a and np.array_equal(a, c["after"]), c["conseq"]
+
+
+@pytest.mark.parametrize("k", [1, 4, 8, 11, 14, 15])
+def test_fused_count_tables_vs_oracle(ENG, k):
+    rng = np.random.default_rng(100 + k)
+    # short reads (warp path), 300-7000 bp reads (block path), one 30 kb read (bitmap path), repeats, N's, empties
+    special = ["A" * 80, "CA" * 60, "", "N", "ACG", "ACGTTGCA" * 150, ("ACGTAGCTAGCTAGGATCGAT" * 1500)[:30000]]
+    reads, seq, borders = rand_reads(rng, 400, 0, 120, p_n=0.01, special=special)
+    reads2, seq2, borders2 = rand_reads(rng, 6, 300, 7000, p_n=0.001)
+    seq = np.concatenate([seq, seq2])
+    borders = np.concatenate([borders, borders2 + borders[-1, 1] + 1])
+    dev = ENG.SeqOnDevice.from_numpy(seq, borders)
+    for dedup in (False, True):
+        got = ENG.to_host(dev.count(k, dedup=dedup), np.uint32)
+        want = dense_table_from_oracle(seq, borders, k, dedup)
+        assert np.array_equal(got, want), (k, dedup, int(np.abs(got.astype(np.int64) - want).sum()))
+
+
+@pytest.mark.parametrize("k", [2, 5, 6, 9, 12])
+def test_compact_merge_order_exact(ENG, k):
+    rng = np.random.default_rng(k)
+    reads, seq, borders = rand_reads(rng, 500, 5, 60, p_n=0.01, special=["ACGT" * 10, "AATT" * 8, "GC" * 20])
+    dev = ENG.SeqOnDevice.from_numpy(seq, borders)
+    for dedup in (True, False):
+        table = dev.count(k, dedup=dedup)
+        h = O.comp_kmer_hash(seq, k)
+        if dedup:
+            h = O.remove_duplicate_hash_per_seq(h, borders, np.uint32(0xFFFFFFFF))
+        u, c = O.count_uniq_hash(h, k)
+        kh, cnt = ENG.compact_merge(table, k, revcom=False)
+        assert np.array_equal(ENG.to_host(kh, np.uint32), u) and np.array_equal(ENG.to_host(cnt, np.int32), c)
+        mk, mc = O.merge_revcom(u.copy(), c.copy(), k)
+        kh, cnt = ENG.compact_merge(table, k, revcom=True)
+        assert np.array_equal(ENG.to_host(kh, np.uint32), mk) and np.array_equal(ENG.to_host(cnt, np.int32), mc)
+
+
+@pytest.mark.parametrize("k,d", [(4, 0), (6, 1), (8, 2), (10, 3), (12, 4), (13, 5)])
+def test_hamball_sums_enumeration_and_list(ENG, k, d):
+    rng = np.random.default_rng(k * 10 + d)
+    n = 4000 if k >= 10 else 600
+    reads, seq, borders = rand_reads(rng, n, 20, 60, special=["ACGT" * 12, "GGATCC" * 9])
+    dev = ENG.SeqOnDevice.from_numpy(seq, borders)
+    table = dev.count(k, dedup=True)
+    u, c = O.count_uniq_hash(O.remove_duplicate_hash_per_seq(O.comp_kmer_hash(seq, k), borders, np.uint32(0xFFFFFFFF)), k)
+    pal = [int(O.kmer2hash(("ACGT" * 4)[:k]))] if k % 2 == 0 else []
+    cand = [int(x) for x in rng.choice(u, 6)] + pal + [0, 4 ** k - 1]
+    for revcom in (True, False):
+        if revcom:
+            mk, mc = O.merge_revcom(u.copy(), c.copy(), k)
+        else:
+            mk, mc = u, c
+        want = np.array([O.hamball_count(mk, mc, np.uint32(x), k, d, revcom) for x in cand], dtype=np.int64)
+        got = ENG.hamball_sums(table, k, cand, d, revcom)
+        assert np.array_equal(got, want), (k, d, revcom)
+        got2 = ENG.hamball_sums_list(ENG.to_device(mk), ENG.to_device(mc), k, cand, d, revcom)
+        assert np.array_equal(got2, want), (k, d, revcom)
+
+
+@pytest.mark.parametrize("idx", range(16))
+def test_find_motif_small_all_modes(MD, K, small_cases, motif_def_file, idx, tmp_path):
+    import pickle
+    mdd = K.init_motif_def_dict(motif_def_file)
+    c = small_cases["cases"][idx]
+    k = c["k"]
+    m = mdd[k]
+    bfile = tmp_path / "b.pkl"
+    with open(bfile, "wb") as fh:
+        pickle.dump(small_cases["borders"], fh)
+    pkl = tmp_path / f"k{k}.pkl"
+    seq = small_cases["seq"].copy()
+    res = MD.find_motif(seq, k, m.max_ham_dist, m.p_uniform, m.ratio_mu, m.ratio_std, m.ratio_cutoff, 5, 10, c["revcom"],
+                        c["rep"], save_kmer_cnt_flag=True, kmer_cnt_pkl_file=pkl, boarder_pkl_file=bfile)
+    with open(pkl, "rb") as fh:
+        kk, ukh, ucnt = pickle.load(fh)
+    assert kk == k and np.array_equal(ukh, c["uniq_kh"]) and np.array_equal(ucnt, c["uniq_cnt"])
+    assert ukh.dtype == c["uniq_kh"].dtype and ucnt.dtype == c["uniq_cnt"].dtype
+    assert [int(x) for x in res] == [int(x) for x in c["consensus"]]
+    assert np.array_equal(np.array([list(v) for v in res.values()], dtype=np.float64).reshape(-1, 3), c["stats"])
+    assert np.array_equal(seq, c["masked"])
+    # second call resumes from the pickle (md:621-624) and must give the same answer
+    seq2 = small_cases["seq"].copy()
+    res2 = MD.find_motif(seq2, k, m.max_ham_dist, m.p_uniform, m.ratio_mu, m.ratio_std, m.ratio_cutoff, 5, 10, c["revcom"],
+                         c["rep"], save_kmer_cnt_flag=True, kmer_cnt_pkl_file=pkl, boarder_pkl_file=bfile)
+    assert [int(x) for x in res2] == [int(x) for x in c["consensus"]] and np.array_equal(seq2, c["masked"])
+
+
+@pytest.mark.parametrize("k", [6, 7, 8, 9, 10, 11, 12, 13, 14, 15])
+def test_find_motif_testfa(MD, K, testfa, motif_def_file, k, tmp_path):
+    import pickle
+    mdd = K.init_motif_def_dict(motif_def_file)
+    c = next(x for x in testfa["find_motif"] if x["k"] == k)
+    m = mdd[k]
+    bfile = tmp_path / "b.pkl"
+    with open(bfile, "wb") as fh:
+        pickle.dump(testfa["borders"], fh)
+    pkl = tmp_path / f"k{k}.pkl"
+    seq = testfa["input_bin"].copy()
+    res = MD.find_motif(seq, k, m.max_ham_dist, m.p_uniform, m.ratio_mu, m.ratio_std, m.ratio_cutoff, 5, 10, True, False,
+                        save_kmer_cnt_flag=True, kmer_cnt_pkl_file=pkl, boarder_pkl_file=bfile)
+    with open(pkl, "rb") as fh:
+        kk, ukh, ucnt = pickle.load(fh)
+    assert np.array_equal(ukh, c["uniq_kh"]) and np.array_equal(ucnt, c["uniq_cnt"])
+    assert ukh.dtype == c["uniq_kh"].dtype and ucnt.dtype == c["uniq_cnt"].dtype
+    assert [int(x) for x in res] == [int(x) for x in c["consensus"]]
+    assert np.array_equal(np.array([list(v) for v in res.values()], dtype=np.float64).reshape(-1, 3), c["stats"])
+    assert np.array_equal(seq, c["masked"])
+
+
+def test_ex_hamball_and_cnt_mat(MD, testfa):
+    fm = {c["k"]: c for c in testfa["find_motif"]}
+    for g in testfa["ex_hamball"]:
+        cs = g["conseq"]
+        k = len(cs)
+        d = g.get("d", 5)
+        kh, cnt, mat = MD._hamball_extract(fm[k]["uniq_kh"], fm[k]["uniq_cnt"], int(O.kmer2hash(cs)), k, d, g.get("revcom", True))
+        assert np.array_equal(kh, g["kh"]) and np.array_equal(cnt, g["cnt"]) and np.array_equal(mat, g["cnt_mat"])
+        cm = MD.cal_cnt_mat(g["kh"], g["cnt"], k)
+        assert cm.dtype == g["cnt_mat"].dtype and np.array_equal(cm, g["cnt_mat"])
+
+
+def test_occurrence_unit_cases(MD, K, unit_vectors, motif_def_file):
+    g = unit_vectors["occurrence"]
+    mdd = K.init_motif_def_dict(motif_def_file)
+    for case in g["cases"]:
+        arr = K.dna2arr(case["read"], append_missing_val_flag=False)
+        np.random.seed(1)
+        flag, s = MD.get_motif_occurence(arr, g["conseqs"], mdd, case["revcom_mode"])
+        if case["locs"].count(",") >= 19 and s != case["locs"]:       # > 20 hits: random pick in the reference
+            assert flag == case["flag"] and s.count(",") == case["locs"].count(",")
+        else:
+            assert (flag, s) == (case["flag"], case["locs"]), case
+
+
+def test_hamdist_matrix_vectors(MD, unit_vectors, testfa):
+    for g in unit_vectors["hamdist_mat"]:
+        um = MD.cal_samp_kmer_hamdist_mat(g["kh"], g["cnts"], g["labels"], g["conseq_list"], g["k"], uniq_dist_flag=True)
+        bm = MD.cal_samp_kmer_hamdist_mat(g["kh"], g["cnts"], g["labels"], g["conseq_list"], g["k"])
+        assert str(bm.dtype) == g["ref_dtype"]
+        assert np.array_equal(um, g["uniq"]) and np.array_equal(bm, g["block"]), g["k"]
+    kh, cnts, labels, conseq_list = testfa["sample_kmers"]
+    g = testfa["hamdist"]
+    mat = MD.cal_samp_kmer_hamdist_mat(kh, cnts, labels, conseq_list, g["k"])
+    assert np.array_equal(mat, g["mat"]) and np.array_equal(MD._convert_to_block_arr(labels, cnts), g["labels"])
+
+
+def test_hamdist_row_blocks_and_properties(MD):
+    # row-block partition (multi-GPU layout): any row range equals the corresponding slice of the full matrix
+    rng = np.random.default_rng(3)
+    k, n = 14, 1616
+    kh = np.unique(rng.integers(0, 4 ** k, n + 50, dtype=np.uint64))[:n].astype(np.uint32)
+    rng.shuffle(kh)
+    labels = rng.integers(0, 3, n)
+    full = MD.hamdist_matrix_u8(kh, labels, [14, 12], k).cpu().numpy()
+    assert np.array_equal(full, O.cal_samp_kmer_hamdist_mat(kh, np.ones(n, dtype=int), labels, ["A" * 14, "A" * 12], k).astype(np.uint8))
+    assert np.all(full.diagonal() == 0) and np.array_equal(full, full.T)
+    for r0, r1 in ((0, 1), (5, 700), (700, 1616), (1615, 1616)):
+        part = MD.hamdist_matrix_u8(kh, labels, [14, 12], k, r0, r1).cpu().numpy()
+        assert np.array_equal(part, full[r0:r1])
+
+
+def test_synth_device_matches_numpy(ENG):
+    from kmap_b200 import synth
+    for spec in (synth.CFG2, synth.CFG2_N, synth.CFG3):
+        seq_d, b_d = synth.generate_device(spec, 1000, 3000)
+        seq, b = synth.generate_numpy(spec, 1000, 3000)
+        assert np.array_equal(seq_d.cpu().numpy(), seq) and np.array_equal(b_d.cpu().numpy(), b)
+
+
+def test_scan_motif_workflow_testfa(MD, K, testfa, tmp_path):
+    """README workflow (preproc + scan_motif, k=8..14) on test.fa: every text output equals the reference's."""
+    import tomli_w
+    import tomllib
+    seq, borders = testfa["input_bin"], testfa["borders"]
+    fa = tmp_path / "test.fa"
+    with open(fa, "w") as fh:
+        for i, (st, en) in enumerate(borders):
+            fh.write(f">r{i}\n{K.arr2dna(seq[st:en])}\n")
+    res_dir = tmp_path / "res"
+    res_dir.mkdir()
+    cfg = tomllib.loads(testfa["text_files"]["config.toml"])
+    cfg["general"]["input_fasta_file"] = str(fa)
+    cfg["general"]["res_dir"] = str(res_dir)
+    with open(res_dir / "config.toml", "wb") as fh:
+        tomli_w.dump(cfg, fh)
+    K._preproc(str(fa), str(res_dir))
+    import pickle
+    with open(res_dir / "input.bin.pkl", "rb") as fh:
+        assert np.array_equal(pickle.load(fh), seq)
+    with open(res_dir / "input.seqboarder.bin.pkl", "rb") as fh:
+        b = pickle.load(fh)
+        assert np.array_equal(b, borders) and b.dtype == borders.dtype
+    assert (res_dir / "motif_def_table.csv").read_text() == testfa["text_files"]["motif_def_table.csv"]
+    np.random.seed(20240414)
+    MD._scan_motif(str(res_dir))
+    tf = testfa["text_files"]
+    for name in ("candidate_conseq.csv", "final_conseq.txt", "final_conseq.info.csv",
+                 "hamming_balls/cntmat_motif0_AGGACCTACGTAC.csv", "hamming_balls/cntmat_motif1_AATCGATAGCGAA.csv"):
+        assert (res_dir / name).read_text() == tf[name], name
+    for name in [n for n in tf if n.endswith("motif_occurence.csv")]:
+        assert_occurrence_text_equal((res_dir / name).read_text().splitlines(), tf[name])
+    fm = {c["k"]: c for c in testfa["find_motif"]}
+    for k in range(8, 15):
+        with open(res_dir / "kmer_count" / f"k{k}.pkl", "rb") as fh:
+            kk, ukh, ucnt = pickle.load(fh)
+        assert kk == k and np.array_equal(ukh, fm[k]["uniq_kh"]) and np.array_equal(ucnt, fm[k]["uniq_cnt"])
+    # the sample is drawn with numpy's global RNG from identical arrays in the identical call order
+    with open(res_dir / "sample_kmers.pkl", "rb") as fh:
+        skh, scnt, slab, sconseq = pickle.load(fh)
+    gkh, gcnt, glab, gconseq = testfa["sample_kmers"]
+    assert sconseq == gconseq and np.array_equal(skh, gkh) and np.array_equal(scnt, gcnt) and np.array_equal(slab, glab)
+    with open(res_dir / "sample_kmer_hamdist_mat.pkl", "rb") as fh:
+        kk, mat, lab = pickle.load(fh)
+    assert kk == testfa["hamdist"]["k"] and str(mat.dtype) == testfa["hamdist"]["ref_dtype"]
+    assert np.array_equal(mat, testfa["hamdist"]["mat"]) and np.array_equal(lab, testfa["hamdist"]["labels"])
+    assert (res_dir / "sample_kmers.tsv").read_text() == tf["sample_kmers.tsv"]
