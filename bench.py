@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Headline benchmark of kmap_b200: Gbases/s of k-mers counted for k = 8..14 (BASELINE.json metric) on the
+ChIP-like synthetic workload (1e8 reads x 100 bp), sharded by reads over N GPUs of one
+node with an NCCL all-reduce of every dense 4^k table.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                          # the reference's CPU algorithm (oracle port)
+
+One step = one pass of the counting hot path over the whole input: for every k in 8..14 zero the uint32[4^k] table,
+count every read's distinct k-mers into it (the reference's default, non-repetitive mode: comp_kmer_hash +
+remove_duplicate_hash_per_seq + count_uniq_hash fused), and for N > 1 all-reduce the table.  `value` is measured
+with the packed reads resident in HBM; `e2e` is the same work through the public host-buffer API
+(`kmap_b200.api.count_kmers`: pinned uint8 input.bin + int64 borders H2D, pack, count, order-exact compaction +
+reverse-complement merge, the merged (kh, cnt) lists D2H).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+KMIN, KMAX = 8, 14
+METRIC = "gbases_per_s_kmers_counted_k8_14"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=float, default=1e8, help="total reads over all GPUs (cfg3: 1e8)")
+    ap.add_argument("--read-len", type=int, default=100)
+    ap.add_argument("--mode", default="dedup", choices=["dedup", "rep"], help="dedup = reference default (repetitive_mode=false)")
+    ap.add_argument("--algo", default="allk", choices=["allk", "perk"],
+                    help="allk = one atomic pass at k=14 + 4:1 table reductions (csrc/count_all.cu); perk = 7 independent passes")
+    ap.add_argument("--partitions", type=int, default=0, help="key-range passes for the k=14 table (0 = auto)")
+    ap.add_argument("--cpu-sample-reads", type=int, default=40000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--extras", action="store_true", help="also time compaction / Hamming-ball / mask / distance-matrix kernels")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def n_kmers_total(n_reads, L):
+    return sum(n_reads * max(0, L - k + 1) for k in range(KMIN, KMAX + 1))
+
+
+def algorithmic_bytes_count(n_reads, L, k):
+    """SURVEY.md section 8d per-unit figure for one counting launch: 0.375 B per base (2-bit code + validity bit) +
+    8 B per counted k-mer (uint32 read-modify-write).  The 8 * 4^k table zero/read-out term belongs to the memset and
+    the compaction, not to this kernel."""
+    return 0.375 * n_reads * L + 8.0 * n_reads * max(0, L - k + 1)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(seq, borders, mode):
+    """the reference's CPU algorithm for the same step (oracle port): per k hash every position, de-duplicate per read
+    (the reference's per-read Python loop), np.unique-count.  Returns seconds."""
+    from oracle import kmap_oracle as O
+    t0 = time.perf_counter()
+    for k in range(KMIN, KMAX + 1):
+        h = O.comp_kmer_hash(seq, k)
+        if mode == "dedup":
+            h = O.remove_duplicate_hash_per_seq(h, borders, np.uint32(0xFFFFFFFF))
+        O.count_uniq_hash(h, k)
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from kmap_b200 import synth
+    spec = synth.CFG3 if args.read_len == 100 else synth.SynthSpec(seed=20240413, read_len=args.read_len)
+    n_sample = int(min(args.cpu_sample_reads, args.reads))
+    seq, borders = synth.generate_numpy(spec, 0, n_sample)
+    for _ in range(args.warmup):
+        cpu_reference_step(seq, borders, args.mode)
+    times = [cpu_reference_step(seq, borders, args.mode) for _ in range(args.steps)]
+    t = float(np.mean(times))
+    bases = n_sample * args.read_len
+    value = bases * (KMAX - KMIN + 1) / t / 1e9
+    sample = f"first {n_sample} reads x {args.read_len} bp of the same synthetic workload, k={KMIN}..{KMAX}, mode={args.mode}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": f"cfg3 ChIP-like {int(args.reads)} reads x {args.read_len} bp, dense 4^k counting k={KMIN}..{KMAX}, "
+                               f"{args.mode} mode (bounded CPU sample)", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Gbases/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from kmap_b200 import api, engine as E, synth
+    from kmap_b200._lib import check, lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+    L = args.read_len
+    n_total = int(args.reads)
+    r0 = n_total * rank // world
+    r1 = n_total * (rank + 1) // world
+    n_local = r1 - r0
+    spec = synth.CFG3 if L == 100 else synth.SynthSpec(seed=20240413, read_len=L)
+    dedup = args.mode == "dedup"
+
+    # ---- device-resident input (generated on the device by the counter-based generator) -----------------------------
+    seq_d, borders_d = synth.generate_device(spec, r0, n_local)
+    dev = E.SeqOnDevice.from_device_u8(seq_d, borders_d)
+    tables = {k: E.zeros(1 << (2 * k), torch.int32) for k in range(KMIN, KMAX + 1)}
+    torch.cuda.synchronize()
+
+    count_events = []
+
+    def step(record=False):
+        if args.algo == "allk":
+            if record:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            dev.count_all(KMIN, KMAX, dedup, tables, n_partitions=args.partitions)
+            if record:
+                e1.record()
+                count_events.append(("all", e0, e1))
+            if world > 1:
+                for k in range(KMIN, KMAX + 1):
+                    dist.all_reduce(tables[k])
+            return
+        for k in range(KMIN, KMAX + 1):
+            if record:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            dev.count(k, dedup=dedup, table=tables[k], zero=True)
+            if record:
+                e1.record()
+                count_events.append((k, e0, e1))
+            if world > 1:
+                dist.all_reduce(tables[k])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step(record=True)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_local = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_local], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = n_total * L * (KMAX - KMIN + 1) / (ms_per_step * 1e-3) / 1e9
+
+    # per-k count time (memset + kernel) on this rank, averaged over the timed steps
+    per_k = {}
+    for k, e0, e1 in count_events:
+        per_k.setdefault(k, []).append(e0.elapsed_time(e1))
+    per_k_ms = {k: float(np.mean(v)) for k, v in per_k.items()}
+
+    # sanity of the timed work (integer identities, not timing): sum of the rep-mode table == number of valid windows
+    checks = {}
+    tot14 = int(tables[KMAX].to(torch.int64).sum().item())
+    checks["sum_table_k14"] = tot14
+
+    # ---- roofline of the dominant kernel (the counting kernel), measured live with CUDA events ----------------------
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak, peak_src = json.loads(peaks_file.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    alg_bytes = sum(algorithmic_bytes_count(n_local, L, k) for k in range(KMIN, KMAX + 1))
+    kern_s = sum(per_k_ms.values()) * 1e-3
+    achieved = alg_bytes / kern_s / 1e9
+    traffic = None
+    tfile = ROOT / "profiles" / "count_traffic.json"
+    if tfile.exists():
+        try:
+            traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "count_dedup_warp_kernel" if dedup else "count_dense_kernel", "peak_source": peak_src,
+                "algorithmic_bytes_per_step": alg_bytes, "count_ms_per_step": kern_s * 1e3, "algo": args.algo,
+                "per_k_ms": {str(k): v for k, v in per_k_ms.items()}, "frac_of_8TBs_nominal": achieved / 8000.0}
+
+    # ---- end-to-end through the public API with host buffers -------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        seq_host = torch.empty(seq_d.numel(), dtype=torch.uint8, pin_memory=True)
+        seq_host.copy_(seq_d)
+        borders_host = torch.empty(borders_d.shape, dtype=torch.int64, pin_memory=True)
+        borders_host.copy_(borders_d)
+        torch.cuda.synchronize()
+        del seq_d
+        dev.seq_u8 = None
+        seq_np, borders_np = seq_host.numpy(), borders_host.numpy()
+        comm = api.TableAllReduce() if world > 1 else None
+
+        def e2e_step():
+            res = api.count_kmers(seq_np, borders_np, range(KMIN, KMAX + 1), rep_mode=not dedup, revcom_mode=True, validate=False,
+                                  table_allreduce=comm, lists_on=0)
+            return sum(a.nbytes + b.nbytes for a, b in res.values()) if res else 0
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 3))
+        d2h = 0
+        for _ in range(n_e2e):
+            d2h = e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / n_e2e
+        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": n_total * L * (KMAX - KMIN + 1) / dt / 1e9, "unit": "Gbases/s",
+               "h2d_bytes_per_step": int(seq_np.nbytes + borders_np.nbytes), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": dt * 1e3, "steps": n_e2e,
+               "api": "kmap_b200.api.count_kmers(seq_np_arr, boarder_mat, k=8..14) -> {k: (uniq_kh_arr, uniq_kh_cnt_arr)}"}
+
+    extras = None
+    if args.extras and rank == 0:
+        from bench_extras import run_extras
+        extras = run_extras(dev, tables, n_local, L)
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) --------------------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n_sample = int(min(args.cpu_sample_reads, n_total))
+        seq_s, borders_s = synth.generate_numpy(spec, 0, n_sample)
+        tcpu = cpu_reference_step(seq_s, borders_s, args.mode)
+        cpu_baseline = {"value": n_sample * L * (KMAX - KMIN + 1) / tcpu / 1e9, "unit": "Gbases/s", "cores": 1, "kind": "port",
+                        "sample": f"first {n_sample} reads x {L} bp of the same workload, k={KMIN}..{KMAX}, {args.mode} mode, "
+                                  f"NumPy oracle port of the reference (single-threaded np.unique + per-read Python loop)",
+                        "seconds": tcpu, "host_cpus": os.cpu_count()}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic",
+            "config": {"workload": f"cfg3 ChIP-like {n_total} reads x {L} bp (10% carry GTACGTAGGTCCTA, 5% mutation), dense 4^k "
+                                   f"counting k={KMIN}..{KMAX}, {args.mode} mode, reads sharded over {n_gpus} GPU(s) with NCCL table merge",
+                       "l2": "inputs larger than L2 (packed reads + borders = %.1f GB per GPU)" % ((dev.packed.numel() * 4 + dev.valid.numel() * 4 + n_local * 16) / 1e9),
+                       "parallelism": f"reads x{n_gpus}"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (KMAX - KMIN + 1),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "checks": checks,
+        }
+        if extras:
+            out["extras"] = extras
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

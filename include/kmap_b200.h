@@ -88,6 +88,17 @@ int kmap_count_dense_dedup(const uint32_t* packed, const uint32_t* valid, int64_
                            int64_t n_seq, int k, uint32_t* table, uint32_t* work, uint32_t* bitmap, void* stream);
 int64_t kmap_dedup_work_words(int64_t n_seq);
 
+/* The first-round counts of scan_motif for EVERY k in [kmin, kmax] at once (motif_discovery.py:262-273 calling
+ * 627-636 per k): fills tables_host[k - kmin] = uint32[4^k] for each k (tables_host is a HOST array of device
+ * pointers; every table is zeroed first).  Only the level-kmax table is built with one atomic per window, in
+ * n_partitions key-range passes (0 = choose so that a slice stays L2 resident); each smaller table is the 4:1
+ * reduction of the next one plus the per-read corrections derived in csrc/count_all.cu.  Results are identical to
+ * kmax-kmin+1 calls of kmap_count_dense[_dedup].  dupmask = uint32[kmap_valid_words(n)] scratch, work/bitmap as in
+ * kmap_count_dense_dedup (dedup != 0 only).  Synchronises the stream once when dedup != 0. */
+int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
+                     int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
+                     uint32_t* bitmap, int n_partitions, void* stream);
+
 int kmap_fill_u32(uint32_t* p, int64_t n_words, uint32_t value, void* stream);
 
 /* count_uniq_hash (kmer_count.py:476-491) for callers that hold a materialised hash array: table[h] += 1 for every

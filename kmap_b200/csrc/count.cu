@@ -218,6 +218,50 @@ static unsigned int strided_grid(int64_t n) {
 
 }  // namespace
 
+// reads too long for the warp path, listed in `work` (medium ids at work+4, long ids at work+4+n_seq)
+int kmap_count_long_reads(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
+                          int k, uint32_t* table, uint32_t* work, uint32_t* bitmap, const uint32_t counts[2], cudaStream_t s) {
+    cudaError_t e = cudaSuccess;
+    int rc;
+    if (counts[0]) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(count_dedup_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_BLOCK_SLOTS * 4);
+            attr_set = true;
+        }
+        const unsigned int g = counts[0] < 148u * 3u ? counts[0] : 148u * 3u;
+        count_dedup_block_kernel<<<g, 256, DD_BLOCK_SLOTS * 4, s>>>(packed, valid, n, borders, n_seq, k, table, work);
+        rc = kmap_check_launch("count_dedup_block");
+        if (rc) return rc;
+    }
+    if (counts[1]) {
+        if (!bitmap) { kmap_set_error("count_dense_dedup: %u reads need the bitmap scratch", counts[1]); return KMAP_ERR_NEED_SCRATCH; }
+        // read the ids and borders of the long reads back (few, by construction)
+        uint32_t* ids = new uint32_t[counts[1]];
+        e = cudaMemcpyAsync(ids, work + 4 + n_seq, (size_t)counts[1] * 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        const int64_t bitmap_words = ((int64_t)1 << (2 * k)) / 32 > 0 ? ((int64_t)1 << (2 * k)) / 32 : 1;
+        for (uint32_t q = 0; q < counts[1] && e == cudaSuccess; ++q) {
+            int64_t b[2];
+            e = cudaMemcpyAsync(b, borders + 2 * (int64_t)ids[q], 16, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) break;
+            int64_t st = b[0] < 0 ? 0 : b[0], en = b[1] > n ? n : b[1];
+            const int64_t n_win = en - st - k + 1;
+            if (n_win <= 0) continue;
+            e = cudaMemsetAsync(bitmap, 0, (size_t)bitmap_words * 4, s);
+            if (e != cudaSuccess) break;
+            int64_t g = (n_win + 255) / 256;
+            if (g > 148 * 16) g = 148 * 16;
+            count_dedup_bitmap_kernel<<<(unsigned int)g, 256, 0, s>>>(packed, valid, st, n_win, k, table, bitmap);
+            e = cudaGetLastError();
+        }
+        delete[] ids;
+        if (e != cudaSuccess) { kmap_set_error("count_dense_dedup(long reads): %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    return KMAP_OK;
+}
+
 extern "C" {
 
 int kmap_count_hashes_u32(const uint32_t* hash, int64_t n, int k, uint32_t* table, void* stream) {
@@ -272,41 +316,7 @@ int kmap_count_dense_dedup(const uint32_t* packed, const uint32_t* valid, int64_
     e = cudaMemcpyAsync(counts, work, 8, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { kmap_set_error("count_dense_dedup: %s", cudaGetErrorString(e)); return (int)e; }
-    if (counts[0]) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(count_dedup_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_BLOCK_SLOTS * 4);
-            attr_set = true;
-        }
-        const unsigned int g = counts[0] < 148u * 3u ? counts[0] : 148u * 3u;
-        count_dedup_block_kernel<<<g, 256, DD_BLOCK_SLOTS * 4, s>>>(packed, valid, n, borders, n_seq, k, table, work);
-        rc = kmap_check_launch("count_dedup_block");
-        if (rc) return rc;
-    }
-    if (counts[1]) {
-        if (!bitmap) { kmap_set_error("count_dense_dedup: %u reads need the bitmap scratch", counts[1]); return KMAP_ERR_NEED_SCRATCH; }
-        // read the ids and borders of the long reads back (few, by construction)
-        uint32_t* ids = new uint32_t[counts[1]];
-        e = cudaMemcpyAsync(ids, work + 4 + n_seq, (size_t)counts[1] * 4, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        const int64_t bitmap_words = ((int64_t)1 << (2 * k)) / 32 > 0 ? ((int64_t)1 << (2 * k)) / 32 : 1;
-        for (uint32_t q = 0; q < counts[1] && e == cudaSuccess; ++q) {
-            int64_t b[2];
-            e = cudaMemcpyAsync(b, borders + 2 * (int64_t)ids[q], 16, cudaMemcpyDeviceToHost, s);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-            if (e != cudaSuccess) break;
-            int64_t st = b[0] < 0 ? 0 : b[0], en = b[1] > n ? n : b[1];
-            const int64_t n_win = en - st - k + 1;
-            e = cudaMemsetAsync(bitmap, 0, (size_t)bitmap_words * 4, s);
-            if (e != cudaSuccess) break;
-            int64_t g = (n_win + 255) / 256;
-            if (g > 148 * 16) g = 148 * 16;
-            count_dedup_bitmap_kernel<<<(unsigned int)g, 256, 0, s>>>(packed, valid, st, n_win, k, table, bitmap);
-            e = cudaGetLastError();
-        }
-        delete[] ids;
-        if (e != cudaSuccess) { kmap_set_error("count_dense_dedup(long reads): %s", cudaGetErrorString(e)); return (int)e; }
-    }
+    if (counts[0] || counts[1]) return kmap_count_long_reads(packed, valid, n, borders, n_seq, k, table, work, bitmap, counts, s);
     return KMAP_OK;
 }
 

@@ -1,0 +1,365 @@
+// Counting every k of a range in one go (the first-round counts of scan_motif, motif_discovery.py:262-273 +
+// 627-636, for all k in [kmin, kmax]) with ~1/(kmax-kmin+1) of the atomic traffic of k independent passes.
+//
+// Identity used.  Let fresh_k(i) = 1 iff the window of k bases at position i is valid and is
+// the first occurrence of its k-mer inside its read (repetitive mode: iff it is valid).  The reference's table is
+//     T_k[h] = sum_i fresh_k(i) [w_k(i) = h].
+// A (k+1)-window's k-prefix is the k-window at the same position, so
+//     T_k[h] = sum_b T_{k+1}[4h + b] + sum_i (fresh_k(i) - fresh_{k+1}(i)) [w_k(i) = h].
+// With vlen(i) = number of consecutive valid bases from i and dd(i) = the longest prefix (in bases, 0 if none >= kmin)
+// that the window at i shares with an EARLIER window of the same read, fresh_k(i) = [k <= vlen(i)] [k > dd(i)], hence
+// the correction term is +1 at level k = vlen(i) (a window that cannot be extended: one per valid run and level) and
+// -1 at level k = dd(i) (a repeated k-mer whose extension is new: rare).  So only T_kmax needs one atomic per
+// window; every smaller table is a 4:1 streaming reduction of the next one plus a few corrections.
+//
+// T_kmax itself (1 GiB at k = 14) is filled in key-range passes so that the slice being updated stays L2 resident.
+#include "common.cuh"
+
+namespace {
+
+constexpr int AK_WARPS = 4;
+constexpr int AK_WARP_MAX = 256;          // windows (at level kmin) a warp de-duplicates on chip
+constexpr int AK_BLOCK_MAX = 8192;        // beyond this a read goes to the bitmap path
+
+struct TableSet { uint32_t* t[16]; };     // t[k] = dense table of level k (only kmin..kmax are set)
+
+__device__ __forceinline__ int run_length(uint32_t vb) { return vb == 0xFFFFFFFFu ? 32 : __ffs(~vb) - 1; }
+
+// ---- A: per-read duplicate analysis at level kmin, corrections for kmin..kmax-1, duplicate mask for level kmax -------
+// One warp = one read.  Lane j owns the C = ceil(n_pos / 32) consecutive windows j*C .. j*C+C-1 (C <= 8): it fetches its
+// stretch of the packed read and of the validity mask once (two funnel shifts each) and rolls through its windows with
+// compile-time shifts.  Windows are visited in rounds (round t = window t of every lane); "earlier" below means an
+// earlier (round, lane) pair -- any fixed total order gives the same tables.
+// Repeats inside a read are rare, so the common path is a filter, not a set: every warp owns AK_MARKS 16-bit marks
+// in shared memory; a window hashes its kmin-mer to a mark, reads it and stamps it with (epoch of the read, round,
+// lane) -- no clearing between reads, no atomics, no probing loop.  Only a window whose mark already carried the epoch,
+// or that had to share its mark with another lane of the same round, can be a repeat; for those the warp compares the
+// window with every earlier window of the read -- all of them are still in registers -- and gets the exact repeat depth.
+constexpr int AK_MARKS = 4096;
+constexpr int AK_MAXC = AK_WARP_MAX / 32;
+
+__device__ __forceinline__ int common_prefix(uint32_t a, uint32_t b) {       // equal leading bases of two 16-base words
+    const uint32_t diff = a ^ b;
+    return diff ? (__clz(diff) >> 1) : 16;
+}
+
+__global__ void __launch_bounds__(AK_WARPS * 32) dedup_scan_kernel(
+    const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid, int64_t n, const int64_t* __restrict__ borders,
+    int64_t n_seq, int kmin, int kmax, TableSet tabs, uint32_t* __restrict__ dupmask, uint32_t* __restrict__ work) {
+    __shared__ __align__(16) uint16_t marks_all[AK_WARPS][AK_MARKS];
+    __shared__ uint32_t* stab[16];
+    if (threadIdx.x < 16) stab[threadIdx.x] = tabs.t[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint16_t* marks = marks_all[wib];
+    const int64_t warp0 = (int64_t)blockIdx.x * AK_WARPS + wib;
+    const int64_t n_warps = (int64_t)gridDim.x * AK_WARPS;
+    const int key_shift = 32 - 2 * kmin;
+    uint32_t epoch = 255;                                           // forces a clear before the first read
+    uint32_t* medium_ids = work + 4;
+    uint32_t* long_ids = work + 4 + n_seq;
+
+    // Software pipeline over this warp's reads: borders are fetched two reads ahead and the read's words one read ahead,
+    // so the two dependent DRAM latencies (borders -> words) overlap the processing of earlier reads.
+    struct Staged { int64_t st, en; uint32_t va, vb, w0, w1, w2; };
+    auto stage_borders = [&](int64_t r, Staged& g) {
+        g.st = 0; g.en = 0;
+        if (r < n_seq) {
+            const longlong2 be = __ldg(reinterpret_cast<const longlong2*>(borders) + r);
+            g.st = be.x < 0 ? 0 : be.x;
+            g.en = be.y > n ? n : be.y;
+        }
+    };
+    auto stage_words = [&](Staged& g) {                              // raw words of this lane's stretch (no use yet)
+        g.va = g.vb = g.w0 = g.w1 = g.w2 = 0;
+        const int64_t n_pos64 = g.en - g.st - kmin + 1;
+        if (n_pos64 <= 0 || n_pos64 > AK_WARP_MAX) return;
+        const int C = ((int)n_pos64 + 31) >> 5;
+        const int base = lane * C;
+        if (base >= (int)n_pos64) return;
+        const uint32_t* vd = valid + (g.st >> 5);
+        const int bv = (int)(g.st & 31) + base;
+        g.va = __ldg(vd + (bv >> 5)); g.vb = __ldg(vd + (bv >> 5) + 1);
+        const uint32_t* pk = packed + (g.st >> 4);
+        const int bp = (int)(g.st & 15) + base;
+        g.w0 = __ldg(pk + (bp >> 4)); g.w1 = __ldg(pk + (bp >> 4) + 1); g.w2 = __ldg(pk + (bp >> 4) + 2);
+    };
+    Staged cur, nxt, nxt2;
+    stage_borders(warp0, cur);
+    stage_borders(warp0 + n_warps, nxt);
+    stage_words(cur);
+
+    for (int64_t r = warp0; r < n_seq; r += n_warps) {
+        stage_borders(r + 2 * n_warps, nxt2);
+        stage_words(nxt);
+        const Staged g = cur;
+        cur = nxt; nxt = nxt2;
+        const int64_t st = g.st, en = g.en;
+        const int64_t L64 = en - st;
+        if (L64 - kmin + 1 <= 0) continue;
+        if (L64 - kmin + 1 > AK_WARP_MAX) {
+            // too long for the on-chip path: hide the read from the masked count and queue it for the direct kernels
+            for (int64_t w = (st >> 5) + lane; w <= ((en - 1) >> 5); w += 32) {
+                const int64_t lo = w << 5;
+                uint32_t bits = 0xFFFFFFFFu;
+                if (lo < st) bits &= 0xFFFFFFFFu << (st - lo);
+                if (lo + 32 > en) bits &= 0xFFFFFFFFu >> (lo + 32 - en);
+                atomicOr(dupmask + w, bits);
+            }
+            if (lane == 0) {
+                if (L64 - kmin + 1 <= AK_BLOCK_MAX) medium_ids[atomicAdd(&work[0], 1u)] = (uint32_t)r;
+                else long_ids[atomicAdd(&work[1], 1u)] = (uint32_t)r;
+            }
+            continue;
+        }
+        if (++epoch > 255u) {
+            uint4* m4 = reinterpret_cast<uint4*>(marks);
+#pragma unroll
+            for (int j = 0; j < AK_MARKS / 8 / 32; ++j) m4[lane + 32 * j] = make_uint4(0, 0, 0, 0);
+            epoch = 1;
+            __syncwarp();
+        }
+        // this lane's stretch of the read, in 32-bit arithmetic relative to the read start
+        const int L = (int)L64;
+        const int n_pos = L - kmin + 1;
+        const int C = (n_pos + 31) >> 5;                            // windows per lane, 1..8
+        const int base = lane * C;
+        const int mine = min(max(n_pos - base, 0), C);              // windows this lane really has
+        uint32_t vbits = 0, hi = 0, lo = 0;
+        if (mine > 0) {
+            vbits = __funnelshift_r(g.va, g.vb, ((int)(st & 31) + base) & 31);
+            const int room = L - base;                              // positions of the read from `base` on
+            if (room < 32) vbits &= (1u << room) - 1u;              // never look past the read end
+            const int sh = ((int)(st & 15) + base) & 15;
+            hi = __funnelshift_l(g.w1, g.w0, 2 * sh);               // bases base .. base+15
+            lo = __funnelshift_l(g.w2, g.w1, 2 * sh);               // bases base+16 .. base+31
+        }
+        uint32_t xs[AK_MAXC];
+        int vs[AK_MAXC];
+#pragma unroll
+        for (int t = 0; t < AK_MAXC; ++t) {
+            if (t >= C) break;                                      // warp-uniform
+            const int vlen = (t < mine) ? run_length(vbits >> t) : 0;
+            const uint32_t x = __funnelshift_l(lo, hi, 2 * t);     // 16 bases from window base+t
+            const bool ok = vlen >= kmin;
+            // filter: stamp the mark of this window's kmin-mer.  A mark that already carries the read's epoch means an
+            // earlier round used it; a contest for the mark inside this round is detected without __match_any_sync
+            // (which saturates the ADU pipe): everybody writes its tag, the losers write again, and whoever does not
+            // read its own tag back at either step shared the mark with another lane.
+            const uint32_t idx = ((x >> key_shift) * 0x9E3779B1u) >> 20;
+            const uint32_t tag = (epoch << 8) | ((uint32_t)t << 5) | (uint32_t)lane;
+            uint32_t seen = 0;
+            if (ok) seen = marks[idx];
+            __syncwarp();
+            if (ok) marks[idx] = (uint16_t)tag;
+            __syncwarp();
+            bool maybe = false;
+            if (ok) {
+                const bool lost = marks[idx] != tag;
+                maybe = lost || (seen >> 8) == epoch;
+                if (lost) marks[idx] = (uint16_t)tag;
+            }
+            __syncwarp();
+            if (ok && !maybe) maybe = marks[idx] != tag;
+            __syncwarp();
+            // rare: exact depth of the longest repeat with an earlier window of the read
+            int dd = 0;
+            uint32_t todo = __ballot_sync(0xFFFFFFFFu, maybe);
+            while (todo) {
+                const int b = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t xi = __shfl_sync(0xFFFFFFFFu, x, b);
+                const int vi = min(__shfl_sync(0xFFFFFFFFu, vlen, b), kmax);
+                int best = 0;
+#pragma unroll
+                for (int u = 0; u < t; ++u) best = max(best, min(common_prefix(xs[u], xi), min(vs[u], vi)));
+                if (lane < b) best = max(best, min(common_prefix(x, xi), min(vlen, vi)));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+                if (lane == b) dd = best;
+            }
+            xs[t] = x;
+            vs[t] = ok ? vlen : 0;                                  // windows shorter than kmin never match anything
+            if (ok) {
+                if (vlen >= kmax) {
+                    if (dd >= kmax) {                                                   // repeated at every level
+                        const int64_t p = st + base + t;
+                        atomicOr(dupmask + (p >> 5), 1u << (p & 31));
+                    }
+                } else if (dd < vlen) {
+                    atomicAdd(stab[vlen] + (x >> (32 - 2 * vlen)), 1u);                 // cannot be extended: +1 at level vlen
+                }
+                if (dd >= kmin && dd < kmax && vlen > dd)
+                    atomicAdd(stab[dd] + (x >> (32 - 2 * dd)), 0xFFFFFFFFu);           // repeated k-mer, new extension: -1
+            }
+        }
+    }
+}
+
+// ---- repetitive mode: only the "+1 at level vlen" corrections exist ---------------------------------------------------
+__global__ void __launch_bounds__(256) terminal_corrections_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
+                                                                   int64_t n_words, int kmin, int kmax, TableSet tabs) {
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= n_words) return;
+    const uint32_t v0 = __ldg(valid + t), v1 = __ldg(valid + t + 1);
+    if (v0 == 0) return;
+    // a window that cannot be extended ends a valid run: bit j set, bit j+1 clear.  Cheap pre-test on the word.
+    const uint64_t v = ((uint64_t)v1 << 32) | v0;
+    if (((v & ~(v >> 1)) & 0x7FFFFFFFFFFFull) == 0) return;          // no run ends inside bits [0, 47)
+#pragma unroll 1
+    for (int i = 0; i < 32; ++i) {
+        const int vlen = run_length((uint32_t)(v >> i));
+        if (vlen >= kmin && vlen < kmax) {
+            const uint32_t x = window16(packed, t * 32 + i);
+            atomicAdd(tabs.t[vlen] + (x >> (32 - 2 * vlen)), 1u);
+        }
+    }
+}
+
+// ---- B: level-kmax count restricted to the keys that start with a given prefix of PB bases -----------------------------
+// One thread = 32 consecutive window positions.  Instead of hashing all 32 windows and filtering, the thread first
+// builds the set of positions whose first PB bases equal the pass prefix with a few bit operations on the packed words
+// (2-bit groups compared in place, position i at bit 62-2i of a 64-bit mask), then visits only those (32 / 4^PB on
+// average).  A pass therefore costs ~1/6 of a full count and issues atomics only for its own key range, whose slice of
+// the table (4^(k-PB) cells) stays L2 resident.
+__device__ __forceinline__ uint32_t eq_groups(uint32_t w, uint32_t rep) {      // bit 2g set iff 2-bit group g of w == rep's
+    const uint32_t x = w ^ rep;
+    return ~(x | (x >> 1)) & 0x55555555u;
+}
+
+template <int PB>
+__global__ void __launch_bounds__(256) count_prefix_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
+                                                           const uint32_t* __restrict__ hide_mask, int64_t n_groups, int k,
+                                                           uint32_t* __restrict__ table, uint32_t prefix) {
+    // one thread = 4 validity words = 128 window positions; everything it needs arrives in six 128-bit / 32-bit
+    // streaming loads issued together (the inputs are read once per pass: evict-first keeps the table slice in L2)
+    const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= n_groups) return;
+    const uint4 v4 = __ldcs(reinterpret_cast<const uint4*>(valid) + g);
+    const uint32_t v_next = __ldcs(valid + 4 * g + 4);
+    const uint4 pa = __ldcs(reinterpret_cast<const uint4*>(packed) + 2 * g);
+    const uint4 pb = __ldcs(reinterpret_cast<const uint4*>(packed) + 2 * g + 1);
+    const uint32_t p_next = __ldcs(packed + 8 * g + 8);
+    uint4 h4 = make_uint4(0, 0, 0, 0);
+    if (hide_mask) h4 = __ldcs(reinterpret_cast<const uint4*>(hide_mask) + g);
+    const uint32_t vw[5] = {v4.x, v4.y, v4.z, v4.w, v_next};
+    const uint32_t pw[9] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w, p_next};
+    const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
+    const uint32_t km = (1u << k) - 1u;
+    const int sh = 32 - 2 * k;
+    uint32_t reps[PB > 0 ? PB : 1];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) reps[j] = ((prefix >> (2 * (PB - 1 - j))) & 3u) * 0x55555555u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t v0 = vw[q];
+        if (v0 == 0) continue;
+        const uint32_t w0 = pw[2 * q], w1 = pw[2 * q + 1], w2 = pw[2 * q + 2];
+        // candidate positions: base j of the window equals base j of the prefix, j = 0..PB-1
+        uint64_t sel = 0x5555555555555555ull;
+#pragma unroll
+        for (int j = 0; j < PB; ++j) {
+            const uint64_t e01 = ((uint64_t)eq_groups(w0, reps[j]) << 32) | eq_groups(w1, reps[j]);
+            sel &= j == 0 ? e01 : ((e01 << (2 * j)) | (eq_groups(w2, reps[j]) >> (32 - 2 * j)));
+        }
+        const uint32_t v1 = vw[q + 1], hide = hw[q];
+        while (sel) {
+            const int b = __clzll(sel);
+            sel &= ~(0x8000000000000000ull >> b);
+            const int i = b >> 1;                                    // window position inside this word
+            const uint32_t vb = __funnelshift_r(v0, v1, i);
+            if ((vb & km) != km || ((hide >> i) & 1u)) continue;
+            const uint32_t x = (i < 16) ? __funnelshift_l(w1, w0, 2 * i) : __funnelshift_l(w2, w1, 2 * (i - 16));
+            atomicAdd(table + (x >> sh), 1u);
+        }
+    }
+}
+
+// ---- derive: T_k[h] += T_{k+1}[4h] + .. + T_{k+1}[4h+3] -----------------------------------------------------------------
+__global__ void __launch_bounds__(256) derive_table_kernel(const uint4* __restrict__ upper, uint32_t* __restrict__ lower, int64_t n_cells) {
+    int64_t h = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (; h < n_cells; h += stride) {
+        const uint4 v = __ldg(upper + h);
+        lower[h] += v.x + v.y + v.z + v.w;
+    }
+}
+
+}  // namespace
+
+// implemented in count.cu: direct per-k handling of reads too long for the warp path, driven by the lists in `work`
+int kmap_count_long_reads(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
+                          int k, uint32_t* table, uint32_t* work, uint32_t* bitmap, const uint32_t counts[2], cudaStream_t s);
+
+extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
+                                int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
+                                uint32_t* bitmap, int n_partitions, void* stream) {
+    KMAP_REQUIRE(n >= 0 && n_seq >= 0 && kmin >= 1 && kmin <= kmax && kmax <= 15, "need 1 <= kmin <= kmax <= 15");
+    KMAP_REQUIRE(n_seq < (int64_t)0xFFFFFFFFll, "too many reads for one call (shard the input)");
+    KMAP_REQUIRE(tables_host, "null pointer");
+    cudaStream_t s = as_stream(stream);
+    TableSet tabs;
+    for (int k = 0; k < 16; ++k) tabs.t[k] = nullptr;
+    for (int k = kmin; k <= kmax; ++k) {
+        tabs.t[k] = tables_host[k - kmin];
+        KMAP_REQUIRE(tabs.t[k], "null table");
+        cudaError_t e = cudaMemsetAsync(tabs.t[k], 0, ((size_t)1 << (2 * k)) * 4, s);
+        if (e != cudaSuccess) { kmap_set_error("count_all_k: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    if (n == 0) return KMAP_OK;
+    KMAP_REQUIRE(packed && valid, "null pointer");
+    const int64_t n_words = (n + 31) / 32;
+    uint32_t counts[2] = {0, 0};
+    cudaError_t e = cudaSuccess;
+    if (dedup) {
+        KMAP_REQUIRE(borders && dupmask && work, "de-duplication needs borders, dupmask and work scratch");
+        if (n_seq == 0) return KMAP_OK;
+        e = cudaMemsetAsync(dupmask, 0, (size_t)kmap_valid_words(n) * 4, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(work, 0, 16, s);
+        if (e != cudaSuccess) { kmap_set_error("count_all_k: %s", cudaGetErrorString(e)); return (int)e; }
+        int64_t blocks = (n_seq + AK_WARPS - 1) / AK_WARPS;
+        if (blocks > 148 * 7 * 8) blocks = 148 * 7 * 8;           // 7 blocks of 4 warps (32 KB of marks each) per SM
+        dedup_scan_kernel<<<(unsigned int)blocks, AK_WARPS * 32, 0, s>>>(packed, valid, n, borders, n_seq, kmin, kmax, tabs, dupmask, work);
+    } else if (kmin < kmax) {
+        terminal_corrections_kernel<<<grid_for(n_words, 256), 256, 0, s>>>(packed, valid, n_words, kmin, kmax, tabs);
+    }
+    int rc = kmap_check_launch("count_all_k(scan)");
+    if (rc) return rc;
+    // level kmax in key-prefix passes: 4^PB passes, each updating a 4^(kmax-PB)-cell slice that stays in L2
+    int PB = 0;
+    if (n_partitions <= 0) { while (PB < 3 && PB < kmax && (((size_t)4 << (2 * kmax)) >> (2 * PB)) > ((size_t)96 << 20)) ++PB; }
+    else { while (PB < 3 && PB < kmax && (1 << (2 * PB)) < n_partitions) ++PB; }
+    const uint32_t* hide = dedup ? dupmask : nullptr;
+    const int64_t n_groups = (n_words + 3) / 4;
+    const unsigned int gB = grid_for(n_groups, 256);
+    for (uint32_t prefix = 0; prefix < (1u << (2 * PB)); ++prefix) {
+        switch (PB) {
+            case 0: count_prefix_kernel<0><<<gB, 256, 0, s>>>(packed, valid, hide, n_groups, kmax, tabs.t[kmax], prefix); break;
+            case 1: count_prefix_kernel<1><<<gB, 256, 0, s>>>(packed, valid, hide, n_groups, kmax, tabs.t[kmax], prefix); break;
+            case 2: count_prefix_kernel<2><<<gB, 256, 0, s>>>(packed, valid, hide, n_groups, kmax, tabs.t[kmax], prefix); break;
+            default: count_prefix_kernel<3><<<gB, 256, 0, s>>>(packed, valid, hide, n_groups, kmax, tabs.t[kmax], prefix); break;
+        }
+    }
+    rc = kmap_check_launch("count_all_k(count)");
+    if (rc) return rc;
+    for (int k = kmax - 1; k >= kmin; --k) {
+        const int64_t cells = (int64_t)1 << (2 * k);
+        int64_t g = (cells + 255) / 256;
+        if (g > 148 * 32) g = 148 * 32;
+        derive_table_kernel<<<(unsigned int)g, 256, 0, s>>>(reinterpret_cast<const uint4*>(tabs.t[k + 1]), tabs.t[k], cells);
+    }
+    rc = kmap_check_launch("count_all_k(derive)");
+    if (rc) return rc;
+    if (dedup) {
+        e = cudaMemcpyAsync(counts, work, 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { kmap_set_error("count_all_k: %s", cudaGetErrorString(e)); return (int)e; }
+        if (counts[0] || counts[1]) {
+            for (int k = kmin; k <= kmax; ++k) {
+                rc = kmap_count_long_reads(packed, valid, n, borders, n_seq, k, tabs.t[k], work, bitmap, counts, s);
+                if (rc) return rc;
+            }
+        }
+    }
+    return KMAP_OK;
+}

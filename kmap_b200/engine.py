@@ -150,6 +150,37 @@ class SeqOnDevice:
                   "kmap_count_dense")
         return table
 
+    def count_all(self, kmin: int, kmax: int, dedup: bool, tables: Optional[dict] = None, n_partitions: int = 0) -> dict:
+        """Dense forward tables for every k in [kmin, kmax] from ONE pass of atomics at level kmax (csrc/count_all.cu);
+        identical to {k: self.count(k, dedup)}.  Returns {k: int32-bit-pattern tensor of 4^k cells}."""
+        L = lib()
+        if not (1 <= kmin <= kmax <= 15):
+            raise KmapError("count_all needs 1 <= kmin <= kmax <= 15")
+        if tables is None:
+            tables = {}
+        for k in range(kmin, kmax + 1):
+            if k not in tables:
+                tables[k] = empty(1 << (2 * k), torch.int32)
+        ptrs = (ctypes.c_void_p * (kmax - kmin + 1))(*[tables[k].data_ptr() for k in range(kmin, kmax + 1)])
+        dupmask = work = bitmap = None
+        if dedup:
+            if self.borders is None:
+                raise KmapError("per-read de-duplication needs the border matrix")
+            if getattr(self, "_dupmask", None) is None:
+                self._dupmask = empty(self.valid.numel(), torch.int32)
+            need = L.kmap_dedup_work_words(self.n_seq)
+            if self._work is None or self._work.numel() < need:
+                self._work = empty(need, torch.int32)
+            dupmask, work = self._dupmask, self._work
+        rc = L.kmap_count_all_k(_ptr(self.packed), _ptr(self.valid), self.n, _ptr(self.borders), self.n_seq, kmin, kmax,
+                                int(dedup), ptrs, _ptr(dupmask), _ptr(work), None, int(n_partitions), _stream_ptr())
+        if rc == -3:   # a read beyond the block path: rerun with the bitmap scratch (tables are re-zeroed by the call)
+            bitmap = zeros(max((1 << (2 * kmax)) // 32, 1), torch.int32)
+            rc = L.kmap_count_all_k(_ptr(self.packed), _ptr(self.valid), self.n, _ptr(self.borders), self.n_seq, kmin, kmax,
+                                    int(dedup), ptrs, _ptr(dupmask), _ptr(work), _ptr(bitmap), int(n_partitions), _stream_ptr())
+        check(rc, "kmap_count_all_k")
+        return tables
+
     # ---- masking ----------------------------------------------------------------------------------------------
     def mask(self, k: int, consensus_kh: Sequence[int], max_dist: Sequence[int]):
         L = lib()

@@ -149,6 +149,30 @@ def test_fused_count_tables_vs_oracle(ENG, k):
         assert np.array_equal(got, want), (k, dedup, int(np.abs(got.astype(np.int64) - want).sum()))
 
 
+@pytest.mark.parametrize("kmin,kmax,parts", [(8, 14, 0), (8, 14, 3), (1, 6, 0), (5, 5, 1), (11, 15, 5), (3, 9, 2)])
+def test_count_all_k_equals_per_k_counts(ENG, kmin, kmax, parts):
+    """the hierarchical all-k count (one atomic pass at kmax + 4:1 reductions + corrections) == independent per-k counts
+    == oracle, in both modes, incl. repeats inside reads, N's, reads shorter than k, block-path and bitmap-path reads"""
+    rng = np.random.default_rng(1000 + 17 * kmin + kmax)
+    special = ["A" * 80, "CA" * 60, "", "N", "ACG", "ACGTTGCA" * 30, "ACGTACGTAC" * 9 + "T", "GGGGGGGGGGGGGGGGGGGGAGGGGGGGGGGGGGGGGGGG",
+               ("ACGTAGCTAGCTAGGATCGAT" * 500)[:9000], "ACGTTGCAAC" * 40]
+    reads, seq, borders = rand_reads(rng, 500, 0, 130, p_n=0.02, special=special)
+    reads2, seq2, borders2 = rand_reads(rng, 3, 300, 2000, p_n=0.002)
+    seq = np.concatenate([seq, seq2])
+    borders = np.concatenate([borders, borders2 + borders[-1, 1] + 1])
+    # tandem repeats so that k-mers repeat inside reads with different extensions
+    dev = ENG.SeqOnDevice.from_numpy(seq, borders)
+    for dedup in (True, False):
+        tabs = dev.count_all(kmin, kmax, dedup, n_partitions=parts)
+        for k in range(kmin, kmax + 1):
+            got = ENG.to_host(tabs[k], np.uint32)
+            if k in (kmin, kmax, (kmin + kmax) // 2):
+                want = dense_table_from_oracle(seq, borders, k, dedup)
+            else:
+                want = ENG.to_host(dev.count(k, dedup=dedup), np.uint32)
+            assert np.array_equal(got, want), (k, dedup, int(np.abs(got.astype(np.int64) - want.astype(np.int64)).sum()))
+
+
 @pytest.mark.parametrize("k", [2, 5, 6, 9, 12])
 def test_compact_merge_order_exact(ENG, k):
     rng = np.random.default_rng(k)
