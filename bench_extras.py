@@ -1,0 +1,76 @@
+"""Secondary measurements reported under "extras" by `bench.py --extras`: the other kernels of the scan_motif counting
+path on the same device-resident workload.  CUDA-event timed, after warm-up."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def _time(fn, reps=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
+def run_extras(dev, tables, n_reads, L, peak_gbs=6455.3):
+    from kmap_b200 import engine as E
+    from kmap_b200.motif_discovery import hamdist_matrix_u8
+    from kmap_b200.kmer_count import kmer2hash, revcom_hash
+    res = {}
+    k, d = 14, 5
+    table = tables[k]
+    # order-exact compaction + reverse-complement merge of the k=14 table (count_uniq_hash + merge_revcom)
+    ms, (kh, cnt) = _time(lambda: E.compact_merge(table, k, True, upper_bound=1 << 28))
+    n_m = int(kh.numel())
+    res["compact_merge_k14"] = {"ms": ms, "n_merged": n_m, "table_GB": 4 ** k * 4 / 1e9,
+                                "GBs_table_read_twice_plus_lists": (2 * 4 ** k * 4 + 8 * n_m) / ms / 1e6}
+    # Hamming-ball sums for top_k = 5 candidates (fwd + rc), k = 14, d = 5
+    cnt_host = cnt.cpu().numpy()
+    top = np.argpartition(cnt_host, -5)[-5:]
+    cand = [int(x) & 0xFFFFFFFF for x in kh[torch.from_numpy(top).cuda()].cpu().numpy().view(np.uint32)]
+    ms_e, sums_e = _time(lambda: E.hamball_sums(table, k, cand, d, True), reps=5)
+    ms_l, sums_l = _time(lambda: E.hamball_sums_list(kh, cnt, k, cand, d, True), reps=3)
+    assert np.array_equal(sums_e, sums_l), "enumeration and list formulations disagree"
+    pairs = 2 * len(cand) * n_m          # reference formulation: every merged k-mer against each candidate and its rc
+    res["hamball_sum_k14_d5_top5"] = {
+        "enumeration_ms": ms_e, "list_scan_ms": ms_l, "pairs_reference_formulation": pairs,
+        "pairs_per_s_enumeration": pairs / ms_e * 1e3, "pairs_per_s_list_scan": pairs / ms_l * 1e3,
+        "list_scan_GBs": 8.0 * n_m / ms_l / 1e6, "list_scan_frac_of_hbm": 8.0 * n_m / ms_l / 1e6 / peak_gbs}
+    # mask_input with one consensus + its reverse complement over the whole input, then restore
+    c = int(kmer2hash("GTACGTAGGTCCTA"))
+    rc = int(revcom_hash(c, k))
+    dev.snapshot_valid()
+
+    def do_mask():
+        dev.restore_valid()
+        dev.mask(k, [c, rc], [d, d])
+    ms, _ = _time(do_mask)
+    ms_restore, _ = _time(dev.restore_valid)
+    dev.restore_valid()
+    n_pos = dev.n
+    res["mask_k14_d5"] = {"ms": ms - ms_restore, "positions": n_pos, "Gpositions_per_s": n_pos / (ms - ms_restore) / 1e6,
+                          "algorithmic_GBs": 0.5 * n_pos / (ms - ms_restore) / 1e6}
+    # occurrence scan of one consensus over all reads (count + scan + fill)
+    ms, (mind, offs, pos) = _time(lambda: E.occurrence_scan(dev, k, c, d, True), reps=2)
+    res["occurrence_scan_k14_d5"] = {"ms_incl_d2h": ms, "reads": n_reads, "reads_with_hit": int((np.diff(offs) > 0).sum()),
+                                     "hits": int(len(pos))}
+    # sampled k-mer distance matrix: 100 000 distinct 14-mers, second consensus of length 12 (head override), uint8 output
+    rng = np.random.default_rng(20240414)
+    n = 100_000
+    khs = np.unique(rng.integers(0, 4 ** k, int(n * 1.01), dtype=np.uint64))[:n].astype(np.uint32)
+    rng.shuffle(khs)
+    labels = rng.integers(0, 3, n).astype(np.int32)
+    out = E.empty(n * n, torch.uint8)
+    ms, _ = _time(lambda: hamdist_matrix_u8(khs, labels, [14, 12], k, 0, n, out=out), reps=5)
+    res["hamdist_matrix_100k_k14"] = {"ms": ms, "pairs": n * n, "pairs_per_s": n * n / ms * 1e3, "write_GBs": n * n / ms / 1e6,
+                                      "frac_of_hbm": n * n / ms / 1e6 / peak_gbs,
+                                      "note": "1 B written per pair (uint8); includes the H2D of the 100k keys/labels"}
+    del out
+    return res

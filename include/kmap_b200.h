@@ -94,10 +94,12 @@ int64_t kmap_dedup_work_words(int64_t n_seq);
  * n_partitions key-range passes (0 = choose so that a slice stays L2 resident); each smaller table is the 4:1
  * reduction of the next one plus the per-read corrections derived in csrc/count_all.cu.  Results are identical to
  * kmax-kmin+1 calls of kmap_count_dense[_dedup].  dupmask = uint32[kmap_valid_words(n)] scratch, work/bitmap as in
- * kmap_count_dense_dedup (dedup != 0 only).  Synchronises the stream once when dedup != 0. */
+ * kmap_count_dense_dedup (dedup != 0 only).  phase_events = NULL, or a HOST array of 4 cudaEvent_t that are recorded
+ * on the stream after zeroing / after the per-read scan / after the level-kmax passes / after the reductions
+ * (instrumentation for bench.py).  Synchronises the stream once when dedup != 0. */
 int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
                      int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
-                     uint32_t* bitmap, int n_partitions, void* stream);
+                     uint32_t* bitmap, int n_partitions, void* const* phase_events, void* stream);
 
 int kmap_fill_u32(uint32_t* p, int64_t n_words, uint32_t value, void* stream);
 

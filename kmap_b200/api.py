@@ -73,20 +73,50 @@ def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterabl
     compaction; `lists_on=r` returns the lists on rank r only (others get {})."""
     dev = upload_reads(seq_np_arr, boarder_mat, validate)
     out: Dict[int, Tuple[np.ndarray, np.ndarray]] = {}
-    table = None
-    for k in k_list:
-        n_cells = 1 << (2 * k)
-        if table is None or table.numel() < n_cells:
-            table = E.empty(n_cells, torch.int32)
-        tk = table[:n_cells]
-        dev.count(k, dedup=not rep_mode, table=tk, zero=True)
-        if table_allreduce is not None:
-            table_allreduce(tk)
-            if lists_on is not None and table_allreduce.rank != lists_on:
-                continue
-        kh, cnt = E.compact_merge(tk, k, revcom_mode)
-        out[k] = (_to_host_pinned(kh, np.uint32), _to_host_pinned(cnt, np.int32))
+    ks = sorted(set(int(k) for k in k_list))
+    if not ks:
+        return out
+    if ks == list(range(ks[0], ks[-1] + 1)) and ks[-1] <= 15:
+        tables = dev.count_all(ks[0], ks[-1], dedup=not rep_mode)          # one atomic pass at kmax, the rest derived
+    else:
+        tables = {k: dev.count(k, dedup=not rep_mode) for k in ks}
+    if table_allreduce is not None:
+        for k in ks:
+            table_allreduce(tables[k])
+        if lists_on is not None and table_allreduce.rank != lists_on:
+            return out
+    # compaction of table k+1 overlaps the device-to-host copy of the lists of k (copy stream + pinned buffers)
+    copy_stream = _copy_stream()
+    pending = []
+    for k in ks:
+        kh, cnt = E.compact_merge(tables[k], k, revcom_mode, upper_bound=_upper_bound(dev, k))
+        done = torch.cuda.Event()
+        done.record()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            h_kh, h_cnt = _pinned_like(kh), _pinned_like(cnt)
+            h_kh.copy_(kh, non_blocking=True)
+            h_cnt.copy_(cnt, non_blocking=True)
+        pending.append((k, kh, cnt, h_kh, h_cnt))
+    copy_stream.synchronize()
+    for k, kh, cnt, h_kh, h_cnt in pending:
+        out[k] = (h_kh.numpy().view(np.uint32), h_cnt.numpy())
     return out
+
+
+_copy_streams = {}
+
+
+def _copy_stream() -> torch.cuda.Stream:
+    dev = torch.cuda.current_device()
+    if dev not in _copy_streams:
+        _copy_streams[dev] = torch.cuda.Stream()
+    return _copy_streams[dev]
+
+
+def _upper_bound(dev: E.SeqOnDevice, k: int) -> int:
+    """no table can hold more distinct k-mers than cells or than windows"""
+    return int(min(1 << (2 * k), max(dev.n - k + 1, 0)))
 
 
 def hamdist_matrix_rows(kh: np.ndarray, labels: np.ndarray, head_len: Sequence[int], kmer_len: int, rank: int, world: int):

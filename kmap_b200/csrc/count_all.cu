@@ -293,7 +293,7 @@ int kmap_count_long_reads(const uint32_t* packed, const uint32_t* valid, int64_t
 
 extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
                                 int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
-                                uint32_t* bitmap, int n_partitions, void* stream) {
+                                uint32_t* bitmap, int n_partitions, void* const* phase_events, void* stream) {
     KMAP_REQUIRE(n >= 0 && n_seq >= 0 && kmin >= 1 && kmin <= kmax && kmax <= 15, "need 1 <= kmin <= kmax <= 15");
     KMAP_REQUIRE(n_seq < (int64_t)0xFFFFFFFFll, "too many reads for one call (shard the input)");
     KMAP_REQUIRE(tables_host, "null pointer");
@@ -308,6 +308,10 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
     }
     if (n == 0) return KMAP_OK;
     KMAP_REQUIRE(packed && valid, "null pointer");
+    // optional instrumentation (bench.py): 4 caller-owned cudaEvent_t recorded after zeroing, after the per-read scan,
+    // after the level-kmax passes and after the table reductions
+    auto mark = [&](int i) { if (phase_events && phase_events[i]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(phase_events[i]), s); };
+    mark(0);
     const int64_t n_words = (n + 31) / 32;
     uint32_t counts[2] = {0, 0};
     cudaError_t e = cudaSuccess;
@@ -325,6 +329,7 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
     }
     int rc = kmap_check_launch("count_all_k(scan)");
     if (rc) return rc;
+    mark(1);
     // level kmax in key-prefix passes: 4^PB passes, each updating a 4^(kmax-PB)-cell slice that stays in L2
     int PB = 0;
     if (n_partitions <= 0) { while (PB < 3 && PB < kmax && (((size_t)4 << (2 * kmax)) >> (2 * PB)) > ((size_t)96 << 20)) ++PB; }
@@ -342,6 +347,7 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
     }
     rc = kmap_check_launch("count_all_k(count)");
     if (rc) return rc;
+    mark(2);
     for (int k = kmax - 1; k >= kmin; --k) {
         const int64_t cells = (int64_t)1 << (2 * k);
         int64_t g = (cells + 255) / 256;
@@ -350,6 +356,7 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
     }
     rc = kmap_check_launch("count_all_k(derive)");
     if (rc) return rc;
+    mark(3);
     if (dedup) {
         e = cudaMemcpyAsync(counts, work, 8, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);

@@ -150,7 +150,8 @@ class SeqOnDevice:
                   "kmap_count_dense")
         return table
 
-    def count_all(self, kmin: int, kmax: int, dedup: bool, tables: Optional[dict] = None, n_partitions: int = 0) -> dict:
+    def count_all(self, kmin: int, kmax: int, dedup: bool, tables: Optional[dict] = None, n_partitions: int = 0,
+                  phase_events: Optional[Sequence[torch.cuda.Event]] = None) -> dict:
         """Dense forward tables for every k in [kmin, kmax] from ONE pass of atomics at level kmax (csrc/count_all.cu);
         identical to {k: self.count(k, dedup)}.  Returns {k: int32-bit-pattern tensor of 4^k cells}."""
         L = lib()
@@ -172,12 +173,15 @@ class SeqOnDevice:
             if self._work is None or self._work.numel() < need:
                 self._work = empty(need, torch.int32)
             dupmask, work = self._dupmask, self._work
+        ev = None
+        if phase_events is not None:                    # 4 torch events (already recorded once so that the handles exist)
+            ev = (ctypes.c_void_p * 4)(*[e.cuda_event for e in phase_events])
         rc = L.kmap_count_all_k(_ptr(self.packed), _ptr(self.valid), self.n, _ptr(self.borders), self.n_seq, kmin, kmax,
-                                int(dedup), ptrs, _ptr(dupmask), _ptr(work), None, int(n_partitions), _stream_ptr())
+                                int(dedup), ptrs, _ptr(dupmask), _ptr(work), None, int(n_partitions), ev, _stream_ptr())
         if rc == -3:   # a read beyond the block path: rerun with the bitmap scratch (tables are re-zeroed by the call)
             bitmap = zeros(max((1 << (2 * kmax)) // 32, 1), torch.int32)
             rc = L.kmap_count_all_k(_ptr(self.packed), _ptr(self.valid), self.n, _ptr(self.borders), self.n_seq, kmin, kmax,
-                                    int(dedup), ptrs, _ptr(dupmask), _ptr(work), _ptr(bitmap), int(n_partitions), _stream_ptr())
+                                    int(dedup), ptrs, _ptr(dupmask), _ptr(work), _ptr(bitmap), int(n_partitions), ev, _stream_ptr())
         check(rc, "kmap_count_all_k")
         return tables
 
@@ -222,11 +226,18 @@ def _scratch(words: int) -> torch.Tensor:
     return t
 
 
-def compact_merge(table: torch.Tensor, k: int, revcom: bool) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(kh uint32-bits, cnt int32) device tensors in the reference's order (kmer_count.py:476-491, 643-685)."""
+def compact_merge(table: torch.Tensor, k: int, revcom: bool, upper_bound: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(kh uint32-bits, cnt int32) device tensors in the reference's order (kmer_count.py:476-491, 643-685).
+    With `upper_bound` (a safe capacity) the size query is skipped: one counting pass + one writing pass."""
     L = lib()
     scratch = _scratch(L.kmap_compact_scratch_words(k))
     n_out = ctypes.c_int64(0)
+    if upper_bound is not None and upper_bound <= (1 << 29):
+        kh, cnt = empty(upper_bound, torch.int32), empty(upper_bound, torch.int32)
+        if upper_bound > 0:
+            check(L.kmap_compact_merge(_ptr(table), k, int(revcom), _ptr(scratch), _ptr(kh), _ptr(cnt), upper_bound,
+                                       ctypes.byref(n_out), _stream_ptr()), "kmap_compact_merge")
+        return kh[:n_out.value], cnt[:n_out.value]
     check(L.kmap_compact_merge(_ptr(table), k, int(revcom), _ptr(scratch), None, None, 0, ctypes.byref(n_out), _stream_ptr()),
           "kmap_compact_merge(size)")
     n = n_out.value
