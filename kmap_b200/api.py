@@ -124,5 +124,29 @@ def hamdist_matrix_rows(kh: np.ndarray, labels: np.ndarray, head_len: Sequence[i
     returns (row0, row1, uint8 device tensor [(row1-row0), n]) of this rank's slab; no collective is involved."""
     from .motif_discovery import hamdist_matrix_u8
     n = len(kh)
-    row0, row1 = n * rank // world, n * (rank + 1) // world
+    row0, row1 = row_range(n, rank, world)
     return row0, row1, hamdist_matrix_u8(kh, labels, head_len, kmer_len, row0, row1)
+
+
+# ---- sharding (host logic; reads are the independent units of the counting path) --------------------------------------
+def read_range(n_seq: int, rank: int, world: int) -> Tuple[int, int]:
+    """contiguous range of reads [r0, r1) owned by `rank`; the ranges of all ranks tile [0, n_seq)"""
+    if not (0 <= rank < world):
+        raise KmapError(f"rank {rank} outside world of {world}")
+    return n_seq * rank // world, n_seq * (rank + 1) // world
+
+
+def shard_reads(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, rank: int, world: int) -> Tuple[np.ndarray, np.ndarray]:
+    """This rank's slice of input.bin / input.seqboarder.bin (kmer_count.py:326-347 layout): the bytes of its reads,
+    separators included, and the border rows rebased to the slice.  Views, no copies of the sequence."""
+    b = np.asarray(boarder_mat, dtype=np.int64).reshape(-1, 2)
+    r0, r1 = read_range(len(b), rank, world)
+    if r1 == r0:
+        return seq_np_arr[:0], b[:0].copy()
+    p0, p1 = int(b[r0, 0]), int(b[r1 - 1, 1]) + 1          # [first base of read r0, separator of read r1-1]
+    return seq_np_arr[p0:p1], b[r0:r1] - p0
+
+
+def row_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """row block of the distance matrix owned by `rank` (motif_discovery.py:759-808 has no cross-row dependency)"""
+    return read_range(n, rank, world)
