@@ -99,7 +99,18 @@ int64_t kmap_dedup_work_words(int64_t n_seq);
  * (instrumentation for bench.py).  Synchronises the stream once when dedup != 0. */
 int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
                      int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
-                     uint32_t* bitmap, int n_partitions, void* const* phase_events, void* stream);
+                     uint32_t* bitmap, int n_partitions, void* part_scratch, int64_t part_scratch_bytes,
+                     void* const* phase_events, void* stream);
+
+/* kmap_count_dense for tables beyond L2 (9 <= k <= 14) without one global atomic per window: windows are partitioned
+ * by the top bits of their key into 4^(k-8) buckets of 16-bit suffixes (scratch), then every bucket is counted in
+ * shared memory and its 65536-cell slice of the table written once (csrc/partition.cu).  Same result as
+ * kmap_count_dense on a zeroed table (the caller zeroes it).  scratch = kmap_partition_scratch_bytes(n, k) bytes.
+ * kmap_count_all_k uses the same scheme for its level-kmax table when part_scratch is given (12 <= kmax <= 14);
+ * with part_scratch == NULL it falls back to n_partitions key-prefix passes of global atomics. */
+int kmap_count_dense_partitioned(const uint32_t* packed, const uint32_t* valid, int64_t n, int k, uint32_t* table,
+                                 void* scratch, int64_t scratch_bytes, void* stream);
+int64_t kmap_partition_scratch_bytes(int64_t n, int k);
 
 int kmap_fill_u32(uint32_t* p, int64_t n_words, uint32_t value, void* stream);
 

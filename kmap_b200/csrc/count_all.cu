@@ -290,10 +290,14 @@ __global__ void __launch_bounds__(256) derive_table_kernel(const uint4* __restri
 // implemented in count.cu: direct per-k handling of reads too long for the warp path, driven by the lists in `work`
 int kmap_count_long_reads(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
                           int k, uint32_t* table, uint32_t* work, uint32_t* bitmap, const uint32_t counts[2], cudaStream_t s);
+// implemented in partition.cu: level-k count through key partitioning + shared-memory counters
+int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const uint32_t* hide, int64_t n, int k, uint32_t* table,
+                           void* scratch, cudaStream_t s);
 
 extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
                                 int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
-                                uint32_t* bitmap, int n_partitions, void* const* phase_events, void* stream) {
+                                uint32_t* bitmap, int n_partitions, void* part_scratch, int64_t part_scratch_bytes,
+                                void* const* phase_events, void* stream) {
     KMAP_REQUIRE(n >= 0 && n_seq >= 0 && kmin >= 1 && kmin <= kmax && kmax <= 15, "need 1 <= kmin <= kmax <= 15");
     KMAP_REQUIRE(n_seq < (int64_t)0xFFFFFFFFll, "too many reads for one call (shard the input)");
     KMAP_REQUIRE(tables_host, "null pointer");
@@ -330,11 +334,17 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
     int rc = kmap_check_launch("count_all_k(scan)");
     if (rc) return rc;
     mark(1);
+    const uint32_t* hide = dedup ? dupmask : nullptr;
+    if (part_scratch && kmax >= 12 && kmax <= 14) {
+        // level kmax through key partitioning + shared-memory counters (partition.cu)
+        KMAP_REQUIRE(part_scratch_bytes >= kmap_partition_scratch_bytes(n, kmax), "partition scratch too small");
+        rc = kmap_count_partitioned(packed, valid, hide, n, kmax, tabs.t[kmax], part_scratch, s);
+        if (rc) return rc;
+    } else {
     // level kmax in key-prefix passes: 4^PB passes, each updating a 4^(kmax-PB)-cell slice that stays in L2
     int PB = 0;
     if (n_partitions <= 0) { while (PB < 3 && PB < kmax && (((size_t)4 << (2 * kmax)) >> (2 * PB)) > ((size_t)96 << 20)) ++PB; }
     else { while (PB < 3 && PB < kmax && (1 << (2 * PB)) < n_partitions) ++PB; }
-    const uint32_t* hide = dedup ? dupmask : nullptr;
     const int64_t n_groups = (n_words + 3) / 4;
     const unsigned int gB = grid_for(n_groups, 256);
     for (uint32_t prefix = 0; prefix < (1u << (2 * PB)); ++prefix) {
@@ -347,6 +357,7 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
     }
     rc = kmap_check_launch("count_all_k(count)");
     if (rc) return rc;
+    }
     mark(2);
     for (int k = kmax - 1; k >= kmin; --k) {
         const int64_t cells = (int64_t)1 << (2 * k);

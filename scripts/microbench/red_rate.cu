@@ -39,6 +39,19 @@ __global__ void smem_kernel(uint32_t* out, int iters, int cells_log2) {
     if (acc == 0xFFFFFFFFu) out[0] = acc;
 }
 
+// ATOMS whose return value is consumed (rank / overflow test)
+__global__ void smem_ret_kernel(uint32_t* out, int iters, int cells_log2) {
+    extern __shared__ uint32_t sm[];
+    const uint32_t cells = 1u << cells_log2;
+    for (uint32_t i = threadIdx.x; i < cells; i += blockDim.x) sm[i] = 0;
+    __syncthreads();
+    uint32_t s = mix(blockIdx.x * blockDim.x + threadIdx.x + 999u), acc = 0;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) { s = mix(s + i); acc += atomicAdd(&sm[s & (cells - 1)], 1u); }
+    __syncthreads();
+    if (acc == 0xFFFFFFFFu) out[0] = acc;
+}
+
 // plain (non-atomic) smem increments, one warp owns a private table: is the rate limit the atomic or the LSU?
 __global__ void smem_plain_kernel(uint32_t* out, int iters, int cells_log2) {
     extern __shared__ uint32_t sm[];
@@ -88,7 +101,9 @@ int main() {
         const double ops = (double)grid * blk * it;
         float m = time_ms([&] { smem_kernel<<<grid, blk, bytes>>>(out, it, lg); });
         float p = time_ms([&] { smem_plain_kernel<<<grid, blk, bytes>>>(out, it, lg); });
-        printf("smem cells=2^%d blk=%4d grid=%d : ATOMS %7.1f G/s | plain LDS+STS %7.1f G/s\n", lg, blk, grid, ops / m / 1e6, ops / p / 1e6);
+        cudaFuncSetAttribute(smem_ret_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        float r = time_ms([&] { smem_ret_kernel<<<grid, blk, bytes>>>(out, it, lg); });
+        printf("smem cells=2^%d blk=%4d grid=%d : ATOMS %7.1f G/s | ATOMS+return %7.1f G/s | plain LDS+STS %7.1f G/s\n", lg, blk, grid, ops / m / 1e6, ops / r / 1e6, ops / p / 1e6);
     }
     printf("err=%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;

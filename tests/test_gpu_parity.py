@@ -149,7 +149,39 @@ def test_fused_count_tables_vs_oracle(ENG, k):
         assert np.array_equal(got, want), (k, dedup, int(np.abs(got.astype(np.int64) - want).sum()))
 
 
-@pytest.mark.parametrize("kmin,kmax,parts", [(8, 14, 0), (8, 14, 3), (1, 6, 0), (5, 5, 1), (11, 15, 5), (3, 9, 2)])
+@pytest.mark.parametrize("k", [9, 11, 12, 13, 14])
+def test_partitioned_count_equals_direct_count(ENG, k):
+    """key partitioning + shared-memory counters (csrc/partition.cu) == one global atomic per window == oracle; the input
+    spans several partition tiles, has N's, and a homopolymer long enough to fold the 16-bit shared counters (>= 32768)"""
+    rng = np.random.default_rng(77 + k)
+    special = ["A" * 70000, "CA" * 60, "", "N", "ACG", "T" * 40000 + "G" + "T" * 33000]
+    reads, seq, borders = rand_reads(rng, 3000, 0, 150, p_n=0.01, special=special)
+    dev = ENG.SeqOnDevice.from_numpy(seq, borders)
+    got = ENG.to_host(dev.count(k, dedup=False, partitioned=True), np.uint32)
+    direct = ENG.to_host(dev.count(k, dedup=False, partitioned=False), np.uint32)
+    assert np.array_equal(got, direct), (k, int(np.abs(got.astype(np.int64) - direct.astype(np.int64)).sum()))
+    assert np.array_equal(got, dense_table_from_oracle(seq, borders, k, False))
+    assert got[0] >= 69000 and got[4 ** k - 1] >= 39000
+    # a second call re-uses the scratch and must not depend on its previous content
+    again = ENG.to_host(dev.count(k, dedup=False, partitioned=True), np.uint32)
+    assert np.array_equal(again, got)
+
+
+def test_partitioned_count_tiny_and_empty(ENG):
+    for reads in (["ACGTACGTACGTACG"], ["ACGT"], ["N" * 50], ["ACGTTGCAACGTTGCAAC", "", "GGGGGGGGGGGGGGGGGGGG"]):
+        arrs = [O.dna2arr(r) for r in reads]
+        seq = np.concatenate(arrs)
+        lens = np.array([len(a) for a in arrs])
+        ends = np.cumsum(lens)
+        borders = np.stack([ends - lens, ends - 1], axis=1).astype(np.int64)
+        dev = ENG.SeqOnDevice.from_numpy(seq, borders)
+        for k in (9, 14):
+            got = ENG.to_host(dev.count(k, dedup=False, partitioned=True), np.uint32)
+            assert np.array_equal(got, dense_table_from_oracle(seq, borders, k, False))
+
+
+@pytest.mark.parametrize("kmin,kmax,parts", [(8, 14, 0), (8, 14, 3), (1, 6, 0), (5, 5, 1), (11, 15, 5), (3, 9, 2), (9, 13, 0),
+                                             (12, 12, 0)])
 def test_count_all_k_equals_per_k_counts(ENG, kmin, kmax, parts):
     """the hierarchical all-k count (one atomic pass at kmax + 4:1 reductions + corrections) == independent per-k counts
     == oracle, in both modes, incl. repeats inside reads, N's, reads shorter than k, block-path and bitmap-path reads"""
