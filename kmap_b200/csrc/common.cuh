@@ -21,6 +21,9 @@ static inline unsigned int grid_for(int64_t n_threads, int block) {
     return (unsigned int)(g < 1 ? 1 : g);
 }
 
+// dense tables of several levels: t[k] = uint32[4^k] (only the levels a kernel uses are set); passed by value
+struct KmapTableSet { uint32_t* t[16]; };
+
 // ---- 2-bit arithmetic -----------------------------------------------------------------------------------
 // mask of the low 2k bits
 __host__ __device__ __forceinline__ uint32_t lowmask32(int k) { return k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u); }

@@ -21,7 +21,7 @@ constexpr int AK_WARPS = 4;
 constexpr int AK_WARP_MAX = 256;          // windows (at level kmin) a warp de-duplicates on chip
 constexpr int AK_BLOCK_MAX = 8192;        // beyond this a read goes to the bitmap path
 
-struct TableSet { uint32_t* t[16]; };     // t[k] = dense table of level k (only kmin..kmax are set)
+typedef KmapTableSet TableSet;            // t[k] = dense table of level k (only kmin..kmax are set)
 
 __device__ __forceinline__ int run_length(uint32_t vb) { return vb == 0xFFFFFFFFu ? 32 : __ffs(~vb) - 1; }
 
@@ -30,12 +30,16 @@ __device__ __forceinline__ int run_length(uint32_t vb) { return vb == 0xFFFFFFFF
 // stretch of the packed read and of the validity mask once (two funnel shifts each) and rolls through its windows with
 // compile-time shifts.  Windows are visited in rounds (round t = window t of every lane); "earlier" below means an
 // earlier (round, lane) pair -- any fixed total order gives the same tables.
-// Repeats inside a read are rare, so the common path is a filter, not a set: every warp owns AK_MARKS 16-bit marks
-// in shared memory; a window hashes its kmin-mer to a mark, reads it and stamps it with (epoch of the read, round,
-// lane) -- no clearing between reads, no atomics, no probing loop.  Only a window whose mark already carried the epoch,
-// or that had to share its mark with another lane of the same round, can be a repeat; for those the warp compares the
-// window with every earlier window of the read -- all of them are still in registers -- and gets the exact repeat depth.
-constexpr int AK_MARKS = 4096;
+// Repeats inside a read are rare, so the common path is a filter, not a set: every warp owns a bitmap of AK_BM_BITS
+// bits in shared memory, indexed by the window's kmin-mer (exact for kmin <= 8, hashed to 16 bits above).  One
+// ATOMS.OR per window sets the bit and returns whether it was already set; set bits are cleared again (plain stores
+// of zero words) when the read is done, so there are no epochs and no probing.  A window that found its bit set MAY
+// repeat an earlier one: the warp then compares it with every earlier window of the read -- all still in registers --
+// and gets the exact repeat depth.  When several lanes of one round share a bit, the lane that won the atomic need
+// not be the lowest one; every flagged lane therefore also broadcasts its window to the HIGHER lanes of its round,
+// which is how an unflagged winner learns about the earlier windows it repeats.
+constexpr int AK_BM_BITS = 65536;
+constexpr int AK_BM_WORDS = AK_BM_BITS / 32;
 constexpr int AK_MAXC = AK_WARP_MAX / 32;
 
 __device__ __forceinline__ int common_prefix(uint32_t a, uint32_t b) {       // equal leading bases of two 16-base words
@@ -43,34 +47,38 @@ __device__ __forceinline__ int common_prefix(uint32_t a, uint32_t b) {       // 
     return diff ? (__clz(diff) >> 1) : 16;
 }
 
+template <bool HASHED>                                              // 4^kmin > AK_BM_BITS: fold the key to 16 bits
 __global__ void __launch_bounds__(AK_WARPS * 32) dedup_scan_kernel(
     const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid, int64_t n, const int64_t* __restrict__ borders,
     int64_t n_seq, int kmin, int kmax, TableSet tabs, uint32_t* __restrict__ dupmask, uint32_t* __restrict__ work) {
-    __shared__ __align__(16) uint16_t marks_all[AK_WARPS][AK_MARKS];
+    __shared__ __align__(16) uint32_t bm_all[AK_WARPS][AK_BM_WORDS];
     __shared__ uint32_t* stab[16];
     if (threadIdx.x < 16) stab[threadIdx.x] = tabs.t[threadIdx.x];
-    __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint16_t* marks = marks_all[wib];
+    uint32_t* bm = bm_all[wib];
+    {
+        uint4* b4 = reinterpret_cast<uint4*>(bm);
+#pragma unroll
+        for (int j = 0; j < AK_BM_WORDS / 4 / 32; ++j) b4[lane + 32 * j] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
     const int64_t warp0 = (int64_t)blockIdx.x * AK_WARPS + wib;
     const int64_t n_warps = (int64_t)gridDim.x * AK_WARPS;
     const int key_shift = 32 - 2 * kmin;
-    uint32_t epoch = 255;                                           // forces a clear before the first read
+    const uint32_t kmin_mask = (1u << kmin) - 1u;
     uint32_t* medium_ids = work + 4;
     uint32_t* long_ids = work + 4 + n_seq;
 
-    // Software pipeline over this warp's reads: borders are fetched two reads ahead and the read's words one read ahead,
-    // so the two dependent DRAM latencies (borders -> words) overlap the processing of earlier reads.
+    // Software pipeline over this warp's reads: the borders are requested two reads ahead (raw, nothing consumes them
+    // until the next iteration) and the read's words one read ahead, so the two dependent DRAM latencies
+    // (borders -> words) overlap the processing of earlier reads.
     struct Staged { int64_t st, en; uint32_t va, vb, w0, w1, w2; };
-    auto stage_borders = [&](int64_t r, Staged& g) {
-        g.st = 0; g.en = 0;
-        if (r < n_seq) {
-            const longlong2 be = __ldg(reinterpret_cast<const longlong2*>(borders) + r);
-            g.st = be.x < 0 ? 0 : be.x;
-            g.en = be.y > n ? n : be.y;
-        }
+    auto load_borders = [&](int64_t r) {
+        return r < n_seq ? __ldg(reinterpret_cast<const longlong2*>(borders) + r) : make_longlong2(0, 0);
     };
-    auto stage_words = [&](Staged& g) {                              // raw words of this lane's stretch (no use yet)
+    auto stage_words = [&](const longlong2& be, Staged& g) {         // raw words of this lane's stretch (no use yet)
+        g.st = be.x < 0 ? 0 : be.x;
+        g.en = be.y > n ? n : be.y;
         g.va = g.vb = g.w0 = g.w1 = g.w2 = 0;
         const int64_t n_pos64 = g.en - g.st - kmin + 1;
         if (n_pos64 <= 0 || n_pos64 > AK_WARP_MAX) return;
@@ -84,16 +92,16 @@ __global__ void __launch_bounds__(AK_WARPS * 32) dedup_scan_kernel(
         const int bp = (int)(g.st & 15) + base;
         g.w0 = __ldg(pk + (bp >> 4)); g.w1 = __ldg(pk + (bp >> 4) + 1); g.w2 = __ldg(pk + (bp >> 4) + 2);
     };
-    Staged cur, nxt, nxt2;
-    stage_borders(warp0, cur);
-    stage_borders(warp0 + n_warps, nxt);
-    stage_words(cur);
+    Staged cur, nxt;
+    stage_words(load_borders(warp0), cur);
+    longlong2 raw1 = load_borders(warp0 + n_warps);
 
     for (int64_t r = warp0; r < n_seq; r += n_warps) {
-        stage_borders(r + 2 * n_warps, nxt2);
-        stage_words(nxt);
+        const longlong2 raw2 = load_borders(r + 2 * n_warps);
+        stage_words(raw1, nxt);
+        raw1 = raw2;
         const Staged g = cur;
-        cur = nxt; nxt = nxt2;
+        cur = nxt;
         const int64_t st = g.st, en = g.en;
         const int64_t L64 = en - st;
         if (L64 - kmin + 1 <= 0) continue;
@@ -112,13 +120,6 @@ __global__ void __launch_bounds__(AK_WARPS * 32) dedup_scan_kernel(
             }
             continue;
         }
-        if (++epoch > 255u) {
-            uint4* m4 = reinterpret_cast<uint4*>(marks);
-#pragma unroll
-            for (int j = 0; j < AK_MARKS / 8 / 32; ++j) m4[lane + 32 * j] = make_uint4(0, 0, 0, 0);
-            epoch = 1;
-            __syncwarp();
-        }
         // this lane's stretch of the read, in 32-bit arithmetic relative to the read start
         const int L = (int)L64;
         const int n_pos = L - kmin + 1;
@@ -134,84 +135,115 @@ __global__ void __launch_bounds__(AK_WARPS * 32) dedup_scan_kernel(
             hi = __funnelshift_l(g.w1, g.w0, 2 * sh);               // bases base .. base+15
             lo = __funnelshift_l(g.w2, g.w1, 2 * sh);               // bases base+16 .. base+31
         }
+        // (a window that would leave the read has fewer than kmin valid bits left: `room` above already excludes it)
         uint32_t xs[AK_MAXC];
-        int vs[AK_MAXC];
+        uint32_t wd[AK_MAXC];
 #pragma unroll
         for (int t = 0; t < AK_MAXC; ++t) {
             if (t >= C) break;                                      // warp-uniform
-            const int vlen = (t < mine) ? run_length(vbits >> t) : 0;
+            const uint32_t vb = vbits >> t;
             const uint32_t x = __funnelshift_l(lo, hi, 2 * t);     // 16 bases from window base+t
-            const bool ok = vlen >= kmin;
-            // filter: stamp the mark of this window's kmin-mer.  A mark that already carries the read's epoch means an
-            // earlier round used it; a contest for the mark inside this round is detected without __match_any_sync
-            // (which saturates the ADU pipe): everybody writes its tag, the losers write again, and whoever does not
-            // read its own tag back at either step shared the mark with another lane.
-            const uint32_t idx = ((x >> key_shift) * 0x9E3779B1u) >> 20;
-            const uint32_t tag = (epoch << 8) | ((uint32_t)t << 5) | (uint32_t)lane;
-            uint32_t seen = 0;
-            if (ok) seen = marks[idx];
-            __syncwarp();
-            if (ok) marks[idx] = (uint16_t)tag;
-            __syncwarp();
-            bool maybe = false;
-            if (ok) {
-                const bool lost = marks[idx] != tag;
-                maybe = lost || (seen >> 8) == epoch;
-                if (lost) marks[idx] = (uint16_t)tag;
-            }
-            __syncwarp();
-            if (ok && !maybe) maybe = marks[idx] != tag;
-            __syncwarp();
-            // rare: exact depth of the longest repeat with an earlier window of the read
-            int dd = 0;
-            uint32_t todo = __ballot_sync(0xFFFFFFFFu, maybe);
-            while (todo) {
-                const int b = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const uint32_t xi = __shfl_sync(0xFFFFFFFFu, x, b);
-                const int vi = min(__shfl_sync(0xFFFFFFFFu, vlen, b), kmax);
-                int best = 0;
+            const bool ok = (vb & kmin_mask) == kmin_mask;
+            const uint32_t key = x >> key_shift;
+            const uint32_t idx = HASHED ? (key * 0x9E3779B1u) >> 16 : key;
+            const uint32_t bit = 1u << (idx & 31u);
+            wd[t] = idx >> 5;
+            uint32_t old = 0;
+            if (ok) old = atomicOr(bm + wd[t], bit);
+            uint32_t todo = __ballot_sync(0xFFFFFFFFu, (old & bit) != 0);
+            if (todo) {
+                // rare: exact depth dd of the longest repeat with an earlier window of the read (order: round, then lane)
+                const int vlen = ok ? run_length(vb) : 0;           // windows shorter than kmin never match anything
+                int dd = 0;
+                do {
+                    const int b = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const uint32_t xi = __shfl_sync(0xFFFFFFFFu, x, b);
+                    const int vi = min(__shfl_sync(0xFFFFFFFFu, vlen, b), kmax);
+                    int best = 0;
 #pragma unroll
-                for (int u = 0; u < t; ++u) best = max(best, min(common_prefix(xs[u], xi), min(vs[u], vi)));
-                if (lane < b) best = max(best, min(common_prefix(x, xi), min(vlen, vi)));
+                    for (int u = 0; u < t; ++u) {
+                        const uint32_t vu = vbits >> u;
+                        const int lu = (vu & kmin_mask) == kmin_mask ? run_length(vu) : 0;
+                        best = max(best, min(common_prefix(xs[u], xi), min(lu, vi)));
+                    }
+                    const int same = min(common_prefix(x, xi), min(vlen, vi));
+                    if (lane < b) best = max(best, same);
+                    else if (lane > b && same >= kmin) dd = max(dd, same);      // b precedes this lane in the round
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
-                if (lane == b) dd = best;
-            }
-            xs[t] = x;
-            vs[t] = ok ? vlen : 0;                                  // windows shorter than kmin never match anything
-            if (ok) {
-                if (vlen >= kmax) {
-                    if (dd >= kmax) {                                                   // repeated at every level
+                    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+                    if (lane == b) dd = max(dd, best);
+                } while (todo);
+                // fresh_k(i) = [k <= vlen][k > dd]: the window is hidden from level kmax when it repeats at every level;
+                // otherwise level dd loses one count (this cancels either the count its extension brings up from level
+                // dd+1, or -- when dd == vlen -- the +1 terminal_corrections_kernel adds for a window that ends its run)
+                if (dd >= kmin) {
+                    if (dd >= kmax) {
                         const int64_t p = st + base + t;
                         atomicOr(dupmask + (p >> 5), 1u << (p & 31));
+                    } else {
+                        atomicAdd(stab[dd] + (x >> (32 - 2 * dd)), 0xFFFFFFFFu);
                     }
-                } else if (dd < vlen) {
-                    atomicAdd(stab[vlen] + (x >> (32 - 2 * vlen)), 1u);                 // cannot be extended: +1 at level vlen
                 }
-                if (dd >= kmin && dd < kmax && vlen > dd)
-                    atomicAdd(stab[dd] + (x >> (32 - 2 * dd)), 0xFFFFFFFFu);           // repeated k-mer, new extension: -1
             }
+            xs[t] = x;
         }
+        // give the bitmap back: every bit set above lives in one of the words wd[0..C)
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < AK_MAXC; ++t) {
+            if (t >= C) break;
+            bm[wd[t]] = 0;
+        }
+        __syncwarp();
     }
 }
 
-// ---- repetitive mode: only the "+1 at level vlen" corrections exist ---------------------------------------------------
+// ---- "+1 at level v" for the windows that end a valid run (every mode) ----------------------------------------------------
+// A window with exactly v valid bases in front of its run end (kmin <= v < kmax) cannot be extended to the next level, so
+// the 4:1 reduction does not bring it down from above: it is added here.  One thread = one validity word; only run ends
+// are visited (bit j set, bit j+1 clear: about one per read).  One launch handles ONE level, and for a table beyond L2
+// one key-prefix slice of it, so that the scattered updates always land in an L2-resident range (random RED into a
+// DRAM-resident table runs at 1/8 of the L2 rate, profiles/r01_red_rate_microbench.txt); re-reading the validity bits
+// per launch is cheap next to that.  Reads that dedup_scan_kernel routed to the direct per-k kernels are hidden as a
+// whole in `hide` (a window that ends a run is never hidden for any other reason).
 __global__ void __launch_bounds__(256) terminal_corrections_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
-                                                                   int64_t n_words, int kmin, int kmax, TableSet tabs) {
-    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (t >= n_words) return;
-    const uint32_t v0 = __ldg(valid + t), v1 = __ldg(valid + t + 1);
-    if (v0 == 0) return;
-    // a window that cannot be extended ends a valid run: bit j set, bit j+1 clear.  Cheap pre-test on the word.
-    const uint64_t v = ((uint64_t)v1 << 32) | v0;
-    if (((v & ~(v >> 1)) & 0x7FFFFFFFFFFFull) == 0) return;          // no run ends inside bits [0, 47)
-#pragma unroll 1
-    for (int i = 0; i < 32; ++i) {
-        const int vlen = run_length((uint32_t)(v >> i));
-        if (vlen >= kmin && vlen < kmax) {
-            const uint32_t x = window16(packed, t * 32 + i);
-            atomicAdd(tabs.t[vlen] + (x >> (32 - 2 * vlen)), 1u);
+                                                                   const uint32_t* __restrict__ hide, int64_t n_groups, int v_lo,
+                                                                   int v_hi, int prefix_bases, uint32_t prefix, TableSet tabs) {
+    __shared__ uint32_t* stab[16];
+    if (threadIdx.x < 16) stab[threadIdx.x] = tabs.t[threadIdx.x];
+    __syncthreads();
+    // one thread = 4 validity words per step (the arrays are padded: KMAP_PAD_WORDS), grid-stride
+    for (int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * 256) {
+        const uint4 q = __ldcs(reinterpret_cast<const uint4*>(valid) + g);
+        if ((q.x | q.y | q.z | q.w) == 0) continue;
+        const uint32_t vw[6] = {g > 0 ? __ldcs(valid + 4 * g - 1) : 0u, q.x, q.y, q.z, q.w, __ldcs(valid + 4 * g + 4)};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t v0 = vw[c + 1];
+            uint32_t ends = v0 & ~((v0 >> 1) | (vw[c + 2] << 31));
+            if (ends == 0) continue;
+            const int64_t t = 4 * g + c;
+            const uint64_t W = ((uint64_t)v0 << 32) | vw[c];            // position j of this word = bit 32 + j
+            uint64_t H = 0;
+            if (hide) H = ((uint64_t)__ldg(hide + t) << 32) | (t > 0 ? __ldg(hide + t - 1) : 0u);
+            while (ends) {
+                const int j = __ffs(ends) - 1;
+                ends &= ends - 1;
+                const uint64_t inv = ~(W << (31 - j));                   // bit 63 = position j, going down = going back
+                const int back = inv ? __clzll(inv) : 64;                // valid bases ending at position j (>= 1)
+                const int vmax = min(back, v_hi);
+                if (vmax < v_lo) continue;
+                // the windows of v_lo..vmax bases that end at j start at j-v+1: one 32-base fetch covers them all
+                const int64_t p0 = t * 32 + j - vmax + 1;
+                const uint32_t hi = window16(packed, p0), lo = window16(packed, p0 + 16);
+                for (int v = vmax; v >= v_lo; --v) {
+                    if ((H >> (33 + j - v)) & 1ull) continue;
+                    const uint32_t x = __funnelshift_l(lo, hi, 2 * (vmax - v));
+                    if (prefix_bases && (x >> (32 - 2 * prefix_bases)) != prefix) continue;
+                    atomicAdd(stab[v] + (x >> (32 - 2 * v)), 1u);
+                }
+            }
         }
     }
 }
@@ -292,7 +324,7 @@ int kmap_count_long_reads(const uint32_t* packed, const uint32_t* valid, int64_t
                           int k, uint32_t* table, uint32_t* work, uint32_t* bitmap, const uint32_t counts[2], cudaStream_t s);
 // implemented in partition.cu: level-k count through key partitioning + shared-memory counters
 int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const uint32_t* hide, int64_t n, int k, uint32_t* table,
-                           void* scratch, cudaStream_t s);
+                           void* scratch, const KmapTableSet* terminal_tabs, int kmin, cudaStream_t s);
 
 extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
                                 int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
@@ -327,18 +359,44 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
         if (e != cudaSuccess) { kmap_set_error("count_all_k: %s", cudaGetErrorString(e)); return (int)e; }
         int64_t blocks = (n_seq + AK_WARPS - 1) / AK_WARPS;
         if (blocks > 148 * 7 * 8) blocks = 148 * 7 * 8;           // 7 blocks of 4 warps (32 KB of marks each) per SM
-        dedup_scan_kernel<<<(unsigned int)blocks, AK_WARPS * 32, 0, s>>>(packed, valid, n, borders, n_seq, kmin, kmax, tabs, dupmask, work);
-    } else if (kmin < kmax) {
-        terminal_corrections_kernel<<<grid_for(n_words, 256), 256, 0, s>>>(packed, valid, n_words, kmin, kmax, tabs);
+        if (kmin > 8)
+            dedup_scan_kernel<true><<<(unsigned int)blocks, AK_WARPS * 32, 0, s>>>(packed, valid, n, borders, n_seq, kmin, kmax, tabs, dupmask, work);
+        else
+            dedup_scan_kernel<false><<<(unsigned int)blocks, AK_WARPS * 32, 0, s>>>(packed, valid, n, borders, n_seq, kmin, kmax, tabs, dupmask, work);
+    }
+    const bool use_partition = part_scratch && kmax >= 12 && kmax <= 14;
+    if (!use_partition) {          // (the partitioned count does these corrections inside its histogram pass)
+        const int64_t n_groups = (n_words + 3) / 4;
+        int64_t tb = (n_groups + 255) / 256;
+        if (tb > 148 * 16) tb = 148 * 16;
+        // launches: consecutive levels whose tables together stay L2 resident share one pass; a level beyond that is
+        // done in key-prefix slices of 4^12 cells
+        const size_t budget = (size_t)96 << 20;
+        int v = kmin;
+        while (v < kmax) {
+            const int pb = v > 12 ? v - 12 : 0;
+            if (pb > 0) {
+                for (uint32_t prefix = 0; prefix < (1u << (2 * pb)); ++prefix)
+                    terminal_corrections_kernel<<<(unsigned int)tb, 256, 0, s>>>(packed, valid, dedup ? dupmask : nullptr, n_groups, v, v,
+                                                                                 pb, prefix, tabs);
+                ++v;
+                continue;
+            }
+            int hi = v;
+            size_t bytes = (size_t)4 << (2 * v);
+            while (hi + 1 < kmax && hi + 1 <= 12 && bytes + ((size_t)4 << (2 * (hi + 1))) <= budget) { ++hi; bytes += (size_t)4 << (2 * hi); }
+            terminal_corrections_kernel<<<(unsigned int)tb, 256, 0, s>>>(packed, valid, dedup ? dupmask : nullptr, n_groups, v, hi, 0, 0u, tabs);
+            v = hi + 1;
+        }
     }
     int rc = kmap_check_launch("count_all_k(scan)");
     if (rc) return rc;
     mark(1);
     const uint32_t* hide = dedup ? dupmask : nullptr;
-    if (part_scratch && kmax >= 12 && kmax <= 14) {
+    if (use_partition) {
         // level kmax through key partitioning + shared-memory counters (partition.cu)
         KMAP_REQUIRE(part_scratch_bytes >= kmap_partition_scratch_bytes(n, kmax), "partition scratch too small");
-        rc = kmap_count_partitioned(packed, valid, hide, n, kmax, tabs.t[kmax], part_scratch, s);
+        rc = kmap_count_partitioned(packed, valid, hide, n, kmax, tabs.t[kmax], part_scratch, kmin < kmax ? &tabs : nullptr, kmin, s);
         if (rc) return rc;
     } else {
     // level kmax in key-prefix passes: 4^PB passes, each updating a 4^(kmax-PB)-cell slice that stays in L2

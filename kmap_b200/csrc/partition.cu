@@ -7,7 +7,9 @@
 //   1. bucket_hist_kernel   one pass over the packed reads: windows per bucket        -> bucket offsets (scan)
 //   2. partition_kernel     one pass: a CTA counting-sorts a tile of 32768 positions by bucket in shared memory,
 //                           reserves room in every non-empty bucket with one global atomic and writes the 16-bit
-//                           suffixes as runs (lanes of a warp store to consecutive addresses)
+//                           suffixes as runs (lanes of a warp store to consecutive addresses).  (Private per-CTA
+//                           ranges without the atomics were measured: slower, 148 x 4096 open partial lines spill
+//                           out of L2 and DRAM writes grow 2.5x.)
 //   3. bucket_count_kernel  one CTA per bucket: 65536 cells as packed 16-bit counters in shared memory (128 KB),
 //                           suffixes stream in with 128-bit loads, the table slice is written once, coalesced.
 // The result is identical to kmap_count_dense (integer sums are order independent).
@@ -19,6 +21,7 @@ constexpr int PT_THREADS = 1024;
 constexpr int PT_TILE = PT_THREADS * 32;          // positions (= staged entries) per tile
 constexpr int PT_MAX_BUCKETS = 4096;              // k <= 14
 constexpr int PT_MAX_PER = PT_MAX_BUCKETS / PT_THREADS;
+constexpr int PT_WU = 8;                          // write-out entries in flight per thread
 
 // windows of k valid bases starting at bits 0..31 of V = v1:v0 (log-step run-length test, k <= 16)
 __device__ __forceinline__ uint32_t window_mask(uint32_t v0, uint32_t v1, int k) {
@@ -37,24 +40,32 @@ __device__ __forceinline__ uint32_t window_mask(uint32_t v0, uint32_t v1, int k)
 }
 
 struct TileWords { uint32_t fresh, w0, w1, w2; };
+struct RawWords { uint32_t v0, v1, h, w0, w1, w2; };
 
-// this thread's 32 positions of tile `tile`: counted-window mask and the three packed words covering them
-__device__ __forceinline__ TileWords load_tile_words(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
-                                                     const uint32_t* __restrict__ hide, int64_t n_words, int64_t tile, int k) {
-    TileWords t;
-    t.fresh = t.w0 = t.w1 = t.w2 = 0;
+// this thread's 32 positions of tile `tile`: validity (+ one word of look-ahead), hidden windows, the three packed
+// words covering them.  Nothing is consumed here, so the loads of the NEXT tile can be in flight during a whole tile.
+__device__ __forceinline__ RawWords load_raw_words(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
+                                                   const uint32_t* __restrict__ hide, int64_t n_words, int64_t tile) {
+    RawWords r;
+    r.v0 = r.v1 = r.h = r.w0 = r.w1 = r.w2 = 0;
     const int64_t w = tile * PT_THREADS + threadIdx.x;            // validity word index
     if (w < n_words) {                                            // (the arrays carry KMAP_PAD_WORDS zero words of padding)
-        const uint32_t v0 = __ldcs(valid + w), v1 = __ldcs(valid + w + 1);
-        uint32_t m = window_mask(v0, v1, k);
-        if (hide) m &= ~__ldcs(hide + w);
-        t.fresh = m;
-        if (m) {
-            const uint2 p = __ldcs(reinterpret_cast<const uint2*>(packed + 2 * w));
-            t.w0 = p.x; t.w1 = p.y; t.w2 = __ldcs(packed + 2 * w + 2);
-        }
+        r.v0 = __ldcs(valid + w); r.v1 = __ldcs(valid + w + 1);
+        if (hide) r.h = __ldcs(hide + w);
+        const uint2 p = __ldcs(reinterpret_cast<const uint2*>(packed + 2 * w));
+        r.w0 = p.x; r.w1 = p.y; r.w2 = __ldcs(packed + 2 * w + 2);
     }
+    return r;
+}
+__device__ __forceinline__ TileWords cook(const RawWords& r, int k) {
+    TileWords t;
+    t.fresh = window_mask(r.v0, r.v1, k) & ~r.h;
+    t.w0 = r.w0; t.w1 = r.w1; t.w2 = r.w2;
     return t;
+}
+__device__ __forceinline__ TileWords load_tile_words(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
+                                                     const uint32_t* __restrict__ hide, int64_t n_words, int64_t tile, int k) {
+    return cook(load_raw_words(packed, valid, hide, n_words, tile), k);
 }
 
 __device__ __forceinline__ uint32_t key_at(const TileWords& t, int i, int sh) {          // i is a compile-time constant
@@ -62,64 +73,84 @@ __device__ __forceinline__ uint32_t key_at(const TileWords& t, int i, int sh) { 
     return x >> sh;
 }
 
-// ---- 1. windows per bucket ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PT_THREADS) bucket_hist_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
-                                                                 const uint32_t* __restrict__ hide, int64_t n_words, int64_t n_tiles,
-                                                                 int k, int n_buckets, unsigned long long* __restrict__ hist) {
-    __shared__ uint32_t cnt[PT_MAX_BUCKETS];
-    for (int b = threadIdx.x; b < n_buckets; b += PT_THREADS) cnt[b] = 0;
-    __syncthreads();
-    const int sh = 32 - 2 * k;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const TileWords t = load_tile_words(packed, valid, hide, n_words, tile, k);
-        if (t.fresh == 0) continue;
+__device__ __forceinline__ void tile_hist(const TileWords& t, int sh, uint32_t* cnt) {
+    if (t.fresh) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
             if ((t.fresh >> i) & 1u) atomicAdd(&cnt[key_at(t, i, sh) >> 16], 1u);
+    }
+}
+
+// ---- 1. windows per bucket (+ the run-end corrections of the all-k count) -------------------------------------------------
+// With TERMINAL, the pass also does what terminal_corrections_kernel (count_all.cu) does: "+1 at level v" for every
+// window with exactly v valid bases (kmin <= v < k) in front of a run end.  Those are scattered global REDs; issued from
+// this kernel they overlap its shared-memory-bound histogram work instead of costing passes of their own.
+template <bool TERMINAL>
+__global__ void __launch_bounds__(PT_THREADS) bucket_hist_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
+                                                                 const uint32_t* __restrict__ hide, int64_t n_words, int64_t n_tiles,
+                                                                 int k, int n_buckets, unsigned long long* __restrict__ hist,
+                                                                 KmapTableSet tabs, int kmin) {
+    __shared__ uint32_t cnt[PT_MAX_BUCKETS];
+    __shared__ uint32_t* stab[16];
+    if (TERMINAL && threadIdx.x < 16) stab[threadIdx.x] = tabs.t[threadIdx.x];
+    for (int b = threadIdx.x; b < n_buckets; b += PT_THREADS) cnt[b] = 0;
+    __syncthreads();
+    const int sh = 32 - 2 * k;
+    RawWords nxt = load_raw_words(packed, valid, hide, n_words, blockIdx.x);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const RawWords r = nxt;
+        nxt = load_raw_words(packed, valid, hide, n_words, tile + gridDim.x);      // (past the end: zeros)
+        tile_hist(cook(r, k), sh, cnt);
+        if (TERMINAL) {
+            uint32_t ends = r.v0 & ~((r.v0 >> 1) | (r.v1 << 31));                  // bit j: position j valid, j+1 not
+            if (ends) {
+                const int64_t w = tile * PT_THREADS + threadIdx.x;
+                const uint32_t vp = w > 0 ? __ldg(valid + w - 1) : 0u;
+                const uint64_t W = ((uint64_t)r.v0 << 32) | vp;                    // position j of this word = bit 32 + j
+                uint64_t H = 0;
+                if (hide) H = ((uint64_t)r.h << 32) | (w > 0 ? __ldg(hide + w - 1) : 0u);
+                do {
+                    const int j = __ffs(ends) - 1;
+                    ends &= ends - 1;
+                    const uint64_t inv = ~(W << (31 - j));                         // bit 63 = position j, going down = going back
+                    const int back = inv ? __clzll(inv) : 64;                      // valid bases ending at position j (>= 1)
+                    const int vmax = min(back, k - 1);
+                    if (vmax < kmin) continue;
+                    // the windows of kmin..vmax bases that end at j start at j-v+1: one 32-base fetch covers them all
+                    const int64_t p0 = w * 32 + j - vmax + 1;
+                    const uint32_t hi = window16(packed, p0), lo = window16(packed, p0 + 16);
+                    for (int v = vmax; v >= kmin; --v) {
+                        if ((H >> (33 + j - v)) & 1ull) continue;
+                        const uint32_t x = __funnelshift_l(lo, hi, 2 * (vmax - v));
+                        atomicAdd(stab[v] + (x >> (32 - 2 * v)), 1u);
+                    }
+                } while (ends);
+            }
+        }
     }
     __syncthreads();
     for (int b = threadIdx.x; b < n_buckets; b += PT_THREADS)
         if (cnt[b]) atomicAdd(hist + b, (unsigned long long)cnt[b]);
 }
 
-// exclusive scan of the bucket histogram (<= 4096 values, one block): base[0..n_buckets], cursor[b] = base[b]
-__global__ void __launch_bounds__(PT_THREADS) bucket_scan_kernel(const unsigned long long* __restrict__ hist, int n_buckets,
-                                                                 unsigned long long* __restrict__ base, unsigned long long* __restrict__ cursor) {
-    __shared__ unsigned long long part[PT_THREADS];
-    const int per = (n_buckets + PT_THREADS - 1) / PT_THREADS;
-    const int lo = threadIdx.x * per, hi = min(lo + per, n_buckets);
-    unsigned long long s = 0;
-    for (int b = lo; b < hi; ++b) s += hist[b];
-    part[threadIdx.x] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long run = 0;
-        for (int i = 0; i < PT_THREADS; ++i) { const unsigned long long v = part[i]; part[i] = run; run += v; }
-        base[n_buckets] = run;
-    }
-    __syncthreads();
-    unsigned long long run = part[threadIdx.x];
-    for (int b = lo; b < hi; ++b) { base[b] = run; cursor[b] = run; run += hist[b]; }
-}
-
-// ---- 2. partition -------------------------------------------------------------------------------------------------------
-// block-wide exclusive scan of one value per thread
-__device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* warp_sums) {
+// block-wide exclusive scan of one value per thread (PT_THREADS threads; two barriers inside)
+template <typename T>
+__device__ __forceinline__ T block_scan_excl(T v, T* warp_sums) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t incl = v;
+    T incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        const T y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
         if (lane >= o) incl += y;
     }
     if (lane == 31) warp_sums[w] = incl;
     __syncthreads();
     if (w == 0) {
-        const uint32_t s = warp_sums[lane];
-        uint32_t si = s;
+        const T s = warp_sums[lane];
+        T si = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, si, o);
+            const T y = __shfl_up_sync(0xFFFFFFFFu, si, o);
             if (lane >= o) si += y;
         }
         warp_sums[lane] = si - s;
@@ -128,6 +159,26 @@ __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* warp_s
     return warp_sums[w] + incl - v;
 }
 
+// exclusive scan of the bucket histogram (<= 4096 values, one block): base[0..n_buckets], cursor[b] = base[b]
+__global__ void __launch_bounds__(PT_THREADS) bucket_scan_kernel(const unsigned long long* __restrict__ hist, int n_buckets,
+                                                                 unsigned long long* __restrict__ base, unsigned long long* __restrict__ cursor) {
+    __shared__ unsigned long long warp_sums[32];
+    const int per = (n_buckets + PT_THREADS - 1) / PT_THREADS;
+    const int lo = threadIdx.x * per, hi = min(lo + per, n_buckets);
+    unsigned long long mine = 0;
+    for (int b = lo; b < hi; ++b) mine += hist[b];
+    unsigned long long run = block_scan_excl<unsigned long long>(mine, warp_sums);
+    if (threadIdx.x == PT_THREADS - 1) base[n_buckets] = run + mine;
+    for (int b = lo; b < hi; ++b) { base[b] = run; cursor[b] = run; run += hist[b]; }
+}
+
+// ---- 2. partition -------------------------------------------------------------------------------------------------------
+// Per tile: (a) histogram by bucket, (b) exclusive scan -> tile-local starts, (c) room in every non-empty bucket
+// reserved with one global atomic (all CTAs append to the same moving tail of a bucket, so the partial sectors of
+// neighbouring runs meet in L2), (d) scatter of the keys into bucket order in shared memory, (e) write-out: entry i of
+// the sorted tile goes to gdelta[bucket] + i, so consecutive lanes write consecutive addresses inside a run.
+// The tile loop is software-pipelined: the raw words of the next tile are in flight during the whole current tile, and
+// its histogram (fire-and-forget shared-memory atomics) is issued together with the latency-bound write-out.
 template <int PER>       // buckets per thread in the scan step: n_buckets <= PER * PT_THREADS
 __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
                                                                   const uint32_t* __restrict__ hide, int64_t n_words, int64_t n_tiles,
@@ -136,32 +187,29 @@ __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* sorted = reinterpret_cast<uint32_t*>(smem_raw);                                  // PT_TILE keys, grouped by bucket
     unsigned long long* gdelta = reinterpret_cast<unsigned long long*>(sorted + PT_TILE);     // global start - tile start, per bucket
-    uint32_t* off = reinterpret_cast<uint32_t*>(gdelta + PER * PT_THREADS);                   // count, then running tile offset
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(gdelta + PER * PT_THREADS);                   // histogram of the coming tile
+    uint32_t* off = cnt + PER * PT_THREADS;                                                   // running tile offsets
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t tile_total;
     const int sh = 32 - 2 * k;
-    for (int b = threadIdx.x; b < PER * PT_THREADS; b += PT_THREADS) off[b] = 0;
-    __syncthreads();
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const TileWords t = load_tile_words(packed, valid, hide, n_words, tile, k);
-        // (a) tile histogram
-        if (t.fresh) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if ((t.fresh >> i) & 1u) atomicAdd(&off[key_at(t, i, sh) >> 16], 1u);
-        }
-        __syncthreads();
+    for (int j = 0; j < PER; ++j) cnt[PER * threadIdx.x + j] = 0;
+    __syncthreads();
+    TileWords cur = load_tile_words(packed, valid, hide, n_words, blockIdx.x, k);
+    RawWords raw = load_raw_words(packed, valid, hide, n_words, (int64_t)blockIdx.x + gridDim.x);
+    tile_hist(cur, sh, cnt);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();                       // histogram of `cur` complete; write-out of the previous tile complete
         // (b) exclusive scan over the buckets; thread owns buckets [PER*tid, PER*tid + PER)
         uint32_t c[PER], s[PER];
         uint32_t mine = 0;
 #pragma unroll
-        for (int j = 0; j < PER; ++j) { c[j] = off[PER * threadIdx.x + j]; mine += c[j]; }
-        uint32_t run = block_scan_excl(mine, warp_sums);
+        for (int j = 0; j < PER; ++j) { c[j] = cnt[PER * threadIdx.x + j]; cnt[PER * threadIdx.x + j] = 0; mine += c[j]; }
+        uint32_t run = block_scan_excl<uint32_t>(mine, warp_sums);
         if (threadIdx.x == PT_THREADS - 1) tile_total = run + mine;
 #pragma unroll
         for (int j = 0; j < PER; ++j) { s[j] = run; off[PER * threadIdx.x + j] = run; run += c[j]; }
         __syncthreads();
-        const uint32_t total = tile_total;
         // (c) reserve room in the global buckets (latency overlaps the shared-memory scatter below)
         unsigned long long g[PER];
 #pragma unroll
@@ -170,26 +218,39 @@ __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t
             if (c[j]) g[j] = atomicAdd(cursor + PER * threadIdx.x + j, (unsigned long long)c[j]);
         }
         // (d) scatter the keys into bucket order
-        if (t.fresh) {
+        if (cur.fresh) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-                if ((t.fresh >> i) & 1u) {
-                    const uint32_t key = key_at(t, i, sh);
+                if ((cur.fresh >> i) & 1u) {
+                    const uint32_t key = key_at(cur, i, sh);
                     sorted[atomicAdd(&off[key >> 16], 1u)] = key;
                 }
         }
 #pragma unroll
         for (int j = 0; j < PER; ++j) gdelta[PER * threadIdx.x + j] = g[j] - s[j];
+        // the next tile: its words arrived long ago; fetch the one after it
+        cur = cook(raw, k);
+        raw = load_raw_words(packed, valid, hide, n_words, tile + 2 * (int64_t)gridDim.x);
         __syncthreads();
-        // (e) write the runs: entry i of the tile goes to its bucket's reserved range
-        for (uint32_t i = threadIdx.x; i < total; i += PT_THREADS) {
-            const uint32_t key = sorted[i];
-            suffixes[gdelta[key >> 16] + i] = (uint16_t)key;
-        }
-        // reset the counters for the next tile (off[] holds end offsets now)
+        const uint32_t total = tile_total;
+        // (a) histogram of the next tile, then (e) write-out of this one
+        tile_hist(cur, sh, cnt);
+        for (uint32_t i0 = threadIdx.x; i0 < total; i0 += PT_WU * PT_THREADS) {
+            uint32_t key[PT_WU];
 #pragma unroll
-        for (int j = 0; j < PER; ++j) off[PER * threadIdx.x + j] = 0;
-        __syncthreads();
+            for (int u = 0; u < PT_WU; ++u) {
+                const uint32_t i = i0 + u * PT_THREADS;
+                key[u] = i < total ? sorted[i] : 0u;
+            }
+            unsigned long long d[PT_WU];
+#pragma unroll
+            for (int u = 0; u < PT_WU; ++u) d[u] = gdelta[key[u] >> 16];
+#pragma unroll
+            for (int u = 0; u < PT_WU; ++u) {
+                const uint32_t i = i0 + u * PT_THREADS;
+                if (i < total) suffixes[d[u] + i] = (uint16_t)key[u];
+            }
+        }
     }
 }
 
@@ -197,6 +258,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t
 constexpr int BC_THREADS = 1024;
 constexpr int BC_CELLS = 65536;
 constexpr int BC_WORDS = BC_CELLS / 2;            // two 16-bit counters per word
+constexpr int BC_UNROLL = 4;                      // 128-bit loads in flight per thread
 
 // A half-word counter that reaches 0x8000 is folded into the global cell at once (the fold happens long before the
 // half could carry into its neighbour: at most BC_THREADS increments are in flight).
@@ -230,13 +292,22 @@ __global__ void __launch_bounds__(BC_THREADS, 1) bucket_count_kernel(const uint1
         for (unsigned long long i = lo + threadIdx.x; i < a0; i += BC_THREADS) bump(sm, suffixes[i], slice, &my_spill);
         const uint4* v = reinterpret_cast<const uint4*>(suffixes + a0);
         const unsigned long long n_vec = (a1 - a0) >> 3;
-        for (unsigned long long i = threadIdx.x; i < n_vec; i += BC_THREADS) {
-            const uint4 q = __ldcs(v + i);
-            const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+        for (unsigned long long i = threadIdx.x; i < n_vec; i += BC_UNROLL * BC_THREADS) {
+            uint4 q[BC_UNROLL];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                bump(sm, ws[j] & 0xFFFFu, slice, &my_spill);
-                bump(sm, ws[j] >> 16, slice, &my_spill);
+            for (int u = 0; u < BC_UNROLL; ++u) {
+                const unsigned long long iu = i + (unsigned long long)u * BC_THREADS;
+                q[u] = iu < n_vec ? __ldcs(v + iu) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < BC_UNROLL; ++u) {
+                if (i + (unsigned long long)u * BC_THREADS >= n_vec) break;
+                const uint32_t ws[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    bump(sm, ws[j] & 0xFFFFu, slice, &my_spill);
+                    bump(sm, ws[j] >> 16, slice, &my_spill);
+                }
             }
         }
         for (unsigned long long i = a1 + threadIdx.x; i < hi; i += BC_THREADS) bump(sm, suffixes[i], slice, &my_spill);
@@ -286,8 +357,9 @@ extern "C" int64_t kmap_partition_scratch_bytes(int64_t n, int k) {
 
 // table[h] = number of counted windows with key h, for every h (the slice of every bucket is overwritten or, where
 // folded counters were spilled, added to: the caller zeroes the table first).  hide may be NULL.
+// terminal_tabs (may be NULL): also add the run-end corrections of levels kmin..k-1 to those tables (count_all.cu).
 int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const uint32_t* hide, int64_t n, int k, uint32_t* table,
-                           void* scratch, cudaStream_t s) {
+                           void* scratch, const KmapTableSet* terminal_tabs, int kmin, cudaStream_t s) {
     const int n_buckets = 1 << (2 * (k - 8));
     const PartScratch p = carve(scratch, n_buckets);
     const int64_t n_words = (n + 31) / 32;
@@ -295,11 +367,14 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
     cudaError_t e = cudaMemsetAsync(p.hist, 0, (size_t)n_buckets * 8, s);
     if (e != cudaSuccess) { kmap_set_error("count_partitioned: %s", cudaGetErrorString(e)); return (int)e; }
     const unsigned int g1 = (unsigned int)(n_tiles < 148 * 2 ? n_tiles : 148 * 2);
-    bucket_hist_kernel<<<g1, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.hist);
+    if (terminal_tabs)
+        bucket_hist_kernel<true><<<g1, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.hist, *terminal_tabs, kmin);
+    else
+        bucket_hist_kernel<false><<<g1, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.hist, KmapTableSet(), k);
     bucket_scan_kernel<<<1, PT_THREADS, 0, s>>>(p.hist, n_buckets, p.base, p.cursor);
     const unsigned int g2 = (unsigned int)(n_tiles < 148 ? n_tiles : 148);
     static bool attr_set = false;
-    const int smem1 = PT_TILE * 4 + 1 * PT_THREADS * 12, smem4 = PT_TILE * 4 + PT_MAX_PER * PT_THREADS * 12;
+    const int smem1 = PT_TILE * 4 + 1 * PT_THREADS * 16, smem4 = PT_TILE * 4 + PT_MAX_PER * PT_THREADS * 16;
     if (!attr_set) {
         cudaFuncSetAttribute(partition_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
         cudaFuncSetAttribute(partition_kernel<PT_MAX_PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4);
@@ -321,5 +396,5 @@ extern "C" int kmap_count_dense_partitioned(const uint32_t* packed, const uint32
     if (n == 0) return KMAP_OK;
     KMAP_REQUIRE(packed && valid && table && scratch, "null pointer");
     KMAP_REQUIRE(scratch_bytes >= kmap_partition_scratch_bytes(n, k), "scratch too small (kmap_partition_scratch_bytes)");
-    return kmap_count_partitioned(packed, valid, nullptr, n, k, table, scratch, as_stream(stream));
+    return kmap_count_partitioned(packed, valid, nullptr, n, k, table, scratch, nullptr, k, as_stream(stream));
 }
