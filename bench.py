@@ -95,6 +95,16 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def launches_per_step(args, dedup):
+    """kernels of libkmap_b200 launched per step (memsets not counted)"""
+    if args.algo != "allk":
+        return KMAX - KMIN + 1
+    derive = KMAX - KMIN
+    if args.partitions <= 0:                     # dedup_scan + hist + scan + partition + bucket_count + derive
+        return (1 if dedup else 0) + 4 + derive
+    return (1 if dedup else 0) + 5 + max(1, args.partitions) + derive      # + terminal-correction launches + prefix passes
+
+
 def n_kmers_total(n_reads, L):
     return sum(n_reads * max(0, L - k + 1) for k in range(KMIN, KMAX + 1))
 
@@ -188,7 +198,7 @@ def main():
             ph = None
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ph = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                ph = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
                 for e in ph:
                     e.record()                      # creates the cudaEvent_t handles the library re-records
                 e0.record()
@@ -259,36 +269,62 @@ def main():
     alg_bytes = sum(algorithmic_bytes_count(n_local, L, k) for k in range(KMIN, KMAX + 1))
     kern_s = sum(per_k_ms.values()) * 1e-3
     traffic = None
-    tfile = ROOT / "profiles" / "count_traffic.json"
+    tfile = ROOT / "profiles" / "count_traffic.json"      # dram__bytes_read+write of the dominant kernel, one ncu --set full capture
     if tfile.exists():
         try:
-            traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch")
+            tj = json.loads(tfile.read_text())
+            # the capture is taken on a smaller input (ncu replays the kernel ~40 times): scale per position
+            traffic = tj["dram_bytes_per_launch"] * (n_local * (L + 1)) / tj["positions"]
         except Exception:
             traffic = None
     if args.algo == "allk":
         # phases of kmap_count_all_k from the events the library records on the launching stream
-        ph_ms = {"zero": [], "scan": [], "count_kmax": [], "derive": [], "tail": []}
+        partitioned = args.partitions <= 0
+        names = ["zero", "dedup_scan", "bucket_hist", "partition", "bucket_count", "derive", "tail"] if partitioned else \
+                ["zero", "dedup_scan", "count_kmax", "derive", "tail"]
+        ph_ms = {k: [] for k in names}
         for e0, ph, e1 in phase_events:
-            ph_ms["zero"].append(e0.elapsed_time(ph[0])); ph_ms["scan"].append(ph[0].elapsed_time(ph[1]))
-            ph_ms["count_kmax"].append(ph[1].elapsed_time(ph[2])); ph_ms["derive"].append(ph[2].elapsed_time(ph[3]))
-            ph_ms["tail"].append(ph[3].elapsed_time(e1))
+            order = [e0, ph[0], ph[1], ph[4], ph[5], ph[2], ph[3], e1] if partitioned else [e0, ph[0], ph[1], ph[2], ph[3], e1]
+            for name, a, b in zip(names, order[:-1], order[1:]):
+                ph_ms[name].append(a.elapsed_time(b))
         ph_ms = {k: float(np.mean(v)) for k, v in ph_ms.items()}
-        n_pass = 16 if args.partitions <= 0 else max(1, args.partitions)
-        # dominant kernel: count_prefix_kernel, one launch per key-prefix pass.  SURVEY 8d per-unit figure: 0.375 B per
-        # base scanned + 8 B per k-mer counted; a pass scans every base and counts 1/n_pass of the k=14 windows.
-        b_launch = 0.375 * n_local * L + 8.0 * n_local * max(0, L - KMAX + 1) / n_pass
-        t_launch = ph_ms["count_kmax"] * 1e-3 / n_pass
+        n_pos_local = dev.n
+        n_win = n_local * max(0, L - KMAX + 1)
+        if partitioned:
+            # dominant kernel: partition_kernel, one launch per step.  Algorithmic bytes of THIS launch: it reads the packed
+            # bases, the validity bits and (dedup mode) the hidden-window bits once and writes one 16-bit key suffix per
+            # counted k=14 window
+            in_b = (0.375 + (0.125 if dedup else 0.0)) * n_pos_local
+            b_launch = in_b + 2.0 * n_win
+            t_launch = ph_ms["partition"] * 1e-3
+            kernel = "partition_kernel<4> (1 launch per step, k=14)"
+            # the three launches that together are `count at k=14` against SURVEY 8d's figure for one counting pass
+            t_pipe = (ph_ms["bucket_hist"] + ph_ms["partition"] + ph_ms["bucket_count"]) * 1e-3
+            b_pipe = algorithmic_bytes_count(n_local, L, KMAX)
+            pipeline = {"launches": "bucket_hist_kernel + bucket_scan_kernel + partition_kernel + bucket_count_kernel",
+                        "algorithmic_bytes": b_pipe, "ms": t_pipe * 1e3, "achieved_GBs": b_pipe / t_pipe / 1e9,
+                        "frac": b_pipe / t_pipe / 1e9 / peak,
+                        "note": "SURVEY 8d per-unit figure for one counting pass (0.375 B/base + 8 B per k-mer) over the three "
+                                "launches that build the k=14 table"}
+        else:
+            n_pass = max(1, args.partitions)
+            b_launch = 0.375 * n_pos_local + 8.0 * n_win / n_pass
+            t_launch = ph_ms["count_kmax"] * 1e-3 / n_pass
+            kernel = f"count_prefix_kernel ({n_pass} launches per step, k={KMAX})"
+            pipeline = None
         achieved = b_launch / t_launch / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "kernel": f"count_prefix_kernel<2> ({n_pass} launches per step, k={KMAX})", "peak_source": peak_src,
+                    "kernel": kernel, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": b_launch, "avg_launch_ms": t_launch * 1e3,
-                    "share_of_step": ph_ms["count_kmax"] / (kern_s * 1e3), "phases_ms": ph_ms,
+                    "share_of_step": t_launch * 1e3 / (kern_s * 1e3), "phases_ms": ph_ms, "k14_count_pipeline": pipeline,
                     "step_model": {"note": "SURVEY 8d model for 7 independent per-k passes (0.375 B/base + 8 B/k-mer each) over the "
-                                           "measured step time; the all-k algorithm issues one atomic per k=14 window only, so this "
-                                           "can exceed what 7 passes could reach",
+                                           "measured step time; the all-k algorithm updates the k=14 table only and derives the "
+                                           "smaller tables by 4:1 reductions, so this can exceed what 7 passes could reach",
                                    "algorithmic_bytes_per_step": alg_bytes, "achieved_GBs": alg_bytes / kern_s / 1e9,
                                    "frac": alg_bytes / kern_s / 1e9 / peak},
-                    "frac_of_8TBs_nominal": achieved / 8000.0, "algo": "allk"}
+                    "frac_of_8TBs_nominal": achieved / 8000.0, "algo": "allk",
+                    "bound_note": "the level-14 count is bound by shared-memory atomic throughput (3 per window: bucket histogram, "
+                                  "tile scatter, bucket count), not by HBM: see DESIGN.md section 4.5"}
     else:
         achieved = alg_bytes / kern_s / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -357,7 +393,7 @@ def main():
                                    f"counting k={KMIN}..{KMAX}, {args.mode} mode, reads sharded over {n_gpus} GPU(s) with NCCL table merge",
                        "l2": "inputs larger than L2 (packed reads + borders = %.1f GB per GPU)" % ((dev.packed.numel() * 4 + dev.valid.numel() * 4 + n_local * 16) / 1e9),
                        "parallelism": f"reads x{n_gpus}"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * ((1 + 16 + (KMAX - KMIN)) if args.algo == "allk" else (KMAX - KMIN + 1)),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (launches_per_step(args, dedup)),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "checks": checks,
         }
         if extras:

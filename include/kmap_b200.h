@@ -94,23 +94,36 @@ int64_t kmap_dedup_work_words(int64_t n_seq);
  * n_partitions key-range passes (0 = choose so that a slice stays L2 resident); each smaller table is the 4:1
  * reduction of the next one plus the per-read corrections derived in csrc/count_all.cu.  Results are identical to
  * kmax-kmin+1 calls of kmap_count_dense[_dedup].  dupmask = uint32[kmap_valid_words(n)] scratch, work/bitmap as in
- * kmap_count_dense_dedup (dedup != 0 only).  phase_events = NULL, or a HOST array of 4 cudaEvent_t that are recorded
- * on the stream after zeroing / after the per-read scan / after the level-kmax passes / after the reductions
- * (instrumentation for bench.py).  Synchronises the stream once when dedup != 0. */
+ * kmap_count_dense_dedup (dedup != 0 only).  phase_events = NULL, or a HOST array of 6 cudaEvent_t (entries may be
+ * NULL) recorded on the stream after zeroing / after the per-read scan / after the level-kmax count / after the
+ * reductions, and [4], [5] inside the partitioned level-kmax count: after the bucket histogram (KMAP_KMAX_SORTED
+ * only), after the partition pass (instrumentation for bench.py).  Synchronises the stream once when dedup != 0. */
+#define KMAP_KMAX_PREFIX_PASSES 0    /* global atomics in n_partitions key-prefix passes (no scratch) */
+#define KMAP_KMAX_SORTED 1           /* csrc/partition.cu, scratch = kmap_partition_scratch_bytes(n, kmax) */
+#define KMAP_KMAX_SLOTTED 2          /* csrc/slots.cu, scratch = kmap_slot_scratch_bytes(n, kmax) */
 int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
                      int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
-                     uint32_t* bitmap, int n_partitions, void* part_scratch, int64_t part_scratch_bytes,
+                     uint32_t* bitmap, int n_partitions, int scheme, void* part_scratch, int64_t part_scratch_bytes,
                      void* const* phase_events, void* stream);
 
 /* kmap_count_dense for tables beyond L2 (9 <= k <= 14) without one global atomic per window: windows are partitioned
  * by the top bits of their key into 4^(k-8) buckets of 16-bit suffixes (scratch), then every bucket is counted in
  * shared memory and its 65536-cell slice of the table written once (csrc/partition.cu).  Same result as
  * kmap_count_dense on a zeroed table (the caller zeroes it).  scratch = kmap_partition_scratch_bytes(n, k) bytes.
- * kmap_count_all_k uses the same scheme for its level-kmax table when part_scratch is given (12 <= kmax <= 14);
+ * kmap_count_all_k uses the same scheme for its level-kmax table with scheme = KMAP_KMAX_SORTED (12 <= kmax <= 14);
  * with part_scratch == NULL it falls back to n_partitions key-prefix passes of global atomics. */
 int kmap_count_dense_partitioned(const uint32_t* packed, const uint32_t* valid, int64_t n, int k, uint32_t* table,
                                  void* scratch, int64_t scratch_bytes, void* stream);
 int64_t kmap_partition_scratch_bytes(int64_t n, int k);
+
+/* The same count (12 <= k <= 14) by slotted partitioning (csrc/slots.cu): bucket = top 12 bits of the key, and every
+ * (bucket, tile of 32768 positions) pair owns one 32-byte sector of the scratch (a 16-bit count + up to 15 suffixes), so
+ * no histogram pass and no per-tile sort are needed; a window that finds its sector full is counted with a global atomic
+ * instead.  table[h] += count: the caller zeroes the table first.  scratch = kmap_slot_scratch_bytes(n, k) bytes
+ * (4 bytes per position).  kmap_count_all_k: scheme = KMAP_KMAX_SLOTTED. */
+int kmap_count_dense_slotted(const uint32_t* packed, const uint32_t* valid, int64_t n, int k, uint32_t* table,
+                             void* scratch, int64_t scratch_bytes, void* stream);
+int64_t kmap_slot_scratch_bytes(int64_t n, int k);
 
 int kmap_fill_u32(uint32_t* p, int64_t n_words, uint32_t value, void* stream);
 

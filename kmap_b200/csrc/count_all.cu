@@ -324,11 +324,14 @@ int kmap_count_long_reads(const uint32_t* packed, const uint32_t* valid, int64_t
                           int k, uint32_t* table, uint32_t* work, uint32_t* bitmap, const uint32_t counts[2], cudaStream_t s);
 // implemented in partition.cu: level-k count through key partitioning + shared-memory counters
 int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const uint32_t* hide, int64_t n, int k, uint32_t* table,
-                           void* scratch, const KmapTableSet* terminal_tabs, int kmin, cudaStream_t s);
+                           void* scratch, const KmapTableSet* terminal_tabs, int kmin, void* const* step_events, cudaStream_t s);
+// implemented in slots.cu: level-k count through slotted key partitioning (one sector per bucket and tile)
+int kmap_count_slotted(const uint32_t* packed, const uint32_t* valid, const uint32_t* hide, int64_t n, int k, uint32_t* table,
+                       void* scratch, const KmapTableSet* terminal_tabs, int kmin, void* const* step_events, cudaStream_t s);
 
 extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
                                 int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
-                                uint32_t* bitmap, int n_partitions, void* part_scratch, int64_t part_scratch_bytes,
+                                uint32_t* bitmap, int n_partitions, int scheme, void* part_scratch, int64_t part_scratch_bytes,
                                 void* const* phase_events, void* stream) {
     KMAP_REQUIRE(n >= 0 && n_seq >= 0 && kmin >= 1 && kmin <= kmax && kmax <= 15, "need 1 <= kmin <= kmax <= 15");
     KMAP_REQUIRE(n_seq < (int64_t)0xFFFFFFFFll, "too many reads for one call (shard the input)");
@@ -344,8 +347,9 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
     }
     if (n == 0) return KMAP_OK;
     KMAP_REQUIRE(packed && valid, "null pointer");
-    // optional instrumentation (bench.py): 4 caller-owned cudaEvent_t recorded after zeroing, after the per-read scan,
-    // after the level-kmax passes and after the table reductions
+    // optional instrumentation (bench.py): 6 caller-owned cudaEvent_t recorded after zeroing, after the per-read scan,
+    // after the level-kmax passes and after the table reductions; [4], [5] inside the partitioned level-kmax count: after
+    // the bucket histogram (+ run-end corrections) and after the partition pass
     auto mark = [&](int i) { if (phase_events && phase_events[i]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(phase_events[i]), s); };
     mark(0);
     const int64_t n_words = (n + 31) / 32;
@@ -364,7 +368,8 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
         else
             dedup_scan_kernel<false><<<(unsigned int)blocks, AK_WARPS * 32, 0, s>>>(packed, valid, n, borders, n_seq, kmin, kmax, tabs, dupmask, work);
     }
-    const bool use_partition = part_scratch && kmax >= 12 && kmax <= 14;
+    KMAP_REQUIRE(scheme >= KMAP_KMAX_PREFIX_PASSES && scheme <= KMAP_KMAX_SLOTTED, "unknown scheme");
+    const bool use_partition = scheme != KMAP_KMAX_PREFIX_PASSES && part_scratch && kmax >= 12 && kmax <= 14;
     if (!use_partition) {          // (the partitioned count does these corrections inside its histogram pass)
         const int64_t n_groups = (n_words + 3) / 4;
         int64_t tb = (n_groups + 255) / 256;
@@ -395,8 +400,15 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
     const uint32_t* hide = dedup ? dupmask : nullptr;
     if (use_partition) {
         // level kmax through key partitioning + shared-memory counters (partition.cu)
-        KMAP_REQUIRE(part_scratch_bytes >= kmap_partition_scratch_bytes(n, kmax), "partition scratch too small");
-        rc = kmap_count_partitioned(packed, valid, hide, n, kmax, tabs.t[kmax], part_scratch, kmin < kmax ? &tabs : nullptr, kmin, s);
+        if (scheme == KMAP_KMAX_SLOTTED) {
+            KMAP_REQUIRE(part_scratch_bytes >= kmap_slot_scratch_bytes(n, kmax), "slot scratch too small");
+            rc = kmap_count_slotted(packed, valid, hide, n, kmax, tabs.t[kmax], part_scratch, kmin < kmax ? &tabs : nullptr, kmin,
+                                    phase_events ? phase_events + 5 : nullptr, s);
+        } else {
+            KMAP_REQUIRE(part_scratch_bytes >= kmap_partition_scratch_bytes(n, kmax), "partition scratch too small");
+            rc = kmap_count_partitioned(packed, valid, hide, n, kmax, tabs.t[kmax], part_scratch, kmin < kmax ? &tabs : nullptr, kmin,
+                                        phase_events ? phase_events + 4 : nullptr, s);
+        }
         if (rc) return rc;
     } else {
     // level kmax in key-prefix passes: 4^PB passes, each updating a 4^(kmax-PB)-cell slice that stays in L2

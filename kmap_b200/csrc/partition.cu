@@ -14,64 +14,15 @@
 //                           suffixes stream in with 128-bit loads, the table slice is written once, coalesced.
 // The result is identical to kmap_count_dense (integer sums are order independent).
 #include "common.cuh"
+#include "tile.cuh"
 
 namespace {
 
-constexpr int PT_THREADS = 1024;
+constexpr int PT_THREADS = KMAP_TILE_THREADS;
 constexpr int PT_TILE = PT_THREADS * 32;          // positions (= staged entries) per tile
 constexpr int PT_MAX_BUCKETS = 4096;              // k <= 14
 constexpr int PT_MAX_PER = PT_MAX_BUCKETS / PT_THREADS;
 constexpr int PT_WU = 8;                          // write-out entries in flight per thread
-
-// windows of k valid bases starting at bits 0..31 of V = v1:v0 (log-step run-length test, k <= 16)
-__device__ __forceinline__ uint32_t window_mask(uint32_t v0, uint32_t v1, int k) {
-    const uint64_t V = ((uint64_t)v1 << 32) | v0;
-    const uint64_t r2 = V & (V >> 1);             // runs >= 2
-    const uint64_t r4 = r2 & (r2 >> 2);           // >= 4
-    const uint64_t r8 = r4 & (r4 >> 4);           // >= 8
-    uint64_t m = ~0ull;
-    int off = 0;
-    if (k & 16) { m &= r8 & (r8 >> 8); off += 16; }
-    if (k & 8) { m &= r8 >> off; off += 8; }
-    if (k & 4) { m &= r4 >> off; off += 4; }
-    if (k & 2) { m &= r2 >> off; off += 2; }
-    if (k & 1) { m &= V >> off; }
-    return (uint32_t)m;
-}
-
-struct TileWords { uint32_t fresh, w0, w1, w2; };
-struct RawWords { uint32_t v0, v1, h, w0, w1, w2; };
-
-// this thread's 32 positions of tile `tile`: validity (+ one word of look-ahead), hidden windows, the three packed
-// words covering them.  Nothing is consumed here, so the loads of the NEXT tile can be in flight during a whole tile.
-__device__ __forceinline__ RawWords load_raw_words(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
-                                                   const uint32_t* __restrict__ hide, int64_t n_words, int64_t tile) {
-    RawWords r;
-    r.v0 = r.v1 = r.h = r.w0 = r.w1 = r.w2 = 0;
-    const int64_t w = tile * PT_THREADS + threadIdx.x;            // validity word index
-    if (w < n_words) {                                            // (the arrays carry KMAP_PAD_WORDS zero words of padding)
-        r.v0 = __ldcs(valid + w); r.v1 = __ldcs(valid + w + 1);
-        if (hide) r.h = __ldcs(hide + w);
-        const uint2 p = __ldcs(reinterpret_cast<const uint2*>(packed + 2 * w));
-        r.w0 = p.x; r.w1 = p.y; r.w2 = __ldcs(packed + 2 * w + 2);
-    }
-    return r;
-}
-__device__ __forceinline__ TileWords cook(const RawWords& r, int k) {
-    TileWords t;
-    t.fresh = window_mask(r.v0, r.v1, k) & ~r.h;
-    t.w0 = r.w0; t.w1 = r.w1; t.w2 = r.w2;
-    return t;
-}
-__device__ __forceinline__ TileWords load_tile_words(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
-                                                     const uint32_t* __restrict__ hide, int64_t n_words, int64_t tile, int k) {
-    return cook(load_raw_words(packed, valid, hide, n_words, tile), k);
-}
-
-__device__ __forceinline__ uint32_t key_at(const TileWords& t, int i, int sh) {          // i is a compile-time constant
-    const uint32_t x = (i < 16) ? __funnelshift_l(t.w1, t.w0, 2 * i) : __funnelshift_l(t.w2, t.w1, 2 * (i - 16));
-    return x >> sh;
-}
 
 __device__ __forceinline__ void tile_hist(const TileWords& t, int sh, uint32_t* cnt) {
     if (t.fresh) {
@@ -102,30 +53,7 @@ __global__ void __launch_bounds__(PT_THREADS) bucket_hist_kernel(const uint32_t*
         nxt = load_raw_words(packed, valid, hide, n_words, tile + gridDim.x);      // (past the end: zeros)
         tile_hist(cook(r, k), sh, cnt);
         if (TERMINAL) {
-            uint32_t ends = r.v0 & ~((r.v0 >> 1) | (r.v1 << 31));                  // bit j: position j valid, j+1 not
-            if (ends) {
-                const int64_t w = tile * PT_THREADS + threadIdx.x;
-                const uint32_t vp = w > 0 ? __ldg(valid + w - 1) : 0u;
-                const uint64_t W = ((uint64_t)r.v0 << 32) | vp;                    // position j of this word = bit 32 + j
-                uint64_t H = 0;
-                if (hide) H = ((uint64_t)r.h << 32) | (w > 0 ? __ldg(hide + w - 1) : 0u);
-                do {
-                    const int j = __ffs(ends) - 1;
-                    ends &= ends - 1;
-                    const uint64_t inv = ~(W << (31 - j));                         // bit 63 = position j, going down = going back
-                    const int back = inv ? __clzll(inv) : 64;                      // valid bases ending at position j (>= 1)
-                    const int vmax = min(back, k - 1);
-                    if (vmax < kmin) continue;
-                    // the windows of kmin..vmax bases that end at j start at j-v+1: one 32-base fetch covers them all
-                    const int64_t p0 = w * 32 + j - vmax + 1;
-                    const uint32_t hi = window16(packed, p0), lo = window16(packed, p0 + 16);
-                    for (int v = vmax; v >= kmin; --v) {
-                        if ((H >> (33 + j - v)) & 1ull) continue;
-                        const uint32_t x = __funnelshift_l(lo, hi, 2 * (vmax - v));
-                        atomicAdd(stab[v] + (x >> (32 - 2 * v)), 1u);
-                    }
-                } while (ends);
-            }
+            run_end_corrections(packed, valid, hide, r, tile * PT_THREADS + threadIdx.x, kmin, k, stab);
         }
     }
     __syncthreads();
@@ -146,7 +74,7 @@ __device__ __forceinline__ T block_scan_excl(T v, T* warp_sums) {
     if (lane == 31) warp_sums[w] = incl;
     __syncthreads();
     if (w == 0) {
-        const T s = warp_sums[lane];
+        const T s = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : T(0);
         T si = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -177,6 +105,9 @@ __global__ void __launch_bounds__(PT_THREADS) bucket_scan_kernel(const unsigned 
 // reserved with one global atomic (all CTAs append to the same moving tail of a bucket, so the partial sectors of
 // neighbouring runs meet in L2), (d) scatter of the keys into bucket order in shared memory, (e) write-out: entry i of
 // the sorted tile goes to gdelta[bucket] + i, so consecutive lanes write consecutive addresses inside a run.
+// (Measured alternatives, 1e8 reads x 100 bp, k = 14: two resident CTAs of 512 threads with tiles of 16384 positions
+// take 66.6 ms against 40.1 ms -- the per-tile costs (scan over 4096 buckets, 4096 cursor atomics, barriers) double and
+// the runs get shorter; private per-CTA destination ranges without cursor atomics take 51 ms, see the file header.)
 // The tile loop is software-pipelined: the raw words of the next tile are in flight during the whole current tile, and
 // its histogram (fire-and-forget shared-memory atomics) is issued together with the latency-bound write-out.
 template <int PER>       // buckets per thread in the scan step: n_buckets <= PER * PT_THREADS
@@ -359,7 +290,7 @@ extern "C" int64_t kmap_partition_scratch_bytes(int64_t n, int k) {
 // folded counters were spilled, added to: the caller zeroes the table first).  hide may be NULL.
 // terminal_tabs (may be NULL): also add the run-end corrections of levels kmin..k-1 to those tables (count_all.cu).
 int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const uint32_t* hide, int64_t n, int k, uint32_t* table,
-                           void* scratch, const KmapTableSet* terminal_tabs, int kmin, cudaStream_t s) {
+                           void* scratch, const KmapTableSet* terminal_tabs, int kmin, void* const* step_events, cudaStream_t s) {
     const int n_buckets = 1 << (2 * (k - 8));
     const PartScratch p = carve(scratch, n_buckets);
     const int64_t n_words = (n + 31) / 32;
@@ -372,6 +303,7 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
     else
         bucket_hist_kernel<false><<<g1, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.hist, KmapTableSet(), k);
     bucket_scan_kernel<<<1, PT_THREADS, 0, s>>>(p.hist, n_buckets, p.base, p.cursor);
+    if (step_events && step_events[0]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(step_events[0]), s);
     const unsigned int g2 = (unsigned int)(n_tiles < 148 ? n_tiles : 148);
     static bool attr_set = false;
     const int smem1 = PT_TILE * 4 + 1 * PT_THREADS * 16, smem4 = PT_TILE * 4 + PT_MAX_PER * PT_THREADS * 16;
@@ -385,6 +317,7 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
         partition_kernel<1><<<g2, PT_THREADS, smem1, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.cursor, p.suffixes);
     else
         partition_kernel<PT_MAX_PER><<<g2, PT_THREADS, smem4, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.cursor, p.suffixes);
+    if (step_events && step_events[1]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(step_events[1]), s);
     const unsigned int g3 = (unsigned int)(n_buckets < 148 ? n_buckets : 148);
     bucket_count_kernel<<<g3, BC_THREADS, BC_WORDS * 4, s>>>(p.suffixes, p.base, n_buckets, table);
     return kmap_check_launch("count_partitioned");
@@ -396,5 +329,5 @@ extern "C" int kmap_count_dense_partitioned(const uint32_t* packed, const uint32
     if (n == 0) return KMAP_OK;
     KMAP_REQUIRE(packed && valid && table && scratch, "null pointer");
     KMAP_REQUIRE(scratch_bytes >= kmap_partition_scratch_bytes(n, k), "scratch too small (kmap_partition_scratch_bytes)");
-    return kmap_count_partitioned(packed, valid, nullptr, n, k, table, scratch, nullptr, k, as_stream(stream));
+    return kmap_count_partitioned(packed, valid, nullptr, n, k, table, scratch, nullptr, k, nullptr, as_stream(stream));
 }

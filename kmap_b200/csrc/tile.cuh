@@ -1,0 +1,88 @@
+// Tile helpers shared by the level-k partition kernels (partition.cu, slots.cu): a CTA walks the packed reads in tiles
+// of blockDim.x validity words, one word (32 window positions) per thread.
+#pragma once
+#include "common.cuh"
+
+#define KMAP_TILE_THREADS 1024
+
+// windows of k valid bases starting at bits 0..31 of V = v1:v0 (log-step run-length test, k <= 16)
+__device__ __forceinline__ uint32_t window_mask(uint32_t v0, uint32_t v1, int k) {
+    const uint64_t V = ((uint64_t)v1 << 32) | v0;
+    const uint64_t r2 = V & (V >> 1);             // runs >= 2
+    const uint64_t r4 = r2 & (r2 >> 2);           // >= 4
+    const uint64_t r8 = r4 & (r4 >> 4);           // >= 8
+    uint64_t m = ~0ull;
+    int off = 0;
+    if (k & 16) { m &= r8 & (r8 >> 8); off += 16; }
+    if (k & 8) { m &= r8 >> off; off += 8; }
+    if (k & 4) { m &= r4 >> off; off += 4; }
+    if (k & 2) { m &= r2 >> off; off += 2; }
+    if (k & 1) { m &= V >> off; }
+    return (uint32_t)m;
+}
+
+struct TileWords { uint32_t fresh, w0, w1, w2; };
+struct RawWords { uint32_t v0, v1, h, w0, w1, w2; };
+
+// this thread's 32 positions of tile `tile`: validity (+ one word of look-ahead), hidden windows, the three packed
+// words covering them.  Nothing is consumed here, so the loads of the NEXT tile can be in flight during a whole tile.
+__device__ __forceinline__ RawWords load_raw_words(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
+                                                   const uint32_t* __restrict__ hide, int64_t n_words, int64_t tile) {
+    RawWords r;
+    r.v0 = r.v1 = r.h = r.w0 = r.w1 = r.w2 = 0;
+    const int64_t w = tile * blockDim.x + threadIdx.x;                    // validity word index
+    if (w < n_words) {                                            // (the arrays carry KMAP_PAD_WORDS zero words of padding)
+        r.v0 = __ldcs(valid + w); r.v1 = __ldcs(valid + w + 1);
+        if (hide) r.h = __ldcs(hide + w);
+        const uint2 p = __ldcs(reinterpret_cast<const uint2*>(packed + 2 * w));
+        r.w0 = p.x; r.w1 = p.y; r.w2 = __ldcs(packed + 2 * w + 2);
+    }
+    return r;
+}
+__device__ __forceinline__ TileWords cook(const RawWords& r, int k) {
+    TileWords t;
+    t.fresh = window_mask(r.v0, r.v1, k) & ~r.h;
+    t.w0 = r.w0; t.w1 = r.w1; t.w2 = r.w2;
+    return t;
+}
+__device__ __forceinline__ TileWords load_tile_words(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
+                                                     const uint32_t* __restrict__ hide, int64_t n_words, int64_t tile, int k) {
+    return cook(load_raw_words(packed, valid, hide, n_words, tile), k);
+}
+
+__device__ __forceinline__ uint32_t key_at(const TileWords& t, int i, int sh) {          // i is a compile-time constant
+    const uint32_t x = (i < 16) ? __funnelshift_l(t.w1, t.w0, 2 * i) : __funnelshift_l(t.w2, t.w1, 2 * (i - 16));
+    return x >> sh;
+}
+
+
+// "+1 at level v" for every window with exactly v valid bases (kmin <= v < k) in front of a run end inside this thread's
+// word w (bit j set, bit j+1 clear): such a window cannot be extended, so the 4:1 table reductions of the all-k count
+// (count_all.cu) do not bring it down from the level above.  Windows hidden in `hide` belong to reads that are counted
+// by the direct per-k kernels.  stab[v] = table of level v.
+__device__ __forceinline__ void run_end_corrections(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
+                                                    const uint32_t* __restrict__ hide, const RawWords& r, int64_t w, int kmin,
+                                                    int k, uint32_t* const* stab) {
+    uint32_t ends = r.v0 & ~((r.v0 >> 1) | (r.v1 << 31));                  // bit j: position j valid, j+1 not
+    if (ends == 0) return;
+    const uint32_t vp = w > 0 ? __ldg(valid + w - 1) : 0u;
+    const uint64_t W = ((uint64_t)r.v0 << 32) | vp;                        // position j of this word = bit 32 + j
+    uint64_t H = 0;
+    if (hide) H = ((uint64_t)r.h << 32) | (w > 0 ? __ldg(hide + w - 1) : 0u);
+    do {
+        const int j = __ffs(ends) - 1;
+        ends &= ends - 1;
+        const uint64_t inv = ~(W << (31 - j));                             // bit 63 = position j, going down = going back
+        const int back = inv ? __clzll(inv) : 64;                          // valid bases ending at position j (>= 1)
+        const int vmax = min(back, k - 1);
+        if (vmax < kmin) continue;
+        // the windows of kmin..vmax bases that end at j start at j-v+1: one 32-base fetch covers them all
+        const int64_t p0 = w * 32 + j - vmax + 1;
+        const uint32_t hi = window16(packed, p0), lo = window16(packed, p0 + 16);
+        for (int v = vmax; v >= kmin; --v) {
+            if ((H >> (33 + j - v)) & 1ull) continue;
+            const uint32_t x = __funnelshift_l(lo, hi, 2 * (vmax - v));
+            atomicAdd(stab[v] + (x >> (32 - 2 * v)), 1u);
+        }
+    } while (ends);
+}

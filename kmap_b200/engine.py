@@ -90,8 +90,11 @@ class SeqOnDevice:
     # L2 resident and direct atomics win (measured)
     PARTITION_MIN_K = 13
 
-    def _part_scratch(self, k: int) -> torch.Tensor:
-        need = lib().kmap_partition_scratch_bytes(self.n, k)
+    # schemes for a level-k table beyond L2 (include/kmap_b200.h)
+    PREFIX_PASSES, SORTED, SLOTTED = 0, 1, 2
+
+    def _part_scratch(self, k: int, scheme: int = 1) -> torch.Tensor:
+        need = lib().kmap_slot_scratch_bytes(self.n, k) if scheme == self.SLOTTED else lib().kmap_partition_scratch_bytes(self.n, k)
         if self._part is None or self._part.numel() < need:
             self._part = None                      # release before growing
             self._part = empty(need, torch.uint8)
@@ -131,9 +134,10 @@ class SeqOnDevice:
 
     # ---- counting ---------------------------------------------------------------------------------------------
     def count(self, k: int, dedup: bool, table: Optional[torch.Tensor] = None, zero: bool = True,
-              partitioned: Optional[bool] = None) -> torch.Tensor:
+              partitioned: Optional[bool] = None, scheme: Optional[int] = None) -> torch.Tensor:
         """dense forward table uint32[4^k] (held as int32 bits).  dedup=True fuses remove_duplicate_hash_per_seq.
-        partitioned: None = choose by k (PARTITION_MIN_K), True/False = force (plain counts with 9 <= k <= 14 only)."""
+        partitioned: None = choose by k (PARTITION_MIN_K), True/False = force (plain counts with 9 <= k <= 14 only);
+        scheme: SORTED (default) or SLOTTED (12 <= k <= 14)."""
         L = lib()
         if not 1 <= k <= 15:
             raise KmapError(f"dense counting supports 1 <= k <= 15 (got {k}); k >= 16 uses 64-bit hashes "
@@ -159,6 +163,10 @@ class SeqOnDevice:
                 rc = L.kmap_count_dense_dedup(_ptr(self.packed), _ptr(self.valid), self.n, _ptr(self.borders), self.n_seq,
                                               k, _ptr(table), _ptr(self._work), _ptr(bitmap), _stream_ptr())
             check(rc, "kmap_count_dense_dedup")
+        elif scheme == self.SLOTTED and 12 <= k <= 14 and zero:
+            scratch = self._part_scratch(k, self.SLOTTED)
+            check(L.kmap_count_dense_slotted(_ptr(self.packed), _ptr(self.valid), self.n, k, _ptr(table), _ptr(scratch),
+                                             scratch.numel(), _stream_ptr()), "kmap_count_dense_slotted")
         elif (partitioned if partitioned is not None else k >= self.PARTITION_MIN_K) and 9 <= k <= 14 and zero:
             scratch = self._part_scratch(k)
             check(L.kmap_count_dense_partitioned(_ptr(self.packed), _ptr(self.valid), self.n, k, _ptr(table), _ptr(scratch),
@@ -169,9 +177,13 @@ class SeqOnDevice:
         return table
 
     def count_all(self, kmin: int, kmax: int, dedup: bool, tables: Optional[dict] = None, n_partitions: int = 0,
-                  phase_events: Optional[Sequence[torch.cuda.Event]] = None, partitioned: Optional[bool] = None) -> dict:
-        """Dense forward tables for every k in [kmin, kmax] from ONE pass of atomics at level kmax (csrc/count_all.cu);
-        identical to {k: self.count(k, dedup)}.  Returns {k: int32-bit-pattern tensor of 4^k cells}."""
+                  phase_events: Optional[Sequence[torch.cuda.Event]] = None, partitioned: Optional[bool] = None,
+                  scheme: Optional[int] = None) -> dict:
+        """Dense forward tables for every k in [kmin, kmax] from ONE update per window at level kmax (csrc/count_all.cu);
+        identical to {k: self.count(k, dedup)}.  Returns {k: int32-bit-pattern tensor of 4^k cells}.
+        scheme: how the level-kmax table is built when 12 <= kmax <= 14 -- SORTED (default: measured fastest), SLOTTED,
+        or PREFIX_PASSES (global atomics in n_partitions key-prefix passes; also what `partitioned=False` /
+        n_partitions > 0 select)."""
         L = lib()
         if not (1 <= kmin <= kmax <= 15):
             raise KmapError("count_all needs 1 <= kmin <= kmax <= 15")
@@ -192,20 +204,26 @@ class SeqOnDevice:
                 self._work = empty(need, torch.int32)
             dupmask, work = self._dupmask, self._work
         part, part_bytes = None, 0
-        if (partitioned if partitioned is not None else n_partitions <= 0) and 12 <= kmax <= 14:
-            part = self._part_scratch(kmax)
+        if scheme is None:
+            scheme = self.SORTED if (partitioned if partitioned is not None else n_partitions <= 0) else self.PREFIX_PASSES
+        if not 12 <= kmax <= 14:
+            scheme = self.PREFIX_PASSES
+        if scheme != self.PREFIX_PASSES:
+            part = self._part_scratch(kmax, scheme)
             part_bytes = part.numel()
         ev = None
-        if phase_events is not None:                    # 4 torch events (already recorded once so that the handles exist)
-            ev = (ctypes.c_void_p * 4)(*[e.cuda_event for e in phase_events])
+        if phase_events is not None:                    # 6 torch events (already recorded once so that the handles exist)
+            if len(phase_events) != 6:
+                raise KmapError("phase_events must hold 6 events")
+            ev = (ctypes.c_void_p * 6)(*[e.cuda_event for e in phase_events])
         rc = L.kmap_count_all_k(_ptr(self.packed), _ptr(self.valid), self.n, _ptr(self.borders), self.n_seq, kmin, kmax,
-                                int(dedup), ptrs, _ptr(dupmask), _ptr(work), None, int(n_partitions), _ptr(part), part_bytes, ev,
-                                _stream_ptr())
+                                int(dedup), ptrs, _ptr(dupmask), _ptr(work), None, int(n_partitions), int(scheme), _ptr(part), part_bytes,
+                                ev, _stream_ptr())
         if rc == -3:   # a read beyond the block path: rerun with the bitmap scratch (tables are re-zeroed by the call)
             bitmap = zeros(max((1 << (2 * kmax)) // 32, 1), torch.int32)
             rc = L.kmap_count_all_k(_ptr(self.packed), _ptr(self.valid), self.n, _ptr(self.borders), self.n_seq, kmin, kmax,
-                                    int(dedup), ptrs, _ptr(dupmask), _ptr(work), _ptr(bitmap), int(n_partitions), _ptr(part),
-                                    part_bytes, ev, _stream_ptr())
+                                    int(dedup), ptrs, _ptr(dupmask), _ptr(work), _ptr(bitmap), int(n_partitions), int(scheme),
+                                    _ptr(part), part_bytes, ev, _stream_ptr())
         check(rc, "kmap_count_all_k")
         return tables
 

@@ -1,4 +1,5 @@
-"""Phase times of kmap_count_all_k (library-recorded events) + equality against the global-atomic prefix-pass scheme."""
+"""Phase times of kmap_count_all_k (library-recorded events) per level-kmax scheme + equality against the prefix-pass scheme."""
+import os
 import sys
 sys.path.insert(0, ".")
 import torch
@@ -10,22 +11,30 @@ seq_d, b_d = synth.generate_device(synth.CFG3, 0, n_reads)
 dev = E.SeqOnDevice.from_device_u8(seq_d, b_d)
 del seq_d
 tables = {k: E.zeros(1 << (2 * k), torch.int32) for k in range(8, 15)}
+S = E.SeqOnDevice
 for dedup in (True, False):
-    res = []
-    for it in range(4):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ph = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        for e in ph:
-            e.record()
-        e0.record()
-        dev.count_all(8, 14, dedup, tables, phase_events=ph)
-        e1.record()
-        torch.cuda.synchronize()
-        res.append((e0.elapsed_time(ph[0]), ph[0].elapsed_time(ph[1]), ph[1].elapsed_time(ph[2]), ph[2].elapsed_time(ph[3]), e0.elapsed_time(e1)))
-    r = res[-1]
-    print(f"dedup={dedup}: zero {r[0]:.2f} scan {r[1]:.2f} count_kmax {r[2]:.2f} derive {r[3]:.2f} total {r[4]:.2f} ms "
-          f"(min total {min(x[4] for x in res[1:]):.2f})", flush=True)
-    if check:
-        ref = {k: tables[k].clone() for k in range(8, 15)}
-        dev.count_all(8, 14, dedup, tables, partitioned=False)
-        print("  equal to prefix-pass scheme:", all(torch.equal(ref[k], tables[k]) for k in ref), flush=True)
+    ref = None
+    for scheme, name in [x for x in ((S.SLOTTED, "slotted"), (S.SORTED, "sorted")) if x[1] in os.environ.get("SCHEMES", "slotted,sorted")]:
+        res = []
+        for it in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ph = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            for e in ph:
+                e.record()
+            e0.record()
+            dev.count_all(8, 14, dedup, tables, phase_events=ph, scheme=scheme)
+            e1.record()
+            torch.cuda.synchronize()
+            order = [e0, ph[0], ph[1]] + ([ph[4]] if scheme == S.SORTED else []) + [ph[5], ph[2], ph[3], e1]
+            res.append([a.elapsed_time(b) for a, b in zip(order[:-1], order[1:])] + [e0.elapsed_time(e1)])
+        r = res[-1]
+        names = ["zero", "scan"] + (["hist"] if scheme == S.SORTED else []) + ["partition", "count", "derive", "tail", "total"]
+        print(f"dedup={dedup} {name:8s}: " + " ".join(f"{n} {v:.2f}" for n, v in zip(names, r)) +
+              f" ms (min total {min(x[-1] for x in res[1:]):.2f})", flush=True)
+        if check:
+            if ref is None:
+                ref = {k: tables[k].clone() for k in range(8, 15)}
+                dev.count_all(8, 14, dedup, tables, partitioned=False)
+                print("  equal to prefix-pass scheme:", all(torch.equal(ref[k], tables[k]) for k in ref), flush=True)
+            else:
+                print("  equal to the first scheme:", all(torch.equal(ref[k], tables[k]) for k in ref), flush=True)

@@ -157,9 +157,12 @@ def test_partitioned_count_equals_direct_count(ENG, k):
     special = ["A" * 70000, "CA" * 60, "", "N", "ACG", "T" * 40000 + "G" + "T" * 33000]
     reads, seq, borders = rand_reads(rng, 3000, 0, 150, p_n=0.01, special=special)
     dev = ENG.SeqOnDevice.from_numpy(seq, borders)
-    got = ENG.to_host(dev.count(k, dedup=False, partitioned=True), np.uint32)
+    got = ENG.to_host(dev.count(k, dedup=False, partitioned=True, scheme=ENG.SeqOnDevice.SORTED), np.uint32)
     direct = ENG.to_host(dev.count(k, dedup=False, partitioned=False), np.uint32)
     assert np.array_equal(got, direct), (k, int(np.abs(got.astype(np.int64) - direct.astype(np.int64)).sum()))
+    if k >= 12:     # the slotted scheme: most sectors overflow here (homopolymers), so the direct-count path is exercised too
+        slotted = ENG.to_host(dev.count(k, dedup=False, partitioned=True, scheme=ENG.SeqOnDevice.SLOTTED), np.uint32)
+        assert np.array_equal(slotted, direct), (k, int(np.abs(slotted.astype(np.int64) - direct.astype(np.int64)).sum()))
     assert np.array_equal(got, dense_table_from_oracle(seq, borders, k, False))
     assert got[0] >= 69000 and got[4 ** k - 1] >= 39000
     # a second call re-uses the scratch and must not depend on its previous content
@@ -176,8 +179,9 @@ def test_partitioned_count_tiny_and_empty(ENG):
         borders = np.stack([ends - lens, ends - 1], axis=1).astype(np.int64)
         dev = ENG.SeqOnDevice.from_numpy(seq, borders)
         for k in (9, 14):
-            got = ENG.to_host(dev.count(k, dedup=False, partitioned=True), np.uint32)
-            assert np.array_equal(got, dense_table_from_oracle(seq, borders, k, False))
+            for scheme in (ENG.SeqOnDevice.SORTED, ENG.SeqOnDevice.SLOTTED):
+                got = ENG.to_host(dev.count(k, dedup=False, partitioned=True, scheme=scheme), np.uint32)
+                assert np.array_equal(got, dense_table_from_oracle(seq, borders, k, False))
 
 
 @pytest.mark.parametrize("kmin,kmax,parts", [(8, 14, 0), (8, 14, 3), (1, 6, 0), (5, 5, 1), (11, 15, 5), (3, 9, 2), (9, 13, 0),
@@ -194,8 +198,8 @@ def test_count_all_k_equals_per_k_counts(ENG, kmin, kmax, parts):
     borders = np.concatenate([borders, borders2 + borders[-1, 1] + 1])
     # tandem repeats so that k-mers repeat inside reads with different extensions
     dev = ENG.SeqOnDevice.from_numpy(seq, borders)
-    for dedup in (True, False):
-        tabs = dev.count_all(kmin, kmax, dedup, n_partitions=parts)
+    for dedup, scheme in ((True, None), (False, None), (True, ENG.SeqOnDevice.SLOTTED)):
+        tabs = dev.count_all(kmin, kmax, dedup, n_partitions=parts, scheme=scheme)
         for k in range(kmin, kmax + 1):
             got = ENG.to_host(tabs[k], np.uint32)
             if k in (kmin, kmax, (kmin + kmax) // 2):
