@@ -126,6 +126,12 @@ int kmap_count_dense_slotted(const uint32_t* packed, const uint32_t* valid, int6
 int64_t kmap_slot_scratch_bytes(int64_t n, int k);
 
 int kmap_fill_u32(uint32_t* p, int64_t n_words, uint32_t value, void* stream);
+/* dst[i] += src[i]: merges the tables of one chunk of reads into the running totals when the reads are streamed through
+ * the device in chunks (kmap_b200/api.py; reads are independent units, kmer_count.py:755-759).  16-byte aligned. */
+int kmap_add_u32(uint32_t* dst, const uint32_t* src, int64_t n_words, void* stream);
+/* borders[i][0..1] -= offset, in place: the rows of input.seqboarder.bin.pkl that belong to a chunk of reads, made
+ * relative to the first position of the chunk */
+int kmap_rebase_borders(int64_t* borders, int64_t n_seq, int64_t offset, void* stream);
 
 /* count_uniq_hash (kmer_count.py:476-491) for callers that hold a materialised hash array: table[h] += 1 for every
  * h < 4^k (the invalid hash is skipped) */

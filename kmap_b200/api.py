@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import engine as E
-from ._lib import KmapError
+from ._lib import KmapError, check as _check, lib as _lib
 
 
 class TableAllReduce:
@@ -66,20 +66,31 @@ def upload_reads(seq_np_arr: np.ndarray, boarder_mat: Optional[np.ndarray], vali
 
 def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterable[int], rep_mode: bool = False,
                 revcom_mode: bool = True, validate: bool = True, table_allreduce: Optional[TableAllReduce] = None,
-                lists_on: Optional[int] = None) -> Dict[int, Tuple[np.ndarray, np.ndarray]]:
+                lists_on: Optional[int] = None, chunk_positions: int = 1 << 29) -> Dict[int, Tuple[np.ndarray, np.ndarray]]:
     """First-round counts of find_motif for every k (reference motif_discovery.py:627-640): per k the
     `(uniq_kh_arr uint32, uniq_kh_cnt_arr int32)` pair that the reference pickles into kmer_count/k{k}.pkl, in the
     reference's order.  With `table_allreduce` each rank passes ITS shard of the reads and the tables are merged before
-    compaction; `lists_on=r` returns the lists on rank r only (others get {})."""
-    dev = upload_reads(seq_np_arr, boarder_mat, validate)
+    compaction; `lists_on=r` returns the lists on rank r only (others get {}).
+    Inputs larger than `chunk_positions` are streamed through the device in chunks of whole reads: the host-to-device copy
+    of chunk i+1 (copy stream, from pinned memory) overlaps packing and counting of chunk i (`count_tables_streamed`)."""
     out: Dict[int, Tuple[np.ndarray, np.ndarray]] = {}
     ks = sorted(set(int(k) for k in k_list))
     if not ks:
         return out
-    if ks == list(range(ks[0], ks[-1] + 1)) and ks[-1] <= 15:
-        tables = dev.count_all(ks[0], ks[-1], dedup=not rep_mode)          # one atomic pass at kmax, the rest derived
+    contiguous = ks == list(range(ks[0], ks[-1] + 1)) and ks[-1] <= 15
+    bounds = _chunk_bounds(seq_np_arr, boarder_mat, chunk_positions) if contiguous else None
+    if bounds is not None and len(bounds) > 2:
+        if validate:
+            E.check_borders_tile(np.asarray(boarder_mat).reshape(-1, 2), len(seq_np_arr))
+        tables, n_total = count_tables_streamed(seq_np_arr, boarder_mat, ks[0], ks[-1], rep_mode, bounds)
     else:
-        tables = {k: dev.count(k, dedup=not rep_mode) for k in ks}
+        dev = upload_reads(seq_np_arr, boarder_mat, validate)
+        n_total = dev.n
+        if contiguous:
+            tables = dev.count_all(ks[0], ks[-1], dedup=not rep_mode)      # one update per window at kmax, the rest derived
+        else:
+            tables = {k: dev.count(k, dedup=not rep_mode) for k in ks}
+        del dev
     if table_allreduce is not None:
         for k in ks:
             table_allreduce(tables[k])
@@ -89,7 +100,7 @@ def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterabl
     copy_stream = _copy_stream()
     pending = []
     for k in ks:
-        kh, cnt = E.compact_merge(tables[k], k, revcom_mode, upper_bound=_upper_bound(dev, k))
+        kh, cnt = E.compact_merge(tables[k], k, revcom_mode, upper_bound=_upper_bound(n_total, k))
         done = torch.cuda.Event()
         done.record()
         with torch.cuda.stream(copy_stream):
@@ -114,9 +125,104 @@ def _copy_stream() -> torch.cuda.Stream:
     return _copy_streams[dev]
 
 
-def _upper_bound(dev: E.SeqOnDevice, k: int) -> int:
+def _upper_bound(n: int, k: int) -> int:
     """no table can hold more distinct k-mers than cells or than windows"""
-    return int(min(1 << (2 * k), max(dev.n - k + 1, 0)))
+    return int(min(1 << (2 * k), max(n - k + 1, 0)))
+
+
+def _first_read_at_or_after(b: np.ndarray, pos: int) -> int:
+    """index of the first read whose start is >= pos (bisection on the border matrix itself: no strided copy)"""
+    lo, hi = 0, len(b)
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if b[mid, 0] < pos:
+            lo = mid + 1
+        else:
+            hi = mid
+    return lo
+
+
+def _chunk_bounds(seq_np_arr: np.ndarray, boarder_mat, chunk_positions: int):
+    """read indices [r_0 = 0 < r_1 < ... < r_m = n_seq] cutting the input into chunks of about chunk_positions positions,
+    or None when the input is small or the border matrix is not the back-to-back layout `kmap preproc` writes at the cuts
+    (kmer_count.py:335-343)."""
+    n = len(seq_np_arr)
+    if boarder_mat is None or n <= chunk_positions:
+        return None
+    b = np.asarray(boarder_mat).reshape(-1, 2)
+    n_seq = len(b)
+    if n_seq < 2 or b[0, 0] != 0 or b[-1, 1] != n - 1:
+        return None
+    m = -(-n // chunk_positions)
+    cuts = [0]
+    for i in range(1, m):
+        r = _first_read_at_or_after(b, n * i // m)
+        if cuts[-1] < r < n_seq:
+            if b[r, 0] != b[r - 1, 1] + 1:
+                return None
+            cuts.append(r)
+    cuts.append(n_seq)
+    return cuts
+
+
+def count_tables_streamed(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, kmin: int, kmax: int, rep_mode: bool, cuts):
+    """Dense forward tables of every k in [kmin, kmax] with the reads streamed through the device chunk by chunk.
+    Reads are independent units (per-read de-duplication never crosses a read, kmer_count.py:755-759), so the table of the
+    whole input is the sum of the chunk tables: chunk i is packed and counted (SeqOnDevice.count_all) on the current
+    stream while chunk i+1 travels on the copy stream into the other half of a double buffer.  Returns ({k: table}, n)."""
+    E.require_cuda()
+    L = _lib()
+    b = np.asarray(boarder_mat).reshape(-1, 2)
+    if b.dtype != np.int64 or not b.flags.c_contiguous:
+        b = np.ascontiguousarray(b, dtype=np.int64)
+    seq_t = torch.from_numpy(np.ascontiguousarray(seq_np_arr))
+    b_t = torch.from_numpy(b)
+    spans = []
+    for r0, r1 in zip(cuts[:-1], cuts[1:]):
+        spans.append((r0, r1, int(b[r0, 0]), int(b[r1 - 1, 1]) + 1))
+    max_pos = max(p1 - p0 for _, _, p0, p1 in spans)
+    max_rows = max(r1 - r0 for r0, r1, _, _ in spans)
+    u8 = [E.empty(max_pos, torch.uint8) for _ in range(2)]
+    rows = [torch.empty((max_rows, 2), dtype=torch.int64, device="cuda") for _ in range(2)]
+    compute = torch.cuda.current_stream()
+    copy = _copy_stream()
+    copy.wait_stream(compute)
+    uploaded = [None] * len(spans)
+    released = [None] * len(spans)
+
+    def upload(i):
+        r0, r1, p0, p1 = spans[i]
+        with torch.cuda.stream(copy):
+            if i >= 2:
+                copy.wait_event(released[i - 2])
+            u8[i % 2][:p1 - p0].copy_(seq_t[p0:p1], non_blocking=True)
+            rows[i % 2][:r1 - r0].copy_(b_t[r0:r1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+            uploaded[i] = ev
+
+    totals = {k: E.empty(1 << (2 * k), torch.int32) for k in range(kmin, kmax + 1)}
+    part = {k: E.empty(1 << (2 * k), torch.int32) for k in range(kmin, kmax + 1)}
+    chunk = None
+    upload(0)
+    for i, (r0, r1, p0, p1) in enumerate(spans):
+        if i + 1 < len(spans):
+            upload(i + 1)
+        compute.wait_event(uploaded[i])
+        borders_d = rows[i % 2][:r1 - r0]
+        _check(L.kmap_rebase_borders(borders_d.data_ptr(), r1 - r0, p0, compute.cuda_stream), "kmap_rebase_borders")
+        if chunk is None:
+            chunk = E.SeqOnDevice.from_device_u8(u8[i % 2][:p1 - p0], borders_d, capacity=max_pos)
+        else:
+            chunk.rebind(u8[i % 2][:p1 - p0], borders_d)
+        chunk.count_all(kmin, kmax, dedup=not rep_mode, tables=totals if i == 0 else part)
+        if i > 0:
+            for k in range(kmin, kmax + 1):
+                _check(L.kmap_add_u32(totals[k].data_ptr(), part[k].data_ptr(), 1 << (2 * k), compute.cuda_stream), "kmap_add_u32")
+        ev = torch.cuda.Event()
+        ev.record(compute)
+        released[i] = ev
+    return totals, len(seq_np_arr)
 
 
 def hamdist_matrix_rows(kh: np.ndarray, labels: np.ndarray, head_len: Sequence[int], kmer_len: int, rank: int, world: int):

@@ -72,9 +72,52 @@ __global__ void fill_u32_kernel(uint32_t* __restrict__ p, int64_t n, uint32_t va
     for (; i < n; i += stride) p[i] = value;
 }
 
+// dst[i] += src[i], four cells per thread
+__global__ void add_u32_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, int64_t n4, uint32_t* __restrict__ dst1,
+                               const uint32_t* __restrict__ src1, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = i; j < n4; j += stride) {
+        uint4 a = dst[j];
+        const uint4 b = __ldcs(src + j);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        dst[j] = a;
+    }
+    for (int64_t j = 4 * n4 + i; j < n; j += stride) dst1[j] += src1[j];
+}
+
+__global__ void rebase_borders_kernel(int64_t* __restrict__ borders, int64_t n_values, int64_t offset) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n_values; i += stride) borders[i] -= offset;
+}
+
 }  // namespace
 
 extern "C" {
+
+int kmap_add_u32(uint32_t* dst, const uint32_t* src, int64_t n_words, void* stream) {
+    KMAP_REQUIRE(n_words >= 0, "negative size");
+    if (n_words == 0) return KMAP_OK;
+    KMAP_REQUIRE(dst && src, "null pointer");
+    KMAP_REQUIRE(((uintptr_t)dst & 15) == 0 && ((uintptr_t)src & 15) == 0, "tables must be 16-byte aligned");
+    int64_t g = (n_words / 4 + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    add_u32_kernel<<<(unsigned int)g, 256, 0, as_stream(stream)>>>(reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src),
+                                                                  n_words / 4, dst, src, n_words);
+    return kmap_check_launch("add_u32");
+}
+
+int kmap_rebase_borders(int64_t* borders, int64_t n_seq, int64_t offset, void* stream) {
+    KMAP_REQUIRE(n_seq >= 0, "negative size");
+    if (n_seq == 0 || offset == 0) return KMAP_OK;
+    KMAP_REQUIRE(borders, "null pointer");
+    int64_t g = (2 * n_seq + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    rebase_borders_kernel<<<(unsigned int)g, 256, 0, as_stream(stream)>>>(borders, 2 * n_seq, offset);
+    return kmap_check_launch("rebase_borders");
+}
 
 int64_t kmap_valid_words(int64_t n) { return (n + 31) / 32 + KMAP_PAD_WORDS; }
 int64_t kmap_packed_words(int64_t n) { return 2 * kmap_valid_words(n); }

@@ -102,14 +102,27 @@ class SeqOnDevice:
 
     # ---- construction ---------------------------------------------------------------------------------------
     @classmethod
-    def from_device_u8(cls, seq_u8: torch.Tensor, borders: Optional[torch.Tensor], keep_u8: bool = False) -> "SeqOnDevice":
+    def from_device_u8(cls, seq_u8: torch.Tensor, borders: Optional[torch.Tensor], keep_u8: bool = False,
+                       capacity: Optional[int] = None) -> "SeqOnDevice":
+        """capacity: positions to size the packed buffers for (>= len(seq_u8)) when the object will be `rebind`-ed."""
         L = lib()
         n = int(seq_u8.numel())
-        packed = empty(L.kmap_packed_words(n), torch.int32)
-        valid = empty(L.kmap_valid_words(n), torch.int32)
+        cap = max(n, int(capacity or 0))
+        packed = empty(L.kmap_packed_words(cap), torch.int32)
+        valid = empty(L.kmap_valid_words(cap), torch.int32)
         check(L.kmap_pack2bit(_ptr(seq_u8), n, _ptr(packed), _ptr(valid), _stream_ptr()), "kmap_pack2bit")
         n_seq = 0 if borders is None else int(borders.shape[0])
         return cls(n, packed, valid, borders, n_seq, seq_u8 if keep_u8 else None)
+
+    def rebind(self, seq_u8: torch.Tensor, borders: Optional[torch.Tensor]):
+        """re-use this object (packed buffers and every scratch buffer) for another chunk of reads of at most the same size"""
+        L = lib()
+        n = int(seq_u8.numel())
+        if L.kmap_valid_words(n) > self.valid.numel():
+            raise KmapError("rebind: the chunk is larger than the buffers of this SeqOnDevice")
+        check(L.kmap_pack2bit(_ptr(seq_u8), n, _ptr(self.packed), _ptr(self.valid), _stream_ptr()), "kmap_pack2bit")
+        self.n, self.borders, self.n_seq = n, borders, (0 if borders is None else int(borders.shape[0]))
+        self.seq_u8, self._valid0 = None, None
 
     @classmethod
     def from_numpy(cls, seq_np_arr: np.ndarray, boarder_mat: Optional[np.ndarray] = None, keep_u8: bool = False,

@@ -406,3 +406,21 @@ def test_scan_motif_workflow_testfa(MD, K, testfa, tmp_path):
     assert kk == testfa["hamdist"]["k"] and str(mat.dtype) == testfa["hamdist"]["ref_dtype"]
     assert np.array_equal(mat, testfa["hamdist"]["mat"]) and np.array_equal(lab, testfa["hamdist"]["labels"])
     assert (res_dir / "sample_kmers.tsv").read_text() == tf["sample_kmers.tsv"]
+
+
+def test_streamed_count_kmers_equals_single_upload(ENG):
+    """api.count_kmers with the reads streamed through the device in chunks (double-buffered H2D on a copy stream) returns
+    the same lists as one upload, in both modes; reads of every path (warp / block / bitmap) sit in different chunks"""
+    from kmap_b200 import api
+    rng = np.random.default_rng(4242)
+    special = ["A" * 80, "CA" * 60, "", "N", "ACGTTGCA" * 150, ("ACGTAGCTAGCTAGGATCGAT" * 1500)[:30000], "ACGTTGCAAC" * 40]
+    reads, seq, borders = rand_reads(rng, 3000, 0, 130, p_n=0.01, special=special)
+    for rep_mode in (False, True):
+        one = api.count_kmers(seq, borders, range(8, 15), rep_mode=rep_mode, chunk_positions=1 << 40)
+        many = api.count_kmers(seq, borders, range(8, 15), rep_mode=rep_mode, chunk_positions=len(seq) // 7)
+        assert api._chunk_bounds(seq, borders, len(seq) // 7) is not None
+        for k in range(8, 15):
+            assert np.array_equal(one[k][0], many[k][0]) and np.array_equal(one[k][1], many[k][1]), (k, rep_mode)
+        want = O.merge_revcom(*O.count_uniq_hash(O.comp_kmer_hash(seq, 11) if rep_mode else
+                                                 O.remove_duplicate_hash_per_seq(O.comp_kmer_hash(seq, 11), borders, np.uint32(0xFFFFFFFF)), 11), 11)
+        assert np.array_equal(many[11][0], want[0]) and np.array_equal(many[11][1], want[1])

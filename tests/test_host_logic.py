@@ -1,0 +1,46 @@
+"""Host-side logic that needs no GPU: how api.count_kmers cuts the reads into chunks for the streamed upload."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from kmap_b200 import api, synth  # noqa: E402
+from oracle import kmap_oracle as O  # noqa: E402
+
+
+def test_chunk_bounds_cut_at_read_starts_and_cover_everything():
+    seq, borders = synth.generate_numpy(synth.CFG2_N, 0, 1000)          # 1000 reads x 40 bp (+ separators)
+    n = len(seq)
+    cuts = api._chunk_bounds(seq, borders, n // 6)
+    assert cuts[0] == 0 and cuts[-1] == len(borders) and cuts == sorted(set(cuts)) and len(cuts) >= 6
+    for r0, r1 in zip(cuts[:-1], cuts[1:]):
+        p0, p1 = int(borders[r0, 0]), int(borders[r1 - 1, 1]) + 1
+        assert seq[p1 - 1] == 255 and (p0 == 0 or seq[p0 - 1] == 255)     # a chunk starts after a separator, ends on one
+        assert p1 - p0 <= n // 6 + 2 * 41
+    # chunk tables add up to the table of the whole input (reads are independent units, kmer_count.py:755-759)
+    k = 5
+    whole = np.zeros(4 ** k, dtype=np.int64)
+    u, c = O.count_uniq_hash(O.remove_duplicate_hash_per_seq(O.comp_kmer_hash(seq, k), borders, np.uint32(0xFFFFFFFF)), k)
+    whole[u] = c
+    acc = np.zeros(4 ** k, dtype=np.int64)
+    for r0, r1 in zip(cuts[:-1], cuts[1:]):
+        p0, p1 = int(borders[r0, 0]), int(borders[r1 - 1, 1]) + 1
+        b = borders[r0:r1] - p0
+        u, c = O.count_uniq_hash(O.remove_duplicate_hash_per_seq(O.comp_kmer_hash(seq[p0:p1], k), b, np.uint32(0xFFFFFFFF)), k)
+        acc[u] += c
+    assert np.array_equal(acc, whole)
+
+
+def test_chunk_bounds_declines_small_or_foreign_layouts():
+    seq, borders = synth.generate_numpy(synth.CFG2_N, 0, 200)
+    assert api._chunk_bounds(seq, borders, len(seq)) is None             # fits one chunk
+    assert api._chunk_bounds(seq, None, 100) is None
+    gappy = borders.copy()
+    gappy[:, 1] -= 1                                                     # not the back-to-back layout preproc writes
+    assert api._chunk_bounds(seq, gappy, len(seq) // 4) is None
+    shifted = borders.copy()
+    shifted[0, 0] = 1
+    assert api._chunk_bounds(seq, shifted, len(seq) // 4) is None
