@@ -187,7 +187,7 @@ def main():
     # ---- device-resident input (generated on the device by the counter-based generator) -----------------------------
     seq_d, borders_d = synth.generate_device(spec, r0, n_local)
     dev = E.SeqOnDevice.from_device_u8(seq_d, borders_d)
-    tables = {k: E.zeros(1 << (2 * k), torch.int32) for k in range(KMIN, KMAX + 1)}
+    flat_tables, tables = E.alloc_tables(KMIN, KMAX, zero=True)      # one buffer: the NCCL merge is one all-reduce
     torch.cuda.synchronize()
 
     count_events = []
@@ -208,8 +208,7 @@ def main():
                 count_events.append(("all", e0, e1))
                 phase_events.append((e0, ph, e1))
             if world > 1:
-                for k in range(KMIN, KMAX + 1):
-                    dist.all_reduce(tables[k])
+                dist.all_reduce(flat_tables)
             return
         for k in range(KMIN, KMAX + 1):
             if record:

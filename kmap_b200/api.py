@@ -79,21 +79,26 @@ def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterabl
         return out
     contiguous = ks == list(range(ks[0], ks[-1] + 1)) and ks[-1] <= 15
     bounds = _chunk_bounds(seq_np_arr, boarder_mat, chunk_positions) if contiguous else None
+    flat = None
     if bounds is not None and len(bounds) > 2:
         if validate:
             E.check_borders_tile(np.asarray(boarder_mat).reshape(-1, 2), len(seq_np_arr))
-        tables, n_total = count_tables_streamed(seq_np_arr, boarder_mat, ks[0], ks[-1], rep_mode, bounds)
+        flat, tables, n_total = count_tables_streamed(seq_np_arr, boarder_mat, ks[0], ks[-1], rep_mode, bounds)
     else:
         dev = upload_reads(seq_np_arr, boarder_mat, validate)
         n_total = dev.n
         if contiguous:
-            tables = dev.count_all(ks[0], ks[-1], dedup=not rep_mode)      # one update per window at kmax, the rest derived
+            flat, tables = E.alloc_tables(ks[0], ks[-1])
+            dev.count_all(ks[0], ks[-1], dedup=not rep_mode, tables=tables)   # one update per window at kmax, the rest derived
         else:
             tables = {k: dev.count(k, dedup=not rep_mode) for k in ks}
         del dev
     if table_allreduce is not None:
-        for k in ks:
-            table_allreduce(tables[k])
+        if flat is not None:
+            table_allreduce(flat)                                  # every level in one call
+        else:
+            for k in ks:
+                table_allreduce(tables[k])
         if lists_on is not None and table_allreduce.rank != lists_on:
             return out
     # compaction of table k+1 overlaps the device-to-host copy of the lists of k (copy stream + pinned buffers)
@@ -169,7 +174,8 @@ def count_tables_streamed(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, kmin:
     """Dense forward tables of every k in [kmin, kmax] with the reads streamed through the device chunk by chunk.
     Reads are independent units (per-read de-duplication never crosses a read, kmer_count.py:755-759), so the table of the
     whole input is the sum of the chunk tables: chunk i is packed and counted (SeqOnDevice.count_all) on the current
-    stream while chunk i+1 travels on the copy stream into the other half of a double buffer.  Returns ({k: table}, n)."""
+    stream while chunk i+1 travels on the copy stream into the other half of a double buffer.
+    Returns (flat buffer, {k: table view}, n)."""
     E.require_cuda()
     L = _lib()
     b = np.asarray(boarder_mat).reshape(-1, 2)
@@ -201,8 +207,8 @@ def count_tables_streamed(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, kmin:
             ev.record(copy)
             uploaded[i] = ev
 
-    totals = {k: E.empty(1 << (2 * k), torch.int32) for k in range(kmin, kmax + 1)}
-    part = {k: E.empty(1 << (2 * k), torch.int32) for k in range(kmin, kmax + 1)}
+    flat, totals = E.alloc_tables(kmin, kmax)
+    part_flat, part = E.alloc_tables(kmin, kmax)
     chunk = None
     upload(0)
     for i, (r0, r1, p0, p1) in enumerate(spans):
@@ -217,12 +223,11 @@ def count_tables_streamed(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, kmin:
             chunk.rebind(u8[i % 2][:p1 - p0], borders_d)
         chunk.count_all(kmin, kmax, dedup=not rep_mode, tables=totals if i == 0 else part)
         if i > 0:
-            for k in range(kmin, kmax + 1):
-                _check(L.kmap_add_u32(totals[k].data_ptr(), part[k].data_ptr(), 1 << (2 * k), compute.cuda_stream), "kmap_add_u32")
+            _check(L.kmap_add_u32(flat.data_ptr(), part_flat.data_ptr(), flat.numel(), compute.cuda_stream), "kmap_add_u32")
         ev = torch.cuda.Event()
         ev.record(compute)
         released[i] = ev
-    return totals, len(seq_np_arr)
+    return flat, totals, len(seq_np_arr)
 
 
 def hamdist_matrix_rows(kh: np.ndarray, labels: np.ndarray, head_len: Sequence[int], kmer_len: int, rank: int, world: int):

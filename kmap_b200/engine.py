@@ -59,6 +59,18 @@ def zeros(n: int, dtype: torch.dtype) -> torch.Tensor:
     return torch.zeros(max(int(n), 0), dtype=dtype, device=require_cuda())
 
 
+def alloc_tables(kmin: int, kmax: int, zero: bool = False):
+    """(flat, {k: view}) -- the dense tables of levels kmin..kmax as views of ONE buffer (largest first), so that the
+    multi-GPU merge is a single all-reduce call instead of one per level."""
+    total = sum(1 << (2 * k) for k in range(kmin, kmax + 1))
+    flat = zeros(total, torch.int32) if zero else empty(total, torch.int32)
+    views, o = {}, 0
+    for k in range(kmax, kmin - 1, -1):
+        views[k] = flat[o:o + (1 << (2 * k))]
+        o += 1 << (2 * k)
+    return flat, views
+
+
 def check_borders_tile(borders: np.ndarray, n: int):
     """The fused de-duplicating count walks reads, so every non-separator position must belong to exactly one read:
     borders must be the layout preproc writes (kmer_count.py:335-343): st_0 = 0, en_i + 1 = st_{i+1}, en_last = n-1."""
@@ -201,7 +213,7 @@ class SeqOnDevice:
         if not (1 <= kmin <= kmax <= 15):
             raise KmapError("count_all needs 1 <= kmin <= kmax <= 15")
         if tables is None:
-            tables = {}
+            tables = alloc_tables(kmin, kmax)[1]
         for k in range(kmin, kmax + 1):
             if k not in tables:
                 tables[k] = empty(1 << (2 * k), torch.int32)
