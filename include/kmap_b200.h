@@ -144,7 +144,8 @@ int kmap_list_add_rc_counts(const uint32_t* kh, int32_t* cnt, int64_t n, int k, 
 
 /* count_uniq_hash + merge_revcom (kmer_count.py:476-491, 643-685) from the dense forward table, in the
  * reference's exact output order (ascending forward hash of the surviving entries; value = min(h, rc h) when
- * revcom; palindromes doubled).  scratch = uint64[kmap_compact_scratch_words(k)].
+ * revcom; palindromes doubled).  scratch = uint64[kmap_compact_scratch_words(k)] (256-byte aligned; for k >= 13 it
+ * also holds a permuted copy of the table, G[h] = F[rc h], so that the merge reads its partner cell without a gather).
  * Two-step: call with capacity 0 (out pointers may be NULL) to get *n_out_host, then with buffers.
  * Synchronises the stream. */
 int kmap_compact_merge(const uint32_t* table, int k, int revcom, uint64_t* scratch, uint32_t* kh_out,

@@ -43,56 +43,122 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
     return off;
 }
 
+// ---- G[h] = F[rc(h)] as a tiled permutation ------------------------------------------------------------------------------
+// The merge needs F[rc(h)] next to F[h]; for a table beyond L2 a gather costs one random 32-byte sector per cell
+// (2.7e8 of them at k = 14: 9 of the 12.7 ms the merge used to take).  Write h = [A | M | B] with A, B of 3 bases:
+// rc(h) = [rc B | rc M | rc A], so the 4096 cells that share the middle M are the reverse complements of the 4096 cells
+// that share the middle rc(M), and both sets consist of 64 runs of 64 consecutive cells (256 B).  One block moves one
+// such tile through shared memory: coalesced reads, a 64 x 64 transpose with the 3-base reverse complement applied to
+// both indices, coalesced writes.
+__device__ __forceinline__ uint32_t rc3(uint32_t x) {          // reverse complement of 3 bases (6 bits)
+    x = ~x & 63u;
+    return ((x & 3u) << 4) | (x & 12u) | (x >> 4);
+}
+
+__global__ void __launch_bounds__(256) revcom_permute_kernel(const uint32_t* __restrict__ F, uint32_t* __restrict__ G, int k) {
+    __shared__ uint32_t S[64][65];
+    const int km = k - 6;                                       // bases in the middle
+    const uint32_t mid = blockIdx.x;
+    const uint32_t rcmid = km ? revcom32(mid, km) : 0u;
+    const int top = 2 * (k - 3);
+    const uint32_t t = threadIdx.x, y = t & 63u;
+#pragma unroll 4
+    for (uint32_t it = 0; it < 16; ++it) {
+        const uint32_t x = it * 4 + (t >> 6);
+        S[x][y] = __ldcs(F + (((size_t)x << top) | ((size_t)rcmid << 6) | y));
+    }
+    __syncthreads();
+    const uint32_t ry = rc3(y);
+#pragma unroll 4
+    for (uint32_t it = 0; it < 16; ++it) {
+        const uint32_t a = it * 4 + (t >> 6);
+        G[((size_t)a << top) | ((size_t)mid << 6) | y] = S[ry][rc3(a)];
+    }
+}
+
 // ---- merged-entry rule on the forward table F (SURVEY Q6 recipe; kmer_count.py:656-683) ------------------
 // h survives iff F[h] > 0 and not (rc(h) present and h > rc(h)); value = min(h, rc h); count = F[h] + F[rc h]
-// (a palindrome is its own partner, so its count doubles).
-__device__ __forceinline__ bool merged_entry(const uint32_t* __restrict__ F, uint32_t h, uint32_t fh, int k, int revcom,
-                                             uint32_t* value, uint32_t* count) {
+// (a palindrome is its own partner, so its count doubles).  frc = F[rc h].
+__device__ __forceinline__ bool merged_entry(uint32_t h, uint32_t fh, uint32_t frc, int k, uint32_t* value, uint32_t* count) {
     if (fh == 0) return false;
-    if (!revcom) { *value = h; *count = fh; return true; }
     const uint32_t rc = revcom32(h, k);
-    const uint32_t frc = (rc == h) ? fh : __ldg(F + rc);
     if (frc > 0 && h > rc) return false;
     *value = h < rc ? h : rc;
     *count = fh + frc;
     return true;
 }
 
-__global__ void __launch_bounds__(CP_BLOCK) table_tile_count_kernel(const uint32_t* __restrict__ F, int64_t n_cells, int k,
-                                                                    int revcom, uint64_t* __restrict__ tile_counts) {
+// this thread's CP_ITEMS consecutive cells of F and their partners (from G when given, else gathered from F)
+__device__ __forceinline__ void load_items(const uint32_t* __restrict__ F, const uint32_t* __restrict__ G, int64_t n_cells, int k,
+                                           int revcom, int64_t base, uint32_t* fh, uint32_t* frc) {
+    if (base + CP_ITEMS <= n_cells) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(F + base)), b = __ldg(reinterpret_cast<const uint4*>(F + base) + 1);
+        fh[0] = a.x; fh[1] = a.y; fh[2] = a.z; fh[3] = a.w; fh[4] = b.x; fh[5] = b.y; fh[6] = b.z; fh[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < CP_ITEMS; ++j) fh[j] = base + j < n_cells ? __ldg(F + base + j) : 0u;
+    }
+    if (!revcom) {
+#pragma unroll
+        for (int j = 0; j < CP_ITEMS; ++j) frc[j] = 0;
+    } else if (G && base + CP_ITEMS <= n_cells) {
+        const uint4 a = __ldcs(reinterpret_cast<const uint4*>(G + base)), b = __ldcs(reinterpret_cast<const uint4*>(G + base) + 1);
+        frc[0] = a.x; frc[1] = a.y; frc[2] = a.z; frc[3] = a.w; frc[4] = b.x; frc[5] = b.y; frc[6] = b.z; frc[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < CP_ITEMS; ++j)
+            frc[j] = (base + j < n_cells && fh[j]) ? __ldg(F + revcom32((uint32_t)(base + j), k)) : 0u;
+    }
+}
+
+__device__ __forceinline__ bool item_entry(uint32_t h, uint32_t fh, uint32_t frc, int k, int revcom, uint32_t* value, uint32_t* count) {
+    if (!revcom) { *value = h; *count = fh; return fh != 0; }
+    return merged_entry(h, fh, frc, k, value, count);
+}
+
+__global__ void __launch_bounds__(CP_BLOCK) table_tile_count_kernel(const uint32_t* __restrict__ F, const uint32_t* __restrict__ G,
+                                                                    int64_t n_cells, int k, int revcom,
+                                                                    uint64_t* __restrict__ tile_counts) {
     const int64_t base = (int64_t)blockIdx.x * CP_TILE + (int64_t)threadIdx.x * CP_ITEMS;
+    uint32_t fh[CP_ITEMS], frc[CP_ITEMS];
+    load_items(F, G, n_cells, k, revcom, base, fh, frc);
     uint32_t c = 0;
 #pragma unroll
     for (int j = 0; j < CP_ITEMS; ++j) {
-        const int64_t h = base + j;
-        if (h < n_cells) {
-            uint32_t v, cnt;
-            c += merged_entry(F, (uint32_t)h, __ldg(F + h), k, revcom, &v, &cnt);
-        }
+        uint32_t v, cnt;
+        c += item_entry((uint32_t)(base + j), fh[j], frc[j], k, revcom, &v, &cnt);
     }
     uint32_t total;
     block_exclusive_scan(c, &total);
     if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(CP_BLOCK) table_tile_write_kernel(const uint32_t* __restrict__ F, int64_t n_cells, int k,
-                                                                    int revcom, const uint64_t* __restrict__ tile_offsets,
+__global__ void __launch_bounds__(CP_BLOCK) table_tile_write_kernel(const uint32_t* __restrict__ F, const uint32_t* __restrict__ G,
+                                                                    int64_t n_cells, int k, int revcom,
+                                                                    const uint64_t* __restrict__ tile_offsets,
                                                                     uint32_t* __restrict__ kh_out, int32_t* __restrict__ cnt_out) {
+    __shared__ uint32_t svals[CP_TILE], scnts[CP_TILE];           // the tile's entries in order: coalesced write-out
     const int64_t base = (int64_t)blockIdx.x * CP_TILE + (int64_t)threadIdx.x * CP_ITEMS;
+    uint32_t fh[CP_ITEMS], frc[CP_ITEMS];
+    load_items(F, G, n_cells, k, revcom, base, fh, frc);
     uint32_t vals[CP_ITEMS], cnts[CP_ITEMS];
     uint32_t c = 0;
 #pragma unroll
     for (int j = 0; j < CP_ITEMS; ++j) {
-        const int64_t h = base + j;
-        if (h < n_cells) {
-            uint32_t v, cnt;
-            if (merged_entry(F, (uint32_t)h, __ldg(F + h), k, revcom, &v, &cnt)) { vals[c] = v; cnts[c] = cnt; ++c; }
-        }
+        uint32_t v, cnt;
+        if (item_entry((uint32_t)(base + j), fh[j], frc[j], k, revcom, &v, &cnt)) { vals[c] = v; cnts[c] = cnt; ++c; }
     }
     uint32_t total;
     const uint32_t off = block_exclusive_scan(c, &total);
-    const uint64_t o = tile_offsets[blockIdx.x] + off;
-    for (uint32_t j = 0; j < c; ++j) { kh_out[o + j] = vals[j]; cnt_out[o + j] = (int32_t)cnts[j]; }
+#pragma unroll
+    for (uint32_t j = 0; j < CP_ITEMS; ++j)
+        if (j < c) { svals[off + j] = vals[j]; scnts[off + j] = cnts[j]; }
+    __syncthreads();
+    const uint64_t o = tile_offsets[blockIdx.x];
+    for (uint32_t i = threadIdx.x; i < total; i += CP_BLOCK) {
+        __stcs(kh_out + o + i, svals[i]);
+        __stcs(reinterpret_cast<uint32_t*>(cnt_out) + o + i, scnts[i]);
+    }
 }
 
 // exclusive scan of n_tiles uint64 values in place, total appended at [n_tiles]; one block
@@ -225,7 +291,11 @@ int sync_read_total(const uint64_t* dev, int64_t* host, cudaStream_t s, const ch
 extern "C" {
 
 int64_t kmap_list_scratch_words(int64_t n) { return (n + CP_TILE - 1) / CP_TILE + 2; }
-int64_t kmap_compact_scratch_words(int k) { return kmap_list_scratch_words((int64_t)1 << (2 * k)); }
+// tile counts, and for a table beyond L2 (k >= 13) the permuted copy G[h] = F[rc h]
+int64_t kmap_compact_scratch_words(int k) {
+    const int64_t tiles = kmap_list_scratch_words((int64_t)1 << (2 * k));
+    return k >= 13 ? ((tiles + 31) & ~(int64_t)31) + ((int64_t)1 << (2 * k - 1)) : tiles;
+}
 
 int kmap_compact_merge(const uint32_t* table, int k, int revcom, uint64_t* scratch, uint32_t* kh_out, int32_t* cnt_out,
                        int64_t capacity, int64_t* n_out_host, void* stream) {
@@ -234,7 +304,12 @@ int kmap_compact_merge(const uint32_t* table, int k, int revcom, uint64_t* scrat
     cudaStream_t s = as_stream(stream);
     const int64_t n_cells = (int64_t)1 << (2 * k);
     const int64_t n_tiles = (n_cells + CP_TILE - 1) / CP_TILE;
-    table_tile_count_kernel<<<(unsigned int)n_tiles, CP_BLOCK, 0, s>>>(table, n_cells, k, revcom, scratch);
+    uint32_t* G = nullptr;
+    if (revcom && k >= 13) {
+        G = reinterpret_cast<uint32_t*>(scratch + ((kmap_list_scratch_words(n_cells) + 31) & ~(int64_t)31));
+        revcom_permute_kernel<<<1u << (2 * (k - 6)), 256, 0, s>>>(table, G, k);
+    }
+    table_tile_count_kernel<<<(unsigned int)n_tiles, CP_BLOCK, 0, s>>>(table, G, n_cells, k, revcom, scratch);
     scan_tiles_kernel<<<1, 1024, 0, s>>>(scratch, n_tiles);
     int rc = kmap_check_launch("compact_merge(count)");
     if (rc) return rc;
@@ -246,7 +321,7 @@ int kmap_compact_merge(const uint32_t* table, int k, int revcom, uint64_t* scrat
         return KMAP_ERR_CAPACITY;
     }
     if (*n_out_host == 0) return KMAP_OK;
-    table_tile_write_kernel<<<(unsigned int)n_tiles, CP_BLOCK, 0, s>>>(table, n_cells, k, revcom, scratch, kh_out, cnt_out);
+    table_tile_write_kernel<<<(unsigned int)n_tiles, CP_BLOCK, 0, s>>>(table, G, n_cells, k, revcom, scratch, kh_out, cnt_out);
     return kmap_check_launch("compact_merge(write)");
 }
 
