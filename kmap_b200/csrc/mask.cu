@@ -11,18 +11,51 @@ constexpr int MK_MAXM = 16;
 // ---- mask: pass 1, flag word per 32 positions ----------------------------------------------------------------
 // flag bit i <=> some consensus j has dist(window_i, cons[j]) <= d[j], where an invalid window (touches 255 or
 // leaves the array) compares like the all-ones hash, i.e. like T..T (kmer_count.py:592-598).
+//
+// Bit-sliced: one thread = 32 window positions.  The 48 bases it can see are split into a plane of high bits and a
+// plane of low bits (bit p = base at position p); for consensus base i the positions whose base at offset i differs are
+// ((HI >> i) ^ hi_i) | ((LO >> i) ^ lo_i) with hi_i / lo_i all-ones or zero, so every logic instruction works on 32
+// windows at once.  The k mismatch planes are summed by a carry-save adder tree into a 5-bit bit-sliced count and
+// compared with d bit-serially: ~100 logic instructions per consensus and word, no POPC, instead of ~8 per window.
+__device__ __forceinline__ uint32_t even_bits32(uint32_t x) {
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    x = (x | (x >> 8)) & 0x0000FFFFu;
+    return x;
+}
+__device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
+    sum = a ^ b ^ c;
+    carry = (a & b) | (c & (a | b));
+}
+__device__ __forceinline__ void half_add(uint32_t a, uint32_t b, uint32_t& sum, uint32_t& carry) {
+    sum = a ^ b;
+    carry = a & b;
+}
+
 __global__ void __launch_bounds__(MK_BLOCK) mask_flag_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
                                                              int64_t n, int64_t n_words, int k, const uint32_t* __restrict__ cons,
                                                              const int32_t* __restrict__ dmax, int m, uint32_t* __restrict__ flags) {
-    __shared__ uint32_t sc[MK_MAXM];
+    __shared__ uint2 smask[MK_MAXM][16];       // (.x, .y) = (hi_i, lo_i) of consensus j, all-ones or zero
     __shared__ int sd[MK_MAXM];
     __shared__ int inv_hit;                    // does an invalid window fall inside some ball?
     const uint32_t low = lowmask32(k);
+    if (threadIdx.x < MK_MAXM * 16) {
+        const int j = threadIdx.x >> 4, i = threadIdx.x & 15;
+        uint2 v = make_uint2(0, 0);
+        if (j < m && i < k) {
+            const uint32_t base = ((cons[j] & low) >> (2 * (k - 1 - i))) & 3u;     // base i of the consensus, first base first
+            v.x = 0u - (base >> 1);
+            v.y = 0u - (base & 1u);
+        }
+        smask[j][i] = v;
+    }
     if (threadIdx.x == 0) {
         int hit = 0;
         for (int j = 0; j < m; ++j) {
-            sc[j] = cons[j] & low; sd[j] = dmax[j];
-            hit |= (int)nz_groups32(0xFFFFFFFFu ^ sc[j], low) <= sd[j];
+            sd[j] = dmax[j];
+            hit |= (int)nz_groups32(0xFFFFFFFFu ^ (cons[j] & low), low) <= dmax[j];
         }
         inv_hit = hit;
     }
@@ -32,23 +65,76 @@ __global__ void __launch_bounds__(MK_BLOCK) mask_flag_kernel(const uint32_t* __r
     const uint32_t v0 = __ldg(valid + t), v1 = __ldg(valid + t + 1);
     const uint2 w01 = __ldg(reinterpret_cast<const uint2*>(packed + 2 * t));
     const uint32_t w2 = __ldg(packed + 2 * t + 2);
-    const uint32_t km = (1u << k) - 1u;
-    const int sh = 32 - 2 * k;
-    uint32_t f = 0;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const uint32_t vb = __funnelshift_r(v0, v1, i);
-        bool hit;
-        if ((vb & km) == km) {
-            const uint32_t x = (i < 16) ? __funnelshift_l(w01.y, w01.x, 2 * i) : __funnelshift_l(w2, w01.y, 2 * (i - 16));
-            const uint32_t h = x >> sh;
-            hit = false;
-            for (int j = 0; j < m; ++j) hit |= (int)nz_groups32(h ^ sc[j], low) <= sd[j];
-        } else {
-            hit = inv_hit;
-        }
-        f |= (uint32_t)hit << i;
+    // planes: after a bit reversal base p' of a word sits at bits (2p', 2p'+1) = (high bit, low bit)
+    const uint32_t r0 = __brev(w01.x), r1 = __brev(w01.y), r2 = __brev(w2);
+    const uint32_t hi_a = even_bits32(r0) | (even_bits32(r1) << 16), hi_b = even_bits32(r2);        // positions 0..31, 32..47
+    const uint32_t lo_a = even_bits32(r0 >> 1) | (even_bits32(r1 >> 1) << 16), lo_b = even_bits32(r2 >> 1);
+    // windows of k valid bases starting at bits 0..31 (log-step run-length test, k <= 16)
+    uint32_t wm;
+    {
+        const uint64_t V = ((uint64_t)v1 << 32) | v0;
+        const uint64_t q2 = V & (V >> 1), q4 = q2 & (q2 >> 2), q8 = q4 & (q4 >> 4);
+        uint64_t mm = ~0ull;
+        int off = 0;
+        if (k & 16) { mm &= q8 & (q8 >> 8); off += 16; }
+        if (k & 8) { mm &= q8 >> off; off += 8; }
+        if (k & 4) { mm &= q4 >> off; off += 4; }
+        if (k & 2) { mm &= q2 >> off; off += 2; }
+        if (k & 1) { mm &= V >> off; }
+        wm = (uint32_t)mm;
     }
+    uint32_t hit = 0;
+    if (wm) {
+        for (int j = 0; j < m; ++j) {
+            uint32_t x[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint2 c = smask[j][i];                                   // (zero planes for i >= k: see below)
+                x[i] = (__funnelshift_r(hi_a, hi_b, i) ^ c.x) | (__funnelshift_r(lo_a, lo_b, i) ^ c.y);
+            }
+            // offsets i >= k do not belong to the window
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (i >= k) x[i] = 0;
+            // carry-save adder tree: 16 planes of weight 1 -> 5-bit count (b4 b3 b2 b1 b0)
+            uint32_t s1[6], c2[8];
+#pragma unroll
+            for (int g = 0; g < 5; ++g) full_add(x[3 * g], x[3 * g + 1], x[3 * g + 2], s1[g], c2[g]);
+            s1[5] = x[15];
+            uint32_t t0, t1, b0;
+            full_add(s1[0], s1[1], s1[2], t0, c2[5]);
+            full_add(s1[3], s1[4], s1[5], t1, c2[6]);
+            half_add(t0, t1, b0, c2[7]);
+            uint32_t u0, u1, c4[4];
+            full_add(c2[0], c2[1], c2[2], u0, c4[0]);
+            full_add(c2[3], c2[4], c2[5], u1, c4[1]);
+            uint32_t u2, b1;
+            full_add(u0, u1, c2[6], u2, c4[2]);
+            half_add(u2, c2[7], b1, c4[3]);
+            uint32_t y0, c8a, c8b, b2, b3, b4;
+            full_add(c4[0], c4[1], c4[2], y0, c8a);
+            half_add(y0, c4[3], b2, c8b);
+            half_add(c8a, c8b, b3, b4);
+            // count <= d, bit-serial from the top
+            const int d = sd[j];
+            uint32_t le;
+            if (d >= 16) {
+                le = ~0u;
+            } else if (d < 0) {
+                le = 0u;
+            } else {
+                const uint32_t bits[4] = {b0, b1, b2, b3};
+                uint32_t lt = 0, eq = ~b4;                                      // count < 16 required (d < 16)
+#pragma unroll
+                for (int q = 3; q >= 0; --q) {
+                    if ((d >> q) & 1) { lt |= eq & ~bits[q]; eq &= bits[q]; }
+                    else eq &= ~bits[q];
+                }
+                le = lt | eq;
+            }
+            hit |= le;
+        }
+    }
+    uint32_t f = (hit & wm) | (inv_hit ? ~wm : 0u);
     // positions >= n do not exist
     const int64_t p0 = t * 32;
     if (p0 + 32 > n) f &= (p0 >= n) ? 0u : ((1u << (n - p0)) - 1u);
