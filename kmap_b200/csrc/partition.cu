@@ -4,10 +4,11 @@
 // Measured on B200: random RED.ADD into an L2-resident table sustains ~187 G updates/s (22 G/s when the table lives in
 // HBM), shared-memory ATOMS ~2000 G/s.  So instead of one global atomic per window, every counted window's key is
 // split into (bucket = key >> 16, suffix = key & 0xFFFF):
-//   1. bucket_hist_kernel   one pass over the packed reads: windows per bucket        -> bucket offsets (scan)
-//   2. partition_kernel     one pass: a CTA counting-sorts a tile of 32768 positions by bucket in shared memory,
-//                           reserves room in every non-empty bucket with one global atomic and writes the 16-bit
-//                           suffixes as runs (lanes of a warp store to consecutive addresses).  (Private per-CTA
+//   1. bucket_hist_kernel   one pass over the packed reads: windows per (tile of 32768 positions, bucket), with running
+//                           sums -> after a small scan, the exact place of every tile's run in every bucket
+//   2. partition_kernel     one pass: a CTA counting-sorts a tile by bucket in shared memory (one shared-memory atomic
+//                           per window) and writes the 16-bit suffixes as runs (lanes of a warp store to consecutive
+//                           addresses) at the precomputed places: no histogram of its own, no global atomics.  (Private per-CTA
 //                           ranges without the atomics were measured: slower, 148 x 4096 open partial lines spill
 //                           out of L2 and DRAM writes grow 2.5x.)
 //   3. bucket_count_kernel  one CTA per bucket: 65536 cells as packed 16-bit counters in shared memory (128 KB),
@@ -32,36 +33,74 @@ __device__ __forceinline__ void tile_hist(const TileWords& t, int sh, uint32_t* 
     }
 }
 
-// ---- 1. windows per bucket (+ the run-end corrections of the all-k count) -------------------------------------------------
+// ---- 1. windows per (tile, bucket) (+ the run-end corrections of the all-k count) ------------------------------------------
+// CTA h walks the contiguous tile range [n_tiles*h/H, n_tiles*(h+1)/H).  For every tile it histograms the windows by
+// bucket in shared memory and writes the row counts[tile][*] (uint16) together with off[tile][*] = the number of windows
+// the EARLIER tiles of this range put into each bucket (a thread owns PER buckets; their running sums live in its
+// registers).  chunk_total[h][*] is what the whole range holds.  After the scan below, the first entry tile t writes into
+// bucket b is chunk_base[h(t)][b] + off[t][b]: exact, so the partition pass needs neither a histogram of its own nor
+// cursor atomics, and the runs of consecutive tiles are adjacent in every bucket (partial sectors meet in L2).
 // With TERMINAL, the pass also does what terminal_corrections_kernel (count_all.cu) does: "+1 at level v" for every
 // window with exactly v valid bases (kmin <= v < k) in front of a run end.  Those are scattered global REDs; issued from
 // this kernel they overlap its shared-memory-bound histogram work instead of costing passes of their own.
-template <bool TERMINAL>
+constexpr int PT_HGRID = 296;                     // CTAs of the histogram pass (two resident per SM)
+
+__host__ __device__ __forceinline__ int64_t chunk_first_tile(int64_t n_tiles, int h) { return n_tiles * h / PT_HGRID; }
+
+template <bool TERMINAL, int PER>
 __global__ void __launch_bounds__(PT_THREADS) bucket_hist_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
                                                                  const uint32_t* __restrict__ hide, int64_t n_words, int64_t n_tiles,
-                                                                 int k, int n_buckets, unsigned long long* __restrict__ hist,
+                                                                 int k, int n_buckets, uint16_t* __restrict__ counts,
+                                                                 uint32_t* __restrict__ off, uint32_t* __restrict__ chunk_total,
                                                                  KmapTableSet tabs, int kmin) {
-    __shared__ uint32_t cnt[PT_MAX_BUCKETS];
+    __shared__ __align__(16) uint32_t cnt2[2][PT_MAX_BUCKETS];      // double buffer: one barrier per tile
     __shared__ uint32_t* stab[16];
     if (TERMINAL && threadIdx.x < 16) stab[threadIdx.x] = tabs.t[threadIdx.x];
-    for (int b = threadIdx.x; b < n_buckets; b += PT_THREADS) cnt[b] = 0;
+    for (int b = threadIdx.x; b < 2 * PT_MAX_BUCKETS; b += PT_THREADS) (&cnt2[0][0])[b] = 0;
     __syncthreads();
     const int sh = 32 - 2 * k;
-    RawWords nxt = load_raw_words(packed, valid, hide, n_words, blockIdx.x);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t t0 = chunk_first_tile(n_tiles, blockIdx.x), t1 = chunk_first_tile(n_tiles, blockIdx.x + 1);
+    const int b0 = PER * threadIdx.x;                              // this thread's buckets: b0 .. b0 + PER - 1
+    uint32_t run[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) run[j] = 0;
+    RawWords nxt = load_raw_words(packed, valid, hide, n_words, t0 < t1 ? t0 : n_tiles);
+    RawPrev nxt_prev;
+    nxt_prev.vp = nxt_prev.hp = nxt_prev.wp = 0;
+    if (TERMINAL) nxt_prev = load_raw_prev(packed, valid, hide, n_words, t0 < t1 ? t0 : n_tiles);
+    for (int64_t tile = t0; tile < t1; ++tile) {
+        uint32_t* cnt = cnt2[(tile - t0) & 1];
         const RawWords r = nxt;
-        nxt = load_raw_words(packed, valid, hide, n_words, tile + gridDim.x);      // (past the end: zeros)
+        const RawPrev rp = nxt_prev;
+        nxt = load_raw_words(packed, valid, hide, n_words, tile + 1 < t1 ? tile + 1 : n_tiles);      // (past the end: zeros)
+        if (TERMINAL) nxt_prev = load_raw_prev(packed, valid, hide, n_words, tile + 1 < t1 ? tile + 1 : n_tiles);
         tile_hist(cook(r, k), sh, cnt);
-        if (TERMINAL) {
-            run_end_corrections(packed, valid, hide, r, tile * PT_THREADS + threadIdx.x, kmin, k, stab);
+        if (TERMINAL) run_end_corrections(r, rp, kmin, k, stab);
+        __syncthreads();       // this tile's counts are complete; the other buffer was zeroed before the previous barrier
+        if (b0 < n_buckets) {
+            uint32_t c[PER];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) { c[j] = cnt[b0 + j]; cnt[b0 + j] = 0; }
+            uint16_t* crow = counts + (size_t)tile * n_buckets + b0;
+            uint32_t* orow = off + (size_t)tile * n_buckets + b0;
+            if (PER == 4) {
+                __stcs(reinterpret_cast<uint2*>(crow), make_uint2(c[0] | (c[1 % PER] << 16), c[2 % PER] | (c[3 % PER] << 16)));
+                __stcs(reinterpret_cast<uint4*>(orow), make_uint4(run[0], run[1 % PER], run[2 % PER], run[3 % PER]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < PER; ++j) { crow[j] = (uint16_t)c[j]; orow[j] = run[j]; }
+            }
+#pragma unroll
+            for (int j = 0; j < PER; ++j) run[j] += c[j];
         }
     }
-    __syncthreads();
-    for (int b = threadIdx.x; b < n_buckets; b += PT_THREADS)
-        if (cnt[b]) atomicAdd(hist + b, (unsigned long long)cnt[b]);
+    if (b0 < n_buckets) {
+#pragma unroll
+        for (int j = 0; j < PER; ++j) chunk_total[(size_t)blockIdx.x * n_buckets + b0 + j] = run[j];
+    }
 }
 
-// block-wide exclusive scan of one value per thread (PT_THREADS threads; two barriers inside)
+// block-wide exclusive scan of one value per thread (two barriers inside)
 template <typename T>
 __device__ __forceinline__ T block_scan_excl(T v, T* warp_sums) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -87,67 +126,135 @@ __device__ __forceinline__ T block_scan_excl(T v, T* warp_sums) {
     return warp_sums[w] + incl - v;
 }
 
-// exclusive scan of the bucket histogram (<= 4096 values, one block): base[0..n_buckets], cursor[b] = base[b]
-__global__ void __launch_bounds__(PT_THREADS) bucket_scan_kernel(const unsigned long long* __restrict__ hist, int n_buckets,
-                                                                 unsigned long long* __restrict__ base, unsigned long long* __restrict__ cursor) {
+// one block: base[b] = first entry of bucket b (base[n_buckets] = total),
+// chunk_base[h][b] = base[b] + what the ranges before h put into bucket b
+__global__ void __launch_bounds__(PT_THREADS) bucket_scan_kernel(const uint32_t* __restrict__ chunk_total, int n_buckets,
+                                                                 unsigned long long* __restrict__ base,
+                                                                 unsigned long long* __restrict__ chunk_base) {
     __shared__ unsigned long long warp_sums[32];
-    const int per = (n_buckets + PT_THREADS - 1) / PT_THREADS;
-    const int lo = threadIdx.x * per, hi = min(lo + per, n_buckets);
+    const int per = (n_buckets + PT_THREADS - 1) / PT_THREADS;       // <= PT_MAX_PER
+    const int lo = threadIdx.x * per;
+    unsigned long long tot[PT_MAX_PER];
     unsigned long long mine = 0;
-    for (int b = lo; b < hi; ++b) mine += hist[b];
+#pragma unroll
+    for (int j = 0; j < PT_MAX_PER; ++j) {
+        tot[j] = 0;
+        if (j < per && lo + j < n_buckets)
+            for (int h = 0; h < PT_HGRID; ++h) tot[j] += chunk_total[(size_t)h * n_buckets + lo + j];
+        mine += tot[j];
+    }
     unsigned long long run = block_scan_excl<unsigned long long>(mine, warp_sums);
     if (threadIdx.x == PT_THREADS - 1) base[n_buckets] = run + mine;
-    for (int b = lo; b < hi; ++b) { base[b] = run; cursor[b] = run; run += hist[b]; }
+#pragma unroll
+    for (int j = 0; j < PT_MAX_PER; ++j) {
+        if (j < per && lo + j < n_buckets) {
+            base[lo + j] = run;
+            unsigned long long r = run;
+            for (int h = 0; h < PT_HGRID; ++h) {
+                chunk_base[(size_t)h * n_buckets + lo + j] = r;
+                r += chunk_total[(size_t)h * n_buckets + lo + j];
+            }
+            run += tot[j];
+        }
+    }
 }
 
 // ---- 2. partition -------------------------------------------------------------------------------------------------------
-// Per tile: (a) histogram by bucket, (b) exclusive scan -> tile-local starts, (c) room in every non-empty bucket
-// reserved with one global atomic (all CTAs append to the same moving tail of a bucket, so the partial sectors of
-// neighbouring runs meet in L2), (d) scatter of the keys into bucket order in shared memory, (e) write-out: entry i of
-// the sorted tile goes to gdelta[bucket] + i, so consecutive lanes write consecutive addresses inside a run.
-// (Measured alternatives, 1e8 reads x 100 bp, k = 14: two resident CTAs of 512 threads with tiles of 16384 positions
-// take 66.6 ms against 40.1 ms -- the per-tile costs (scan over 4096 buckets, 4096 cursor atomics, barriers) double and
-// the runs get shorter; private per-CTA destination ranges without cursor atomics take 51 ms, see the file header.)
-// The tile loop is software-pipelined: the raw words of the next tile are in flight during the whole current tile, and
-// its histogram (fire-and-forget shared-memory atomics) is issued together with the latency-bound write-out.
+// Per tile: (b) exclusive scan of the tile's bucket counts (read from pass 1) -> tile-local starts, (d) counting-sort
+// scatter of the keys into bucket order in shared memory (one shared-memory atomic per window), (e) write-out: entry i of
+// the sorted tile goes to gdelta[bucket] + i, so consecutive lanes write consecutive addresses inside a run.  Tiles are
+// dealt round-robin, so the tiles in flight are neighbours and so are their runs in every bucket.  The raw words and the
+// count / offset rows of the next tile are requested a tile ahead.
+// (Measured alternatives, 1e8 reads x 100 bp, k = 14: a tile histogram inside this pass + one global cursor atomic per
+// (tile, bucket) 40.1 ms -- ncu: 3.3k shared-memory wavefronts for the histogram and 4.1k sectors of cursor atomics of
+// 25k LSU cycles per tile; two resident CTAs of 512 threads with tiles of 16384 positions 66.6 ms; private per-CTA
+// destination ranges 51 ms, see the file header.)
+template <int PER>
+struct TileRow { uint32_t c[PER]; uint32_t o[PER]; };
+
+template <int PER>
+__device__ __forceinline__ TileRow<PER> load_tile_row(const uint16_t* __restrict__ counts, const uint32_t* __restrict__ off,
+                                                     int64_t n_tiles, int64_t tile, int n_buckets) {
+    TileRow<PER> r;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) r.c[j] = r.o[j] = 0;
+    const int b0 = PER * threadIdx.x;
+    if (tile < n_tiles && b0 < n_buckets) {
+        const uint16_t* crow = counts + (size_t)tile * n_buckets + b0;
+        const uint32_t* orow = off + (size_t)tile * n_buckets + b0;
+        if (PER == 4) {
+            const uint2 c = __ldcs(reinterpret_cast<const uint2*>(crow));
+            const uint4 o = __ldcs(reinterpret_cast<const uint4*>(orow));
+            r.c[0] = c.x & 0xFFFFu; r.c[1] = c.x >> 16; r.c[2 % PER] = c.y & 0xFFFFu; r.c[3 % PER] = c.y >> 16;
+            r.o[0] = o.x; r.o[1 % PER] = o.y; r.o[2 % PER] = o.z; r.o[3 % PER] = o.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < PER; ++j) { r.c[j] = __ldcs(crow + j); r.o[j] = __ldcs(orow + j); }
+        }
+    }
+    return r;
+}
+
 template <int PER>       // buckets per thread in the scan step: n_buckets <= PER * PT_THREADS
 __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
                                                                   const uint32_t* __restrict__ hide, int64_t n_words, int64_t n_tiles,
-                                                                  int k, int n_buckets, unsigned long long* __restrict__ cursor,
-                                                                  uint16_t* __restrict__ suffixes) {
+                                                                  int k, int n_buckets, const uint16_t* __restrict__ counts,
+                                                                  const uint32_t* __restrict__ off_rows,
+                                                                  const unsigned long long* __restrict__ chunk_base,
+                                                                  uint16_t* __restrict__ suffixes, unsigned long long* __restrict__ ticket) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* sorted = reinterpret_cast<uint32_t*>(smem_raw);                                  // PT_TILE keys, grouped by bucket
     unsigned long long* gdelta = reinterpret_cast<unsigned long long*>(sorted + PT_TILE);     // global start - tile start, per bucket
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(gdelta + PER * PT_THREADS);                   // histogram of the coming tile
-    uint32_t* off = cnt + PER * PT_THREADS;                                                   // running tile offsets
+    uint32_t* off = reinterpret_cast<uint32_t*>(gdelta + PER * PT_THREADS);                   // running tile offsets
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t tile_total;
     const int sh = 32 - 2 * k;
-#pragma unroll
-    for (int j = 0; j < PER; ++j) cnt[PER * threadIdx.x + j] = 0;
+    const int b0 = PER * threadIdx.x;
+    // Tiles are handed out in order by an atomic ticket: the tiles in flight are then always the ~148 most recent ones,
+    // so a run written into a bucket gets its neighbours (the runs of the adjacent tiles) within a tile time and the
+    // partial lines complete in L2.  (A static round-robin lets the CTAs drift apart: 4x the DRAM writes, measured.)
+    __shared__ long long s_ticket[2];
+    if (threadIdx.x == 0) {
+        s_ticket[0] = (long long)atomicAdd(ticket, 1ull);
+        s_ticket[1] = (long long)atomicAdd(ticket, 1ull);
+    }
     __syncthreads();
-    TileWords cur = load_tile_words(packed, valid, hide, n_words, blockIdx.x, k);
-    RawWords raw = load_raw_words(packed, valid, hide, n_words, (int64_t)blockIdx.x + gridDim.x);
-    tile_hist(cur, sh, cnt);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        __syncthreads();                       // histogram of `cur` complete; write-out of the previous tile complete
+    int64_t tile = s_ticket[0], tile_next = s_ticket[1];
+    __syncthreads();
+    RawWords raw = load_raw_words(packed, valid, hide, n_words, tile);
+    TileRow<PER> row = load_tile_row<PER>(counts, off_rows, n_tiles, tile, n_buckets);
+    int h = -1;                                        // range of pass 1 that holds the current tile
+    unsigned long long cb[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) cb[j] = 0;
+    while (tile < n_tiles) {
+        if (threadIdx.x == 0) s_ticket[0] = (long long)atomicAdd(ticket, 1ull);       // the tile after the next one
+        const TileWords cur = cook(raw, k);
+        const TileRow<PER> tr = row;
+        raw = load_raw_words(packed, valid, hide, n_words, tile_next);
+        row = load_tile_row<PER>(counts, off_rows, n_tiles, tile_next, n_buckets);
+        int hh = (int)((tile * PT_HGRID) / n_tiles);
+        while (hh + 1 < PT_HGRID && chunk_first_tile(n_tiles, hh + 1) <= tile) ++hh;
+        while (hh > 0 && chunk_first_tile(n_tiles, hh) > tile) --hh;
+        if (hh != h) {                                 // (block-uniform) a new range: fetch its bucket bases
+            h = hh;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) cb[j] = b0 + j < n_buckets ? __ldg(chunk_base + (size_t)h * n_buckets + b0 + j) : 0ull;
+        }
         // (b) exclusive scan over the buckets; thread owns buckets [PER*tid, PER*tid + PER)
-        uint32_t c[PER], s[PER];
         uint32_t mine = 0;
 #pragma unroll
-        for (int j = 0; j < PER; ++j) { c[j] = cnt[PER * threadIdx.x + j]; cnt[PER * threadIdx.x + j] = 0; mine += c[j]; }
-        uint32_t run = block_scan_excl<uint32_t>(mine, warp_sums);
+        for (int j = 0; j < PER; ++j) mine += tr.c[j];
+        uint32_t run = block_scan_excl<uint32_t>(mine, warp_sums);   // (its barriers also fence the previous write-out)
+        const int64_t tile_after = s_ticket[0];                      // (thread 0 writes it again only after two more barriers)
         if (threadIdx.x == PT_THREADS - 1) tile_total = run + mine;
 #pragma unroll
-        for (int j = 0; j < PER; ++j) { s[j] = run; off[PER * threadIdx.x + j] = run; run += c[j]; }
-        __syncthreads();
-        // (c) reserve room in the global buckets (latency overlaps the shared-memory scatter below)
-        unsigned long long g[PER];
-#pragma unroll
         for (int j = 0; j < PER; ++j) {
-            g[j] = 0;
-            if (c[j]) g[j] = atomicAdd(cursor + PER * threadIdx.x + j, (unsigned long long)c[j]);
+            off[b0 + j] = run;
+            gdelta[b0 + j] = cb[j] + tr.o[j] - run;
+            run += tr.c[j];
         }
+        __syncthreads();
         // (d) scatter the keys into bucket order
         if (cur.fresh) {
 #pragma unroll
@@ -157,15 +264,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t
                     sorted[atomicAdd(&off[key >> 16], 1u)] = key;
                 }
         }
-#pragma unroll
-        for (int j = 0; j < PER; ++j) gdelta[PER * threadIdx.x + j] = g[j] - s[j];
-        // the next tile: its words arrived long ago; fetch the one after it
-        cur = cook(raw, k);
-        raw = load_raw_words(packed, valid, hide, n_words, tile + 2 * (int64_t)gridDim.x);
         __syncthreads();
         const uint32_t total = tile_total;
-        // (a) histogram of the next tile, then (e) write-out of this one
-        tile_hist(cur, sh, cnt);
+        // (e) write-out
         for (uint32_t i0 = threadIdx.x; i0 < total; i0 += PT_WU * PT_THREADS) {
             uint32_t key[PT_WU];
 #pragma unroll
@@ -182,6 +283,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t
                 if (i < total) suffixes[d[u] + i] = (uint16_t)key[u];
             }
         }
+        tile = tile_next;
+        tile_next = tile_after;
     }
 }
 
@@ -262,28 +365,47 @@ __global__ void __launch_bounds__(BC_THREADS, 1) bucket_count_kernel(const uint1
 }
 
 struct PartScratch {
-    unsigned long long *hist, *base, *cursor;
-    uint16_t* suffixes;
+    uint32_t* chunk_total;            // [PT_HGRID][n_buckets]
+    unsigned long long* base;         // [n_buckets + 1]
+    unsigned long long* chunk_base;   // [PT_HGRID][n_buckets]
+    uint16_t* counts;                 // [n_tiles][n_buckets]
+    uint32_t* off;                    // [n_tiles][n_buckets]
+    uint16_t* suffixes;               // one per counted window
+    unsigned long long* ticket;       // tile dispenser of the partition pass
 };
 
 static int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
-static PartScratch carve(void* scratch, int n_buckets) {
-    PartScratch p;
+static int64_t carve(void* scratch, int n_buckets, int64_t n, PartScratch* p) {
+    const int64_t n_words = (n + 31) / 32;
+    const int64_t n_tiles = (n_words + PT_THREADS - 1) / PT_THREADS;
     uint8_t* q = reinterpret_cast<uint8_t*>(scratch);
-    p.hist = reinterpret_cast<unsigned long long*>(q);
-    p.base = p.hist + n_buckets;
-    p.cursor = p.base + n_buckets + 1;
-    p.suffixes = reinterpret_cast<uint16_t*>(q + align_up((int64_t)(3 * n_buckets + 1) * 8, 256));
-    return p;
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) { uint8_t* r = q ? q + o : nullptr; o += align_up(bytes, 256); return r; };
+    uint8_t* a0 = take((int64_t)PT_HGRID * n_buckets * 4);
+    uint8_t* a1 = take((int64_t)(n_buckets + 1) * 8);
+    uint8_t* a2 = take((int64_t)PT_HGRID * n_buckets * 8);
+    uint8_t* a3 = take(n_tiles * n_buckets * 2);
+    uint8_t* a4 = take(n_tiles * n_buckets * 4);
+    uint8_t* a5 = take(2 * n);
+    uint8_t* a6 = take(8);
+    if (p) {
+        p->chunk_total = reinterpret_cast<uint32_t*>(a0);
+        p->base = reinterpret_cast<unsigned long long*>(a1);
+        p->chunk_base = reinterpret_cast<unsigned long long*>(a2);
+        p->counts = reinterpret_cast<uint16_t*>(a3);
+        p->off = reinterpret_cast<uint32_t*>(a4);
+        p->suffixes = reinterpret_cast<uint16_t*>(a5);
+        p->ticket = reinterpret_cast<unsigned long long*>(a6);
+    }
+    return o + 256;
 }
 
 }  // namespace
 
 extern "C" int64_t kmap_partition_scratch_bytes(int64_t n, int k) {
     if (k < 9 || k > 14 || n < 0) return 0;
-    const int n_buckets = 1 << (2 * (k - 8));
-    return align_up((int64_t)(3 * n_buckets + 1) * 8, 256) + align_up(2 * n, 256) + 256;
+    return carve(nullptr, 1 << (2 * (k - 8)), n, nullptr);
 }
 
 // table[h] = number of counted windows with key h, for every h (the slice of every bucket is overwritten or, where
@@ -292,21 +414,26 @@ extern "C" int64_t kmap_partition_scratch_bytes(int64_t n, int k) {
 int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const uint32_t* hide, int64_t n, int k, uint32_t* table,
                            void* scratch, const KmapTableSet* terminal_tabs, int kmin, void* const* step_events, cudaStream_t s) {
     const int n_buckets = 1 << (2 * (k - 8));
-    const PartScratch p = carve(scratch, n_buckets);
+    PartScratch p;
+    carve(scratch, n_buckets, n, &p);
     const int64_t n_words = (n + 31) / 32;
     const int64_t n_tiles = (n_words + PT_THREADS - 1) / PT_THREADS;
-    cudaError_t e = cudaMemsetAsync(p.hist, 0, (size_t)n_buckets * 8, s);
-    if (e != cudaSuccess) { kmap_set_error("count_partitioned: %s", cudaGetErrorString(e)); return (int)e; }
-    const unsigned int g1 = (unsigned int)(n_tiles < 148 * 2 ? n_tiles : 148 * 2);
-    if (terminal_tabs)
-        bucket_hist_kernel<true><<<g1, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.hist, *terminal_tabs, kmin);
-    else
-        bucket_hist_kernel<false><<<g1, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.hist, KmapTableSet(), k);
-    bucket_scan_kernel<<<1, PT_THREADS, 0, s>>>(p.hist, n_buckets, p.base, p.cursor);
+    const KmapTableSet none = KmapTableSet();
+    const KmapTableSet& tt = terminal_tabs ? *terminal_tabs : none;
+    const int km = terminal_tabs ? kmin : k;
+    if (n_buckets <= PT_THREADS) {
+        if (terminal_tabs) bucket_hist_kernel<true, 1><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.counts, p.off, p.chunk_total, tt, km);
+        else bucket_hist_kernel<false, 1><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.counts, p.off, p.chunk_total, tt, km);
+    } else {
+        if (terminal_tabs) bucket_hist_kernel<true, PT_MAX_PER><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.counts, p.off, p.chunk_total, tt, km);
+        else bucket_hist_kernel<false, PT_MAX_PER><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.counts, p.off, p.chunk_total, tt, km);
+    }
+    bucket_scan_kernel<<<1, PT_THREADS, 0, s>>>(p.chunk_total, n_buckets, p.base, p.chunk_base);
+    cudaMemsetAsync(p.ticket, 0, 8, s);
     if (step_events && step_events[0]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(step_events[0]), s);
     const unsigned int g2 = (unsigned int)(n_tiles < 148 ? n_tiles : 148);
     static bool attr_set = false;
-    const int smem1 = PT_TILE * 4 + 1 * PT_THREADS * 16, smem4 = PT_TILE * 4 + PT_MAX_PER * PT_THREADS * 16;
+    const int smem1 = PT_TILE * 4 + 1 * PT_THREADS * 12, smem4 = PT_TILE * 4 + PT_MAX_PER * PT_THREADS * 12;
     if (!attr_set) {
         cudaFuncSetAttribute(partition_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
         cudaFuncSetAttribute(partition_kernel<PT_MAX_PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4);
@@ -314,9 +441,9 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
         attr_set = true;
     }
     if (n_buckets <= PT_THREADS)
-        partition_kernel<1><<<g2, PT_THREADS, smem1, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.cursor, p.suffixes);
+        partition_kernel<1><<<g2, PT_THREADS, smem1, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.counts, p.off, p.chunk_base, p.suffixes, p.ticket);
     else
-        partition_kernel<PT_MAX_PER><<<g2, PT_THREADS, smem4, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.cursor, p.suffixes);
+        partition_kernel<PT_MAX_PER><<<g2, PT_THREADS, smem4, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.counts, p.off, p.chunk_base, p.suffixes, p.ticket);
     if (step_events && step_events[1]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(step_events[1]), s);
     const unsigned int g3 = (unsigned int)(n_buckets < 148 ? n_buckets : 148);
     bucket_count_kernel<<<g3, BC_THREADS, BC_WORDS * 4, s>>>(p.suffixes, p.base, n_buckets, table);

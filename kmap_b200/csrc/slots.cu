@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) slot_partition_kernel(const uin
                     else atomicAdd(table + key, 1u);                                // sector full: count it directly
                 }
         }
-        if (TERMINAL) run_end_corrections(packed, valid, hide, r, tile * SL_THREADS + threadIdx.x, kmin, k, stab);
+        if (TERMINAL) run_end_corrections(r, load_raw_prev(packed, valid, hide, n_words, tile), kmin, k, stab);
         __syncthreads();
         // write-out: 8192 x 16 bytes; lanes 2i, 2i+1 carry the two halves of one sector
         const uint4* st4 = reinterpret_cast<const uint4*>(stage);

@@ -56,19 +56,33 @@ __device__ __forceinline__ uint32_t key_at(const TileWords& t, int i, int sh) { 
 }
 
 
+// what run_end_corrections needs beyond RawWords: the validity / hidden bits of the 32 positions before this thread's
+// word and the packed word before its first one.  Loaded together with the tile (no dependent loads later).
+struct RawPrev { uint32_t vp, hp, wp; };
+
+__device__ __forceinline__ RawPrev load_raw_prev(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
+                                                 const uint32_t* __restrict__ hide, int64_t n_words, int64_t tile) {
+    RawPrev r;
+    r.vp = r.hp = r.wp = 0;
+    const int64_t w = tile * blockDim.x + threadIdx.x;
+    if (w < n_words && w > 0) {
+        r.vp = __ldcs(valid + w - 1);
+        if (hide) r.hp = __ldcs(hide + w - 1);
+        r.wp = __ldcs(packed + 2 * w - 1);
+    }
+    return r;
+}
+
 // "+1 at level v" for every window with exactly v valid bases (kmin <= v < k) in front of a run end inside this thread's
-// word w (bit j set, bit j+1 clear): such a window cannot be extended, so the 4:1 table reductions of the all-k count
+// word (bit j set, bit j+1 clear): such a window cannot be extended, so the 4:1 table reductions of the all-k count
 // (count_all.cu) do not bring it down from the level above.  Windows hidden in `hide` belong to reads that are counted
-// by the direct per-k kernels.  stab[v] = table of level v.
-__device__ __forceinline__ void run_end_corrections(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
-                                                    const uint32_t* __restrict__ hide, const RawWords& r, int64_t w, int kmin,
-                                                    int k, uint32_t* const* stab) {
+// by the direct per-k kernels.  stab[v] = table of level v.  Everything comes from registers: the only memory operations
+// are the REDs.
+__device__ __forceinline__ void run_end_corrections(const RawWords& r, const RawPrev& q, int kmin, int k, uint32_t* const* stab) {
     uint32_t ends = r.v0 & ~((r.v0 >> 1) | (r.v1 << 31));                  // bit j: position j valid, j+1 not
     if (ends == 0) return;
-    const uint32_t vp = w > 0 ? __ldg(valid + w - 1) : 0u;
-    const uint64_t W = ((uint64_t)r.v0 << 32) | vp;                        // position j of this word = bit 32 + j
-    uint64_t H = 0;
-    if (hide) H = ((uint64_t)r.h << 32) | (w > 0 ? __ldg(hide + w - 1) : 0u);
+    const uint64_t W = ((uint64_t)r.v0 << 32) | q.vp;                      // position j of this word = bit 32 + j
+    const uint64_t H = ((uint64_t)r.h << 32) | q.hp;
     do {
         const int j = __ffs(ends) - 1;
         ends &= ends - 1;
@@ -76,9 +90,13 @@ __device__ __forceinline__ void run_end_corrections(const uint32_t* __restrict__
         const int back = inv ? __clzll(inv) : 64;                          // valid bases ending at position j (>= 1)
         const int vmax = min(back, k - 1);
         if (vmax < kmin) continue;
-        // the windows of kmin..vmax bases that end at j start at j-v+1: one 32-base fetch covers them all
-        const int64_t p0 = w * 32 + j - vmax + 1;
-        const uint32_t hi = window16(packed, p0), lo = window16(packed, p0 + 16);
+        // the windows of kmin..vmax bases that end at j start at j-v+1 >= -14: 32 bases from offset o = 16 + j - vmax + 1 of
+        // the 64 bases [wp w0 w1 w2] cover them all
+        const int o = 17 + j - vmax;                                       // 2 .. 48
+        const uint32_t a = o < 16 ? q.wp : (o < 32 ? r.w0 : r.w1);
+        const uint32_t b = o < 16 ? r.w0 : (o < 32 ? r.w1 : r.w2);
+        const uint32_t c = o < 16 ? r.w1 : (o < 32 ? r.w2 : 0u);
+        const uint32_t hi = __funnelshift_l(b, a, 2 * (o & 15)), lo = __funnelshift_l(c, b, 2 * (o & 15));
         for (int v = vmax; v >= kmin; --v) {
             if ((H >> (33 + j - v)) & 1ull) continue;
             const uint32_t x = __funnelshift_l(lo, hi, 2 * (vmax - v));
