@@ -100,8 +100,8 @@ def launches_per_step(args, dedup):
     if args.algo != "allk":
         return KMAX - KMIN + 1
     derive = KMAX - KMIN
-    if args.partitions <= 0:                     # dedup_scan + hist + scan + partition + bucket_count + derive
-        return (1 if dedup else 0) + 4 + derive
+    if args.partitions <= 0:                     # dedup_scan + hist + 3 scan kernels + partition + bucket_count + derive
+        return (1 if dedup else 0) + 6 + derive
     return (1 if dedup else 0) + 5 + max(1, args.partitions) + derive      # + terminal-correction launches + prefix passes
 
 
@@ -291,9 +291,10 @@ def main():
         n_win = n_local * max(0, L - KMAX + 1)
         if partitioned:
             # dominant kernel: partition_kernel, one launch per step.  Algorithmic bytes of THIS launch: it reads the packed
-            # bases, the validity bits and (dedup mode) the hidden-window bits once and writes one 16-bit key suffix per
-            # counted k=14 window
-            in_b = (0.375 + (0.125 if dedup else 0.0)) * n_pos_local
+            # bases, the validity bits and (dedup mode) the hidden-window bits once, the per-tile bucket counts + offsets of
+            # pass 1 (6 B x 4096 buckets per tile of 32768 positions = 0.75 B per position) and writes one 16-bit key suffix
+            # per counted k=14 window
+            in_b = (0.375 + (0.125 if dedup else 0.0) + 0.75) * n_pos_local
             b_launch = in_b + 2.0 * n_win
             t_launch = ph_ms["partition"] * 1e-3
             kernel = "partition_kernel<4> (1 launch per step, k=14)"
@@ -322,8 +323,9 @@ def main():
                                    "algorithmic_bytes_per_step": alg_bytes, "achieved_GBs": alg_bytes / kern_s / 1e9,
                                    "frac": alg_bytes / kern_s / 1e9 / peak},
                     "frac_of_8TBs_nominal": achieved / 8000.0, "algo": "allk",
-                    "bound_note": "the level-14 count is bound by shared-memory atomic throughput (3 per window: bucket histogram, "
-                                  "tile scatter, bucket count), not by HBM: see DESIGN.md section 4.5"}
+                    "bound_note": "the level-14 count is bound by the shared-memory / LSU pipe (three shared-memory atomics per window "
+                                  "over the three launches, a random STS and 7 sectors per store request in the write-out), not "
+                                  "by HBM: see DESIGN.md section 4.5"}
     else:
         achieved = alg_bytes / kern_s / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

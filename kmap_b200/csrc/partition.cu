@@ -126,36 +126,39 @@ __device__ __forceinline__ T block_scan_excl(T v, T* warp_sums) {
     return warp_sums[w] + incl - v;
 }
 
-// one block: base[b] = first entry of bucket b (base[n_buckets] = total),
-// chunk_base[h][b] = base[b] + what the ranges before h put into bucket b
-__global__ void __launch_bounds__(PT_THREADS) bucket_scan_kernel(const uint32_t* __restrict__ chunk_total, int n_buckets,
-                                                                 unsigned long long* __restrict__ base,
-                                                                 unsigned long long* __restrict__ chunk_base) {
+// base[b] = first entry of bucket b (base[n_buckets] = total), chunk_base[h][b] = base[b] + what the ranges before h put
+// into bucket b.  Three small launches: column sums (one thread per bucket), a one-block scan of the totals, column
+// prefixes.
+__global__ void __launch_bounds__(256) bucket_total_kernel(const uint32_t* __restrict__ chunk_total, int n_buckets,
+                                                           unsigned long long* __restrict__ total) {
+    const int b = blockIdx.x * 256 + threadIdx.x;
+    if (b >= n_buckets) return;
+    unsigned long long t = 0;
+    for (int h = 0; h < PT_HGRID; ++h) t += chunk_total[(size_t)h * n_buckets + b];
+    total[b] = t;
+}
+
+__global__ void __launch_bounds__(PT_THREADS) bucket_scan_kernel(const unsigned long long* __restrict__ total, int n_buckets,
+                                                                 unsigned long long* __restrict__ base) {
     __shared__ unsigned long long warp_sums[32];
     const int per = (n_buckets + PT_THREADS - 1) / PT_THREADS;       // <= PT_MAX_PER
-    const int lo = threadIdx.x * per;
-    unsigned long long tot[PT_MAX_PER];
+    const int lo = threadIdx.x * per, hi = min(lo + per, n_buckets);
     unsigned long long mine = 0;
-#pragma unroll
-    for (int j = 0; j < PT_MAX_PER; ++j) {
-        tot[j] = 0;
-        if (j < per && lo + j < n_buckets)
-            for (int h = 0; h < PT_HGRID; ++h) tot[j] += chunk_total[(size_t)h * n_buckets + lo + j];
-        mine += tot[j];
-    }
+    for (int b = lo; b < hi; ++b) mine += total[b];
     unsigned long long run = block_scan_excl<unsigned long long>(mine, warp_sums);
     if (threadIdx.x == PT_THREADS - 1) base[n_buckets] = run + mine;
-#pragma unroll
-    for (int j = 0; j < PT_MAX_PER; ++j) {
-        if (j < per && lo + j < n_buckets) {
-            base[lo + j] = run;
-            unsigned long long r = run;
-            for (int h = 0; h < PT_HGRID; ++h) {
-                chunk_base[(size_t)h * n_buckets + lo + j] = r;
-                r += chunk_total[(size_t)h * n_buckets + lo + j];
-            }
-            run += tot[j];
-        }
+    for (int b = lo; b < hi; ++b) { base[b] = run; run += total[b]; }
+}
+
+__global__ void __launch_bounds__(256) chunk_base_kernel(const uint32_t* __restrict__ chunk_total, int n_buckets,
+                                                         const unsigned long long* __restrict__ base,
+                                                         unsigned long long* __restrict__ chunk_base) {
+    const int b = blockIdx.x * 256 + threadIdx.x;
+    if (b >= n_buckets) return;
+    unsigned long long r = base[b];
+    for (int h = 0; h < PT_HGRID; ++h) {
+        chunk_base[(size_t)h * n_buckets + b] = r;
+        r += chunk_total[(size_t)h * n_buckets + b];
     }
 }
 
@@ -372,6 +375,7 @@ struct PartScratch {
     uint32_t* off;                    // [n_tiles][n_buckets]
     uint16_t* suffixes;               // one per counted window
     unsigned long long* ticket;       // tile dispenser of the partition pass
+    unsigned long long* total;        // [n_buckets]
 };
 
 static int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -389,6 +393,7 @@ static int64_t carve(void* scratch, int n_buckets, int64_t n, PartScratch* p) {
     uint8_t* a4 = take(n_tiles * n_buckets * 4);
     uint8_t* a5 = take(2 * n);
     uint8_t* a6 = take(8);
+    uint8_t* a7 = take((int64_t)n_buckets * 8);
     if (p) {
         p->chunk_total = reinterpret_cast<uint32_t*>(a0);
         p->base = reinterpret_cast<unsigned long long*>(a1);
@@ -397,6 +402,7 @@ static int64_t carve(void* scratch, int n_buckets, int64_t n, PartScratch* p) {
         p->off = reinterpret_cast<uint32_t*>(a4);
         p->suffixes = reinterpret_cast<uint16_t*>(a5);
         p->ticket = reinterpret_cast<unsigned long long*>(a6);
+        p->total = reinterpret_cast<unsigned long long*>(a7);
     }
     return o + 256;
 }
@@ -428,7 +434,9 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
         if (terminal_tabs) bucket_hist_kernel<true, PT_MAX_PER><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.counts, p.off, p.chunk_total, tt, km);
         else bucket_hist_kernel<false, PT_MAX_PER><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.counts, p.off, p.chunk_total, tt, km);
     }
-    bucket_scan_kernel<<<1, PT_THREADS, 0, s>>>(p.chunk_total, n_buckets, p.base, p.chunk_base);
+    bucket_total_kernel<<<(n_buckets + 255) / 256, 256, 0, s>>>(p.chunk_total, n_buckets, p.total);
+    bucket_scan_kernel<<<1, PT_THREADS, 0, s>>>(p.total, n_buckets, p.base);
+    chunk_base_kernel<<<(n_buckets + 255) / 256, 256, 0, s>>>(p.chunk_total, n_buckets, p.base, p.chunk_base);
     cudaMemsetAsync(p.ticket, 0, 8, s);
     if (step_events && step_events[0]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(step_events[0]), s);
     const unsigned int g2 = (unsigned int)(n_tiles < 148 ? n_tiles : 148);
