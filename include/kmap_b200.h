@@ -201,6 +201,27 @@ int kmap_hamdist_matrix_u64(const uint64_t* kh, const int32_t* labels, int64_t n
 int kmap_exclusive_scan_u32(const uint32_t* in, int64_t n, int64_t* out, uint64_t* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * preproc ingest (csrc/fasta.cu): FASTA text -> the contents of input.bin.pkl / input.seqboarder.bin.pkl
+ * (kmer_count.py:244-263 dna2arr, 308-323 read_dnaseq_file, 326-347 convert_fasta_to_binary) on the device.
+ * The text (device bytes, 16-byte aligned, starting at the first header line) may be fed in chunks; `state` is a HOST
+ * int64[4] carried from chunk to chunk: {sequence characters so far, records so far, type of the line in progress
+ * (0 sequence line, 1 header line), last byte}; before the first chunk {0, 0, 0, 10}.
+ * kmap_fasta_scan : fills scratch = uint64[kmap_fasta_scratch_words(n)] and state_out_host.  Synchronises the stream.
+ * kmap_fasta_emit : writes the encoded bytes of the chunk (upper-cased; A0 C1 G2 T3, anything else 255; one 255 after
+ *                   every record) to seq_out[p - seq_origin] for their positions p in input.bin, and rec_start_out[j] =
+ *                   first position of the j-th record that begins in this chunk.  A chunk produces positions
+ *                   [in[0] + max(in[1]-1, 0), out[0] + out[1] - 1) plus, with final_chunk, the last separator.
+ * kmap_borders_from_starts : borders[r] = {start_r, start_{r+1} - 1} with start_{n_rec} = total_len, the
+ *                   [start, separator index] rows of input.seqboarder.bin (kmer_count.py:335-343).
+ * ---------------------------------------------------------------------------------------------------------- */
+int64_t kmap_fasta_scratch_words(int64_t n);
+int kmap_fasta_scan(const uint8_t* text, int64_t n, const int64_t* state_in_host, uint64_t* scratch, int64_t* state_out_host,
+                    void* stream);
+int kmap_fasta_emit(const uint8_t* text, int64_t n, const int64_t* state_in_host, const uint64_t* scratch, uint8_t* seq_out,
+                    int64_t seq_origin, int64_t* rec_start_out, int final_chunk, const int64_t* state_out_host, void* stream);
+int kmap_borders_from_starts(const int64_t* rec_start, int64_t n_rec, int64_t total_len, int64_t* borders, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * synthetic reads (bench / tests): counter-based generator, identical to kmap_b200/synth.py
  * seq = uint8[n_reads*(L+1)] in the input.bin layout, borders = int64[n_reads][2] (may be NULL)
  * ---------------------------------------------------------------------------------------------------------- */

@@ -1,0 +1,350 @@
+// preproc ingest: FASTA text -> input.bin / input.seqboarder.bin contents (kmer_count.py:244-263 dna2arr,
+// 308-323 read_dnaseq_file, 326-347 convert_fasta_to_binary) on the device.
+//
+// The reference walks the file twice through Bio.SeqIO and encodes base by base in a Python loop.  Here the file bytes
+// are parsed data-parallel.  What a byte becomes depends on the TYPE OF ITS LINE (header line = starts with '>', or
+// sequence line), i.e. on the most recent line start, which can be arbitrarily far back.  So:
+//   1. fasta_tile_summary_kernel   per tile of 4096 bytes: (type of the last line started in the tile or UNKNOWN, sequence
+//                                  characters on lines of known type SEQUENCE, characters on the line that was already in
+//                                  progress when the tile began, header lines started)
+//   2. fasta_tile_scan_kernel      one block: scan of the summaries under the (associative, non-commutative) operator `comb`
+//                                  -> per tile: type of the line in progress at its first byte, sequence characters and
+//                                  records before it
+//   3. fasta_emit_kernel           per tile again, now with everything known: every sequence character becomes its code
+//                                  (upper-cased; A0 C1 G2 T3, anything else 255), every header line start except the very
+//                                  first becomes the 255 separator that closes the previous record, and announces where its
+//                                  own record starts.  The tile's outputs are contiguous: staged in shared memory, written
+//                                  coalesced.
+// Text conventions (what the reference's text-mode file iteration + "".join(line.split()) amount to for ASCII input):
+// '\n' and '\r' both end a line; white space (9-13, 28-32) inside sequence lines is dropped; UTF-8 continuation bytes are
+// dropped so that one non-ASCII character gives one 255 as it does in text mode; text before the first header line is
+// ignored (the host passes the text from the first header on).
+// The text may be fed in chunks: the 4-value state {sequence characters so far, records so far, type of the line in
+// progress, last byte} carries over.
+#include "common.cuh"
+
+namespace {
+
+constexpr int FA_THREADS = 256;
+constexpr int FA_PER = 16;                          // bytes per thread: one 128-bit load
+constexpr int FA_TILE = FA_THREADS * FA_PER;
+enum : int { FA_SEQ = 0, FA_HDR = 1, FA_UNK = 2 };
+
+__device__ __forceinline__ bool fa_eol(uint32_t c) { return c == 10u || c == 13u; }
+// dropped from sequence lines: white space as str.split() sees it, and UTF-8 continuation bytes
+__device__ __forceinline__ bool fa_dropped(uint32_t c) { return (c >= 9u && c <= 13u) || (c >= 28u && c <= 32u) || (c & 0xC0u) == 0x80u; }
+__device__ __forceinline__ uint32_t fa_code(uint32_t c) {
+    c |= 0x20u;                                     // upper() (kmer_count.py:316), folded to lower case here
+    return c == 'a' ? 0u : c == 'c' ? 1u : c == 'g' ? 2u : c == 't' ? 3u : 255u;
+}
+
+struct ThreadBytes {
+    uint32_t w[4];        // the 16 bytes, byte j = (w[j >> 2] >> (8 * (j & 3))) & 255
+    uint32_t ls, hdr, ch; // bit j: byte j starts a line / starts a header line / is a character if its line is a sequence line
+    int n;                // bytes that exist (0..16)
+};
+__device__ __forceinline__ uint32_t byte_of(const ThreadBytes& t, int j) { return (t.w[j >> 2] >> (8 * (j & 3))) & 255u; }
+
+__device__ __forceinline__ ThreadBytes load_thread_bytes(const uint8_t* __restrict__ text, int64_t n, int64_t tile, uint32_t carry_last_byte) {
+    ThreadBytes t;
+    t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0;
+    t.ls = t.hdr = t.ch = 0;
+    const int64_t i0 = tile * FA_TILE + (int64_t)threadIdx.x * FA_PER;
+    t.n = (int)(n - i0 < 0 ? 0 : (n - i0 > FA_PER ? FA_PER : n - i0));
+    if (t.n == 0) return t;
+    if (t.n == FA_PER) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + i0));
+        t.w[0] = v.x; t.w[1] = v.y; t.w[2] = v.z; t.w[3] = v.w;
+    } else {
+        for (int j = 0; j < t.n; ++j) t.w[j >> 2] |= (uint32_t)__ldg(text + i0 + j) << (8 * (j & 3));
+    }
+    uint32_t prev = i0 > 0 ? (uint32_t)__ldg(text + i0 - 1) : carry_last_byte;
+#pragma unroll
+    for (int j = 0; j < FA_PER; ++j) {
+        if (j < t.n) {
+            const uint32_t c = byte_of(t, j);
+            if (fa_eol(prev)) { t.ls |= 1u << j; if (c == '>') t.hdr |= 1u << j; }
+            if (!fa_dropped(c)) t.ch |= 1u << j;
+            prev = c;
+        }
+    }
+    return t;
+}
+
+// what a thread's 16 bytes hold, by line type: characters on lines that begin inside the thread's bytes and are sequence
+// lines (known), characters on the line that was in progress at the thread's first byte (pending), the type of the last
+// line started (FA_UNK if none)
+struct ThreadCounts { uint32_t known_seq, pending; int last; };
+__device__ __forceinline__ ThreadCounts count_thread(const ThreadBytes& t) {
+    ThreadCounts c;
+    const uint32_t first_ls = t.ls ? (uint32_t)(__ffs(t.ls) - 1) : 32u;
+    const uint32_t before = first_ls >= 32u ? 0xFFFFFFFFu : ((1u << first_ls) - 1u);
+    c.pending = __popc(t.ch & before);
+    // a byte after the first line start belongs to a sequence line iff the latest line start at or before it is not a header
+    uint32_t seq_bytes = 0;
+    uint32_t ls = t.ls;
+    while (ls) {
+        const int j = __ffs(ls) - 1;
+        ls &= ls - 1;
+        const uint32_t upto = ls ? ((1u << (__ffs(ls) - 1)) - 1u) : 0xFFFFFFFFu;       // bytes before the next line start
+        const uint32_t span = upto & ~((1u << j) - 1u);
+        if (!((t.hdr >> j) & 1u)) seq_bytes |= span;
+    }
+    c.known_seq = __popc(t.ch & seq_bytes);
+    c.last = t.ls ? (((t.hdr >> (31 - __clz(t.ls))) & 1u) ? FA_HDR : FA_SEQ) : FA_UNK;
+    return c;
+}
+
+// type of the line in progress at this thread's first byte: the last line started by an earlier thread of the tile, else
+// `carry` (the tile's own incoming type; FA_UNK in pass 1).  *tile_last = the same for the byte after the tile.
+__device__ __forceinline__ int incoming_type(int last, int carry, int* warp_last, int* tile_last) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = last;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o && incl == FA_UNK) incl = y;
+    }
+    if (lane == 31) warp_last[w] = incl;
+    __syncthreads();
+    int pre = carry;
+    for (int q = 0; q < w; ++q) if (warp_last[q] != FA_UNK) pre = warp_last[q];
+    int excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+    if (lane == 0 || excl == FA_UNK) excl = pre;
+    int tl = carry;
+    for (int q = 0; q < FA_THREADS / 32; ++q) if (warp_last[q] != FA_UNK) tl = warp_last[q];
+    *tile_last = tl;
+    __syncthreads();
+    return excl;
+}
+
+__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* ws) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t t = 0;
+    for (int q = 0; q < FA_THREADS / 32; ++q) t += ws[q];
+    __syncthreads();
+    return t;
+}
+
+// ---- 1. per-tile summaries ---------------------------------------------------------------------------------------
+struct TileSummary { uint32_t last, known_seq, pending, n_hdr; };
+
+__global__ void __launch_bounds__(FA_THREADS) fasta_tile_summary_kernel(const uint8_t* __restrict__ text, int64_t n, uint32_t carry_last_byte,
+                                                                        TileSummary* __restrict__ summ) {
+    __shared__ int warp_last[FA_THREADS / 32];
+    __shared__ uint32_t ws[FA_THREADS / 32];
+    const ThreadBytes t = load_thread_bytes(text, n, blockIdx.x, carry_last_byte);
+    const ThreadCounts c = count_thread(t);
+    int tile_last;
+    const int in_type = incoming_type(c.last, FA_UNK, warp_last, &tile_last);
+    const uint32_t known = block_sum_u32(c.known_seq + (in_type == FA_SEQ ? c.pending : 0u), ws);
+    const uint32_t pending = block_sum_u32(in_type == FA_UNK ? c.pending : 0u, ws);
+    const uint32_t n_hdr = block_sum_u32(__popc(t.hdr), ws);
+    if (threadIdx.x == 0) {
+        TileSummary s;
+        s.last = (uint32_t)tile_last; s.known_seq = known; s.pending = pending; s.n_hdr = n_hdr;
+        summ[blockIdx.x] = s;
+    }
+}
+
+// ---- 2. scan of the summaries -----------------------------------------------------------------------------------------
+struct Span { int last; unsigned long long seq, pending, n_hdr; };
+__device__ __forceinline__ Span span_identity() { Span s; s.last = FA_UNK; s.seq = s.pending = s.n_hdr = 0; return s; }
+// the text of a followed by the text of b
+__device__ __forceinline__ Span comb(const Span& a, const Span& b) {
+    Span r;
+    r.last = b.last != FA_UNK ? b.last : a.last;
+    r.seq = a.seq + b.seq + (a.last == FA_SEQ ? b.pending : 0ull);
+    r.pending = a.pending + (a.last == FA_UNK ? b.pending : 0ull);
+    r.n_hdr = a.n_hdr + b.n_hdr;
+    return r;
+}
+__device__ __forceinline__ Span span_of(const TileSummary& t) {
+    Span s; s.last = (int)t.last; s.seq = t.known_seq; s.pending = t.pending; s.n_hdr = t.n_hdr; return s;
+}
+__device__ __forceinline__ Span shfl_up_span(const Span& s, int o) {
+    Span r;
+    r.last = __shfl_up_sync(0xFFFFFFFFu, s.last, o);
+    r.seq = __shfl_up_sync(0xFFFFFFFFu, s.seq, o);
+    r.pending = __shfl_up_sync(0xFFFFFFFFu, s.pending, o);
+    r.n_hdr = __shfl_up_sync(0xFFFFFFFFu, s.n_hdr, o);
+    return r;
+}
+
+struct TileStart { unsigned long long seq_and_type, n_hdr; };      // (sequence characters before the tile) << 2 | line type; records before
+
+constexpr int FS_THREADS = 1024;
+// totals[0..3] = sequence characters, records, type of the line in progress, last byte -- after this chunk (global counts)
+__global__ void __launch_bounds__(FS_THREADS) fasta_tile_scan_kernel(const TileSummary* __restrict__ summ, int64_t n_tiles,
+                                                                     const uint8_t* __restrict__ text, int64_t n,
+                                                                     unsigned long long seq0, unsigned long long hdr0, int type0,
+                                                                     uint32_t last_byte0, TileStart* __restrict__ starts,
+                                                                     unsigned long long* __restrict__ totals) {
+    __shared__ Span warp_tot[FS_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t per = (n_tiles + FS_THREADS - 1) / FS_THREADS;
+    const int64_t lo = (int64_t)threadIdx.x * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
+    Span mine = span_identity();
+    for (int64_t t = lo; t < hi; ++t) mine = comb(mine, span_of(summ[t]));
+    Span incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const Span y = shfl_up_span(incl, o);
+        if (lane >= o) incl = comb(y, incl);
+    }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    Span pre;                                       // everything before this thread's range, the carried state included
+    pre.last = type0; pre.seq = seq0; pre.pending = 0; pre.n_hdr = hdr0;
+    for (int q = 0; q < w; ++q) pre = comb(pre, warp_tot[q]);
+    Span excl = shfl_up_span(incl, 1);
+    if (lane == 0) excl = span_identity();
+    pre = comb(pre, excl);
+    for (int64_t t = lo; t < hi; ++t) {
+        TileStart ts;
+        ts.seq_and_type = (pre.seq << 2) | (unsigned long long)pre.last;
+        ts.n_hdr = pre.n_hdr;
+        starts[t] = ts;
+        pre = comb(pre, span_of(summ[t]));
+    }
+    if (threadIdx.x == FS_THREADS - 1) {            // its range is the last one (possibly empty): pre = the whole chunk
+        totals[0] = pre.seq; totals[1] = pre.n_hdr; totals[2] = (unsigned long long)pre.last;
+        totals[3] = n > 0 ? (unsigned long long)text[n - 1] : (unsigned long long)last_byte0;
+    }
+}
+
+// ---- 3. emit ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FA_THREADS) fasta_emit_kernel(const uint8_t* __restrict__ text, int64_t n, uint32_t carry_last_byte,
+                                                                const TileStart* __restrict__ starts, uint8_t* __restrict__ seq_out,
+                                                                long long seq_origin, long long* __restrict__ rec_start,
+                                                                unsigned long long hdr0) {
+    __shared__ int warp_last[FA_THREADS / 32];
+    __shared__ uint32_t wsum[FA_THREADS / 32];
+    __shared__ uint8_t stage[FA_TILE];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const ThreadBytes t = load_thread_bytes(text, n, blockIdx.x, carry_last_byte);
+    const ThreadCounts c = count_thread(t);
+    const TileStart ts = starts[blockIdx.x];
+    int tile_last;
+    const int in_type = incoming_type(c.last, (int)(ts.seq_and_type & 3ull), warp_last, &tile_last);
+    const uint32_t n_seq = c.known_seq + (in_type == FA_SEQ ? c.pending : 0u);
+    const uint32_t n_hdr = __popc(t.hdr);
+    // exclusive scan of (outputs, headers) per thread; both fit 16 bits (a tile has 4096 bytes)
+    const uint32_t v = (n_seq + n_hdr) | (n_hdr << 16);
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    uint32_t pre = 0, total = 0;
+    for (int q = 0; q < FA_THREADS / 32; ++q) { if (q < w) pre += wsum[q]; total += wsum[q]; }
+    const uint32_t excl = pre + incl - v;
+    uint32_t pos = excl & 0xFFFFu;                              // index among the tile's outputs
+    unsigned long long rec = ts.n_hdr + (excl >> 16);           // global index of the next record to start
+    // global position of the tile's output number i: first + i, where (sequence characters + separators) written before the
+    // tile = seq + max(records - 1, 0); the very first header of the file has no separator in front, its slot is position -1
+    const long long first = (long long)(ts.seq_and_type >> 2) + (long long)ts.n_hdr - 1;
+    int type = in_type;
+#pragma unroll
+    for (int j = 0; j < FA_PER; ++j) {
+        if (j < t.n) {
+            if ((t.ls >> j) & 1u) type = ((t.hdr >> j) & 1u) ? FA_HDR : FA_SEQ;
+            if ((t.hdr >> j) & 1u) {
+                stage[pos] = 255;                               // closes the previous record (kmer_count.py:261-262)
+                rec_start[rec - hdr0] = first + (long long)pos + 1;
+                ++pos; ++rec;
+            } else if (type == FA_SEQ && ((t.ch >> j) & 1u)) {
+                stage[pos++] = (uint8_t)fa_code(byte_of(t, j));
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t n_out = total & 0xFFFFu;
+    for (uint32_t i = threadIdx.x; i < n_out; i += FA_THREADS) {
+        const long long p = first + (long long)i;
+        if (p >= seq_origin && p >= 0) seq_out[p - seq_origin] = stage[i];
+    }
+}
+
+__global__ void fasta_final_separator_kernel(uint8_t* seq_out, long long index) { seq_out[index] = 255; }
+
+__global__ void __launch_bounds__(256) borders_from_starts_kernel(const long long* __restrict__ rec_start, int64_t n_rec, long long total_len,
+                                                                  long long* __restrict__ borders) {
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (r >= n_rec) return;
+    const long long st = rec_start[r];
+    const long long nx = r + 1 < n_rec ? rec_start[r + 1] : total_len;
+    borders[2 * r] = st;
+    borders[2 * r + 1] = nx - 1;                                // index of the record's separator (kmer_count.py:339-340)
+}
+
+static int64_t fa_tiles(int64_t n) { return (n + FA_TILE - 1) / FA_TILE; }
+
+}  // namespace
+
+extern "C" {
+
+int64_t kmap_fasta_scratch_words(int64_t n) { return n < 0 ? 0 : 4 + 4 * fa_tiles(n); }
+
+int kmap_fasta_scan(const uint8_t* text, int64_t n, const int64_t* state_in_host, uint64_t* scratch, int64_t* state_out_host, void* stream) {
+    KMAP_REQUIRE(n >= 0 && state_in_host && state_out_host && scratch, "bad argument");
+    KMAP_REQUIRE(n == 0 || text, "null pointer");
+    KMAP_REQUIRE((reinterpret_cast<uintptr_t>(text) & 15u) == 0, "text must be 16-byte aligned");
+    KMAP_REQUIRE(state_in_host[2] == FA_SEQ || state_in_host[2] == FA_HDR, "state: line type must be 0 or 1");
+    cudaStream_t s = as_stream(stream);
+    const int64_t n_tiles = fa_tiles(n);
+    unsigned long long* totals = reinterpret_cast<unsigned long long*>(scratch);
+    TileSummary* summ = reinterpret_cast<TileSummary*>(scratch + 4);
+    TileStart* starts = reinterpret_cast<TileStart*>(scratch + 4 + 2 * n_tiles);
+    if (n_tiles) fasta_tile_summary_kernel<<<(unsigned int)n_tiles, FA_THREADS, 0, s>>>(text, n, (uint32_t)state_in_host[3], summ);
+    fasta_tile_scan_kernel<<<1, FS_THREADS, 0, s>>>(summ, n_tiles, text, n, (unsigned long long)state_in_host[0],
+                                                    (unsigned long long)state_in_host[1], (int)state_in_host[2],
+                                                    (uint32_t)state_in_host[3], starts, totals);
+    int rc = kmap_check_launch("fasta_scan");
+    if (rc) return rc;
+    unsigned long long h[4];
+    cudaError_t e = cudaMemcpyAsync(h, totals, 32, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { kmap_set_error("fasta_scan: %s", cudaGetErrorString(e)); return (int)e; }
+    for (int i = 0; i < 4; ++i) state_out_host[i] = (int64_t)h[i];
+    return KMAP_OK;
+}
+
+int kmap_fasta_emit(const uint8_t* text, int64_t n, const int64_t* state_in_host, const uint64_t* scratch, uint8_t* seq_out,
+                    int64_t seq_origin, int64_t* rec_start_out, int final_chunk, const int64_t* state_out_host, void* stream) {
+    KMAP_REQUIRE(n >= 0 && state_in_host && state_out_host && scratch, "bad argument");
+    cudaStream_t s = as_stream(stream);
+    const int64_t n_tiles = fa_tiles(n);
+    const int64_t new_records = state_out_host[1] - state_in_host[1];
+    const int64_t outputs = (state_out_host[0] - state_in_host[0]) + new_records;
+    KMAP_REQUIRE(outputs == 0 || seq_out, "null pointer (seq_out)");
+    KMAP_REQUIRE(new_records == 0 || rec_start_out, "null pointer (rec_start_out)");
+    const TileStart* starts = reinterpret_cast<const TileStart*>(scratch + 4 + 2 * n_tiles);
+    if (n_tiles) {
+        fasta_emit_kernel<<<(unsigned int)n_tiles, FA_THREADS, 0, s>>>(text, n, (uint32_t)state_in_host[3], starts, seq_out, (long long)seq_origin,
+                                                                       reinterpret_cast<long long*>(rec_start_out),
+                                                                       (unsigned long long)state_in_host[1]);
+    }
+    if (final_chunk && state_out_host[1] > 0) {     // the separator of the last record
+        const long long last = state_out_host[0] + state_out_host[1] - 1;
+        fasta_final_separator_kernel<<<1, 1, 0, s>>>(seq_out, last - (long long)seq_origin);
+    }
+    return kmap_check_launch("fasta_emit");
+}
+
+int kmap_borders_from_starts(const int64_t* rec_start, int64_t n_rec, int64_t total_len, int64_t* borders, void* stream) {
+    KMAP_REQUIRE(n_rec >= 0, "bad argument");
+    if (n_rec == 0) return KMAP_OK;
+    KMAP_REQUIRE(rec_start && borders, "null pointer");
+    borders_from_starts_kernel<<<grid_for(n_rec, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(rec_start), n_rec,
+                                                                                   (long long)total_len, reinterpret_cast<long long*>(borders));
+    return kmap_check_launch("borders_from_starts");
+}
+
+}  // extern "C"

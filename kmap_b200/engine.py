@@ -150,6 +150,12 @@ class SeqOnDevice:
             borders = to_device(b.reshape(-1, 2))
         return cls.from_device_u8(to_device(seq_np_arr), borders, keep_u8)
 
+    @classmethod
+    def from_fasta(cls, fasta_file, keep_u8: bool = False) -> "SeqOnDevice":
+        """straight from the FASTA file: parsed, encoded and packed on the device, no host copy of input.bin"""
+        seq, borders = fasta_to_device(fasta_file)
+        return cls.from_device_u8(seq, borders, keep_u8)
+
     # ---- masking state ----------------------------------------------------------------------------------------
     def snapshot_valid(self):
         self._valid0 = self.valid.clone()
@@ -365,3 +371,71 @@ def occurrence_scan(seq: SeqOnDevice, k: int, conseq_kh: int, d: int, revcom: bo
                                      int(revcom), _ptr(min_dist), _ptr(offsets), _ptr(pos), _stream_ptr()),
               "kmap_occurrence_fill")
     return min_dist.cpu().numpy(), offsets.cpu().numpy(), pos.cpu().numpy()
+
+
+# ---- preproc ingest: FASTA text -> device-resident input.bin / input.seqboarder.bin contents --------------------------
+_FIRST_HEADER = None
+
+
+def read_fasta_bytes(fasta_file) -> np.ndarray:
+    """the file's bytes (gunzipped when the name ends in .gz, like kmer_count.py:318-323), from the first header line on"""
+    import gzip
+    import re
+    global _FIRST_HEADER
+    if _FIRST_HEADER is None:
+        _FIRST_HEADER = re.compile(rb"(?:\A|[\r\n])>")
+    if str(fasta_file).endswith(".gz"):
+        with gzip.open(fasta_file, "rb") as fh:
+            raw = np.frombuffer(bytearray(fh.read()), dtype=np.uint8)
+    else:
+        raw = np.fromfile(fasta_file, dtype=np.uint8)
+    m = _FIRST_HEADER.search(memoryview(raw))
+    if m is None:
+        return raw[:0]
+    return raw[m.end() - 1:]
+
+
+def fasta_text_to_device(text: np.ndarray, chunk_bytes: int = 1 << 28) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(seq uint8[n_pos], borders int64[n_seq, 2]) on the device from FASTA text that starts at its first header line
+    (csrc/fasta.cu; reference kmer_count.py:244-263, 326-347).  The text travels in chunks of `chunk_bytes`."""
+    L = lib()
+    dev = require_cuda()
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    n = len(text)
+    state = (ctypes.c_int64 * 4)(0, 0, 0, 10)
+    parts, starts = [], []
+    pos = 0
+    while True:
+        end = min(pos + max(int(chunk_bytes), 16), n)
+        final = end >= n
+        chunk = torch.from_numpy(text[pos:end]).to(dev) if end > pos else torch.empty(0, dtype=torch.uint8, device=dev)
+        nc = end - pos
+        scratch = empty(L.kmap_fasta_scratch_words(nc), torch.int64)
+        out = (ctypes.c_int64 * 4)()
+        check(L.kmap_fasta_scan(_ptr(chunk), nc, state, _ptr(scratch), out, _stream_ptr()), "kmap_fasta_scan")
+        new_rec = out[1] - state[1]
+        n_out = (out[0] - state[0]) + new_rec - (1 if state[1] == 0 and out[1] > 0 else 0) + (1 if final and out[1] > 0 else 0)
+        origin = state[0] + max(state[1] - 1, 0)
+        seq_part = empty(n_out, torch.uint8)
+        rec_start = empty(new_rec, torch.int64)
+        check(L.kmap_fasta_emit(_ptr(chunk), nc, state, _ptr(scratch), _ptr(seq_part), origin, _ptr(rec_start), int(final), out,
+                                _stream_ptr()), "kmap_fasta_emit")
+        parts.append(seq_part)
+        starts.append(rec_start)
+        state = out
+        pos = end
+        if final:
+            break
+    seq = parts[0] if len(parts) == 1 else torch.cat(parts)
+    rec_start = starts[0] if len(starts) == 1 else torch.cat(starts)
+    n_rec = int(state[1])
+    total = int(state[0]) + n_rec if n_rec else 0
+    if int(seq.numel()) != total or int(rec_start.numel()) != n_rec:
+        raise KmapError(f"fasta ingest: {seq.numel()} bytes / {rec_start.numel()} records emitted, {total} / {n_rec} expected")
+    borders = empty(2 * n_rec, torch.int64)
+    check(L.kmap_borders_from_starts(_ptr(rec_start), n_rec, total, _ptr(borders), _stream_ptr()), "kmap_borders_from_starts")
+    return seq, borders.view(n_rec, 2)
+
+
+def fasta_to_device(fasta_file, chunk_bytes: int = 1 << 28) -> Tuple[torch.Tensor, torch.Tensor]:
+    return fasta_text_to_device(read_fasta_bytes(fasta_file), chunk_bytes)

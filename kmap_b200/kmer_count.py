@@ -331,38 +331,11 @@ def gen_motif_def_dict(config_dict: dict, debug=False) -> Dict:
 
 
 # ---- preproc: FASTA -> input.bin.pkl / input.seqboarder.bin.pkl (:139-347) -----------------------------------------
-def read_fasta_records(file_name):
-    """(name, sequence) per FASTA record, as Bio.SeqIO.parse yields them for plain or gzipped FASTA (:308-323)."""
-    import gzip
-    opener = gzip.open if str(file_name).endswith(".gz") else open
-    name, parts = None, []
-    with opener(file_name, "rt") as fh:
-        for line in fh:
-            line = line.rstrip("\r\n")
-            if line.startswith(">"):
-                if name is not None:
-                    yield name, "".join(parts)
-                name, parts = (line[1:].split() or [""])[0], []
-            elif name is not None:
-                parts.append("".join(line.split()))
-    if name is not None:
-        yield name, "".join(parts)
-
-
 def fasta_to_arrays(fasta_file) -> Tuple[np.ndarray, np.ndarray]:
-    """the two arrays preproc pickles (:326-347): uint8 codes with a 255 after every read; int borders [start, separator]"""
-    chunks, lens = [], []
-    for _, s in read_fasta_records(fasta_file):
-        a = dna2arr(s.upper())
-        chunks.append(a)
-        lens.append(len(a))
-    lens = np.asarray(lens, dtype=np.int64)
-    ends = np.cumsum(lens)
-    borders = np.zeros((len(lens), 2), dtype=int)
-    borders[:, 0] = ends - lens
-    borders[:, 1] = ends - 1
-    seq = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.uint8)
-    return seq, borders
+    """the two arrays preproc pickles (:326-347): uint8 codes with a 255 after every read; int borders [start, separator].
+    Parsed and encoded on the device (csrc/fasta.cu) instead of two Bio.SeqIO passes with a per-base Python loop."""
+    seq, borders = E.fasta_to_device(fasta_file)
+    return E.to_host(seq, np.uint8), E.to_host(borders, np.int64).reshape(-1, 2).astype(int, copy=False)
 
 
 def proc_input(input_fasta_file: str, res_dir=".", out_bin_file_name: str = "input.bin.pkl",

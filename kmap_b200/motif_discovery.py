@@ -18,7 +18,7 @@ import torch
 from . import engine as E
 from ._lib import KmapError, check, lib
 from .kmer_count import (FileNameDict, MotifDef, cal_hamming_dist, cal_hamming_dist_head, cal_hamming_dist_tail,
-                         dna2arr, fasta_to_arrays, gen_motif_def_dict, get_hash_dtype, get_revcom_hash_arr, hash2kmer,
+                         dna2arr, gen_motif_def_dict, get_hash_dtype, get_revcom_hash_arr, hash2kmer,
                          init_motif_def_dict, kmer2hash, mask_ham_ball, reverse_complement, revcom_hash)
 
 
@@ -274,8 +274,8 @@ def gen_motif_occurence_file(conseq_list: List[str], motif_def_dict: dict, input
     if _dev_cache is not None:
         dev, borders = _dev_cache
     else:
-        seq, borders = fasta_to_arrays(input_fasta_file)
-        dev = E.SeqOnDevice.from_numpy(seq, borders)
+        dev = E.SeqOnDevice.from_fasta(input_fasta_file)
+        borders = E.to_host(dev.borders, np.int64).reshape(-1, 2)
     write_lines(motif_occurence_lines(dev, borders, conseq_list, motif_def_dict, revcom_mode), output_file)
 
 
@@ -493,8 +493,8 @@ def _scan_motif(res_dir: str, debug=False):
         nonlocal occ_dev
         if occ_dev is None:
             assert input_fasta_file.exists()
-            fa_seq, fa_borders = fasta_to_arrays(input_fasta_file)
-            occ_dev = (E.SeqOnDevice.from_numpy(fa_seq, fa_borders), fa_borders)
+            fa_dev = E.SeqOnDevice.from_fasta(input_fasta_file)       # parsed on the device, never copied back
+            occ_dev = (fa_dev, E.to_host(fa_dev.borders, np.int64).reshape(-1, 2))
         return occ_dev
 
     candidate_conseq_file = res / FileNameDict["candidate_conseq_file"]

@@ -424,3 +424,73 @@ def test_streamed_count_kmers_equals_single_upload(ENG):
         want = O.merge_revcom(*O.count_uniq_hash(O.comp_kmer_hash(seq, 11) if rep_mode else
                                                  O.remove_duplicate_hash_per_seq(O.comp_kmer_hash(seq, 11), borders, np.uint32(0xFFFFFFFF)), 11), 11)
         assert np.array_equal(many[11][0], want[0]) and np.array_equal(many[11][1], want[1])
+
+
+# ---- preproc ingest (csrc/fasta.cu) -------------------------------------------------------------------------------------
+def _random_fasta_text(rng, n_rec, max_lines, max_len, alphabet="ACGTacgtNn >\t x-"):
+    parts = []
+    if rng.random() < 0.3:
+        parts.append(["junk before the first header\n", "\n\n", "ACGT\r\n", " "][int(rng.integers(0, 4))])
+    eols = ["\n", "\r\n", "\r", "\n\n", ""]
+    for _ in range(n_rec):
+        parts.append(">" + "".join(rng.choice(list("abc >x\t"), int(rng.integers(0, 12)))) + eols[int(rng.integers(0, 3))])
+        for _ in range(int(rng.integers(0, max_lines + 1))):
+            parts.append("".join(rng.choice(list(alphabet), int(rng.integers(0, max_len + 1)))) + eols[int(rng.integers(0, 5))])
+    txt = "".join(parts)
+    return txt.rstrip("\r\n") if rng.random() < 0.3 else txt
+
+
+def test_fasta_ingest_matches_oracle(ENG, K, testfa, tmp_path):
+    """FASTA text -> input.bin / input.seqboarder.bin on the device == the oracle's restatement of kmer_count.py:244-347:
+    CRLF / CR line ends, blank lines, lower case, N and other letters, white space inside lines, empty records, '>' inside a
+    sequence line, no trailing newline, text before the first header; lines and records that straddle tiles and chunks."""
+    rng = np.random.default_rng(77)
+    cases = [b"", b"no header at all\nACGT\n", b">", b">\n", b">a", b">a\n\n>b\n>c\nAC", b">r\nACGT", b"\n>r\r\nac gt\r\nNN\r\n",
+             b">x\n" + b"ACGT" * 3000 + b"\n>y\n" + b"T" * 5000, b">" + b"h" * 9000 + b"\nGATTACA\n"]
+    cases += [_random_fasta_text(rng, int(rng.integers(0, 8)), 4, 14).encode() for _ in range(150)]
+    cases += [_random_fasta_text(rng, int(rng.integers(50, 400)), 3, 300).encode() for _ in range(6)]
+    for i, raw in enumerate(cases):
+        fa = tmp_path / f"c{i}.fa"
+        fa.write_bytes(raw)
+        want_seq, want_b = O.fasta_to_binary(fa)
+        text = ENG.read_fasta_bytes(fa)
+        for chunk in (1 << 28, 16, 4096 + 16, 7 * 16):
+            if chunk < 4096 and len(raw) > 20000:
+                continue
+            seq_d, b_d = ENG.fasta_text_to_device(text, chunk_bytes=chunk)
+            assert np.array_equal(seq_d.cpu().numpy(), want_seq), (i, chunk)
+            assert np.array_equal(b_d.cpu().numpy(), np.asarray(want_b, dtype=np.int64).reshape(-1, 2)), (i, chunk)
+    # test.fa itself (rebuilt from the golden arrays, 60 bases per line) and its gzipped copy, through the public function
+    seq, borders = testfa["input_bin"], testfa["borders"]
+    lines = []
+    for r, (st, en) in enumerate(borders):
+        s = K.arr2dna(seq[st:en])
+        lines.append(f">read{r} some description")
+        lines.extend(s[j:j + 60] for j in range(0, len(s), 60))
+    fa = tmp_path / "test.fa"
+    fa.write_text("\n".join(lines) + "\n")
+    import gzip
+    with gzip.open(tmp_path / "test.fa.gz", "wb") as fh:
+        fh.write(fa.read_bytes())
+    for f in (fa, tmp_path / "test.fa.gz"):
+        got_seq, got_b = K.fasta_to_arrays(str(f))
+        assert np.array_equal(got_seq, seq) and np.array_equal(got_b, borders) and got_b.dtype == borders.dtype
+    dev = ENG.SeqOnDevice.from_fasta(fa)
+    ref = ENG.SeqOnDevice.from_numpy(seq, borders)
+    assert dev.n == ref.n and dev.n_seq == ref.n_seq
+    assert np.array_equal(dev.packed.cpu().numpy(), ref.packed.cpu().numpy()) and np.array_equal(dev.valid.cpu().numpy(), ref.valid.cpu().numpy())
+
+
+def test_fasta_ingest_large_synthetic(ENG):
+    """2e5 synthetic reads written as FASTA text: the device parse gives back exactly the arrays the text was made from"""
+    from kmap_b200 import synth
+    seq, borders = synth.generate_numpy(synth.CFG2, 0, 200000)
+    L = int(borders[0, 1] - borders[0, 0])
+    body = np.frombuffer(b"ACGT", dtype=np.uint8)[np.minimum(seq.reshape(-1, L + 1)[:, :L], 3)]
+    body = np.where(seq.reshape(-1, L + 1)[:, :L] == 255, ord("N"), body).astype(np.uint8)
+    rec = np.concatenate([np.full((len(body), 1), ord(">"), np.uint8), np.full((len(body), 1), ord("r"), np.uint8),
+                          np.full((len(body), 1), 10, np.uint8), body, np.full((len(body), 1), 10, np.uint8)], axis=1)
+    text = rec.reshape(-1)
+    for chunk in (1 << 28, 1 << 20):
+        seq_d, b_d = ENG.fasta_text_to_device(text, chunk_bytes=chunk)
+        assert np.array_equal(seq_d.cpu().numpy(), seq) and np.array_equal(b_d.cpu().numpy(), borders)
