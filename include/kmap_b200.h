@@ -201,6 +201,44 @@ int kmap_hamdist_matrix_u64(const uint64_t* kh, const int32_t* labels, int64_t n
 int kmap_exclusive_scan_u32(const uint32_t* in, int64_t n, int64_t* out, uint64_t* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * sort / run-length counting path (csrc/sorted.cu): the same pipeline for k-mers without a dense table
+ * (16 <= k <= 31: uint64 hashes, int64 counts, kmer_count.py:351-365; any 1 <= k <= 31 is accepted so that the
+ * two paths can be measured against each other).  It follows the reference's own flow: one hash per position ->
+ * per-read de-duplication in place -> np.unique.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* comp_kmer_hash_taichi (kmer_count.py:449-473) from the packed reads: keys[p] = hash of the window at p, all-ones when
+ * the window leaves the array or touches a 255 */
+int kmap_window_keys_u64(const uint32_t* packed, const uint32_t* valid, int64_t n, int k, uint64_t* keys, void* stream);
+/* remove_duplicate_hash_per_seq (kmer_count.py:743-760) on a uint64 hash array, in place: later occurrences of a hash
+ * inside a read become all-ones.  work = uint32[kmap_dedup_keys_work_words(n_seq)] scratch. */
+int kmap_dedup_hash_per_read_u64(uint64_t* hash, int64_t n, const int64_t* borders, int64_t n_seq, uint32_t* work, void* stream);
+int64_t kmap_dedup_keys_work_words(int64_t n_seq);
+/* count_uniq_hash (kmer_count.py:476-491), step 1: LSD radix sort of the low key_bits bits, 8 bits per pass; all-ones
+ * keys are dropped by the first pass.  On return keys[0 .. *n_valid_host) is ascending; *n_unique_host = number of
+ * distinct keys.  tmp = uint64[n]; scratch = uint64[kmap_sort_scratch_words(n)].  Synchronises the stream. */
+int kmap_sort_keys_u64(uint64_t* keys, uint64_t* tmp, int64_t n, int key_bits, uint64_t* scratch, int64_t* n_valid_host,
+                       int64_t* n_unique_host, void* stream);
+int64_t kmap_sort_scratch_words(int64_t n);
+/* step 2: run-length encoding of n sorted keys: kh_out = distinct keys ascending, cnt_out = their multiplicities
+ * (capacity >= the number of distinct keys).  scratch as above, pos_scratch = int64[capacity].  Synchronises. */
+int kmap_rle_u64(const uint64_t* sorted_keys, int64_t n, uint64_t* scratch, int64_t* pos_scratch, uint64_t* kh_out,
+                 int64_t* cnt_out, int64_t capacity, void* stream);
+/* merge_revcom (kmer_count.py:643-685) on an ASCENDING unique list: survivors in list order, value min(h, rc h), count
+ * cnt[h] + cnt[rc h] (a palindrome is its own partner: doubled).  Two-step like kmap_compact_merge (capacity 0 = size
+ * query).  summed_cnt (may be NULL, must not alias cnt) = int64[n]: cnt[i] + cnt[partner of i] for every i, what the
+ * reference leaves in the caller's count array (kmer_count.py:661).
+ * scratch = uint64[kmap_merge_sorted_scratch_words(n)].  Synchronises. */
+int kmap_merge_revcom_sorted_u64(const uint64_t* kh, const int64_t* cnt, int64_t n, int k, uint64_t* scratch, uint64_t* kh_out,
+                                 int64_t* cnt_out, int64_t capacity, int64_t* n_out_host, int64_t* summed_cnt, void* stream);
+int64_t kmap_merge_sorted_scratch_words(int64_t n);
+/* kmap_hamball_sum_list / kmap_hamball_extract for uint64 hashes and int64 counts (k <= 31) */
+int kmap_hamball_sum_list_u64(const uint64_t* kh, const int64_t* cnt, int64_t n, int k, const uint64_t* cand, int m, int d,
+                              int revcom, uint64_t* sums, void* stream);
+int kmap_hamball_extract_u64(const uint64_t* kh, const int64_t* cnt, int64_t n, int k, uint64_t conseq, int d, int revcom,
+                             uint64_t* scratch, uint64_t* kh_out, int64_t* cnt_out, int64_t capacity, int64_t* n_out_host,
+                             int64_t* cnt_mat, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * preproc ingest (csrc/fasta.cu): FASTA text -> the contents of input.bin.pkl / input.seqboarder.bin.pkl
  * (kmer_count.py:244-263 dna2arr, 308-323 read_dnaseq_file, 326-347 convert_fasta_to_binary) on the device.
  * The text (device bytes, 16-byte aligned, starting at the first header line) may be fed in chunks; `state` is a HOST

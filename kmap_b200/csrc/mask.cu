@@ -226,7 +226,7 @@ extern "C" {
 
 int kmap_mask(const uint32_t* packed, const uint32_t* valid_pre, uint32_t* valid, int64_t n, int k, const uint32_t* cons,
               const int32_t* d, int m, uint32_t* flag_scratch, void* stream) {
-    KMAP_REQUIRE(n >= 0 && k >= 1 && k <= 15 && m >= 0 && m <= MK_MAXM, "bad argument (k <= 15, m <= 16)");
+    KMAP_REQUIRE(n >= 0 && k >= 1 && k <= 16 && m >= 0 && m <= MK_MAXM, "bad argument (k <= 16, m <= 16)");
     if (n == 0 || m == 0) return KMAP_OK;
     KMAP_REQUIRE(packed && valid_pre && valid && cons && d && flag_scratch, "null pointer");
     cudaStream_t s = as_stream(stream);
@@ -244,7 +244,7 @@ static unsigned int occurrence_grid(int64_t n_seq) {
 
 int kmap_occurrence_count(const uint32_t* packed, const uint32_t* valid, const int64_t* borders, int64_t n_seq, int k,
                           uint32_t conseq, int d, int revcom, uint8_t* min_dist, uint32_t* n_hit, void* stream) {
-    KMAP_REQUIRE(n_seq >= 0 && k >= 1 && k <= 15, "bad argument");
+    KMAP_REQUIRE(n_seq >= 0 && k >= 1 && k <= 16, "bad argument (k <= 16)");
     if (n_seq == 0) return KMAP_OK;
     KMAP_REQUIRE(packed && valid && borders && min_dist && n_hit, "null pointer");
     occurrence_kernel<false><<<occurrence_grid(n_seq), MK_BLOCK, 0, as_stream(stream)>>>(
@@ -255,7 +255,7 @@ int kmap_occurrence_count(const uint32_t* packed, const uint32_t* valid, const i
 int kmap_occurrence_fill(const uint32_t* packed, const uint32_t* valid, const int64_t* borders, int64_t n_seq, int k,
                          uint32_t conseq, int d, int revcom, const uint8_t* min_dist, const int64_t* offsets, int32_t* pos_out,
                          void* stream) {
-    KMAP_REQUIRE(n_seq >= 0 && k >= 1 && k <= 15, "bad argument");
+    KMAP_REQUIRE(n_seq >= 0 && k >= 1 && k <= 16, "bad argument (k <= 16)");
     if (n_seq == 0) return KMAP_OK;
     KMAP_REQUIRE(packed && valid && borders && min_dist && offsets && pos_out, "null pointer");
     occurrence_kernel<true><<<occurrence_grid(n_seq), MK_BLOCK, 0, as_stream(stream)>>>(

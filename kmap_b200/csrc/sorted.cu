@@ -1,0 +1,705 @@
+// The sort / run-length counting path: comp_kmer_hash_taichi + remove_duplicate_hash_per_seq + count_uniq_hash +
+// merge_revcom (kmer_count.py:449-491, 643-685, 743-760) for k-mers whose dense 4^k table is out of reach
+// (16 <= k <= 31: uint64 hashes, int64 counts, kmer_count.py:351-365), and the list-based Hamming-ball kernels of
+// find_motif / ex_hamball for those hashes (motif_discovery.py:666-673, 959-986).
+//
+// It follows the reference's own data flow -- one hash per position, duplicates inside a read turned into the invalid
+// hash, np.unique -- with every step on the device:
+//   window_keys_kernel          one 64-bit key per position from the packed reads (all-ones = invalid: the window leaves
+//                               the array or touches a 255), coalesced 8-byte stores
+//   dedup_keys_warp_kernel      one warp = one read (<= 256 windows): first occurrences win a slot of a per-warp
+//                               shared-memory set, later ones become invalid; longer reads go to the multi-pass block
+//                               kernel (dedup_keys_block_kernel), any length
+//   LSD radix sort              8 bits per pass, ceil(2k / 8) passes: per-tile digit histogram -> per-digit scan over the
+//                               tiles -> stable scatter (ranks inside a tile from __match_any_sync).  The first pass drops
+//                               the invalid keys, so the later ones only move real k-mers.
+//   run-length encoding         heads of runs -> unique keys (ascending, like np.unique) and run lengths
+//   merge_revcom                partner = binary search of rc(h) in the sorted list; survivors keep the list order, value
+//                               min(h, rc h), a palindrome is its own partner (count doubled) -- SURVEY Q6
+#include "common.cuh"
+#include "tile.cuh"
+
+namespace {
+
+constexpr unsigned long long KEY_EMPTY = ~0ull;
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 mix64(u64 z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// 32 bases starting at position p, first base in the most significant bits
+__device__ __forceinline__ u64 window32(const uint32_t* __restrict__ packed, int64_t p) {
+    const int64_t w = p >> 4;
+    const uint32_t s = ((uint32_t)p & 15u) * 2u;
+    const uint32_t a = __ldg(packed + w), b = __ldg(packed + w + 1), c = __ldg(packed + w + 2);
+    return ((u64)__funnelshift_l(b, a, s) << 32) | __funnelshift_l(c, b, s);
+}
+
+// ---- keys -----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) window_keys_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
+                                                          int64_t n, int k, u64* __restrict__ keys) {
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (p >= n) return;
+    u64 key = KEY_EMPTY;
+    if (window_ok(valid, p, k)) key = window32(packed, p) >> (64 - 2 * k);      // (the zero padding makes windows past n invalid)
+    keys[p] = key;
+}
+
+// ---- per-read de-duplication of a key / hash array ---------------------------------------------------------------------
+constexpr int DW_WARPS = 8;
+constexpr int DW_SLOTS = 512;                    // per warp
+constexpr int DW_MAX = 256;                      // positions a warp handles (load factor <= 0.5)
+
+// reads of at most DW_MAX positions; the others are listed in long_ids (count in *n_long)
+template <typename H>
+__global__ void __launch_bounds__(DW_WARPS * 32) dedup_keys_warp_kernel(H* __restrict__ keys, int64_t n, const int64_t* __restrict__ borders,
+                                                                        int64_t n_seq, uint32_t* __restrict__ n_long,
+                                                                        uint32_t* __restrict__ long_ids) {
+    __shared__ H sets[DW_WARPS][DW_SLOTS];
+    const H empty = (H)~(H)0;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    H* set = sets[wib];
+    const int64_t n_warps = (int64_t)gridDim.x * DW_WARPS;
+    for (int64_t r = (int64_t)blockIdx.x * DW_WARPS + wib; r < n_seq; r += n_warps) {
+        int64_t st = __ldg(borders + 2 * r), en = __ldg(borders + 2 * r + 1);
+        if (st < 0) st = 0;
+        if (en > n) en = n;
+        const int64_t len = en - st;
+        if (len <= 1) continue;
+        if (len > DW_MAX) {
+            if (lane == 0) long_ids[atomicAdd(n_long, 1u)] = (uint32_t)r;
+            continue;
+        }
+        for (int j = lane; j < DW_SLOTS; j += 32) set[j] = empty;
+        __syncwarp();
+        for (int64_t i0 = 0; i0 < len; i0 += 32) {
+            const int64_t i = i0 + lane;
+            H h = empty;
+            if (i < len) h = keys[st + i];
+            const bool live = h != empty;
+            // one lane per distinct key of this round: the lowest one (it is the first occurrence inside the round)
+            const H probe = live ? h : (H)(((H)1 << (8 * sizeof(H) - 1)) | (H)lane);     // distinct non-keys for idle lanes (keys have < 64 bits)
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, probe);
+            const bool leader = live && (peers & ((1u << lane) - 1u)) == 0;
+            bool dup = live && !leader;
+            if (leader) {
+                uint32_t slot = (uint32_t)mix64((u64)h) & (DW_SLOTS - 1);
+                while (true) {
+                    const H cur = reinterpret_cast<volatile H*>(set)[slot];      // only leaders of distinct keys write in this round
+                    if (cur == h) { dup = true; break; }      // seen in an earlier round
+                    if (cur == empty) {
+                        const H old = atomicCAS(&set[slot], empty, h);
+                        if (old == empty) break;             // claimed
+                        if (old == h) { dup = true; break; }
+                    }
+                    slot = (slot + 1) & (DW_SLOTS - 1);
+                }
+            }
+            if (dup) keys[st + i] = empty;
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+}
+
+// any length: one block per listed read (or per read when ids == NULL); the set lives in shared memory and the read is
+// taken in n_pass passes, pass p owning the keys with mix(h) % n_pass == p.  Keeps the FIRST occurrence
+// (kmer_count.py:755-759: np.unique(return_index)).
+constexpr int DB_SLOTS = 4096;
+template <typename H>
+__global__ void __launch_bounds__(256) dedup_keys_block_kernel(H* __restrict__ keys, int64_t n, const int64_t* __restrict__ borders,
+                                                               int64_t n_seq, const uint32_t* __restrict__ ids,
+                                                               const uint32_t* __restrict__ n_ids) {
+    __shared__ H skeys[DB_SLOTS];
+    __shared__ uint32_t firsts[DB_SLOTS];
+    const H empty = (H)~(H)0;
+    const int64_t n_reads = ids ? (int64_t)*n_ids : n_seq;
+    for (int64_t q = blockIdx.x; q < n_reads; q += gridDim.x) {
+        const int64_t r = ids ? (int64_t)ids[q] : q;
+        int64_t st = borders[2 * r], en = borders[2 * r + 1];
+        if (st < 0) st = 0;
+        if (en > n) en = n;
+        const int64_t len = en - st;
+        if (len <= 1) continue;
+        const uint32_t n_pass = (uint32_t)((len + DB_SLOTS / 2 - 1) / (DB_SLOTS / 2));
+        for (uint32_t pass = 0; pass < n_pass; ++pass) {
+            for (int i = threadIdx.x; i < DB_SLOTS; i += blockDim.x) { skeys[i] = empty; firsts[i] = 0xFFFFFFFFu; }
+            __syncthreads();
+            for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+                const H h = keys[st + i];
+                if (h == empty) continue;
+                const u64 m = mix64((u64)h);
+                if (n_pass > 1 && (uint32_t)(m >> 32) % n_pass != pass) continue;
+                uint32_t slot = (uint32_t)m & (DB_SLOTS - 1);
+                while (true) {
+                    const H old = atomicCAS(&skeys[slot], empty, h);
+                    if (old == empty || old == h) { atomicMin(&firsts[slot], (uint32_t)i); break; }
+                    slot = (slot + 1) & (DB_SLOTS - 1);
+                }
+            }
+            __syncthreads();
+            for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+                const H h = keys[st + i];
+                if (h == empty) continue;
+                const u64 m = mix64((u64)h);
+                if (n_pass > 1 && (uint32_t)(m >> 32) % n_pass != pass) continue;
+                uint32_t slot = (uint32_t)m & (DB_SLOTS - 1);
+                while (skeys[slot] != h) slot = (slot + 1) & (DB_SLOTS - 1);
+                if (firsts[slot] != (uint32_t)i) keys[st + i] = empty;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- LSD radix sort of 64-bit keys -----------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;        // 4096 keys per tile
+constexpr int RS_WARP_KEYS = RS_TILE / (RS_THREADS / 32);   // 512 consecutive keys per warp
+
+// counts[d * n_tiles + tile] = keys of the tile whose digit is d (invalid keys are not counted when drop_empty)
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const u64* __restrict__ in, int64_t n_upper, const u64* __restrict__ n_dev,
+                                                                int shift, int drop_empty, int64_t n_tiles, uint32_t* __restrict__ counts) {
+    __shared__ uint32_t hist[256];
+    const int64_t n = n_dev ? (int64_t)*n_dev : n_upper;
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        const int64_t i = base + j * RS_THREADS + threadIdx.x;
+        if (i < n) {
+            const u64 key = __ldg(in + i);
+            if (!(drop_empty && key == KEY_EMPTY)) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
+        }
+    }
+    __syncthreads();
+    counts[(size_t)threadIdx.x * n_tiles + blockIdx.x] = hist[threadIdx.x];
+}
+
+// totals[d] = keys with digit d
+__global__ void __launch_bounds__(256) radix_digit_total_kernel(const uint32_t* __restrict__ counts, int64_t n_tiles, u64* __restrict__ totals) {
+    __shared__ u64 ws[8];
+    const uint32_t* row = counts + (size_t)blockIdx.x * n_tiles;
+    u64 s = 0;
+    for (int64_t t = threadIdx.x; t < n_tiles; t += 256) s += row[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { u64 t = 0; for (int q = 0; q < 8; ++q) t += ws[q]; totals[blockIdx.x] = t; }
+}
+
+// offsets[d * n_tiles + tile] = first output index of the tile's keys with digit d; block d scans its row.
+// Block 0 also writes *n_out = number of keys that take part (the sum of the totals).
+__global__ void __launch_bounds__(1024) radix_offsets_kernel(const uint32_t* __restrict__ counts, int64_t n_tiles, const u64* __restrict__ totals,
+                                                             u64* __restrict__ offsets, u64* __restrict__ n_out) {
+    __shared__ u64 partial[1024];
+    __shared__ u64 digit_base;
+    const int d = blockIdx.x;
+    if (threadIdx.x == 0) {
+        u64 b = 0, all = 0;
+        for (int q = 0; q < 256; ++q) { if (q < d) b += totals[q]; all += totals[q]; }
+        digit_base = b;
+        if (d == 0 && n_out) *n_out = all;
+    }
+    const uint32_t* row = counts + (size_t)d * n_tiles;
+    u64* orow = offsets + (size_t)d * n_tiles;
+    const int64_t chunk = (n_tiles + 1023) / 1024;
+    const int64_t lo = (int64_t)threadIdx.x * chunk, hi = lo + chunk < n_tiles ? lo + chunk : n_tiles;
+    u64 s = 0;
+    for (int64_t t = lo; t < hi; ++t) s += row[t];
+    partial[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 run = digit_base;
+        for (int i = 0; i < 1024; ++i) { const u64 t = partial[i]; partial[i] = run; run += t; }
+    }
+    __syncthreads();
+    u64 run = partial[threadIdx.x];
+    for (int64_t t = lo; t < hi; ++t) { orow[t] = run; run += row[t]; }
+}
+
+// stable scatter: warp w of the tile owns keys [w * 512, (w + 1) * 512) in 16 rounds of 32 consecutive keys; inside a
+// round the rank among equal digits comes from __match_any_sync, across rounds from a per-warp counter, across warps and
+// tiles from the scanned histograms.
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u64* __restrict__ in, u64* __restrict__ out, int64_t n_upper,
+                                                                   const u64* __restrict__ n_dev, int shift, int drop_empty,
+                                                                   int64_t n_tiles, const u64* __restrict__ offsets) {
+    __shared__ uint32_t wcnt[RS_THREADS / 32][256];
+    __shared__ u64 wbase[RS_THREADS / 32][256];
+    const int64_t n = n_dev ? (int64_t)*n_dev : n_upper;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int q = 0; q < RS_THREADS / 32; ++q) wcnt[q][threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * RS_WARP_KEYS;
+    u64 key[RS_ITEMS];
+    uint32_t rank[RS_ITEMS];
+    uint32_t live = 0;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const int64_t i = base + r * 32 + lane;
+        key[r] = i < n ? __ldg(in + i) : KEY_EMPTY;
+        const bool ok = i < n && !(drop_empty && key[r] == KEY_EMPTY);
+        const uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, ok ? d : (256u + (uint32_t)lane));
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (ok && lane == leader) { old = wcnt[w][d]; wcnt[w][d] = old + __popc(peers); }
+        old = __shfl_sync(0xFFFFFFFFu, old, leader);
+        rank[r] = old + __popc(peers & ((1u << lane) - 1u));
+        if (ok) live |= 1u << r;
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const uint32_t d = threadIdx.x;
+        u64 run = offsets[(size_t)d * n_tiles + blockIdx.x];
+        for (int q = 0; q < RS_THREADS / 32; ++q) { wbase[q][d] = run; run += wcnt[q][d]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r)
+        if ((live >> r) & 1u) out[wbase[w][(uint32_t)(key[r] >> shift) & 255u] + rank[r]] = key[r];
+}
+
+// ---- run-length encoding of the sorted keys ------------------------------------------------------------------------------------
+constexpr int RL_BLOCK = 256;
+constexpr int RL_ITEMS = 8;
+constexpr int RL_TILE = RL_BLOCK * RL_ITEMS;
+
+__device__ __forceinline__ uint32_t rl_block_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t warp_sums[RL_BLOCK / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    uint32_t pre = 0, all = 0;
+    for (int q = 0; q < RL_BLOCK / 32; ++q) { if (q < w) pre += warp_sums[q]; all += warp_sums[q]; }
+    *total = all;
+    __syncthreads();
+    return pre + incl - v;
+}
+
+__device__ __forceinline__ bool is_head(const u64* __restrict__ keys, int64_t i) { return i == 0 || __ldg(keys + i) != __ldg(keys + i - 1); }
+
+__global__ void __launch_bounds__(RL_BLOCK) head_count_kernel(const u64* __restrict__ keys, int64_t n, uint64_t* __restrict__ tile_counts) {
+    const int64_t base = (int64_t)blockIdx.x * RL_TILE + (int64_t)threadIdx.x * RL_ITEMS;
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < RL_ITEMS; ++j) if (base + j < n) c += is_head(keys, base + j);
+    uint32_t total;
+    rl_block_scan(c, &total);
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(RL_BLOCK) head_write_kernel(const u64* __restrict__ keys, int64_t n, const uint64_t* __restrict__ tile_offsets,
+                                                              u64* __restrict__ kh_out, long long* __restrict__ pos_out) {
+    const int64_t base = (int64_t)blockIdx.x * RL_TILE + (int64_t)threadIdx.x * RL_ITEMS;
+    uint32_t heads = 0, c = 0;
+#pragma unroll
+    for (int j = 0; j < RL_ITEMS; ++j) if (base + j < n && is_head(keys, base + j)) { heads |= 1u << j; ++c; }
+    uint32_t total;
+    uint64_t o = tile_offsets[blockIdx.x] + rl_block_scan(c, &total);
+#pragma unroll
+    for (int j = 0; j < RL_ITEMS; ++j)
+        if ((heads >> j) & 1u) { kh_out[o] = keys[base + j]; pos_out[o] = base + j; ++o; }
+}
+
+__global__ void __launch_bounds__(256) run_length_kernel(const long long* __restrict__ pos, int64_t n_uniq, long long n, long long* __restrict__ cnt) {
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (r >= n_uniq) return;
+    cnt[r] = (r + 1 < n_uniq ? pos[r + 1] : n) - pos[r];
+}
+
+__global__ void __launch_bounds__(1024) scan_tiles64_kernel(uint64_t* __restrict__ v, int64_t n_tiles) {
+    __shared__ uint64_t partial[1024];
+    const int64_t chunk = (n_tiles + 1023) / 1024;
+    const int64_t lo = (int64_t)threadIdx.x * chunk;
+    const int64_t hi = lo + chunk < n_tiles ? lo + chunk : n_tiles;
+    uint64_t s = 0;
+    for (int64_t i = lo; i < hi; ++i) s += v[i];
+    partial[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t run = 0;
+        for (int i = 0; i < 1024; ++i) { const uint64_t t = partial[i]; partial[i] = run; run += t; }
+        v[n_tiles] = run;
+    }
+    __syncthreads();
+    uint64_t run = partial[threadIdx.x];
+    for (int64_t i = lo; i < hi; ++i) { const uint64_t t = v[i]; v[i] = run; run += t; }
+}
+
+// ---- merge_revcom on a sorted unique list ----------------------------------------------------------------------------------------
+// index of x in the ascending array kh[0..n), or -1
+__device__ __forceinline__ int64_t find_key(const u64* __restrict__ kh, int64_t n, u64 x) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(kh + mid) < x) lo = mid + 1; else hi = mid;
+    }
+    return (lo < n && __ldg(kh + lo) == x) ? lo : -1;
+}
+
+// partner[i] = index of rc(kh[i]) in the list or -1; tile_counts = survivors per tile
+// (entry i is dropped iff its partner is present and kh[i] > rc(kh[i]), kmer_count.py:668-676)
+__global__ void __launch_bounds__(RL_BLOCK) merge_plan_kernel(const u64* __restrict__ kh, int64_t n, int k, long long* __restrict__ partner,
+                                                              uint64_t* __restrict__ tile_counts) {
+    const int64_t base = (int64_t)blockIdx.x * RL_TILE + (int64_t)threadIdx.x * RL_ITEMS;
+    uint32_t c = 0;
+    for (int j = 0; j < RL_ITEMS; ++j) {
+        const int64_t i = base + j;
+        if (i < n) {
+            const u64 h = __ldg(kh + i), rc = revcom64(h, k);
+            const int64_t p = find_key(kh, n, rc);
+            partner[i] = p;
+            c += !(p >= 0 && h > rc);
+        }
+    }
+    uint32_t total;
+    rl_block_scan(c, &total);
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+
+// survivors in list order: (min(h, rc h), cnt[h] + cnt[rc h]); summed (may be NULL) gets cnt[i] + cnt[partner] for EVERY i,
+// which is what the reference leaves in the caller's count array (kmer_count.py:661)
+__global__ void __launch_bounds__(RL_BLOCK) merge_write_kernel(const u64* __restrict__ kh, const long long* __restrict__ cnt, int64_t n, int k,
+                                                               const long long* __restrict__ partner, const uint64_t* __restrict__ tile_offsets,
+                                                               u64* __restrict__ kh_out, long long* __restrict__ cnt_out,
+                                                               long long* __restrict__ summed) {
+    const int64_t base = (int64_t)blockIdx.x * RL_TILE + (int64_t)threadIdx.x * RL_ITEMS;
+    u64 val[RL_ITEMS];
+    long long sum[RL_ITEMS];
+    uint32_t keep = 0, c = 0;
+#pragma unroll
+    for (int j = 0; j < RL_ITEMS; ++j) {
+        const int64_t i = base + j;
+        val[j] = 0; sum[j] = 0;
+        if (i < n) {
+            const u64 h = __ldg(kh + i), rc = revcom64(h, k);
+            const long long p = partner[i];
+            sum[j] = cnt[i] + (p >= 0 ? cnt[p] : 0ll);
+            val[j] = h < rc ? h : rc;
+            if (!(p >= 0 && h > rc)) { keep |= 1u << j; ++c; }
+        }
+    }
+    uint32_t total;
+    uint64_t o = tile_offsets[blockIdx.x] + rl_block_scan(c, &total);
+#pragma unroll
+    for (int j = 0; j < RL_ITEMS; ++j) {
+        if (summed && base + j < n) summed[base + j] = sum[j];
+        if ((keep >> j) & 1u) { kh_out[o] = val[j]; cnt_out[o] = sum[j]; ++o; }
+    }
+}
+
+// ---- Hamming-ball sums and extraction on (uint64 kh, int64 cnt) lists --------------------------------------------------------------
+constexpr int HL_BLOCK = 256;
+constexpr int HL_MAXM = 16;
+
+__global__ void __launch_bounds__(HL_BLOCK) hamball_sum_list64_kernel(const u64* __restrict__ kh, const long long* __restrict__ cnt, int64_t n,
+                                                                      int k, const u64* __restrict__ cand, int m, int d, int revcom,
+                                                                      u64* __restrict__ sums) {
+    __shared__ u64 sc[HL_MAXM], src[HL_MAXM];
+    __shared__ u64 ws[HL_BLOCK / 32];
+    const u64 low = lowmask64(k);
+    if (threadIdx.x < m) { const u64 c = cand[threadIdx.x] & low; sc[threadIdx.x] = c; src[threadIdx.x] = revcom64(c, k); }
+    __syncthreads();
+    u64 acc[HL_MAXM];
+#pragma unroll
+    for (int i = 0; i < HL_MAXM; ++i) acc[i] = 0;
+    for (int64_t j = (int64_t)blockIdx.x * HL_BLOCK + threadIdx.x; j < n; j += (int64_t)gridDim.x * HL_BLOCK) {
+        const u64 h = __ldg(kh + j);
+        const u64 wgt = (u64)__ldg(cnt + j);
+#pragma unroll
+        for (int i = 0; i < HL_MAXM; ++i) {
+            if (i < m) {
+                uint32_t dist = nz_groups64(h ^ sc[i], low);
+                if (revcom) { const uint32_t rd = nz_groups64(h ^ src[i], low); dist = rd < dist ? rd : dist; }
+                if ((int)dist <= d) acc[i] += wgt;
+            }
+        }
+    }
+    for (int i = 0; i < m; ++i) {
+        u64 v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+        if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u64 t = 0;
+            for (int q = 0; q < HL_BLOCK / 32; ++q) t += ws[q];
+            if (t) atomicAdd(sums + i, t);
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ bool ball_member64(u64 h, u64 conseq, u64 rc_conseq, int k, int d, int revcom, u64 low, u64* value) {
+    uint32_t dist = nz_groups64(h ^ conseq, low);
+    bool flip = false;
+    if (revcom) {
+        const uint32_t rd = nz_groups64(h ^ rc_conseq, low);
+        flip = rd < dist;                           // ties stay forward (motif_discovery.py:965)
+        dist = rd < dist ? rd : dist;
+    }
+    if ((int)dist > d) return false;
+    *value = flip ? revcom64(h & low, k) : h;
+    return true;
+}
+
+__global__ void __launch_bounds__(RL_BLOCK) ball64_count_kernel(const u64* __restrict__ kh, int64_t n, u64 conseq, u64 rc_conseq, int k, int d,
+                                                                int revcom, uint64_t* __restrict__ tile_counts) {
+    const int64_t base = (int64_t)blockIdx.x * RL_TILE + (int64_t)threadIdx.x * RL_ITEMS;
+    const u64 low = lowmask64(k);
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < RL_ITEMS; ++j) {
+        u64 v;
+        if (base + j < n) c += ball_member64(__ldg(kh + base + j), conseq, rc_conseq, k, d, revcom, low, &v);
+    }
+    uint32_t total;
+    rl_block_scan(c, &total);
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(RL_BLOCK) ball64_write_kernel(const u64* __restrict__ kh, const long long* __restrict__ cnt, int64_t n, u64 conseq,
+                                                                u64 rc_conseq, int k, int d, int revcom, const uint64_t* __restrict__ tile_offsets,
+                                                                u64* __restrict__ kh_out, long long* __restrict__ cnt_out, u64* __restrict__ cnt_mat) {
+    __shared__ u64 smat[4 * 32];
+    if (threadIdx.x < 128) smat[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RL_TILE + (int64_t)threadIdx.x * RL_ITEMS;
+    const u64 low = lowmask64(k);
+    u64 vals[RL_ITEMS];
+    long long cnts[RL_ITEMS];
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < RL_ITEMS; ++j) {
+        u64 v;
+        if (base + j < n && ball_member64(__ldg(kh + base + j), conseq, rc_conseq, k, d, revcom, low, &v)) {
+            vals[c] = v; cnts[c] = __ldg(cnt + base + j); ++c;
+        }
+    }
+    uint32_t total;
+    const uint64_t o = tile_offsets[blockIdx.x] + rl_block_scan(c, &total);
+    for (uint32_t j = 0; j < c; ++j) {
+        if (kh_out) { kh_out[o + j] = vals[j]; cnt_out[o + j] = cnts[j]; }
+        for (int pos = 0; pos < k; ++pos) {
+            const uint32_t b = (uint32_t)(vals[j] >> (2 * (k - 1 - pos))) & 3u;
+            atomicAdd(&smat[b * 32 + pos], (u64)cnts[j]);
+        }
+    }
+    __syncthreads();
+    if (total && threadIdx.x < 128) {
+        const int b = threadIdx.x >> 5, pos = threadIdx.x & 31;
+        if (pos < k && smat[threadIdx.x]) atomicAdd(&cnt_mat[b * k + pos], smat[threadIdx.x]);
+    }
+}
+
+int read_u64(const void* dev, int64_t* host, cudaStream_t s, const char* what) {
+    uint64_t t = 0;
+    cudaError_t e = cudaMemcpyAsync(&t, dev, 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { kmap_set_error("%s: %s", what, cudaGetErrorString(e)); return (int)e; }
+    *host = (int64_t)t;
+    return KMAP_OK;
+}
+
+int64_t rs_tiles(int64_t n) { return (n + RS_TILE - 1) / RS_TILE; }
+int64_t rl_tiles(int64_t n) { return (n + RL_TILE - 1) / RL_TILE; }
+
+template <typename H>
+int dedup_keys(H* keys, int64_t n, const int64_t* borders, int64_t n_seq, uint32_t* work, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(work, 0, 16, s);
+    if (e != cudaSuccess) { kmap_set_error("dedup_keys: %s", cudaGetErrorString(e)); return (int)e; }
+    int64_t blocks = (n_seq + DW_WARPS - 1) / DW_WARPS;
+    if (blocks > 148 * 8 * 4) blocks = 148 * 8 * 4;
+    dedup_keys_warp_kernel<H><<<(unsigned int)blocks, DW_WARPS * 32, 0, s>>>(keys, n, borders, n_seq, work, work + 4);
+    dedup_keys_block_kernel<H><<<148 * 4, 256, 0, s>>>(keys, n, borders, n_seq, work + 4, work);
+    return kmap_check_launch("dedup_keys");
+}
+
+}  // namespace
+
+extern "C" {
+
+int kmap_window_keys_u64(const uint32_t* packed, const uint32_t* valid, int64_t n, int k, uint64_t* keys, void* stream) {
+    KMAP_REQUIRE(n >= 0 && k >= 1 && k <= 31, "the 64-bit key path covers 1 <= k <= 31");
+    if (n == 0) return KMAP_OK;
+    KMAP_REQUIRE(packed && valid && keys, "null pointer");
+    window_keys_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(packed, valid, n, k, reinterpret_cast<u64*>(keys));
+    return kmap_check_launch("window_keys");
+}
+
+int64_t kmap_dedup_keys_work_words(int64_t n_seq) { return 4 + (n_seq < 0 ? 0 : n_seq); }
+
+int kmap_dedup_hash_per_read_u64(uint64_t* hash, int64_t n, const int64_t* borders, int64_t n_seq, uint32_t* work, void* stream) {
+    KMAP_REQUIRE(n >= 0 && n_seq >= 0 && n_seq < (int64_t)0xFFFFFFFFll, "bad size");
+    if (n == 0 || n_seq == 0) return KMAP_OK;
+    KMAP_REQUIRE(hash && borders && work, "null pointer");
+    return dedup_keys<u64>(reinterpret_cast<u64*>(hash), n, borders, n_seq, work, as_stream(stream));
+}
+
+// scratch (uint64 words): [0..255] digit totals, [256] n after the first pass, [257] spare, then the per-tile digit counts
+// (uint32) and offsets (uint64) of one pass; the run-length step re-uses the front of it for its tile counts
+int64_t kmap_sort_scratch_words(int64_t n) {
+    if (n < 0) return 0;
+    const int64_t t = rs_tiles(n);
+    const int64_t sort_words = 258 + 128 * t + 256 * t;
+    const int64_t rl_words = rl_tiles(n) + 2;
+    return (sort_words > rl_words ? sort_words : rl_words) + 2;
+}
+
+int kmap_sort_keys_u64(uint64_t* keys, uint64_t* tmp, int64_t n, int key_bits, uint64_t* scratch, int64_t* n_valid_host,
+                       int64_t* n_unique_host, void* stream) {
+    KMAP_REQUIRE(n >= 0 && key_bits >= 1 && key_bits <= 64 && n_valid_host && n_unique_host, "bad argument");
+    *n_valid_host = 0; *n_unique_host = 0;
+    if (n == 0) return KMAP_OK;
+    KMAP_REQUIRE(keys && tmp && scratch, "null pointer");
+    cudaStream_t s = as_stream(stream);
+    const int64_t n_tiles = rs_tiles(n);
+    u64* totals = reinterpret_cast<u64*>(scratch);
+    u64* n_dev = totals + 256;
+    uint32_t* counts = reinterpret_cast<uint32_t*>(scratch + 258);
+    u64* offsets = reinterpret_cast<u64*>(scratch + 258 + 128 * n_tiles);
+    u64* a = reinterpret_cast<u64*>(keys);
+    u64* b = reinterpret_cast<u64*>(tmp);
+    const int passes = (key_bits + 7) / 8;
+    for (int p = 0; p < passes; ++p) {
+        const int drop = p == 0;
+        const u64* nd = p == 0 ? nullptr : n_dev;
+        radix_hist_kernel<<<(unsigned int)n_tiles, RS_THREADS, 0, s>>>(a, n, nd, 8 * p, drop, n_tiles, counts);
+        radix_digit_total_kernel<<<256, 256, 0, s>>>(counts, n_tiles, totals);
+        radix_offsets_kernel<<<256, 1024, 0, s>>>(counts, n_tiles, totals, offsets, p == 0 ? n_dev : nullptr);
+        radix_scatter_kernel<<<(unsigned int)n_tiles, RS_THREADS, 0, s>>>(a, b, n, nd, 8 * p, drop, n_tiles, offsets);
+        u64* t = a; a = b; b = t;
+    }
+    int rc = kmap_check_launch("sort_keys");
+    if (rc) return rc;
+    rc = read_u64(n_dev, n_valid_host, s, "sort_keys");
+    if (rc) return rc;
+    const int64_t nv = *n_valid_host;
+    if (a != reinterpret_cast<u64*>(keys) && nv > 0) {        // odd number of passes: bring the result home
+        cudaError_t e = cudaMemcpyAsync(keys, a, (size_t)nv * 8, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) { kmap_set_error("sort_keys: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    if (nv == 0) return KMAP_OK;
+    const int64_t tiles = rl_tiles(nv);
+    head_count_kernel<<<(unsigned int)tiles, RL_BLOCK, 0, s>>>(reinterpret_cast<const u64*>(keys), nv, scratch);
+    scan_tiles64_kernel<<<1, 1024, 0, s>>>(scratch, tiles);
+    rc = kmap_check_launch("sort_keys(heads)");
+    if (rc) return rc;
+    return read_u64(scratch + tiles, n_unique_host, s, "sort_keys(heads)");
+}
+
+int kmap_rle_u64(const uint64_t* sorted_keys, int64_t n, uint64_t* scratch, int64_t* pos_scratch, uint64_t* kh_out, int64_t* cnt_out,
+                 int64_t capacity, void* stream) {
+    KMAP_REQUIRE(n >= 0, "bad argument");
+    if (n == 0) return KMAP_OK;
+    KMAP_REQUIRE(sorted_keys && scratch && pos_scratch && kh_out && cnt_out, "null pointer");
+    cudaStream_t s = as_stream(stream);
+    const int64_t tiles = rl_tiles(n);
+    const u64* keys = reinterpret_cast<const u64*>(sorted_keys);
+    head_count_kernel<<<(unsigned int)tiles, RL_BLOCK, 0, s>>>(keys, n, scratch);
+    scan_tiles64_kernel<<<1, 1024, 0, s>>>(scratch, tiles);
+    int rc = kmap_check_launch("rle(count)");
+    if (rc) return rc;
+    int64_t n_uniq = 0;
+    rc = read_u64(scratch + tiles, &n_uniq, s, "rle");
+    if (rc) return rc;
+    if (capacity < n_uniq) { kmap_set_error("rle: capacity %lld < %lld", (long long)capacity, (long long)n_uniq); return KMAP_ERR_CAPACITY; }
+    head_write_kernel<<<(unsigned int)tiles, RL_BLOCK, 0, s>>>(keys, n, scratch, reinterpret_cast<u64*>(kh_out), reinterpret_cast<long long*>(pos_scratch));
+    run_length_kernel<<<grid_for(n_uniq, 256), 256, 0, s>>>(reinterpret_cast<const long long*>(pos_scratch), n_uniq, (long long)n,
+                                                            reinterpret_cast<long long*>(cnt_out));
+    return kmap_check_launch("rle(write)");
+}
+
+int64_t kmap_merge_sorted_scratch_words(int64_t n) { return n < 0 ? 0 : n + rl_tiles(n) + 2; }
+
+int kmap_merge_revcom_sorted_u64(const uint64_t* kh, const int64_t* cnt, int64_t n, int k, uint64_t* scratch, uint64_t* kh_out,
+                                 int64_t* cnt_out, int64_t capacity, int64_t* n_out_host, int64_t* summed_cnt, void* stream) {
+    KMAP_REQUIRE(n >= 0 && k >= 1 && k <= 31 && n_out_host, "bad argument (1 <= k <= 31)");
+    *n_out_host = 0;
+    if (n == 0) return KMAP_OK;
+    KMAP_REQUIRE(kh && cnt && scratch, "null pointer");
+    cudaStream_t s = as_stream(stream);
+    const int64_t tiles = rl_tiles(n);
+    long long* partner = reinterpret_cast<long long*>(scratch);
+    uint64_t* tile_counts = scratch + n;
+    const u64* khp = reinterpret_cast<const u64*>(kh);
+    merge_plan_kernel<<<(unsigned int)tiles, RL_BLOCK, 0, s>>>(khp, n, k, partner, tile_counts);
+    scan_tiles64_kernel<<<1, 1024, 0, s>>>(tile_counts, tiles);
+    int rc = kmap_check_launch("merge_revcom_sorted(plan)");
+    if (rc) return rc;
+    rc = read_u64(tile_counts + tiles, n_out_host, s, "merge_revcom_sorted");
+    if (rc) return rc;
+    if (capacity < *n_out_host || !kh_out || !cnt_out) {
+        if (capacity == 0) return KMAP_OK;           // size query
+        kmap_set_error("merge_revcom_sorted: capacity %lld < %lld", (long long)capacity, (long long)*n_out_host);
+        return KMAP_ERR_CAPACITY;
+    }
+    merge_write_kernel<<<(unsigned int)tiles, RL_BLOCK, 0, s>>>(khp, reinterpret_cast<const long long*>(cnt), n, k, partner, tile_counts,
+                                                               reinterpret_cast<u64*>(kh_out), reinterpret_cast<long long*>(cnt_out),
+                                                               reinterpret_cast<long long*>(summed_cnt));
+    return kmap_check_launch("merge_revcom_sorted(write)");
+}
+
+int kmap_hamball_sum_list_u64(const uint64_t* kh, const int64_t* cnt, int64_t n, int k, const uint64_t* cand, int m, int d, int revcom,
+                              uint64_t* sums, void* stream) {
+    KMAP_REQUIRE(k >= 1 && k <= 31 && m >= 0 && m <= HL_MAXM && d >= 0 && n >= 0, "bad argument (k <= 31, m <= 16)");
+    if (m == 0) return KMAP_OK;
+    KMAP_REQUIRE(cand && sums, "null pointer");
+    cudaStream_t s = as_stream(stream);
+    cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)m * 8, s);
+    if (e != cudaSuccess) { kmap_set_error("hamball_sum_list_u64: %s", cudaGetErrorString(e)); return (int)e; }
+    if (n == 0) return KMAP_OK;
+    int64_t blocks = (n + HL_BLOCK - 1) / HL_BLOCK;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    hamball_sum_list64_kernel<<<(unsigned int)blocks, HL_BLOCK, 0, s>>>(reinterpret_cast<const u64*>(kh), reinterpret_cast<const long long*>(cnt),
+                                                                        n, k, reinterpret_cast<const u64*>(cand), m, d, revcom,
+                                                                        reinterpret_cast<u64*>(sums));
+    return kmap_check_launch("hamball_sum_list_u64");
+}
+
+int kmap_hamball_extract_u64(const uint64_t* kh, const int64_t* cnt, int64_t n, int k, uint64_t conseq, int d, int revcom, uint64_t* scratch,
+                             uint64_t* kh_out, int64_t* cnt_out, int64_t capacity, int64_t* n_out_host, int64_t* cnt_mat, void* stream) {
+    KMAP_REQUIRE(k >= 1 && k <= 31 && n >= 0, "k out of range");
+    KMAP_REQUIRE(scratch && n_out_host && cnt_mat, "null pointer");
+    cudaStream_t s = as_stream(stream);
+    cudaError_t e = cudaMemsetAsync(cnt_mat, 0, (size_t)4 * k * 8, s);
+    if (e != cudaSuccess) { kmap_set_error("hamball_extract_u64: %s", cudaGetErrorString(e)); return (int)e; }
+    *n_out_host = 0;
+    if (n == 0) return KMAP_OK;
+    KMAP_REQUIRE(kh && cnt, "null pointer");
+    uint64_t rc = 0, com = (~conseq) & lowmask64(k);
+    for (int i = 0; i < k; ++i) { rc = (rc << 2) | (com & 3ull); com >>= 2; }
+    const int64_t tiles = rl_tiles(n);
+    const u64* khp = reinterpret_cast<const u64*>(kh);
+    ball64_count_kernel<<<(unsigned int)tiles, RL_BLOCK, 0, s>>>(khp, n, conseq, rc, k, d, revcom, scratch);
+    scan_tiles64_kernel<<<1, 1024, 0, s>>>(scratch, tiles);
+    int r = kmap_check_launch("hamball_extract_u64(count)");
+    if (r) return r;
+    r = read_u64(scratch + tiles, n_out_host, s, "hamball_extract_u64");
+    if (r) return r;
+    const bool want_list = capacity > 0;
+    if (want_list && (capacity < *n_out_host || !kh_out || !cnt_out)) {
+        kmap_set_error("hamball_extract_u64: capacity %lld < %lld", (long long)capacity, (long long)*n_out_host);
+        return KMAP_ERR_CAPACITY;
+    }
+    ball64_write_kernel<<<(unsigned int)tiles, RL_BLOCK, 0, s>>>(khp, reinterpret_cast<const long long*>(cnt), n, conseq, rc, k, d, revcom, scratch,
+                                                                want_list ? reinterpret_cast<u64*>(kh_out) : nullptr,
+                                                                reinterpret_cast<long long*>(cnt_out), reinterpret_cast<u64*>(cnt_mat));
+    return kmap_check_launch("hamball_extract_u64(write)");
+}
+
+}  // extern "C"

@@ -258,12 +258,31 @@ class SeqOnDevice:
         check(rc, "kmap_count_all_k")
         return tables
 
+    def count_sorted(self, k: int, dedup: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(kh, cnt) = ascending distinct k-mer hashes (uint64 bits in int64) and their int64 counts by the sort /
+        run-length path (csrc/sorted.cu): what count_uniq_hash returns (kmer_count.py:476-491), for any 1 <= k <= 31.
+        dedup=True applies remove_duplicate_hash_per_seq (kmer_count.py:743-760) to the keys first."""
+        L = lib()
+        if not 1 <= k <= 31:
+            raise KmapError(f"k-mer hashes are 64-bit: 1 <= k <= 31 (got {k})")
+        keys = empty(self.n, torch.int64)
+        check(L.kmap_window_keys_u64(_ptr(self.packed), _ptr(self.valid), self.n, k, _ptr(keys), _stream_ptr()), "kmap_window_keys_u64")
+        if dedup:
+            if self.borders is None:
+                raise KmapError("per-read de-duplication needs the border matrix")
+            work = empty(L.kmap_dedup_keys_work_words(self.n_seq), torch.int32)
+            check(L.kmap_dedup_hash_per_read_u64(_ptr(keys), self.n, _ptr(self.borders), self.n_seq, _ptr(work), _stream_ptr()),
+                  "kmap_dedup_hash_per_read_u64")
+        return sort_count_keys(keys, 2 * k)
+
     # ---- masking ----------------------------------------------------------------------------------------------
     def mask(self, k: int, consensus_kh: Sequence[int], max_dist: Sequence[int]):
         L = lib()
         m = len(consensus_kh)
         if m == 0 or self.n == 0:
             return
+        if not 1 <= k <= 16:
+            raise KmapError(f"mask_input on the device covers k <= 16 (got {k})")
         cons = to_device(np.asarray([int(c) & 0xFFFFFFFF for c in consensus_kh], dtype=np.uint32))
         d = to_device(np.asarray([int(x) for x in max_dist], dtype=np.int32))
         if self._flag_scratch is None:
@@ -371,6 +390,55 @@ def occurrence_scan(seq: SeqOnDevice, k: int, conseq_kh: int, d: int, revcom: bo
                                      int(revcom), _ptr(min_dist), _ptr(offsets), _ptr(pos), _stream_ptr()),
               "kmap_occurrence_fill")
     return min_dist.cpu().numpy(), offsets.cpu().numpy(), pos.cpu().numpy()
+
+
+# ---- sort / run-length path (csrc/sorted.cu): uint64 hashes, int64 counts ------------------------------------------------
+def sort_count_keys(keys: torch.Tensor, key_bits: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """np.unique(return_counts) of a uint64 key array on the device (all-ones keys dropped).  `keys` is consumed."""
+    L = lib()
+    n = int(keys.numel())
+    if n == 0:
+        return empty(0, torch.int64), empty(0, torch.int64)
+    tmp = empty(n, torch.int64)
+    scratch = empty(L.kmap_sort_scratch_words(n), torch.int64)
+    n_valid, n_uniq = ctypes.c_int64(0), ctypes.c_int64(0)
+    check(L.kmap_sort_keys_u64(_ptr(keys), _ptr(tmp), n, int(key_bits), _ptr(scratch), ctypes.byref(n_valid), ctypes.byref(n_uniq),
+                               _stream_ptr()), "kmap_sort_keys_u64")
+    kh, cnt = empty(n_uniq.value, torch.int64), empty(n_uniq.value, torch.int64)
+    if n_uniq.value:
+        check(L.kmap_rle_u64(_ptr(keys), n_valid.value, _ptr(scratch), _ptr(tmp), _ptr(kh), _ptr(cnt), n_uniq.value, _stream_ptr()),
+              "kmap_rle_u64")
+    return kh, cnt
+
+
+def merge_revcom_sorted(kh: torch.Tensor, cnt: torch.Tensor, k: int, want_summed: bool = False):
+    """merge_revcom (kmer_count.py:643-685) on an ascending unique (uint64 kh, int64 cnt) device list -> (kh, cnt) in the
+    reference's order [, the summed counts the reference leaves in the caller's array]."""
+    L = lib()
+    n = int(kh.numel())
+    if n == 0:
+        return (kh, cnt, cnt) if want_summed else (kh, cnt)
+    scratch = empty(L.kmap_merge_sorted_scratch_words(n), torch.int64)
+    n_out = ctypes.c_int64(0)
+    out_kh, out_cnt = empty(n, torch.int64), empty(n, torch.int64)      # survivors <= n: one call
+    summed = empty(n, torch.int64) if want_summed else None
+    check(L.kmap_merge_revcom_sorted_u64(_ptr(kh), _ptr(cnt), n, k, _ptr(scratch), _ptr(out_kh), _ptr(out_cnt), n, ctypes.byref(n_out),
+                                         _ptr(summed), _stream_ptr()), "kmap_merge_revcom_sorted_u64")
+    out = (out_kh[:n_out.value], out_cnt[:n_out.value])
+    return out + (summed,) if want_summed else out
+
+
+def hamball_sums_list64(kh: torch.Tensor, cnt: torch.Tensor, k: int, cand: Sequence[int], d: int, revcom: bool) -> np.ndarray:
+    L = lib()
+    out = np.zeros(len(cand), dtype=np.int64)
+    for i in range(0, len(cand), 16):
+        part = list(cand[i:i + 16])
+        c = to_device(np.asarray([int(x) for x in part], dtype=np.uint64))
+        sums = empty(len(part), torch.int64)
+        check(L.kmap_hamball_sum_list_u64(_ptr(kh), _ptr(cnt), int(kh.numel()), k, _ptr(c), len(part), int(d), int(revcom),
+                                          _ptr(sums), _stream_ptr()), "kmap_hamball_sum_list_u64")
+        out[i:i + 16] = sums.cpu().numpy()
+    return out
 
 
 # ---- preproc ingest: FASTA text -> device-resident input.bin / input.seqboarder.bin contents --------------------------

@@ -199,13 +199,19 @@ def get_revcom_hash_arr(in_hash_arr: np.ndarray, kmer_len: int) -> np.ndarray:
 def remove_duplicate_hash_per_seq(hash_arr: np.ndarray, boarder_mat: np.ndarray, invalid_hash) -> np.ndarray:
     """:743-760.  In place + returned: inside each read keep the first occurrence of every hash."""
     assert boarder_mat.shape[1] == 2
-    if hash_arr.dtype != np.uint32:
-        raise KmapError("remove_duplicate_hash_per_seq: 64-bit hashes (k >= 16) are not built yet")
+    if hash_arr.dtype not in (np.dtype(np.uint32), np.dtype(np.uint64)):
+        raise KmapError("remove_duplicate_hash_per_seq expects the uint32 / uint64 hash array of comp_kmer_hash_taichi")
     n = len(hash_arr)
     if n == 0 or len(boarder_mat) == 0:
         return hash_arr
     h_d = E.to_device(hash_arr)
     b_d = E.to_device(np.ascontiguousarray(boarder_mat, dtype=np.int64))
+    if hash_arr.dtype == np.uint64:          # k >= 16 (csrc/sorted.cu)
+        work = E.empty(lib().kmap_dedup_keys_work_words(len(boarder_mat)), torch.int32)
+        check(lib().kmap_dedup_hash_per_read_u64(h_d.data_ptr(), n, b_d.data_ptr(), len(boarder_mat), work.data_ptr(), _stream()),
+              "kmap_dedup_hash_per_read_u64")
+        hash_arr[:] = E.to_host(h_d, np.uint64)
+        return hash_arr
     check(lib().kmap_dedup_hash_per_read_u32(h_d.data_ptr(), n, b_d.data_ptr(), len(boarder_mat), _stream()),
           "kmap_dedup_hash_per_read_u32")
     hash_arr[:] = E.to_host(h_d, np.uint32)
@@ -214,13 +220,18 @@ def remove_duplicate_hash_per_seq(hash_arr: np.ndarray, boarder_mat: np.ndarray,
 
 def _require_dense(kmer_len, what):
     if not 1 <= kmer_len <= 15:
-        raise KmapError(f"{what}: dense tables cover 1 <= k <= 15; k >= 16 (uint64 hashes) needs the sort path (not built yet)")
+        raise KmapError(f"{what}: dense tables cover 1 <= k <= 15 and the sort path 16 <= k <= 31 (got {kmer_len})")
 
 
 def count_uniq_hash(hash_arr: np.ndarray, kmer_len):
     """:476-491.  (ascending unique hashes without the invalid hash, counts in the count dtype)"""
-    _require_dense(kmer_len, "count_uniq_hash")
     hash_arr = np.asarray(hash_arr)
+    if 16 <= kmer_len <= 31:                 # no dense table: sort + run-length encoding (csrc/sorted.cu)
+        if hash_arr.dtype != np.uint64:
+            raise KmapError("count_uniq_hash expects the uint64 hash array of comp_kmer_hash_taichi for k >= 16")
+        kh, cnt = E.sort_count_keys(E.to_device(hash_arr.copy()), 2 * kmer_len)
+        return E.to_host(kh, np.uint64), E.to_host(cnt, np.int64).astype(get_cnt_dtype(kmer_len), copy=False)
+    _require_dense(kmer_len, "count_uniq_hash")
     if hash_arr.dtype != np.uint32:
         raise KmapError("count_uniq_hash expects the uint32 hash array of comp_kmer_hash_taichi")
     table = E.zeros(1 << (2 * kmer_len), torch.int32)
@@ -234,13 +245,22 @@ def merge_revcom(uniq_kmer_hash_arr: np.ndarray, uniq_kh_cnt_arr: np.ndarray, km
     """:643-685.  Sums the counts of reverse-complement pairs (a palindrome is its own partner: doubled), keeps the
     lower hash of a pair, relabels lone k-mers to min(h, rc h); result order = ascending forward hash of the survivors.
     Like the reference it also updates the caller's count array in place (the `+=` at :661)."""
-    _require_dense(kmer_len, "merge_revcom")
     if not keep_lower_hash_flag:
         raise KmapError("merge_revcom(keep_lower_hash_flag=False) is never used by scan_motif and is not built")
     kh = np.asarray(uniq_kmer_hash_arr)
     n = len(kh)
     if n == 0:
         return kh.copy(), np.asarray(uniq_kh_cnt_arr).copy()
+    if 16 <= kmer_len <= 31:                 # sorted-list formulation (csrc/sorted.cu)
+        if n > 1 and not np.all(kh[1:] > kh[:-1]):
+            raise KmapError("merge_revcom for k >= 16 expects the ascending unique hashes count_uniq_hash returns")
+        out_kh, out_cnt, summed = E.merge_revcom_sorted(E.to_device(kh.astype(np.uint64, copy=False)),
+                                                        E.to_device(np.asarray(uniq_kh_cnt_arr).astype(np.int64, copy=False)),
+                                                        kmer_len, want_summed=True)
+        uniq_kh_cnt_arr[:] = E.to_host(summed, np.int64).astype(uniq_kh_cnt_arr.dtype, copy=False)
+        return (E.to_host(out_kh, np.uint64).astype(kh.dtype, copy=False),
+                E.to_host(out_cnt, np.int64).astype(uniq_kh_cnt_arr.dtype, copy=False))
+    _require_dense(kmer_len, "merge_revcom")
     L = lib()
     kh_d = E.to_device(kh.astype(np.uint32, copy=False))
     cnt_d = E.to_device(np.asarray(uniq_kh_cnt_arr).astype(np.int32, copy=False))
@@ -257,7 +277,8 @@ def merge_revcom(uniq_kmer_hash_arr: np.ndarray, uniq_kh_cnt_arr: np.ndarray, km
 def mask_input(seq_np_arr: np.ndarray, kmer_len: int, consensus_kh_arr: np.ndarray, max_hamball_dist_arr: np.ndarray):
     """:580-610.  Mutates seq_np_arr in place and returns it.  Windows are compared on the PRE-mask array for every
     consensus; invalid windows behave like T..T (the reference compares their all-ones hash)."""
-    _require_dense(kmer_len, "mask_input")
+    if not 1 <= kmer_len <= 16:
+        raise KmapError(f"mask_input: the device kernel covers k <= 16 (got {kmer_len})")
     if len(seq_np_arr) == 0 or len(consensus_kh_arr) == 0:
         return seq_np_arr
     dev = E.SeqOnDevice.from_numpy(seq_np_arr, None, keep_u8=True)

@@ -18,7 +18,7 @@ import torch
 from . import engine as E
 from ._lib import KmapError, check, lib
 from .kmer_count import (FileNameDict, MotifDef, cal_hamming_dist, cal_hamming_dist_head, cal_hamming_dist_tail,
-                         dna2arr, gen_motif_def_dict, get_hash_dtype, get_revcom_hash_arr, hash2kmer,
+                         dna2arr, gen_motif_def_dict, get_cnt_dtype, get_hash_dtype, get_revcom_hash_arr, hash2kmer,
                          init_motif_def_dict, kmer2hash, mask_ham_ball, reverse_complement, revcom_hash)
 
 
@@ -32,13 +32,16 @@ def write_lines(str_list: List, outfile):
 # find_motif (:594-702)
 # ======================================================================================================================
 class _CountState:
-    """Counts of the current (possibly masked) sequence: dense forward table on the device + the reference's merged
-    lists on the host (np.argpartition has to see exactly those arrays)."""
+    """Counts of the current (possibly masked) sequence: dense forward table on the device (k <= 15) or 64-bit merged
+    lists from the sort path (k >= 16), + the reference's merged lists on the host (np.argpartition has to see exactly
+    those arrays)."""
 
-    def __init__(self, k, revcom, table=None, kh_dev=None, cnt_dev=None):
-        self.k, self.revcom, self.table, self.kh_dev, self.cnt_dev = k, revcom, table, kh_dev, cnt_dev
-        self.kh = E.to_host(kh_dev, np.uint32) if kh_dev is not None else None
-        self.cnt = E.to_host(cnt_dev, np.int32) if cnt_dev is not None else None
+    def __init__(self, k, revcom, table=None, kh_dev=None, cnt_dev=None, wide=False):
+        self.k, self.revcom, self.table, self.kh_dev, self.cnt_dev, self.wide = k, revcom, table, kh_dev, cnt_dev, wide
+        self.kh = self.cnt = None
+        if kh_dev is not None:
+            self.kh = E.to_host(kh_dev, np.uint64 if wide else np.uint32).astype(get_hash_dtype(k), copy=False)
+            self.cnt = E.to_host(cnt_dev, np.int64 if wide else np.int32).astype(get_cnt_dtype(k), copy=False)
 
     @classmethod
     def from_table(cls, table, k, revcom):
@@ -46,29 +49,43 @@ class _CountState:
         return cls(k, revcom, table, kh_dev, cnt_dev)
 
     @classmethod
+    def from_sorted(cls, dev, k, revcom, dedup):
+        kh_dev, cnt_dev = dev.count_sorted(k, dedup)
+        if revcom:
+            kh_dev, cnt_dev = E.merge_revcom_sorted(kh_dev, cnt_dev, k)
+        return cls(k, revcom, None, kh_dev, cnt_dev, wide=True)
+
+    @classmethod
     def from_lists(cls, kh, cnt, k, revcom):
-        st = cls(k, revcom)
+        wide = k >= 16
+        st = cls(k, revcom, wide=wide)
         st.kh, st.cnt = np.asarray(kh), np.asarray(cnt)
-        st.kh_dev = E.to_device(st.kh.astype(np.uint32, copy=False))
-        st.cnt_dev = E.to_device(st.cnt.astype(np.int32, copy=False))
+        st.kh_dev = E.to_device(st.kh.astype(np.uint64 if wide else np.uint32, copy=False))
+        st.cnt_dev = E.to_device(st.cnt.astype(np.int64 if wide else np.int32, copy=False))
         return st
 
     def ball_sums(self, cand, d):
         if self.table is not None:
             return E.hamball_sums(self.table, self.k, cand, d, self.revcom)
+        if self.wide:
+            return E.hamball_sums_list64(self.kh_dev, self.cnt_dev, self.k, cand, d, self.revcom)
         return E.hamball_sums_list(self.kh_dev, self.cnt_dev, self.k, cand, d, self.revcom)
 
 
 def find_motif_on_device(dev: E.SeqOnDevice, kmer_len: int, max_ham_dist, p_unif, ratio_mu, ratio_std, ratio_cutoff,
                          top_k=5, n_trial=10, merge_revcom_mode=True, rep_mode=False, first_lists=None,
-                         first_table: Optional[torch.Tensor] = None, debug=False):
+                         first_table: Optional[torch.Tensor] = None, debug=False, sorted_path: Optional[bool] = None):
     """Core of find_motif on a device-resident sequence (mutates dev.valid).  Returns (result dict, (uniq_kh, uniq_cnt)
     of the first round).  `first_lists` plays the role of a pre-existing k{k}.pkl (:621-624); `first_table` lets a
-    caller that counted every k in one pass hand in the forward table."""
+    caller that counted every k in one pass hand in the forward table.  sorted_path: count by sorting 64-bit keys
+    (csrc/sorted.cu) instead of a dense table; None = only where there is no dense table (k >= 16)."""
     from scipy.stats import norm
     k = kmer_len
+    use_sorted = (k >= 16) if sorted_path is None else bool(sorted_path)
     if first_lists is not None:
         state = _CountState.from_lists(first_lists[0], first_lists[1], k, merge_revcom_mode)
+    elif use_sorted:
+        state = _CountState.from_sorted(dev, k, merge_revcom_mode, dedup=not rep_mode)
     else:
         table = first_table if first_table is not None else dev.count(k, dedup=not rep_mode)
         state = _CountState.from_table(table, k, merge_revcom_mode)
@@ -99,8 +116,11 @@ def find_motif_on_device(dev: E.SeqOnDevice, kmer_len: int, max_ham_dist, p_unif
         if merge_revcom_mode:
             cons.append(int(revcom_hash(consensus_kh, k)))
         dev.mask(k, cons, [max_ham_dist] * len(cons))
-        table = dev.count(k, dedup=False, table=state.table)          # recounts are never de-duplicated (:695-696)
-        state = _CountState.from_table(table, k, merge_revcom_mode)
+        if use_sorted:                                                # recounts are never de-duplicated (:695-696)
+            state = _CountState.from_sorted(dev, k, merge_revcom_mode, dedup=False)
+        else:
+            table = dev.count(k, dedup=False, table=state.table)
+            state = _CountState.from_table(table, k, merge_revcom_mode)
     return found, first
 
 
@@ -138,9 +158,26 @@ def _hamball_extract(uniq_kh_arr, uniq_kh_cnt_arr, conseq_kh: int, kmer_len: int
                      want_list=True):
     L = lib()
     n = len(uniq_kh_arr)
+    import ctypes
+    if kmer_len >= 16:                      # uint64 hashes, int64 counts (kmer_count.py:351-365)
+        kh_d = E.to_device(np.asarray(uniq_kh_arr).astype(np.uint64, copy=False))
+        cnt_d = E.to_device(np.asarray(uniq_kh_cnt_arr).astype(np.int64, copy=False))
+        scratch = E._scratch(L.kmap_list_scratch_words(n))
+        cnt_mat = E.empty(4 * kmer_len, torch.int64)
+        n_out = ctypes.c_int64(0)
+        stream = torch.cuda.current_stream().cuda_stream
+        m = n if want_list else 0
+        out_kh, out_cnt = E.empty(m, torch.int64), E.empty(m, torch.int64)
+        check(L.kmap_hamball_extract_u64(kh_d.data_ptr(), cnt_d.data_ptr(), n, kmer_len, int(conseq_kh), int(max_ham_dist),
+                                         int(revcom_mode), scratch.data_ptr(), out_kh.data_ptr() if m else None,
+                                         out_cnt.data_ptr() if m else None, m, ctypes.byref(n_out), cnt_mat.data_ptr(), stream),
+              "kmap_hamball_extract_u64")
+        mat = cnt_mat.cpu().numpy().reshape(4, kmer_len).astype(int)
+        if not want_list:
+            return None, None, mat
+        return E.to_host(out_kh[:n_out.value], np.uint64), E.to_host(out_cnt[:n_out.value], np.int64), mat
     kh_d = E.to_device(np.asarray(uniq_kh_arr).astype(np.uint32, copy=False))
     cnt_d = E.to_device(np.asarray(uniq_kh_cnt_arr).astype(np.int32, copy=False))
-    import ctypes
     scratch = E._scratch(L.kmap_list_scratch_words(n))
     cnt_mat = E.empty(4 * kmer_len, torch.int64)
     n_out = ctypes.c_int64(0)

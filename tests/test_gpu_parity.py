@@ -277,7 +277,7 @@ def test_find_motif_small_all_modes(MD, K, small_cases, motif_def_file, idx, tmp
     assert [int(x) for x in res2] == [int(x) for x in c["consensus"]] and np.array_equal(seq2, c["masked"])
 
 
-@pytest.mark.parametrize("k", [6, 7, 8, 9, 10, 11, 12, 13, 14, 15])
+@pytest.mark.parametrize("k", [6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16])
 def test_find_motif_testfa(MD, K, testfa, motif_def_file, k, tmp_path):
     import pickle
     mdd = K.init_motif_def_dict(motif_def_file)
@@ -494,3 +494,112 @@ def test_fasta_ingest_large_synthetic(ENG):
     for chunk in (1 << 28, 1 << 20):
         seq_d, b_d = ENG.fasta_text_to_device(text, chunk_bytes=chunk)
         assert np.array_equal(seq_d.cpu().numpy(), seq) and np.array_equal(b_d.cpu().numpy(), borders)
+
+
+# ---- sort / run-length path (csrc/sorted.cu): uint64 hashes, int64 counts ------------------------------------------------
+def _oracle_counts(seq, borders, k, dedup):
+    h = O.comp_kmer_hash(seq, k)
+    if dedup:
+        h = O.remove_duplicate_hash_per_seq(h, borders, O.get_invalid_hash(h.dtype))
+    return O.count_uniq_hash(h, k)
+
+
+def test_radix_sort_and_run_lengths_vs_numpy(ENG):
+    """sort + run-length encoding == np.unique(return_counts) for even / odd pass counts, many duplicates, all-ones keys"""
+    import torch
+    rng = np.random.default_rng(11)
+    for n, bits, n_distinct in [(1, 8, 1), (37, 8, 5), (5000, 16, 300), (100001, 34, 20000), (1 << 20, 62, 1 << 18), (300000, 64, 1000)]:
+        pool = rng.integers(0, 1 << min(bits, 63), n_distinct, dtype=np.uint64)
+        if bits == 64:
+            pool |= np.uint64(1) << np.uint64(63)
+            pool = pool[pool != np.uint64(0xFFFFFFFFFFFFFFFF)]
+        keys = pool[rng.integers(0, len(pool), n)]
+        keys[rng.random(n) < 0.2] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        want_u, want_c = np.unique(keys[keys != np.uint64(0xFFFFFFFFFFFFFFFF)], return_counts=True)
+        kh, cnt = ENG.sort_count_keys(ENG.to_device(keys.copy()), bits)
+        assert np.array_equal(ENG.to_host(kh, np.uint64), want_u) and np.array_equal(ENG.to_host(cnt, np.int64), want_c), (n, bits)
+    kh, cnt = ENG.sort_count_keys(ENG.to_device(np.full(1000, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)), 40)
+    assert kh.numel() == 0 and cnt.numel() == 0
+
+
+@pytest.mark.parametrize("k", [5, 14, 16, 17, 21, 31])
+def test_sorted_count_and_merge_vs_oracle(ENG, K, k):
+    """count_sorted (keys from the packed reads, per-read de-duplication on the warp / block paths, sort, run lengths) and
+    the sorted-list merge_revcom == the oracle, for 64-bit hashes (k >= 16) and, forced, for small k (palindromes)"""
+    rng = np.random.default_rng(100 + k)
+    special = ["A" * 80, "CA" * 60, "", "N", "ACGT", "ACGTTGCA" * 150, ("ACGTAGCTAGCTAGGATCGAT" * 1500)[:30000],
+               "ACGTTGCAAC" * 40, "AATT" * 20, "GAATTC" * 30]
+    reads, seq, borders = rand_reads(rng, 1500, 0, 130, p_n=0.01, special=special)
+    dev = ENG.SeqOnDevice.from_numpy(seq, borders)
+    for dedup in (False, True):
+        want_u, want_c = _oracle_counts(seq, borders, k, dedup)
+        kh, cnt = dev.count_sorted(k, dedup)
+        got_u, got_c = ENG.to_host(kh, np.uint64), ENG.to_host(cnt, np.int64)
+        assert np.array_equal(got_u, want_u.astype(np.uint64)) and np.array_equal(got_c, want_c.astype(np.int64)), (k, dedup)
+        mu, mc = O.merge_revcom(want_u.copy(), want_c.copy(), k)
+        mkh, mcnt = ENG.merge_revcom_sorted(kh, cnt, k)
+        assert np.array_equal(ENG.to_host(mkh, np.uint64), mu.astype(np.uint64)), (k, dedup)
+        assert np.array_equal(ENG.to_host(mcnt, np.int64), mc.astype(np.int64)), (k, dedup)
+    if k >= 16:    # the reference-shaped array functions on uint64 hashes
+        h = K.comp_kmer_hash_taichi(seq, k)
+        assert h.dtype == np.uint64 and np.array_equal(h, O.comp_kmer_hash(seq, k))
+        hd = K.remove_duplicate_hash_per_seq(h.copy(), borders, K.get_invalid_hash(h.dtype))
+        assert np.array_equal(hd, O.remove_duplicate_hash_per_seq(h.copy(), borders, O.get_invalid_hash(h.dtype)))
+        u, c = K.count_uniq_hash(hd, k)
+        wu, wc = O.count_uniq_hash(hd, k)
+        assert u.dtype == wu.dtype and c.dtype == wc.dtype and np.array_equal(u, wu) and np.array_equal(c, wc)
+        c_in, wc_in = c.copy(), wc.copy()
+        m1 = K.merge_revcom(u, c_in, k)
+        m0 = O.merge_revcom(wu, wc_in, k)
+        assert np.array_equal(m1[0], m0[0]) and np.array_equal(m1[1], m0[1]) and np.array_equal(c_in, wc_in)
+        assert m1[0].dtype == m0[0].dtype and m1[1].dtype == m0[1].dtype
+
+
+@pytest.mark.parametrize("k,d", [(16, 5), (18, 4), (24, 6)])
+def test_hamball_lists_u64_vs_oracle(ENG, MD, k, d):
+    rng = np.random.default_rng(k)
+    centre = rng.integers(0, 4, k)
+    kms = []
+    for _ in range(4000):
+        s = centre.copy()
+        idx = rng.choice(k, int(rng.integers(0, d + 3)), replace=False)
+        s[idx] = rng.integers(0, 4, len(idx))
+        kms.append(int(O.kmer2hash(O.arr2dna(s.astype(np.uint8)))))
+    kms += [int(x) for x in rng.integers(0, 4 ** k, 3000, dtype=np.uint64)]
+    kh = np.unique(np.array(kms, dtype=np.uint64))
+    cnt = rng.integers(1, 50, len(kh)).astype(np.int64)
+    c0 = int(O.kmer2hash(O.arr2dna(centre.astype(np.uint8))))
+    cands = [c0, int(O.revcom_hash(np.uint64(c0), k)), int(kh[5]), int(kh[-1])]
+    kh_d, cnt_d = ENG.to_device(kh), ENG.to_device(cnt)
+    for revcom in (True, False):
+        got = ENG.hamball_sums_list64(kh_d, cnt_d, k, cands, d, revcom)
+        want = [O.hamball_count(kh, cnt, np.uint64(c), k, d, revcom) for c in cands]
+        assert [int(x) for x in got] == [int(x) for x in want], (k, d, revcom)
+    cs = O.hash2kmer(min(c0, int(O.revcom_hash(np.uint64(c0), k))), k)
+    for revcom in (True, False):
+        wkh, wcnt = O.ex_hamball_from_arrays(kh, cnt, cs, d, revcom)
+        gkh, gcnt, gmat = MD._hamball_extract(kh, cnt, int(O.kmer2hash(cs)), k, d, revcom)
+        assert np.array_equal(gkh, wkh) and np.array_equal(gcnt, wcnt)
+        assert np.array_equal(gmat, O.cal_cnt_mat(wkh, wcnt, k))
+    assert np.array_equal(MD.cal_cnt_mat(kh, cnt, k), O.cal_cnt_mat(kh, cnt, k))
+
+
+def test_find_motif_sorted_path_equals_dense_path(ENG, MD, K, small_cases, motif_def_file):
+    """the two counting paths are interchangeable: find_motif through the sort path (forced) == through the dense table"""
+    mdd = K.init_motif_def_dict(motif_def_file)
+    for idx in (0, 5, 10, 15):
+        c = small_cases["cases"][idx]
+        k, m = c["k"], mdd[c["k"]]
+        out = []
+        for sorted_path in (False, True):
+            dev = ENG.SeqOnDevice.from_numpy(small_cases["seq"], small_cases["borders"], keep_u8=True)
+            found, first = MD.find_motif_on_device(dev, k, m.max_ham_dist, m.p_uniform, m.ratio_mu, m.ratio_std, m.ratio_cutoff, 5, 10,
+                                                   c["revcom"], c["rep"], sorted_path=sorted_path)
+            seq = small_cases["seq"].copy()
+            dev.masked_seq_to_numpy(seq)
+            out.append((found, first, seq))
+        (f0, a0, s0), (f1, a1, s1) = out
+        assert [int(x) for x in f0] == [int(x) for x in f1] == [int(x) for x in c["consensus"]]
+        assert all(f0[a] == f1[b] for a, b in zip(f0, f1))
+        assert np.array_equal(a0[0], a1[0]) and np.array_equal(a0[1], a1[1]) and a0[0].dtype == a1[0].dtype and a0[1].dtype == a1[1].dtype
+        assert np.array_equal(s0, s1) and np.array_equal(s0, c["masked"])
