@@ -63,6 +63,15 @@ int kmap_ham_dist_tail_u64(const uint64_t* kh, int64_t n, uint64_t target, int k
 /* revcom_hash_kernel_uint32/64 (taichi_core.py:181-224) behind get_revcom_hash_arr (kmer_count.py:613-623) */
 int kmap_revcom_u32(const uint32_t* in, int64_t n, int k, uint32_t* out, void* stream);
 int kmap_revcom_u64(const uint64_t* in, int64_t n, int k, uint64_t* out, void* stream);
+/* the labelling step of sample_disp_kmer (motif_discovery.py:849-892) for all unique k-mers at once: label[i] = index of
+ * the nearest consensus (head distance over the first conseq_len[c] bases to conseq[c], or -- revcom != 0 -- tail distance
+ * over the last conseq_len[c] bases to rc_conseq[c]; a consensus farther than dmax[c] counts as distance k; ties keep
+ * the first), or n_conseq when the nearest is farther than dmax_k; k-mers strictly closer to the reverse complement of
+ * their consensus are reverse-complemented in place. */
+int kmap_label_kmers_u32(uint32_t* kh, int64_t n, int k, const uint32_t* conseq, const uint32_t* rc_conseq, const int32_t* conseq_len,
+                         const int32_t* dmax, int n_conseq, int dmax_k, int revcom, int32_t* label, void* stream);
+int kmap_label_kmers_u64(uint64_t* kh, int64_t n, int k, const uint64_t* conseq, const uint64_t* rc_conseq, const int32_t* conseq_len,
+                         const int32_t* dmax, int n_conseq, int dmax_k, int revcom, int32_t* label, void* stream);
 /* remove_duplicate_hash_per_seq (kmer_count.py:743-760): in place on a hash array; borders = int64[n_seq][2]
  * ([start, end) per read).  Keeps the FIRST occurrence of every hash inside a read. */
 int kmap_dedup_hash_per_read_u32(uint32_t* hash, int64_t n, const int64_t* borders, int64_t n_seq, void* stream);

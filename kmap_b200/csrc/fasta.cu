@@ -322,7 +322,8 @@ int kmap_fasta_emit(const uint8_t* text, int64_t n, const int64_t* state_in_host
     cudaStream_t s = as_stream(stream);
     const int64_t n_tiles = fa_tiles(n);
     const int64_t new_records = state_out_host[1] - state_in_host[1];
-    const int64_t outputs = (state_out_host[0] - state_in_host[0]) + new_records;
+    const int64_t outputs = (state_out_host[0] - state_in_host[0]) + new_records            // (the file's first header has no separator in front)
+                            - (state_in_host[1] == 0 && state_out_host[1] > 0 ? 1 : 0) + (final_chunk && state_out_host[1] > 0 ? 1 : 0);
     KMAP_REQUIRE(outputs == 0 || seq_out, "null pointer (seq_out)");
     KMAP_REQUIRE(new_records == 0 || rec_start_out, "null pointer (rec_start_out)");
     const TileStart* starts = reinterpret_cast<const TileStart*>(scratch + 4 + 2 * n_tiles);

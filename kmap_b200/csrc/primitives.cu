@@ -70,6 +70,47 @@ __global__ void revcom_kernel(const H* __restrict__ in, int64_t n, int k, H* __r
     else out[i] = (H)revcom64((uint64_t)in[i] & lowmask64(k), k);
 }
 
+// sample_disp_kmer's labelling (motif_discovery.py:849-892) fused: for every unique k-mer the nearest consensus by
+// head distance (first len(conseq) bases vs the consensus) or, in revcom mode, tail distance (last len(conseq) bases vs
+// its reverse complement); a consensus farther than its own max distance counts as distance k; label = first nearest
+// consensus, or n_conseq when even the nearest is beyond dmax_k; a k-mer labelled i that is strictly closer to the reverse
+// complement of consensus i is reverse-complemented in place.  One thread = one k-mer; the reference scans the list
+// 2 x n_conseq times and builds two n_conseq x n matrices on the host.
+template <typename H>
+__global__ void __launch_bounds__(256) label_kmers_kernel(H* __restrict__ kh, int64_t n, int k, const H* __restrict__ conseq,
+                                                          const H* __restrict__ rc_conseq, const int32_t* __restrict__ conseq_len,
+                                                          const int32_t* __restrict__ dmax, int n_conseq, int dmax_k, int revcom,
+                                                          int32_t* __restrict__ label) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const H h = kh[i];
+    int best = 0x7FFFFFFF, best_i = 0;
+    bool best_flip = false;
+    for (int c = 0; c < n_conseq; ++c) {
+        const int len = __ldg(conseq_len + c);
+        int d, rd = 0x7FFFFFFF;
+        if (sizeof(H) == 4) {
+            const uint32_t low = lowmask32(len);
+            d = (int)nz_groups32((uint32_t)(h >> (2 * (k - len))) ^ (uint32_t)__ldg(conseq + c), low);
+            if (revcom) rd = (int)nz_groups32((uint32_t)h ^ (uint32_t)__ldg(rc_conseq + c), low);
+        } else {
+            const uint64_t low = lowmask64(len);
+            d = (int)nz_groups64((uint64_t)(h >> (2 * (k - len))) ^ (uint64_t)__ldg(conseq + c), low);
+            if (revcom) rd = (int)nz_groups64((uint64_t)h ^ (uint64_t)__ldg(rc_conseq + c), low);
+        }
+        const bool flip = rd < d;
+        int dist = flip ? rd : d;
+        if (dist > __ldg(dmax + c)) dist = k;
+        if (dist < best) { best = dist; best_i = c; best_flip = flip; }        // strict: np.argmin keeps the first minimum
+    }
+    if (best > dmax_k) { best_i = n_conseq; best_flip = false; }
+    label[i] = best_i;
+    if (best_flip) {
+        if (sizeof(H) == 4) kh[i] = (H)revcom32((uint32_t)(h & lowmask32(k)), k);
+        else kh[i] = (H)revcom64((uint64_t)h & lowmask64(k), k);
+    }
+}
+
 // remove_duplicate_hash_per_seq (kmer_count.py:743-760): one block per read; a shared-memory map
 // hash -> smallest position (open addressing), filled in passes when the read has more distinct hashes than the
 // map holds (pass p owns the hashes with mix(h) % n_pass == p).  Any position that is not the first occurrence
@@ -116,6 +157,17 @@ __global__ void __launch_bounds__(256) dedup_hash_per_read_kernel(uint32_t* __re
             __syncthreads();
         }
     }
+}
+
+template <typename H>
+int launch_label(H* kh, int64_t n, int k, const H* conseq, const H* rc_conseq, const int32_t* conseq_len, const int32_t* dmax,
+                 int n_conseq, int dmax_k, int revcom, int32_t* label, void* stream, int kmax) {
+    KMAP_REQUIRE(n >= 0 && k >= 1 && k <= kmax && n_conseq >= 0, "bad argument");
+    if (n == 0) return KMAP_OK;
+    KMAP_REQUIRE(kh && label && (n_conseq == 0 || (conseq && rc_conseq && conseq_len && dmax)), "null pointer");
+    label_kmers_kernel<H><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(kh, n, k, conseq, rc_conseq, conseq_len, dmax, n_conseq, dmax_k,
+                                                                          revcom, label);
+    return kmap_check_launch("label_kmers");
 }
 
 template <typename H>
@@ -178,6 +230,14 @@ int kmap_revcom_u64(const uint64_t* in, int64_t n, int k, uint64_t* out, void* s
     if (n == 0) return KMAP_OK;
     revcom_kernel<uint64_t><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(in, n, k, out);
     return kmap_check_launch("revcom");
+}
+int kmap_label_kmers_u32(uint32_t* kh, int64_t n, int k, const uint32_t* conseq, const uint32_t* rc_conseq, const int32_t* conseq_len,
+                         const int32_t* dmax, int n_conseq, int dmax_k, int revcom, int32_t* label, void* stream) {
+    return launch_label<uint32_t>(kh, n, k, conseq, rc_conseq, conseq_len, dmax, n_conseq, dmax_k, revcom, label, stream, 15);
+}
+int kmap_label_kmers_u64(uint64_t* kh, int64_t n, int k, const uint64_t* conseq, const uint64_t* rc_conseq, const int32_t* conseq_len,
+                         const int32_t* dmax, int n_conseq, int dmax_k, int revcom, int32_t* label, void* stream) {
+    return launch_label<uint64_t>(kh, n, k, conseq, rc_conseq, conseq_len, dmax, n_conseq, dmax_k, revcom, label, stream, 31);
 }
 int kmap_dedup_hash_per_read_u32(uint32_t* hash, int64_t n, const int64_t* borders, int64_t n_seq, void* stream) {
     KMAP_REQUIRE(n >= 0 && n_seq >= 0, "negative size");

@@ -463,37 +463,26 @@ def read_fasta_bytes(fasta_file) -> np.ndarray:
     return raw[m.end() - 1:]
 
 
-def fasta_text_to_device(text: np.ndarray, chunk_bytes: int = 1 << 28) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(seq uint8[n_pos], borders int64[n_seq, 2]) on the device from FASTA text that starts at its first header line
-    (csrc/fasta.cu; reference kmer_count.py:244-263, 326-347).  The text travels in chunks of `chunk_bytes`."""
+def _fasta_chunks_to_device(chunks) -> Tuple[torch.Tensor, torch.Tensor]:
+    """core of the ingest: `chunks` yields (device uint8 tensor, is_final) in file order"""
     L = lib()
-    dev = require_cuda()
-    text = np.ascontiguousarray(text, dtype=np.uint8)
-    n = len(text)
     state = (ctypes.c_int64 * 4)(0, 0, 0, 10)
     parts, starts = [], []
-    pos = 0
-    while True:
-        end = min(pos + max(int(chunk_bytes), 16), n)
-        final = end >= n
-        chunk = torch.from_numpy(text[pos:end]).to(dev) if end > pos else torch.empty(0, dtype=torch.uint8, device=dev)
-        nc = end - pos
+    for chunk, final in chunks:
+        nc = int(chunk.numel())
         scratch = empty(L.kmap_fasta_scratch_words(nc), torch.int64)
         out = (ctypes.c_int64 * 4)()
-        check(L.kmap_fasta_scan(_ptr(chunk), nc, state, _ptr(scratch), out, _stream_ptr()), "kmap_fasta_scan")
+        check(L.kmap_fasta_scan(_ptr(chunk) if nc else None, nc, state, _ptr(scratch), out, _stream_ptr()), "kmap_fasta_scan")
         new_rec = out[1] - state[1]
         n_out = (out[0] - state[0]) + new_rec - (1 if state[1] == 0 and out[1] > 0 else 0) + (1 if final and out[1] > 0 else 0)
         origin = state[0] + max(state[1] - 1, 0)
         seq_part = empty(n_out, torch.uint8)
         rec_start = empty(new_rec, torch.int64)
-        check(L.kmap_fasta_emit(_ptr(chunk), nc, state, _ptr(scratch), _ptr(seq_part), origin, _ptr(rec_start), int(final), out,
-                                _stream_ptr()), "kmap_fasta_emit")
+        check(L.kmap_fasta_emit(_ptr(chunk) if nc else None, nc, state, _ptr(scratch), _ptr(seq_part) if n_out else None, origin,
+                                _ptr(rec_start) if new_rec else None, int(final), out, _stream_ptr()), "kmap_fasta_emit")
         parts.append(seq_part)
         starts.append(rec_start)
         state = out
-        pos = end
-        if final:
-            break
     seq = parts[0] if len(parts) == 1 else torch.cat(parts)
     rec_start = starts[0] if len(starts) == 1 else torch.cat(starts)
     n_rec = int(state[1])
@@ -505,5 +494,77 @@ def fasta_text_to_device(text: np.ndarray, chunk_bytes: int = 1 << 28) -> Tuple[
     return seq, borders.view(n_rec, 2)
 
 
+def fasta_text_to_device(text: np.ndarray, chunk_bytes: int = 1 << 28) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(seq uint8[n_pos], borders int64[n_seq, 2]) on the device from FASTA text that starts at its first header line
+    (csrc/fasta.cu; reference kmer_count.py:244-263, 326-347).  The text travels in chunks of `chunk_bytes`."""
+    dev = require_cuda()
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    n = len(text)
+    step = max(int(chunk_bytes), 16)
+
+    def chunks():
+        pos = 0
+        while True:
+            end = min(pos + step, n)
+            yield (torch.from_numpy(text[pos:end]).to(dev) if end > pos else torch.empty(0, dtype=torch.uint8, device=dev)), end >= n
+            pos = end
+            if end >= n:
+                return
+    return _fasta_chunks_to_device(chunks())
+
+
 def fasta_to_device(fasta_file, chunk_bytes: int = 1 << 28) -> Tuple[torch.Tensor, torch.Tensor]:
-    return fasta_text_to_device(read_fasta_bytes(fasta_file), chunk_bytes)
+    """the file -> (seq, borders) on the device.  A plain file is read straight into two alternating pinned staging buffers
+    (no pageable copy of the text); a .gz file is inflated on the host first (kmer_count.py:318-323)."""
+    import os
+    import re
+    if str(fasta_file).endswith(".gz"):
+        return fasta_text_to_device(read_fasta_bytes(fasta_file), chunk_bytes)
+    dev = require_cuda()
+    size = os.path.getsize(fasta_file)
+    step = max(int(chunk_bytes), 1 << 16)
+    first_header = re.compile(rb"(?:\A|[\r\n])>")
+    later_header = re.compile(rb"[\r\n]>")            # (the byte carried over from the previous block is not a line start)
+
+    def chunks():
+        with open(fasta_file, "rb", buffering=0) as fh:
+            # skip whatever precedes the first header line
+            pos, tail = 0, b""
+            start = None
+            while pos < size and start is None:
+                block = fh.read(1 << 20)
+                if not block:
+                    break
+                m = (first_header if pos == 0 else later_header).search(tail + block)
+                if m is not None:
+                    start = pos - len(tail) + m.end() - 1
+                tail = block[-1:]
+                pos += len(block)
+            if start is None:
+                yield torch.empty(0, dtype=torch.uint8, device=dev), True
+                return
+            fh.seek(start)
+            pos = start
+            cap = min(step, size - start)
+            stage = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(2 if size - start > cap else 1)]
+            busy = [None] * len(stage)
+            i = 0
+            while True:
+                buf = stage[i % len(stage)]
+                if busy[i % len(stage)] is not None:
+                    busy[i % len(stage)].synchronize()          # the copy that last used this buffer is done
+                got = fh.readinto(memoryview(buf.numpy())[:min(cap, size - pos)])
+                got = got or 0
+                pos += got
+                final = pos >= size or got == 0
+                d = torch.empty(got, dtype=torch.uint8, device=dev)
+                if got:
+                    d.copy_(buf[:got], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    busy[i % len(stage)] = ev
+                yield d, final
+                if final:
+                    return
+                i += 1
+    return _fasta_chunks_to_device(chunks())

@@ -392,6 +392,32 @@ def cal_samp_kmer_hamdist_mat(samp_kh_arr: np.ndarray, samp_cnts: np.ndarray, sa
 # ======================================================================================================================
 # k-mer sampling for the visualisation (:812-921)
 # ======================================================================================================================
+def label_kmers(uniq_kh_arr, conseq_list: List[str], kmer_len: int, motif_def_dict: dict, revcom_mode=True):
+    """:849-892, the deterministic part of sample_disp_kmer in one device pass (kmap_label_kmers_*): (k-mers with the
+    reverse-complement-closer ones flipped, label per k-mer; label == len(conseq_list) means "no motif")."""
+    hd = get_hash_dtype(kmer_len)
+    kh = np.asarray(uniq_kh_arr)
+    n, n_conseq = len(kh), len(conseq_list)
+    if n == 0:
+        return kh.copy(), np.zeros(0, dtype=np.intp)
+    ckh = [kmer2hash(c) for c in conseq_list]
+    rckh = [revcom_hash(h, len(c)) for h, c in zip(ckh, conseq_list)]
+    if revcom_mode:
+        assert all(int(a) <= int(b) for a, b in zip(ckh, rckh))
+    L = lib()
+    kh_d = E.to_device(kh.astype(hd, copy=True))
+    c_d = E.to_device(np.array([int(x) for x in ckh], dtype=hd))
+    rc_d = E.to_device(np.array([int(x) for x in rckh], dtype=hd))
+    len_d = E.to_device(np.array([len(c) for c in conseq_list], dtype=np.int32))
+    dmax_d = E.to_device(np.array([motif_def_dict[len(c)].max_ham_dist for c in conseq_list], dtype=np.int32))
+    label_d = E.empty(n, torch.int32)
+    fn = L.kmap_label_kmers_u32 if hd == np.uint32 else L.kmap_label_kmers_u64
+    check(fn(kh_d.data_ptr(), n, kmer_len, c_d.data_ptr(), rc_d.data_ptr(), len_d.data_ptr(), dmax_d.data_ptr(), n_conseq,
+             int(motif_def_dict[kmer_len].max_ham_dist), int(revcom_mode), label_d.data_ptr(),
+             torch.cuda.current_stream().cuda_stream), "kmap_label_kmers")
+    return E.to_host(kh_d, hd).astype(kh.dtype, copy=False), label_d.cpu().numpy().astype(np.intp)
+
+
 def sample_disp_kmer(conseq_list: List[str], kmer_len: int, motif_def_dict: dict, kmer_count_dir: Path,
                      n_total_sample=5000, n_motif_kmer=2500, revcom_mode=True) -> Tuple:
     conseq_list = [s for s in conseq_list if 2 < len(s) <= kmer_len]
@@ -407,29 +433,8 @@ def sample_disp_kmer(conseq_list: List[str], kmer_len: int, motif_def_dict: dict
         warnings.warn(f"The number of samples n_sample={n_total_sample} is larger than the original "
                       f"data n_seq={total}, process and return original data.")
         sampling_flag = False
-    n_conseq, n_uniq = len(conseq_list), len(uniq_kh_arr)
-    ham_dist_mat = np.zeros((n_conseq, n_uniq), dtype=int)
-    rc_flag_mat = np.zeros((n_conseq, n_uniq), dtype=bool)
-    for i, conseq in enumerate(conseq_list):
-        conseq_kh = kmer2hash(conseq)
-        dist_arr = cal_hamming_dist_head(uniq_kh_arr, conseq_kh, kmer_len, len(conseq))
-        if revcom_mode:
-            rc_conseq_kh = revcom_hash(conseq_kh, len(conseq))
-            assert conseq_kh <= rc_conseq_kh
-            rc_dist_arr = cal_hamming_dist_tail(uniq_kh_arr, rc_conseq_kh, kmer_len, len(conseq))
-            rc_flag_mat[i] = rc_dist_arr < dist_arr
-            dist_arr = np.minimum(dist_arr, rc_dist_arr)
-        ham_dist_mat[i] = dist_arr
-    for i, conseq in enumerate(conseq_list):
-        ham_dist_mat[i][ham_dist_mat[i] > motif_def_dict[len(conseq)].max_ham_dist] = kmer_len
-    min_dist_arr = np.min(ham_dist_mat, axis=0)
-    label_arr = np.argmin(ham_dist_mat, axis=0)
-    label_arr[min_dist_arr > motif_def_dict[kmer_len].max_ham_dist] = n_conseq
-    if revcom_mode:
-        for i in range(n_conseq):
-            idx = np.where((label_arr == i) & rc_flag_mat[i])[0]
-            if len(idx):
-                uniq_kh_arr[idx] = get_revcom_hash_arr(uniq_kh_arr[idx], kmer_len)
+    n_conseq = len(conseq_list)
+    uniq_kh_arr, label_arr = label_kmers(uniq_kh_arr, conseq_list, kmer_len, motif_def_dict, revcom_mode)
     if not sampling_flag:
         return uniq_kh_arr, uniq_kh_cnt_arr, label_arr, conseq_list
     sample_cnt_arr = np.bincount(label_arr, weights=uniq_kh_cnt_arr)

@@ -50,6 +50,11 @@ def main():
     del seq_d, borders_d
     ms_e2e, (s_d, b_d) = ev_time(lambda: E.fasta_text_to_device(text, chunk_bytes=1 << 28))
     assert np.array_equal(s_d.cpu().numpy(), seq) and np.array_equal(b_d.cpu().numpy(), borders)
+    fa_path = Path("/tmp/kmap_bench_ingest.fa")
+    text.tofile(fa_path)
+    ms_file, (s_d, b_d) = ev_time(lambda: E.fasta_to_device(fa_path))
+    assert np.array_equal(s_d.cpu().numpy(), seq) and np.array_equal(b_d.cpu().numpy(), borders)
+    fa_path.unlink()
     text_d = torch.from_numpy(text).cuda()
     L = E.lib()
     import ctypes
@@ -79,6 +84,7 @@ def main():
         "reads": n_ingest, "text_bytes": int(len(text)), "device_ms_text_resident": ms_dev,
         "text_GBs_resident": len(text) / ms_dev / 1e6, "algorithmic_GBs": (2 * len(text) + len(seq) + 16 * len(borders)) / ms_dev / 1e6,
         "ms_from_host_text": ms_e2e, "text_GBs_from_host": len(text) / ms_e2e / 1e6,
+        "ms_from_file_page_cache": ms_file, "text_GBs_from_file": len(text) / ms_file / 1e6,
         "cpu_oracle_text_MBs": n_cpu * (len(text) // n_ingest) / cpu_s / 1e6, "cpu_sample_reads": n_cpu, "bytes_model": int(bytes_algo)}
     del text_d, scratch, seq_out, rec, s_d, b_d
     # ---- sorted path vs dense path -----------------------------------------------------------------------------------------
@@ -114,7 +120,7 @@ def main():
     s_np, b_np = synth.generate_numpy(spec, 0, n_cpu)
     t0 = time.perf_counter()
     h = O.comp_kmer_hash(s_np, 16)
-    h = O.remove_duplicate_hash_per_seq(h, b_np, O.get_invalid_hash(h.dtype))
+    h = O.remove_duplicate_hash_per_seq(h, b_np, O.get_invalid_hash(h.dtype.type))
     O.merge_revcom(*O.count_uniq_hash(h, 16), 16)
     out["cpu_oracle_k16_dedup_Gbases_per_s"] = n_cpu * spec.read_len / (time.perf_counter() - t0) / 1e9
     res["sorted_path"] = out

@@ -446,7 +446,8 @@ def test_fasta_ingest_matches_oracle(ENG, K, testfa, tmp_path):
     sequence line, no trailing newline, text before the first header; lines and records that straddle tiles and chunks."""
     rng = np.random.default_rng(77)
     cases = [b"", b"no header at all\nACGT\n", b">", b">\n", b">a", b">a\n\n>b\n>c\nAC", b">r\nACGT", b"\n>r\r\nac gt\r\nNN\r\n",
-             b">x\n" + b"ACGT" * 3000 + b"\n>y\n" + b"T" * 5000, b">" + b"h" * 9000 + b"\nGATTACA\n"]
+             b">x\n" + b"ACGT" * 3000 + b"\n>y\n" + b"T" * 5000, b">" + b"h" * 9000 + b"\nGATTACA\n",
+             b"x>y" * 400000 + b"\n>r1\nACGT\n>r2\nTTGA\n", b"j" * ((1 << 20) - 1) + b">\n>q\nAC\n", b"j" * ((1 << 20) - 1) + b"\n>q\nAC\n"]
     cases += [_random_fasta_text(rng, int(rng.integers(0, 8)), 4, 14).encode() for _ in range(150)]
     cases += [_random_fasta_text(rng, int(rng.integers(50, 400)), 3, 300).encode() for _ in range(6)]
     for i, raw in enumerate(cases):
@@ -458,6 +459,10 @@ def test_fasta_ingest_matches_oracle(ENG, K, testfa, tmp_path):
             if chunk < 4096 and len(raw) > 20000:
                 continue
             seq_d, b_d = ENG.fasta_text_to_device(text, chunk_bytes=chunk)
+            assert np.array_equal(seq_d.cpu().numpy(), want_seq), (i, chunk)
+            assert np.array_equal(b_d.cpu().numpy(), np.asarray(want_b, dtype=np.int64).reshape(-1, 2)), (i, chunk)
+        for chunk in (1 << 28, 1 << 16):             # the file path: pinned staging buffers, header search across blocks
+            seq_d, b_d = ENG.fasta_to_device(fa, chunk_bytes=chunk)
             assert np.array_equal(seq_d.cpu().numpy(), want_seq), (i, chunk)
             assert np.array_equal(b_d.cpu().numpy(), np.asarray(want_b, dtype=np.int64).reshape(-1, 2)), (i, chunk)
     # test.fa itself (rebuilt from the golden arrays, 60 bases per line) and its gzipped copy, through the public function
@@ -500,7 +505,7 @@ def test_fasta_ingest_large_synthetic(ENG):
 def _oracle_counts(seq, borders, k, dedup):
     h = O.comp_kmer_hash(seq, k)
     if dedup:
-        h = O.remove_duplicate_hash_per_seq(h, borders, O.get_invalid_hash(h.dtype))
+        h = O.remove_duplicate_hash_per_seq(h, borders, O.get_invalid_hash(h.dtype.type))
     return O.count_uniq_hash(h, k)
 
 
@@ -543,8 +548,8 @@ def test_sorted_count_and_merge_vs_oracle(ENG, K, k):
     if k >= 16:    # the reference-shaped array functions on uint64 hashes
         h = K.comp_kmer_hash_taichi(seq, k)
         assert h.dtype == np.uint64 and np.array_equal(h, O.comp_kmer_hash(seq, k))
-        hd = K.remove_duplicate_hash_per_seq(h.copy(), borders, K.get_invalid_hash(h.dtype))
-        assert np.array_equal(hd, O.remove_duplicate_hash_per_seq(h.copy(), borders, O.get_invalid_hash(h.dtype)))
+        hd = K.remove_duplicate_hash_per_seq(h.copy(), borders, K.get_invalid_hash(h.dtype.type))
+        assert np.array_equal(hd, O.remove_duplicate_hash_per_seq(h.copy(), borders, O.get_invalid_hash(h.dtype.type)))
         u, c = K.count_uniq_hash(hd, k)
         wu, wc = O.count_uniq_hash(hd, k)
         assert u.dtype == wu.dtype and c.dtype == wc.dtype and np.array_equal(u, wu) and np.array_equal(c, wc)
@@ -603,3 +608,31 @@ def test_find_motif_sorted_path_equals_dense_path(ENG, MD, K, small_cases, motif
         assert all(f0[a] == f1[b] for a, b in zip(f0, f1))
         assert np.array_equal(a0[0], a1[0]) and np.array_equal(a0[1], a1[1]) and a0[0].dtype == a1[0].dtype and a0[1].dtype == a1[1].dtype
         assert np.array_equal(s0, s1) and np.array_equal(s0, c["masked"])
+
+
+@pytest.mark.parametrize("k,conseqs", [(14, ["GTACGTAGGTCCTA", "AATCGATAGCGA", "ACGTAG"]), (16, ["AGTACGTAGGTCCTCA", "AATCGATAGCGAAG"]),
+                                      (9, ["ACCTACGTA"]), (12, ["AAAAAAAAAAAA", "CCCCCCCC"])])
+def test_label_kmers_vs_oracle(MD, K, motif_def_file, k, conseqs):
+    """the fused labelling kernel of sample_disp_kmer == the oracle's statement-by-statement restatement (md:849-892)"""
+    mdd = K.init_motif_def_dict(motif_def_file)
+    conseqs = [c if O.kmer2hash(c) <= O.revcom_hash(O.kmer2hash(c), len(c)) else O.reverse_complement(c) for c in conseqs]
+    rng = np.random.default_rng(k)
+    hd = K.get_hash_dtype(k)
+    pool = [rng.integers(0, 4 ** k, 4000, dtype=np.uint64)]
+    for c in conseqs:                       # k-mers around each consensus and around its reverse complement, at every offset
+        for s in (c, O.reverse_complement(c)):
+            base = np.array([int(x) for x in O.dna2arr(s, append_missing_val_flag=False)])
+            for _ in range(600):
+                full = rng.integers(0, 4, k)
+                off = int(rng.integers(0, k - len(s) + 1))
+                full[off:off + len(s)] = base
+                idx = rng.choice(k, int(rng.integers(0, 4)), replace=False)
+                full[idx] = rng.integers(0, 4, len(idx))
+                pool.append(np.array([int(O.kmer2hash(O.arr2dna(full.astype(np.uint8))))], dtype=np.uint64))
+    kh = np.unique(np.concatenate(pool)).astype(hd)
+    for revcom in (True, False):
+        want_kh, want_label = O.label_kmers(kh, conseqs, k, mdd, revcom)
+        got_kh, got_label = MD.label_kmers(kh, conseqs, k, mdd, revcom)
+        assert got_kh.dtype == want_kh.dtype and np.array_equal(got_kh, want_kh), (k, revcom)
+        assert np.array_equal(got_label, want_label), (k, revcom)
+        assert len(set(got_label.tolist())) >= 2
