@@ -25,17 +25,35 @@
 
 namespace {
 
-constexpr int FA_THREADS = 256;
+constexpr int FA_THREADS = 512;
 constexpr int FA_PER = 16;                          // bytes per thread: one 128-bit load
-constexpr int FA_TILE = FA_THREADS * FA_PER;
+constexpr int FA_TILE = FA_THREADS * FA_PER;        // 8192 bytes
 enum : int { FA_SEQ = 0, FA_HDR = 1, FA_UNK = 2 };
 
-__device__ __forceinline__ bool fa_eol(uint32_t c) { return c == 10u || c == 13u; }
-// dropped from sequence lines: white space as str.split() sees it, and UTF-8 continuation bytes
-__device__ __forceinline__ bool fa_dropped(uint32_t c) { return (c >= 9u && c <= 13u) || (c >= 28u && c <= 32u) || (c & 0xC0u) == 0x80u; }
-__device__ __forceinline__ uint32_t fa_code(uint32_t c) {
-    c |= 0x20u;                                     // upper() (kmer_count.py:316), folded to lower case here
-    return c == 'a' ? 0u : c == 'c' ? 1u : c == 'g' ? 2u : c == 't' ? 3u : 255u;
+// Byte classes are computed four bytes per word with plain integer arithmetic (the __vcmp*4 intrinsics are emulated by ~10
+// instructions each on this architecture -- measured: the kernels were bound by them), giving a 0x80 flag per byte, then
+// squeezed to one bit per byte, so that everything after that is bit arithmetic on 16-bit masks.
+__device__ __forceinline__ uint32_t zero80(uint32_t v) { return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u; }   // 0x80 per zero byte
+__device__ __forceinline__ uint32_t eq80(uint32_t w, uint32_t c) { return zero80(w ^ c); }
+__device__ __forceinline__ uint32_t bits80(uint32_t m) { return ((m >> 7) * 0x01020408u) >> 24; }              // 0x80 flags -> 4 bits
+// ASCII bytes with lo <= c <= hi (constants replicated in every byte, < 128)
+__device__ __forceinline__ uint32_t range80(uint32_t w, uint32_t lo, uint32_t hi) {
+    const uint32_t a = w & 0x7F7F7F7Fu;
+    const uint32_t x = a + (0x80808080u - lo), y = a + (0x7F7F7F7Fu - hi);
+    return x & ~y & ~w & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t eol80(uint32_t w) { return eq80(w, 0x0A0A0A0Au) | eq80(w, 0x0D0D0D0Du); }
+// dropped from sequence lines: white space as str.split() sees it (9-13, 28-32) and UTF-8 continuation bytes (10xxxxxx)
+__device__ __forceinline__ uint32_t dropped80(uint32_t w) {
+    return range80(w, 0x09090909u, 0x0D0D0D0Du) | range80(w, 0x1C1C1C1Cu, 0x20202020u) | (w & ~(w << 1) & 0x80808080u);
+}
+// upper() + dna2arr (kmer_count.py:244-263, 316): A0 C1 G2 T3 in either case, anything else 255.
+// (c >> 1) & 3 maps A C T G to 0 1 2 3; x ^ (x >> 1) swaps the last two.
+__device__ __forceinline__ uint32_t code4(uint32_t w) {
+    const uint32_t lower = w | 0x20202020u;
+    const uint32_t ok = (eq80(lower & 0xFDFDFDFDu, 0x61616161u) | eq80(lower, 0x67676767u) | eq80(lower, 0x74747474u)) >> 7;   // 0x01 per a/c/g/t
+    const uint32_t x = (w >> 1) & 0x03030303u;
+    return (x ^ ((x >> 1) & 0x01010101u)) | ((ok ^ 0x01010101u) * 255u);
 }
 
 struct ThreadBytes {
@@ -43,7 +61,6 @@ struct ThreadBytes {
     uint32_t ls, hdr, ch; // bit j: byte j starts a line / starts a header line / is a character if its line is a sequence line
     int n;                // bytes that exist (0..16)
 };
-__device__ __forceinline__ uint32_t byte_of(const ThreadBytes& t, int j) { return (t.w[j >> 2] >> (8 * (j & 3))) & 255u; }
 
 __device__ __forceinline__ ThreadBytes load_thread_bytes(const uint8_t* __restrict__ text, int64_t n, int64_t tile, uint32_t carry_last_byte) {
     ThreadBytes t;
@@ -56,41 +73,41 @@ __device__ __forceinline__ ThreadBytes load_thread_bytes(const uint8_t* __restri
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + i0));
         t.w[0] = v.x; t.w[1] = v.y; t.w[2] = v.z; t.w[3] = v.w;
     } else {
-        for (int j = 0; j < t.n; ++j) t.w[j >> 2] |= (uint32_t)__ldg(text + i0 + j) << (8 * (j & 3));
-    }
-    uint32_t prev = i0 > 0 ? (uint32_t)__ldg(text + i0 - 1) : carry_last_byte;
+        uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int j = 0; j < FA_PER; ++j) {
-        if (j < t.n) {
-            const uint32_t c = byte_of(t, j);
-            if (fa_eol(prev)) { t.ls |= 1u << j; if (c == '>') t.hdr |= 1u << j; }
-            if (!fa_dropped(c)) t.ch |= 1u << j;
-            prev = c;
-        }
+        for (int j = 0; j < FA_PER; ++j)
+            if (j < t.n) w[j >> 2] |= (uint32_t)__ldg(text + i0 + j) << (8 * (j & 3));
+        t.w[0] = w[0]; t.w[1] = w[1]; t.w[2] = w[2]; t.w[3] = w[3];
     }
+    const uint32_t prev = i0 > 0 ? (uint32_t)__ldg(text + i0 - 1) : carry_last_byte;
+    const uint32_t exist = t.n == FA_PER ? 0xFFFFu : ((1u << t.n) - 1u);
+    uint32_t eol = 0, gt = 0, drop = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        eol |= bits80(eol80(t.w[q])) << (4 * q);
+        gt |= bits80(eq80(t.w[q], 0x3E3E3E3Eu)) << (4 * q);
+        drop |= bits80(dropped80(t.w[q])) << (4 * q);
+    }
+    t.ls = ((eol << 1) | (prev == 10u || prev == 13u ? 1u : 0u)) & exist;
+    t.hdr = t.ls & gt;
+    t.ch = ~drop & exist;
     return t;
 }
 
 // what a thread's 16 bytes hold, by line type: characters on lines that begin inside the thread's bytes and are sequence
 // lines (known), characters on the line that was in progress at the thread's first byte (pending), the type of the last
-// line started (FA_UNK if none)
-struct ThreadCounts { uint32_t known_seq, pending; int last; };
+// line started (FA_UNK if none).  seq_fill = the bytes on sequence lines that begin inside the thread's bytes: every
+// sequence-line start is extended upwards to the byte before the next line start by letting a carry ripple through the
+// run of non-start bytes above it; before = the bytes before the first line start.
+struct ThreadCounts { uint32_t known_seq, pending, seq_fill, before; int last; };
 __device__ __forceinline__ ThreadCounts count_thread(const ThreadBytes& t) {
     ThreadCounts c;
-    const uint32_t first_ls = t.ls ? (uint32_t)(__ffs(t.ls) - 1) : 32u;
-    const uint32_t before = first_ls >= 32u ? 0xFFFFFFFFu : ((1u << first_ls) - 1u);
-    c.pending = __popc(t.ch & before);
-    // a byte after the first line start belongs to a sequence line iff the latest line start at or before it is not a header
-    uint32_t seq_bytes = 0;
-    uint32_t ls = t.ls;
-    while (ls) {
-        const int j = __ffs(ls) - 1;
-        ls &= ls - 1;
-        const uint32_t upto = ls ? ((1u << (__ffs(ls) - 1)) - 1u) : 0xFFFFFFFFu;       // bytes before the next line start
-        const uint32_t span = upto & ~((1u << j) - 1u);
-        if (!((t.hdr >> j) & 1u)) seq_bytes |= span;
-    }
-    c.known_seq = __popc(t.ch & seq_bytes);
+    const uint32_t not_start = ~t.ls;
+    const uint32_t seq_start = t.ls & ~t.hdr;
+    c.seq_fill = seq_start | (((not_start + (seq_start << 1)) ^ not_start) & not_start);
+    c.before = t.ls ? ((t.ls & (0u - t.ls)) - 1u) : 0xFFFFFFFFu;
+    c.known_seq = __popc(t.ch & c.seq_fill);
+    c.pending = __popc(t.ch & c.before);
     c.last = t.ls ? (((t.hdr >> (31 - __clz(t.ls))) & 1u) ? FA_HDR : FA_SEQ) : FA_UNK;
     return c;
 }
@@ -250,19 +267,19 @@ __global__ void __launch_bounds__(FA_THREADS) fasta_emit_kernel(const uint8_t* _
     // global position of the tile's output number i: first + i, where (sequence characters + separators) written before the
     // tile = seq + max(records - 1, 0); the very first header of the file has no separator in front, its slot is position -1
     const long long first = (long long)(ts.seq_and_type >> 2) + (long long)ts.n_hdr - 1;
-    int type = in_type;
+    // bytes that produce an output: characters on sequence lines, and header starts (the 255 that closes the previous
+    // record, kmer_count.py:261-262 -- '>' encodes to 255 by itself)
+    const uint32_t sel = ((c.seq_fill | (in_type == FA_SEQ ? c.before : 0u)) & t.ch) | t.hdr;
+    uint32_t code[4];
 #pragma unroll
-    for (int j = 0; j < FA_PER; ++j) {
-        if (j < t.n) {
-            if ((t.ls >> j) & 1u) type = ((t.hdr >> j) & 1u) ? FA_HDR : FA_SEQ;
-            if ((t.hdr >> j) & 1u) {
-                stage[pos] = 255;                               // closes the previous record (kmer_count.py:261-262)
-                rec_start[rec - hdr0] = first + (long long)pos + 1;
-                ++pos; ++rec;
-            } else if (type == FA_SEQ && ((t.ch >> j) & 1u)) {
-                stage[pos++] = (uint8_t)fa_code(byte_of(t, j));
-            }
-        }
+    for (int q = 0; q < 4; ++q) code[q] = code4(t.w[q]);
+#pragma unroll
+    for (int j = 0; j < FA_PER; ++j)
+        if ((sel >> j) & 1u) stage[pos + __popc(sel & ((1u << j) - 1u))] = (uint8_t)(code[j >> 2] >> (8 * (j & 3)));
+    for (uint32_t hb = t.hdr; hb; hb &= hb - 1) {
+        const int j = __ffs(hb) - 1;
+        rec_start[rec - hdr0] = first + (long long)(pos + __popc(sel & ((1u << j) - 1u))) + 1;
+        ++rec;
     }
     __syncthreads();
     const uint32_t n_out = total & 0xFFFFu;

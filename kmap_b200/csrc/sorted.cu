@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(256) window_keys_kernel(const uint32_t* __rest
 constexpr int DW_WARPS = 8;
 constexpr int DW_SLOTS = 512;                    // per warp
 constexpr int DW_MAX = 256;                      // positions a warp handles (load factor <= 0.5)
+constexpr int DW_PRE = 4;                        // rounds of 32 keys fetched one read ahead
 
 // reads of at most DW_MAX positions; the others are listed in long_ids (count in *n_long)
 template <typename H>
@@ -63,40 +64,73 @@ __global__ void __launch_bounds__(DW_WARPS * 32) dedup_keys_warp_kernel(H* __res
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     H* set = sets[wib];
     const int64_t n_warps = (int64_t)gridDim.x * DW_WARPS;
-    for (int64_t r = (int64_t)blockIdx.x * DW_WARPS + wib; r < n_seq; r += n_warps) {
-        int64_t st = __ldg(borders + 2 * r), en = __ldg(borders + 2 * r + 1);
-        if (st < 0) st = 0;
-        if (en > n) en = n;
-        const int64_t len = en - st;
+    // Software pipeline over this warp's reads: the borders are requested two reads ahead and the first DW_PRE rounds of
+    // keys one read ahead, so that the two dependent memory latencies (borders -> keys) overlap the work on earlier reads.
+    // (Another read's keys are never written by this warp, so the early loads see what they should.)
+    struct Staged { int64_t st; int64_t len; H h[DW_PRE]; };
+    auto load_borders = [&](int64_t r) {
+        return r < n_seq ? __ldg(reinterpret_cast<const longlong2*>(borders) + r) : make_longlong2(0, 0);
+    };
+    auto stage = [&](const longlong2& b, Staged& g) {
+        const int64_t st = b.x < 0 ? 0 : b.x, en = b.y > n ? n : b.y;
+        g.st = st;
+        g.len = en - st;
+#pragma unroll
+        for (int q = 0; q < DW_PRE; ++q) {
+            const int64_t i = q * 32 + lane;
+            g.h[q] = (g.len <= DW_MAX && i < g.len) ? keys[st + i] : empty;
+        }
+    };
+    const int64_t r0 = (int64_t)blockIdx.x * DW_WARPS + wib;
+    Staged cur, nxt;
+    stage(load_borders(r0), cur);
+    longlong2 raw1 = load_borders(r0 + n_warps);
+    for (int64_t r = r0; r < n_seq; r += n_warps) {
+        const longlong2 raw2 = load_borders(r + 2 * n_warps);
+        stage(raw1, nxt);
+        raw1 = raw2;
+        const Staged g = cur;
+        cur = nxt;
+        const int64_t st = g.st, len = g.len;
         if (len <= 1) continue;
         if (len > DW_MAX) {
             if (lane == 0) long_ids[atomicAdd(n_long, 1u)] = (uint32_t)r;
             continue;
         }
-        for (int j = lane; j < DW_SLOTS; j += 32) set[j] = empty;
+        // slots = the power of two >= 2 * len (load factor <= 0.5), at least 64: short reads clear and probe a small set
+        uint32_t slots = 64;
+        while (slots < 2u * (uint32_t)len) slots <<= 1;
+        const uint32_t slot_mask = slots - 1u;
+        for (uint32_t j = lane; j < slots; j += 32) set[j] = empty;
         __syncwarp();
-        for (int64_t i0 = 0; i0 < len; i0 += 32) {
-            const int64_t i = i0 + lane;
+#pragma unroll 1
+        for (int q = 0; q * 32 < len; ++q) {
+            const int64_t i = q * 32 + lane;
             H h = empty;
-            if (i < len) h = keys[st + i];
+            if (q < DW_PRE) {
+#pragma unroll
+                for (int u = 0; u < DW_PRE; ++u) if (u == q) h = g.h[u];
+            } else if (i < len) {
+                h = keys[st + i];
+            }
             const bool live = h != empty;
             // one lane per distinct key of this round: the lowest one (it is the first occurrence inside the round)
             const H probe = live ? h : (H)(((H)1 << (8 * sizeof(H) - 1)) | (H)lane);     // distinct non-keys for idle lanes (keys have < 64 bits)
             const uint32_t peers = __match_any_sync(0xFFFFFFFFu, probe);
             const bool leader = live && (peers & ((1u << lane) - 1u)) == 0;
             bool dup = live && !leader;
-            if (leader) {
-                uint32_t slot = (uint32_t)mix64((u64)h) & (DW_SLOTS - 1);
-                while (true) {
-                    const H cur = reinterpret_cast<volatile H*>(set)[slot];      // only leaders of distinct keys write in this round
-                    if (cur == h) { dup = true; break; }      // seen in an earlier round
-                    if (cur == empty) {
-                        const H old = atomicCAS(&set[slot], empty, h);
-                        if (old == empty) break;             // claimed
-                        if (old == h) { dup = true; break; }
-                    }
-                    slot = (slot + 1) & (DW_SLOTS - 1);
-                }
+            // warp-uniform probing loop (predicated body: per-lane breaks out of a divergent loop cost more than the probes)
+            bool pending = leader;
+            uint32_t slot = (uint32_t)mix64((u64)h) & slot_mask;
+            while (__any_sync(0xFFFFFFFFu, pending)) {
+                const H seen = pending ? reinterpret_cast<volatile H*>(set)[slot] : h;      // only leaders of distinct keys write in this round
+                H old = seen;
+                if (pending && seen == empty) old = atomicCAS(&set[slot], empty, h);
+                const bool claimed = pending && seen == empty && old == empty;
+                const bool found = pending && old == h;                  // inserted in an earlier round
+                dup = dup || found;
+                pending = pending && !claimed && !found;
+                slot = (slot + 1) & slot_mask;
             }
             if (dup) keys[st + i] = empty;
             __syncwarp();
@@ -226,45 +260,85 @@ __global__ void __launch_bounds__(1024) radix_offsets_kernel(const uint32_t* __r
 
 // stable scatter: warp w of the tile owns keys [w * 512, (w + 1) * 512) in 16 rounds of 32 consecutive keys; inside a
 // round the rank among equal digits comes from __match_any_sync, across rounds from a per-warp counter, across warps and
-// tiles from the scanned histograms.
-__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u64* __restrict__ in, u64* __restrict__ out, int64_t n_upper,
+// tiles from the scanned histograms.  The keys are first put in digit order in shared memory, so that the write-out stores
+// runs of consecutive addresses (one run per digit present in the tile) instead of one scattered 8-byte store per key.
+__global__ void __launch_bounds__(RS_THREADS, 3) radix_scatter_kernel(const u64* __restrict__ in, u64* __restrict__ out, int64_t n_upper,
                                                                    const u64* __restrict__ n_dev, int shift, int drop_empty,
                                                                    int64_t n_tiles, const u64* __restrict__ offsets) {
-    __shared__ uint32_t wcnt[RS_THREADS / 32][256];
-    __shared__ u64 wbase[RS_THREADS / 32][256];
+    __shared__ u64 skeys[RS_TILE];                         // the tile in digit order
+    __shared__ uint32_t wcnt[RS_THREADS / 32][256];        // per (warp, digit): count, then start inside the tile
+    __shared__ u64 gdelta[256];                            // global index of the digit's run - its start inside the tile
+    __shared__ uint32_t scan_ws[RS_THREADS / 32];
+    __shared__ uint32_t tile_total;
     const int64_t n = n_dev ? (int64_t)*n_dev : n_upper;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int q = 0; q < RS_THREADS / 32; ++q) wcnt[q][threadIdx.x] = 0;
     __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * RS_WARP_KEYS;
     u64 key[RS_ITEMS];
-    uint32_t rank[RS_ITEMS];
+    uint32_t rank[RS_ITEMS];          // while the counters are being filled: count before this round | leader lane << 16 | rank among peers << 21
     uint32_t live = 0;
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         const int64_t i = base + r * 32 + lane;
-        key[r] = i < n ? __ldg(in + i) : KEY_EMPTY;
+        key[r] = i < n ? __ldcs(in + i) : KEY_EMPTY;
+    }
+    // The leader of every group of equal digits adds the group's size to the warp's counter of that digit.  The rounds are
+    // issued back to back (the returned values are only looked at after the loop), and __syncwarp orders the updates of
+    // successive rounds, so earlier rounds get the lower ranks: the scatter is stable.
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const int64_t i = base + r * 32 + lane;
         const bool ok = i < n && !(drop_empty && key[r] == KEY_EMPTY);
         const uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, ok ? d : (256u + (uint32_t)lane));
-        const int leader = __ffs(peers) - 1;
+        const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
         uint32_t old = 0;
-        if (ok && lane == leader) { old = wcnt[w][d]; wcnt[w][d] = old + __popc(peers); }
-        old = __shfl_sync(0xFFFFFFFFu, old, leader);
-        rank[r] = old + __popc(peers & ((1u << lane) - 1u));
+        if (ok && (uint32_t)lane == leader) old = atomicAdd(&wcnt[w][d], (uint32_t)__popc(peers));
+        rank[r] = old | (leader << 16) | ((uint32_t)__popc(peers & ((1u << lane) - 1u)) << 21);
         if (ok) live |= 1u << r;
         __syncwarp();
     }
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const uint32_t before = __shfl_sync(0xFFFFFFFFu, rank[r] & 0xFFFFu, (rank[r] >> 16) & 31u);
+        rank[r] = before + (rank[r] >> 21);
+    }
     __syncthreads();
     {
+        // thread d: digit d's keys of the warps in order; then an exclusive scan over the digits gives the tile layout
         const uint32_t d = threadIdx.x;
-        u64 run = offsets[(size_t)d * n_tiles + blockIdx.x];
-        for (int q = 0; q < RS_THREADS / 32; ++q) { wbase[q][d] = run; run += wcnt[q][d]; }
+        uint32_t cnt_w[RS_THREADS / 32];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int q = 0; q < RS_THREADS / 32; ++q) { cnt_w[q] = wcnt[q][d]; mine += cnt_w[q]; }
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) scan_ws[w] = incl;
+        __syncthreads();
+        uint32_t pre = 0, all = 0;
+#pragma unroll
+        for (int q = 0; q < RS_THREADS / 32; ++q) { if (q < w) pre += scan_ws[q]; all += scan_ws[q]; }
+        uint32_t start = pre + incl - mine;                 // first slot of digit d in the tile
+        if (threadIdx.x == 0) tile_total = all;
+        gdelta[d] = offsets[(size_t)d * n_tiles + blockIdx.x] - start;
+#pragma unroll
+        for (int q = 0; q < RS_THREADS / 32; ++q) { wcnt[q][d] = start; start += cnt_w[q]; }
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r)
-        if ((live >> r) & 1u) out[wbase[w][(uint32_t)(key[r] >> shift) & 255u] + rank[r]] = key[r];
+        if ((live >> r) & 1u) skeys[wcnt[w][(uint32_t)(key[r] >> shift) & 255u] + rank[r]] = key[r];
+    __syncthreads();
+    const uint32_t total = tile_total;
+    for (uint32_t i = threadIdx.x; i < total; i += RS_THREADS) {
+        const u64 kk = skeys[i];
+        out[gdelta[(uint32_t)(kk >> shift) & 255u] + i] = kk;
+    }
 }
 
 // ---- run-length encoding of the sorted keys ------------------------------------------------------------------------------------
