@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--partitions", type=int, default=0, help="key-range passes for the k=14 table (0 = auto)")
     ap.add_argument("--cpu-sample-reads", type=int, default=40000)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-hamdist", action="store_true", help="skip the distance-matrix leg (10 GB / n_gpus of output per GPU)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--extras", action="store_true", help="also time compaction / Hamming-ball / mask / distance-matrix kernels")
     return ap.parse_args()
@@ -333,6 +334,40 @@ def main():
                     "algorithmic_bytes_per_launch": alg_bytes / len(per_k_ms), "avg_launch_ms": kern_s * 1e3 / len(per_k_ms),
                     "per_k_ms": {str(k): v for k, v in per_k_ms.items()}, "frac_of_8TBs_nominal": achieved / 8000.0, "algo": "perk"}
 
+    # ---- second half of the metric: pairwise Hamming-distance matrix of 100 000 sampled 14-mers (BASELINE config 5), rows
+    # partitioned over the ranks in contiguous blocks, no collective (cal_samp_kmer_hamdist_mat, motif_discovery.py:759-808)
+    hamdist = None
+    if not args.no_hamdist:
+        from kmap_b200.motif_discovery import hamdist_matrix_u8
+        rng = np.random.default_rng(20240414)
+        n_h, k_h = 100_000, 14
+        khs = np.unique(rng.integers(0, 4 ** k_h, int(n_h * 1.01), dtype=np.uint64))[:n_h].astype(np.uint32)
+        rng.shuffle(khs)
+        labels_h = rng.integers(0, 3, n_h).astype(np.int32)
+        row0, row1 = api.row_range(n_h, rank, world)
+        out_h = E.empty((row1 - row0) * n_h, torch.uint8)
+        hamdist_matrix_u8(khs, labels_h, [14, 12], k_h, row0, row1, out=out_h)             # warm-up
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(5):
+            hamdist_matrix_u8(khs, labels_h, [14, 12], k_h, row0, row1, out=out_h)
+        h1.record()
+        barrier()
+        th = torch.tensor([h0.elapsed_time(h1) / 5], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(th, op=dist.ReduceOp.MAX)
+        ms_h = float(th.item())
+        diag = out_h.view(row1 - row0, n_h)[torch.arange(min(row1 - row0, 1000), device="cuda"), torch.arange(row0, row0 + min(row1 - row0, 1000), device="cuda")]
+        checks["hamdist_diag_zero"] = bool((diag == 0).all().item())
+        hamdist = {"metric": "hamdist_pairs_per_s", "value": n_h * n_h / ms_h * 1e3, "unit": "pairs/s", "ms": ms_h, "pairs": n_h * n_h,
+                   "n_kmers": n_h, "k": k_h, "rows_per_gpu": row1 - row0, "partition": "contiguous row blocks, no collective",
+                   "bytes_written_per_gpu": (row1 - row0) * n_h, "write_GBs_per_gpu": (row1 - row0) * n_h / ms_h / 1e6,
+                   "frac_of_hbm_copy_peak": (row1 - row0) * n_h / ms_h / 1e6 / peak,
+                   "note": "uint8 output, 1 B per pair; same-label pairs of the 12-base consensus use the head distance; includes the "
+                           "H2D of the keys and labels; a B200 writes at most ~3.9 TB/s (the copy peak counts a read and a write)"}
+        del out_h
+
     # ---- end-to-end through the public API with host buffers -------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -395,7 +430,7 @@ def main():
                        "l2": "inputs larger than L2 (packed reads + borders = %.1f GB per GPU)" % ((dev.packed.numel() * 4 + dev.valid.numel() * 4 + n_local * 16) / 1e9),
                        "parallelism": f"reads x{n_gpus}"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (launches_per_step(args, dedup)),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "checks": checks,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "hamdist": hamdist, "checks": checks,
         }
         if extras:
             out["extras"] = extras

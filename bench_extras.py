@@ -76,4 +76,26 @@ def run_extras(dev, tables, n_reads, L, peak_gbs=6455.3):
                                       "frac_of_hbm": n * n / ms / 1e6 / peak_gbs,
                                       "note": "1 B written per pair (uint8); includes the H2D of the 100k keys/labels"}
     del out
+    # The same matrix through an int8 one-hot GEMM (4k = 56 MACs per pair) as the library offers it: cuBLASLt int8 x int8 ->
+    # int32 (torch._int_mm) on a slab of rows, then an epilogue pass matches -> uint8 distance.  A comparator for the design
+    # decision of DESIGN.md section 4.7 only; nothing in the product calls it.  (A fused tcgen05 kernel with a uint8 epilogue
+    # would skip the int32 round trip and then meet the same 1 B/pair store bound as the popcount kernel.)
+    try:
+        slab = 8192
+        codes = torch.from_numpy(((khs[:, None].astype(np.uint64) >> (2 * (k - 1 - np.arange(k, dtype=np.uint64)))[None, :]) & np.uint64(3)).astype(np.int64)).cuda()
+        onehot = torch.zeros((n, 4 * k), dtype=torch.int8, device="cuda")
+        onehot.scatter_(1, codes + 4 * torch.arange(k, device="cuda")[None, :], 1)
+        bt = onehot.t().contiguous()
+        a = onehot[:slab].contiguous()
+        ms_g, matches = _time(lambda: torch._int_mm(a, bt), reps=5)
+        ms_e, d8 = _time(lambda: (k - matches).to(torch.uint8), reps=5)
+        want = hamdist_matrix_u8(khs, np.full(n, 2, dtype=np.int32), [14, 12], k, 0, slab)
+        ok = bool(torch.equal(d8, want))
+        res["hamdist_int8_onehot_gemm_cublaslt"] = {
+            "slab_rows": slab, "gemm_ms_slab": ms_g, "epilogue_ms_slab": ms_e, "full_matrix_ms_extrapolated": (ms_g + ms_e) * n / slab,
+            "int32_bytes_written_per_pair": 4, "equals_popcount_kernel": ok,
+            "note": "library int8 GEMM (cuBLASLt via torch._int_mm) + elementwise epilogue; comparator only"}
+        del onehot, bt, a, matches, d8, want
+    except Exception as exc:                                   # the comparator must never break the bench
+        res["hamdist_int8_onehot_gemm_cublaslt"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     return res

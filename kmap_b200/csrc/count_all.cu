@@ -69,44 +69,53 @@ __global__ void __launch_bounds__(AK_WARPS * 32) dedup_scan_kernel(
     uint32_t* medium_ids = work + 4;
     uint32_t* long_ids = work + 4 + n_seq;
 
-    // Software pipeline over this warp's reads: the borders are requested two reads ahead (raw, nothing consumes them
-    // until the next iteration) and the read's words one read ahead, so the two dependent DRAM latencies
-    // (borders -> words) overlap the processing of earlier reads.
-    struct Staged { int64_t st, en; uint32_t va, vb, w0, w1, w2; };
-    auto load_borders = [&](int64_t r) {
-        return r < n_seq ? __ldg(reinterpret_cast<const longlong2*>(borders) + r) : make_longlong2(0, 0);
-    };
-    auto stage_words = [&](const longlong2& be, Staged& g) {         // raw words of this lane's stretch (no use yet)
-        g.st = be.x < 0 ? 0 : be.x;
-        g.en = be.y > n ? n : be.y;
-        g.va = g.vb = g.w0 = g.w1 = g.w2 = 0;
-        const int64_t n_pos64 = g.en - g.st - kmin + 1;
-        if (n_pos64 <= 0 || n_pos64 > AK_WARP_MAX) return;
-        const int C = ((int)n_pos64 + 31) >> 5;
+    // A warp takes 32 consecutive reads at a time: lane j fetches and clamps the borders of read j (one coalesced 16-byte
+    // load per read, the 64-bit arithmetic done once per lane instead of once per lane and read), then the warp walks the 32
+    // reads, getting (start, length) of each by shuffles.  The words of read j+1 are requested before read j is processed
+    // (nothing consumes them until the next iteration), so their DRAM latency overlaps the work on read j.
+    struct Staged { uint32_t st_lo, st_hi; int L; uint32_t va, vb, w0, w1, w2; };
+    auto stage_words = [&](uint32_t st_lo, uint32_t st_hi, int L, Staged& g) {      // raw words of this lane's stretch (no use yet)
+        g.st_lo = st_lo; g.st_hi = st_hi; g.L = L;            // (words that are not loaded keep stale values: never looked at)
+        const int n_pos = L - kmin + 1;
+        if (n_pos <= 0 || n_pos > AK_WARP_MAX) return;
+        const int C = (n_pos + 31) >> 5;
         const int base = lane * C;
-        if (base >= (int)n_pos64) return;
-        const uint32_t* vd = valid + (g.st >> 5);
-        const int bv = (int)(g.st & 31) + base;
-        g.va = __ldg(vd + (bv >> 5)); g.vb = __ldg(vd + (bv >> 5) + 1);
-        const uint32_t* pk = packed + (g.st >> 4);
-        const int bp = (int)(g.st & 15) + base;
-        g.w0 = __ldg(pk + (bp >> 4)); g.w1 = __ldg(pk + (bp >> 4) + 1); g.w2 = __ldg(pk + (bp >> 4) + 2);
+        if (base >= n_pos) return;
+        // word indices fit 32 bits (the host side checks n < 2^36)
+        const uint32_t bv = (st_lo & 31u) + (uint32_t)base;
+        const uint32_t* vd = valid + (__funnelshift_r(st_lo, st_hi, 5) + (bv >> 5));
+        g.va = __ldg(vd); g.vb = __ldg(vd + 1);
+        const uint32_t bp = (st_lo & 15u) + (uint32_t)base;
+        const uint32_t* pk = packed + (__funnelshift_r(st_lo, st_hi, 4) + (bp >> 4));
+        g.w0 = __ldg(pk); g.w1 = __ldg(pk + 1); g.w2 = __ldg(pk + 2);
     };
-    Staged cur, nxt;
-    stage_words(load_borders(warp0), cur);
-    longlong2 raw1 = load_borders(warp0 + n_warps);
+    const longlong2* borders2 = reinterpret_cast<const longlong2*>(borders);
 
-    for (int64_t r = warp0; r < n_seq; r += n_warps) {
-        const longlong2 raw2 = load_borders(r + 2 * n_warps);
-        stage_words(raw1, nxt);
-        raw1 = raw2;
-        const Staged g = cur;
-        cur = nxt;
-        const int64_t st = g.st, en = g.en;
-        const int64_t L64 = en - st;
-        if (L64 - kmin + 1 <= 0) continue;
-        if (L64 - kmin + 1 > AK_WARP_MAX) {
+    for (int64_t batch = warp0 * 32; batch < n_seq; batch += n_warps * 32) {
+        const int64_t r_lane = batch + lane;
+        const longlong2 be = r_lane < n_seq ? __ldg(borders2 + r_lane) : make_longlong2(0, 0);
+        const int64_t st_lane = be.x < 0 ? 0 : be.x, en_lane = be.y > n ? n : be.y;
+        const int64_t len_lane = en_lane - st_lane;
+        const int L_lane = (int)(len_lane < 0 ? 0 : (len_lane > 0x3FFFFFFF ? 0x3FFFFFFF : len_lane));
+        const uint32_t stlo_lane = (uint32_t)st_lane, sthi_lane = (uint32_t)((uint64_t)st_lane >> 32);
+        const int n_in = (int)(n_seq - batch < 32 ? n_seq - batch : 32);
+        // read j of the batch -> g (reads past the end of the batch get length 0: nothing is loaded, nothing is done)
+        auto stage_at = [&](int j, Staged& g) {
+            const int jj = j < 31 ? j : 31;
+            const uint32_t a = __shfl_sync(0xFFFFFFFFu, stlo_lane, jj), b = __shfl_sync(0xFFFFFFFFu, sthi_lane, jj);
+            const int len = __shfl_sync(0xFFFFFFFFu, L_lane, jj);
+            stage_words(a, b, j < n_in ? len : 0, g);
+        };
+        // everything that happens to one read; two copies of it alternate on two staging registers sets below, so that the
+        // software pipeline needs no register moves
+        auto process = [&](const Staged& g, const int jr) {
+        const int64_t st = (int64_t)(((uint64_t)g.st_hi << 32) | g.st_lo);
+        if (g.L - kmin + 1 <= 0) return;
+        if (g.L - kmin + 1 > AK_WARP_MAX) {
             // too long for the on-chip path: hide the read from the masked count and queue it for the direct kernels
+            const int64_t r = batch + jr;
+            const int64_t en = __shfl_sync(0xFFFFFFFFu, en_lane, jr);
+            const int64_t L64 = en - st;
             for (int64_t w = (st >> 5) + lane; w <= ((en - 1) >> 5); w += 32) {
                 const int64_t lo = w << 5;
                 uint32_t bits = 0xFFFFFFFFu;
@@ -118,10 +127,10 @@ __global__ void __launch_bounds__(AK_WARPS * 32) dedup_scan_kernel(
                 if (L64 - kmin + 1 <= AK_BLOCK_MAX) medium_ids[atomicAdd(&work[0], 1u)] = (uint32_t)r;
                 else long_ids[atomicAdd(&work[1], 1u)] = (uint32_t)r;
             }
-            continue;
+            return;
         }
+        const int L = g.L;
         // this lane's stretch of the read, in 32-bit arithmetic relative to the read start
-        const int L = (int)L64;
         const int n_pos = L - kmin + 1;
         const int C = (n_pos + 31) >> 5;                            // windows per lane, 1..8
         const int base = lane * C;
@@ -148,8 +157,8 @@ __global__ void __launch_bounds__(AK_WARPS * 32) dedup_scan_kernel(
             const uint32_t idx = HASHED ? (key * 0x9E3779B1u) >> 16 : key;
             const uint32_t bit = 1u << (idx & 31u);
             wd[t] = idx >> 5;
-            uint32_t old = 0;
-            if (ok) old = atomicOr(bm + wd[t], bit);
+            // (a lane without a window ORs nothing in: one unconditional ATOMS is cheaper than a branch around it)
+            const uint32_t old = atomicOr(bm + wd[t], ok ? bit : 0u);
             uint32_t todo = __ballot_sync(0xFFFFFFFFu, (old & bit) != 0);
             if (todo) {
                 // rare: exact depth dd of the longest repeat with an earlier window of the read (order: round, then lane)
@@ -191,11 +200,22 @@ __global__ void __launch_bounds__(AK_WARPS * 32) dedup_scan_kernel(
         // give the bitmap back: every bit set above lives in one of the words wd[0..C)
         __syncwarp();
 #pragma unroll
-        for (int t = 0; t < AK_MAXC; ++t) {
-            if (t >= C) break;
-            bm[wd[t]] = 0;
-        }
+        for (int t = 0; t < AK_MAXC; ++t)
+            if (t < C) bm[wd[t]] = 0;
         __syncwarp();
+        };      // process
+
+        Staged sa, sb;
+        sa.st_lo = sa.st_hi = 0; sa.L = 0; sa.va = sa.vb = sa.w0 = sa.w1 = sa.w2 = 0;
+        sb = sa;
+        stage_at(0, sa);
+#pragma unroll 1
+        for (int jr = 0; jr < n_in; jr += 2) {
+            stage_at(jr + 1, sb);
+            process(sa, jr);
+            stage_at(jr + 2, sa);
+            process(sb, jr + 1);
+        }
     }
 }
 
@@ -335,6 +355,7 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
                                 void* const* phase_events, void* stream) {
     KMAP_REQUIRE(n >= 0 && n_seq >= 0 && kmin >= 1 && kmin <= kmax && kmax <= 15, "need 1 <= kmin <= kmax <= 15");
     KMAP_REQUIRE(n_seq < (int64_t)0xFFFFFFFFll, "too many reads for one call (shard the input)");
+    KMAP_REQUIRE(n < ((int64_t)1 << 36), "too many positions for one call (shard the input)");
     KMAP_REQUIRE(tables_host, "null pointer");
     cudaStream_t s = as_stream(stream);
     TableSet tabs;
@@ -361,7 +382,7 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
         e = cudaMemsetAsync(dupmask, 0, (size_t)kmap_valid_words(n) * 4, s);
         if (e == cudaSuccess) e = cudaMemsetAsync(work, 0, 16, s);
         if (e != cudaSuccess) { kmap_set_error("count_all_k: %s", cudaGetErrorString(e)); return (int)e; }
-        int64_t blocks = (n_seq + AK_WARPS - 1) / AK_WARPS;
+        int64_t blocks = (n_seq + 32 * AK_WARPS - 1) / (32 * AK_WARPS);          // a warp takes 32 reads at a time
         if (blocks > 148 * 7 * 8) blocks = 148 * 7 * 8;           // 7 blocks of 4 warps (32 KB of marks each) per SM
         if (kmin > 8)
             dedup_scan_kernel<true><<<(unsigned int)blocks, AK_WARPS * 32, 0, s>>>(packed, valid, n, borders, n_seq, kmin, kmax, tabs, dupmask, work);
