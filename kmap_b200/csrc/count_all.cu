@@ -427,6 +427,8 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
                                     phase_events ? phase_events + 5 : nullptr, s);
         } else {
             KMAP_REQUIRE(part_scratch_bytes >= kmap_partition_scratch_bytes(n, kmax), "partition scratch too small");
+            // (run-end corrections: fused into the histogram pass, except that a level whose table is beyond L2 -- level 13
+            // under k = 14 -- travels through the partition itself as extra buckets; see partition.cu)
             rc = kmap_count_partitioned(packed, valid, hide, n, kmax, tabs.t[kmax], part_scratch, kmin < kmax ? &tabs : nullptr, kmin,
                                         phase_events ? phase_events + 4 : nullptr, s);
         }

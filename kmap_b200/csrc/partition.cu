@@ -23,13 +23,25 @@ constexpr int PT_THREADS = KMAP_TILE_THREADS;
 constexpr int PT_TILE = PT_THREADS * 32;          // positions (= staged entries) per tile
 constexpr int PT_MAX_BUCKETS = 4096;              // k <= 14
 constexpr int PT_MAX_PER = PT_MAX_BUCKETS / PT_THREADS;
+constexpr int PT_MAX_ALL = PT_MAX_BUCKETS + PT_MAX_BUCKETS / 4;      // + the buckets of the routed level k-1 (one per thread at most)
 constexpr int PT_WU = 8;                          // write-out entries in flight per thread
 
-__device__ __forceinline__ void tile_hist(const TileWords& t, int sh, uint32_t* cnt) {
+// extra_base: index of the first extra bucket (= n_buckets).  A routed correction is the (k-1)-mer at a position with
+// exactly k-1 valid bases: bucket extra_base + (its key >> 16), suffix = its low 16 bits.
+__device__ __forceinline__ void tile_hist(const TileWords& t, int sh, uint32_t* cnt, int extra_base) {
     if (t.fresh) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
             if ((t.fresh >> i) & 1u) atomicAdd(&cnt[key_at(t, i, sh) >> 16], 1u);
+    }
+    if (t.corr) {                                   // about one per read
+        uint32_t c = t.corr;
+        do {
+            const int i = __ffs(c) - 1;
+            c &= c - 1;
+            const uint32_t x = (i < 16) ? __funnelshift_l(t.w1, t.w0, 2 * i) : __funnelshift_l(t.w2, t.w1, 2 * (i - 16));
+            atomicAdd(&cnt[extra_base + (x >> (sh + 18))], 1u);
+        } while (c);
     }
 }
 
@@ -50,18 +62,23 @@ __host__ __device__ __forceinline__ int64_t chunk_first_tile(int64_t n_tiles, in
 template <bool TERMINAL, int PER>
 __global__ void __launch_bounds__(PT_THREADS) bucket_hist_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
                                                                  const uint32_t* __restrict__ hide, int64_t n_words, int64_t n_tiles,
-                                                                 int k, int n_buckets, uint16_t* __restrict__ counts,
+                                                                 int k, int n_buckets, int n_extra, uint16_t* __restrict__ counts,
                                                                  uint32_t* __restrict__ off, uint32_t* __restrict__ chunk_total,
-                                                                 KmapTableSet tabs, int kmin) {
-    __shared__ __align__(16) uint32_t cnt2[2][PT_MAX_BUCKETS];      // double buffer: one barrier per tile
+                                                                 KmapTableSet tabs, int kmin, int kcorr) {
+    __shared__ __align__(16) uint32_t cnt2[2][PT_MAX_ALL];          // double buffer: one barrier per tile
     __shared__ uint32_t* stab[16];
     if (TERMINAL && threadIdx.x < 16) stab[threadIdx.x] = tabs.t[threadIdx.x];
-    for (int b = threadIdx.x; b < 2 * PT_MAX_BUCKETS; b += PT_THREADS) (&cnt2[0][0])[b] = 0;
+    for (int b = threadIdx.x; b < 2 * PT_MAX_ALL; b += PT_THREADS) (&cnt2[0][0])[b] = 0;
     __syncthreads();
     const int sh = 32 - 2 * k;
+    const int n_all = n_buckets + n_extra;                          // row length of counts / off / chunk_total
+    const bool route = n_extra > 0;
     const int64_t t0 = chunk_first_tile(n_tiles, blockIdx.x), t1 = chunk_first_tile(n_tiles, blockIdx.x + 1);
     const int b0 = PER * threadIdx.x;                              // this thread's buckets: b0 .. b0 + PER - 1
+    const int bx = n_buckets + threadIdx.x;                        // ... and, when routing, extra bucket bx
+    const bool has_x = (int)threadIdx.x < n_extra;
     uint32_t run[PER];
+    uint32_t runx = 0;
 #pragma unroll
     for (int j = 0; j < PER; ++j) run[j] = 0;
     RawWords nxt = load_raw_words(packed, valid, hide, n_words, t0 < t1 ? t0 : n_tiles);
@@ -74,15 +91,15 @@ __global__ void __launch_bounds__(PT_THREADS) bucket_hist_kernel(const uint32_t*
         const RawPrev rp = nxt_prev;
         nxt = load_raw_words(packed, valid, hide, n_words, tile + 1 < t1 ? tile + 1 : n_tiles);      // (past the end: zeros)
         if (TERMINAL) nxt_prev = load_raw_prev(packed, valid, hide, n_words, tile + 1 < t1 ? tile + 1 : n_tiles);
-        tile_hist(cook(r, k), sh, cnt);
-        if (TERMINAL) run_end_corrections(r, rp, kmin, k, stab);
+        tile_hist(cook(r, k, route), sh, cnt, n_buckets);
+        if (TERMINAL) run_end_corrections(r, rp, kmin, kcorr, stab);      // levels kmin .. kcorr-1
         __syncthreads();       // this tile's counts are complete; the other buffer was zeroed before the previous barrier
         if (b0 < n_buckets) {
             uint32_t c[PER];
 #pragma unroll
             for (int j = 0; j < PER; ++j) { c[j] = cnt[b0 + j]; cnt[b0 + j] = 0; }
-            uint16_t* crow = counts + (size_t)tile * n_buckets + b0;
-            uint32_t* orow = off + (size_t)tile * n_buckets + b0;
+            uint16_t* crow = counts + (size_t)tile * n_all + b0;
+            uint32_t* orow = off + (size_t)tile * n_all + b0;
             if (PER == 4) {
                 __stcs(reinterpret_cast<uint2*>(crow), make_uint2(c[0] | (c[1 % PER] << 16), c[2 % PER] | (c[3 % PER] << 16)));
                 __stcs(reinterpret_cast<uint4*>(orow), make_uint4(run[0], run[1 % PER], run[2 % PER], run[3 % PER]));
@@ -93,11 +110,19 @@ __global__ void __launch_bounds__(PT_THREADS) bucket_hist_kernel(const uint32_t*
 #pragma unroll
             for (int j = 0; j < PER; ++j) run[j] += c[j];
         }
+        if (has_x) {
+            const uint32_t cx = cnt[bx];
+            cnt[bx] = 0;
+            counts[(size_t)tile * n_all + bx] = (uint16_t)cx;
+            off[(size_t)tile * n_all + bx] = runx;
+            runx += cx;
+        }
     }
     if (b0 < n_buckets) {
 #pragma unroll
-        for (int j = 0; j < PER; ++j) chunk_total[(size_t)blockIdx.x * n_buckets + b0 + j] = run[j];
+        for (int j = 0; j < PER; ++j) chunk_total[(size_t)blockIdx.x * n_all + b0 + j] = run[j];
     }
+    if (has_x) chunk_total[(size_t)blockIdx.x * n_all + bx] = runx;
 }
 
 // block-wide exclusive scan of one value per thread (two barriers inside)
@@ -173,18 +198,20 @@ __global__ void __launch_bounds__(256) chunk_base_kernel(const uint32_t* __restr
 // 25k LSU cycles per tile; two resident CTAs of 512 threads with tiles of 16384 positions 66.6 ms; private per-CTA
 // destination ranges 51 ms, see the file header.)
 template <int PER>
-struct TileRow { uint32_t c[PER]; uint32_t o[PER]; };
+struct TileRow { uint32_t c[PER]; uint32_t o[PER]; uint32_t cx, ox; };        // cx, ox: the thread's extra bucket (routed level k-1)
 
 template <int PER>
 __device__ __forceinline__ TileRow<PER> load_tile_row(const uint16_t* __restrict__ counts, const uint32_t* __restrict__ off,
-                                                     int64_t n_tiles, int64_t tile, int n_buckets) {
+                                                     int64_t n_tiles, int64_t tile, int n_buckets, int n_extra) {
     TileRow<PER> r;
 #pragma unroll
     for (int j = 0; j < PER; ++j) r.c[j] = r.o[j] = 0;
+    r.cx = r.ox = 0;
     const int b0 = PER * threadIdx.x;
+    const int n_all = n_buckets + n_extra;
     if (tile < n_tiles && b0 < n_buckets) {
-        const uint16_t* crow = counts + (size_t)tile * n_buckets + b0;
-        const uint32_t* orow = off + (size_t)tile * n_buckets + b0;
+        const uint16_t* crow = counts + (size_t)tile * n_all + b0;
+        const uint32_t* orow = off + (size_t)tile * n_all + b0;
         if (PER == 4) {
             const uint2 c = __ldcs(reinterpret_cast<const uint2*>(crow));
             const uint4 o = __ldcs(reinterpret_cast<const uint4*>(orow));
@@ -195,24 +222,36 @@ __device__ __forceinline__ TileRow<PER> load_tile_row(const uint16_t* __restrict
             for (int j = 0; j < PER; ++j) { r.c[j] = __ldcs(crow + j); r.o[j] = __ldcs(orow + j); }
         }
     }
+    if (tile < n_tiles && (int)threadIdx.x < n_extra) {
+        r.cx = __ldcs(counts + (size_t)tile * n_all + n_buckets + threadIdx.x);
+        r.ox = __ldcs(off + (size_t)tile * n_all + n_buckets + threadIdx.x);
+    }
     return r;
 }
 
+// Routed corrections (n_extra > 0): the windows with exactly k-1 valid bases go to buckets n_buckets .. n_buckets + n_extra - 1
+// (bucket = n_buckets + the top bits of the (k-1)-mer, suffix = its low 16 bits).  In shared memory they are laid out from
+// the END of the tile buffer downwards, the ordinary entries from the start upwards (together at most one entry per
+// position), so that neither layout needs the other's total; one 64-bit scan carries both running sums.
 template <int PER>       // buckets per thread in the scan step: n_buckets <= PER * PT_THREADS
 __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
                                                                   const uint32_t* __restrict__ hide, int64_t n_words, int64_t n_tiles,
-                                                                  int k, int n_buckets, const uint16_t* __restrict__ counts,
+                                                                  int k, int n_buckets, int n_extra, const uint16_t* __restrict__ counts,
                                                                   const uint32_t* __restrict__ off_rows,
                                                                   const unsigned long long* __restrict__ chunk_base,
                                                                   uint16_t* __restrict__ suffixes, unsigned long long* __restrict__ ticket) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* sorted = reinterpret_cast<uint32_t*>(smem_raw);                                  // PT_TILE keys, grouped by bucket
     unsigned long long* gdelta = reinterpret_cast<unsigned long long*>(sorted + PT_TILE);     // global start - tile start, per bucket
-    uint32_t* off = reinterpret_cast<uint32_t*>(gdelta + PER * PT_THREADS);                   // running tile offsets
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t tile_total;
+    uint32_t* off = reinterpret_cast<uint32_t*>(gdelta + (PER + 1) * PT_THREADS);             // running tile offsets
+    __shared__ unsigned long long warp_sums[32];
+    __shared__ uint32_t tile_total, tile_total_x;
     const int sh = 32 - 2 * k;
     const int b0 = PER * threadIdx.x;
+    const int n_all = n_buckets + n_extra;
+    const bool route = n_extra > 0;
+    const bool has_x = (int)threadIdx.x < n_extra;
+    const int bx = n_buckets + threadIdx.x;
     // Tiles are handed out in order by an atomic ticket: the tiles in flight are then always the ~148 most recent ones,
     // so a run written into a bucket gets its neighbours (the runs of the adjacent tiles) within a tile time and the
     // partial lines complete in L2.  (A static round-robin lets the CTAs drift apart: 4x the DRAM writes, measured.)
@@ -225,37 +264,48 @@ __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t
     int64_t tile = s_ticket[0], tile_next = s_ticket[1];
     __syncthreads();
     RawWords raw = load_raw_words(packed, valid, hide, n_words, tile);
-    TileRow<PER> row = load_tile_row<PER>(counts, off_rows, n_tiles, tile, n_buckets);
+    TileRow<PER> row = load_tile_row<PER>(counts, off_rows, n_tiles, tile, n_buckets, n_extra);
     int h = -1;                                        // range of pass 1 that holds the current tile
     unsigned long long cb[PER];
+    unsigned long long cbx = 0;
 #pragma unroll
     for (int j = 0; j < PER; ++j) cb[j] = 0;
     while (tile < n_tiles) {
         if (threadIdx.x == 0) s_ticket[0] = (long long)atomicAdd(ticket, 1ull);       // the tile after the next one
-        const TileWords cur = cook(raw, k);
+        const TileWords cur = cook(raw, k, route);
         const TileRow<PER> tr = row;
         raw = load_raw_words(packed, valid, hide, n_words, tile_next);
-        row = load_tile_row<PER>(counts, off_rows, n_tiles, tile_next, n_buckets);
+        row = load_tile_row<PER>(counts, off_rows, n_tiles, tile_next, n_buckets, n_extra);
         int hh = (int)((tile * PT_HGRID) / n_tiles);
         while (hh + 1 < PT_HGRID && chunk_first_tile(n_tiles, hh + 1) <= tile) ++hh;
         while (hh > 0 && chunk_first_tile(n_tiles, hh) > tile) --hh;
         if (hh != h) {                                 // (block-uniform) a new range: fetch its bucket bases
             h = hh;
 #pragma unroll
-            for (int j = 0; j < PER; ++j) cb[j] = b0 + j < n_buckets ? __ldg(chunk_base + (size_t)h * n_buckets + b0 + j) : 0ull;
+            for (int j = 0; j < PER; ++j) cb[j] = b0 + j < n_buckets ? __ldg(chunk_base + (size_t)h * n_all + b0 + j) : 0ull;
+            cbx = has_x ? __ldg(chunk_base + (size_t)h * n_all + bx) : 0ull;
         }
-        // (b) exclusive scan over the buckets; thread owns buckets [PER*tid, PER*tid + PER)
+        // (b) exclusive scan over the buckets; thread owns buckets [PER*tid, PER*tid + PER) and extra bucket n_buckets + tid;
+        // low half of the scanned value = ordinary entries, high half = routed ones
         uint32_t mine = 0;
 #pragma unroll
         for (int j = 0; j < PER; ++j) mine += tr.c[j];
-        uint32_t run = block_scan_excl<uint32_t>(mine, warp_sums);   // (its barriers also fence the previous write-out)
+        const unsigned long long both = (unsigned long long)mine | ((unsigned long long)tr.cx << 32);
+        const unsigned long long excl = block_scan_excl<unsigned long long>(both, warp_sums);   // (its barriers also fence the previous write-out)
+        uint32_t run = (uint32_t)excl;
+        const uint32_t runx = (uint32_t)(excl >> 32);
         const int64_t tile_after = s_ticket[0];                      // (thread 0 writes it again only after two more barriers)
-        if (threadIdx.x == PT_THREADS - 1) tile_total = run + mine;
+        if (threadIdx.x == PT_THREADS - 1) { tile_total = run + mine; tile_total_x = runx + tr.cx; }
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
             off[b0 + j] = run;
             gdelta[b0 + j] = cb[j] + tr.o[j] - run;
             run += tr.c[j];
+        }
+        if (has_x) {
+            const uint32_t start = (uint32_t)PT_TILE - runx - tr.cx;  // this bucket's entries: sorted[start .. start + cx)
+            off[bx] = start;
+            gdelta[bx] = cbx + tr.ox - start;
         }
         __syncthreads();
         // (d) scatter the keys into bucket order
@@ -266,6 +316,16 @@ __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t
                     const uint32_t key = key_at(cur, i, sh);
                     sorted[atomicAdd(&off[key >> 16], 1u)] = key;
                 }
+        }
+        if (cur.corr) {
+            uint32_t c = cur.corr;
+            do {
+                const int i = __ffs(c) - 1;
+                c &= c - 1;
+                const uint32_t x = (i < 16) ? __funnelshift_l(cur.w1, cur.w0, 2 * i) : __funnelshift_l(cur.w2, cur.w1, 2 * (i - 16));
+                const uint32_t key = ((uint32_t)n_buckets << 16) + (x >> (sh + 2));       // bucket << 16 | suffix
+                sorted[atomicAdd(&off[key >> 16], 1u)] = key;
+            } while (c);
         }
         __syncthreads();
         const uint32_t total = tile_total;
@@ -284,6 +344,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t
             for (int u = 0; u < PT_WU; ++u) {
                 const uint32_t i = i0 + u * PT_THREADS;
                 if (i < total) suffixes[d[u] + i] = (uint16_t)key[u];
+            }
+        }
+        if (route) {
+            for (uint32_t i = (uint32_t)PT_TILE - tile_total_x + threadIdx.x; i < (uint32_t)PT_TILE; i += PT_THREADS) {
+                const uint32_t key = sorted[i];
+                suffixes[gdelta[key >> 16] + i] = (uint16_t)key;
             }
         }
         tile = tile_next;
@@ -309,17 +375,20 @@ __device__ __forceinline__ void bump(uint32_t* sm, uint32_t s, uint32_t* __restr
     }
 }
 
+// Buckets n_buckets .. n_all-1 hold the routed run-end corrections of level k-1: their counters are ADDED to the slice of
+// `lower` (the level k-1 table, which already carries the -1 corrections of the per-read scan).
 __global__ void __launch_bounds__(BC_THREADS, 1) bucket_count_kernel(const uint16_t* __restrict__ suffixes,
                                                                      const unsigned long long* __restrict__ base, int n_buckets,
-                                                                     uint32_t* __restrict__ table) {
+                                                                     int n_all, uint32_t* __restrict__ table, uint32_t* __restrict__ lower) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* sm = reinterpret_cast<uint32_t*>(smem_raw);
     __shared__ int spilled;
-    for (int b = blockIdx.x; b < n_buckets; b += gridDim.x) {
+    for (int b = blockIdx.x; b < n_all; b += gridDim.x) {
         for (int w = threadIdx.x; w < BC_WORDS; w += BC_THREADS) sm[w] = 0;
         if (threadIdx.x == 0) spilled = 0;
         __syncthreads();
-        uint32_t* slice = table + (size_t)b * BC_CELLS;
+        const bool add_mode = b >= n_buckets;
+        uint32_t* slice = add_mode ? lower + (size_t)(b - n_buckets) * BC_CELLS : table + (size_t)b * BC_CELLS;
         const unsigned long long lo = base[b], hi = base[b + 1];
         // head up to a 16-byte boundary, 8 suffixes per 128-bit load, tail
         unsigned long long a0 = (lo + 7ull) & ~7ull;
@@ -350,7 +419,17 @@ __global__ void __launch_bounds__(BC_THREADS, 1) bucket_count_kernel(const uint1
         for (unsigned long long i = a1 + threadIdx.x; i < hi; i += BC_THREADS) bump(sm, suffixes[i], slice, &my_spill);
         if (my_spill) spilled = 1;
         __syncthreads();
-        if (!spilled) {               // the slice was zero: plain coalesced stores
+        if (add_mode && !spilled) {   // this CTA is the only writer of the slice right now: plain read-modify-write
+            uint4* out = reinterpret_cast<uint4*>(slice);
+            for (int w = threadIdx.x; w < BC_WORDS / 2; w += BC_THREADS) {
+                const uint2 p = reinterpret_cast<const uint2*>(sm)[w];
+                if (p.x | p.y) {
+                    uint4 v = out[w];
+                    v.x += p.x & 0xFFFFu; v.y += p.x >> 16; v.z += p.y & 0xFFFFu; v.w += p.y >> 16;
+                    out[w] = v;
+                }
+            }
+        } else if (!spilled) {        // the slice was zero: plain coalesced stores
             uint4* out = reinterpret_cast<uint4*>(slice);
             for (int w = threadIdx.x; w < BC_WORDS / 2; w += BC_THREADS) {
                 const uint2 p = reinterpret_cast<const uint2*>(sm)[w];
@@ -368,32 +447,34 @@ __global__ void __launch_bounds__(BC_THREADS, 1) bucket_count_kernel(const uint1
 }
 
 struct PartScratch {
-    uint32_t* chunk_total;            // [PT_HGRID][n_buckets]
-    unsigned long long* base;         // [n_buckets + 1]
-    unsigned long long* chunk_base;   // [PT_HGRID][n_buckets]
-    uint16_t* counts;                 // [n_tiles][n_buckets]
-    uint32_t* off;                    // [n_tiles][n_buckets]
-    uint16_t* suffixes;               // one per counted window
+    uint32_t* chunk_total;            // [PT_HGRID][n_all]
+    unsigned long long* base;         // [n_all + 1]
+    unsigned long long* chunk_base;   // [PT_HGRID][n_all]
+    uint16_t* counts;                 // [n_tiles][n_all]
+    uint32_t* off;                    // [n_tiles][n_all]
+    uint16_t* suffixes;               // one per counted window (+ one per routed correction: never the same position)
     unsigned long long* ticket;       // tile dispenser of the partition pass
-    unsigned long long* total;        // [n_buckets]
+    unsigned long long* total;        // [n_all]
 };
 
 static int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
+// sized for n_buckets + n_buckets / 4 rows entries whether or not the corrections of level k-1 are routed
 static int64_t carve(void* scratch, int n_buckets, int64_t n, PartScratch* p) {
     const int64_t n_words = (n + 31) / 32;
     const int64_t n_tiles = (n_words + PT_THREADS - 1) / PT_THREADS;
+    const int64_t n_all = n_buckets + n_buckets / 4;
     uint8_t* q = reinterpret_cast<uint8_t*>(scratch);
     int64_t o = 0;
     auto take = [&](int64_t bytes) { uint8_t* r = q ? q + o : nullptr; o += align_up(bytes, 256); return r; };
-    uint8_t* a0 = take((int64_t)PT_HGRID * n_buckets * 4);
-    uint8_t* a1 = take((int64_t)(n_buckets + 1) * 8);
-    uint8_t* a2 = take((int64_t)PT_HGRID * n_buckets * 8);
-    uint8_t* a3 = take(n_tiles * n_buckets * 2);
-    uint8_t* a4 = take(n_tiles * n_buckets * 4);
-    uint8_t* a5 = take(2 * n);
+    uint8_t* a0 = take((int64_t)PT_HGRID * n_all * 4);
+    uint8_t* a1 = take((int64_t)(n_all + 1) * 8);
+    uint8_t* a2 = take((int64_t)PT_HGRID * n_all * 8);
+    uint8_t* a3 = take(n_tiles * n_all * 2);
+    uint8_t* a4 = take(n_tiles * n_all * 4);
+    uint8_t* a5 = take(2 * n + 64);
     uint8_t* a6 = take(8);
-    uint8_t* a7 = take((int64_t)n_buckets * 8);
+    uint8_t* a7 = take((int64_t)n_all * 8);
     if (p) {
         p->chunk_total = reinterpret_cast<uint32_t*>(a0);
         p->base = reinterpret_cast<unsigned long long*>(a1);
@@ -416,10 +497,18 @@ extern "C" int64_t kmap_partition_scratch_bytes(int64_t n, int k) {
 
 // table[h] = number of counted windows with key h, for every h (the slice of every bucket is overwritten or, where
 // folded counters were spilled, added to: the caller zeroes the table first).  hide may be NULL.
-// terminal_tabs (may be NULL): also add the run-end corrections of levels kmin..k-1 to those tables (count_all.cu).
+// terminal_tabs (may be NULL): also add the run-end corrections of levels kmin..k-1 to those tables (count_all.cu): scattered
+// REDs issued from the histogram pass for the levels whose tables are L2 resident; when the level k-1 table is beyond L2
+// (k = 14: 256 MB) its corrections are ROUTED -- they travel through the partition as n_buckets / 4 extra buckets and are
+// added to the table by the per-bucket count (a scattered RED into a DRAM-resident table costs a sector read-modify-write:
+// 22 G/s against 187 G/s in L2, profiles/r01_red_rate_microbench.txt; measured 4.7 ms of the 13.6 ms histogram pass).
 int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const uint32_t* hide, int64_t n, int k, uint32_t* table,
                            void* scratch, const KmapTableSet* terminal_tabs, int kmin, void* const* step_events, cudaStream_t s) {
     const int n_buckets = 1 << (2 * (k - 8));
+    const bool route = terminal_tabs && k - 1 >= kmin && k - 1 > 12;
+    const int n_extra = route ? n_buckets / 4 : 0;
+    const int n_all = n_buckets + n_extra;
+    const int kcorr = route ? k - 1 : k;                // the fused REDs cover levels kmin .. kcorr-1
     PartScratch p;
     carve(scratch, n_buckets, n, &p);
     const int64_t n_words = (n + 31) / 32;
@@ -428,20 +517,20 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
     const KmapTableSet& tt = terminal_tabs ? *terminal_tabs : none;
     const int km = terminal_tabs ? kmin : k;
     if (n_buckets <= PT_THREADS) {
-        if (terminal_tabs) bucket_hist_kernel<true, 1><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.counts, p.off, p.chunk_total, tt, km);
-        else bucket_hist_kernel<false, 1><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.counts, p.off, p.chunk_total, tt, km);
+        if (terminal_tabs) bucket_hist_kernel<true, 1><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, tt, km, kcorr);
+        else bucket_hist_kernel<false, 1><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, tt, km, kcorr);
     } else {
-        if (terminal_tabs) bucket_hist_kernel<true, PT_MAX_PER><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.counts, p.off, p.chunk_total, tt, km);
-        else bucket_hist_kernel<false, PT_MAX_PER><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.counts, p.off, p.chunk_total, tt, km);
+        if (terminal_tabs) bucket_hist_kernel<true, PT_MAX_PER><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, tt, km, kcorr);
+        else bucket_hist_kernel<false, PT_MAX_PER><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, tt, km, kcorr);
     }
-    bucket_total_kernel<<<(n_buckets + 255) / 256, 256, 0, s>>>(p.chunk_total, n_buckets, p.total);
-    bucket_scan_kernel<<<1, PT_THREADS, 0, s>>>(p.total, n_buckets, p.base);
-    chunk_base_kernel<<<(n_buckets + 255) / 256, 256, 0, s>>>(p.chunk_total, n_buckets, p.base, p.chunk_base);
+    bucket_total_kernel<<<(n_all + 255) / 256, 256, 0, s>>>(p.chunk_total, n_all, p.total);
+    bucket_scan_kernel<<<1, PT_THREADS, 0, s>>>(p.total, n_all, p.base);
+    chunk_base_kernel<<<(n_all + 255) / 256, 256, 0, s>>>(p.chunk_total, n_all, p.base, p.chunk_base);
     cudaMemsetAsync(p.ticket, 0, 8, s);
     if (step_events && step_events[0]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(step_events[0]), s);
     const unsigned int g2 = (unsigned int)(n_tiles < 148 ? n_tiles : 148);
     static bool attr_set = false;
-    const int smem1 = PT_TILE * 4 + 1 * PT_THREADS * 12, smem4 = PT_TILE * 4 + PT_MAX_PER * PT_THREADS * 12;
+    const int smem1 = PT_TILE * 4 + 2 * PT_THREADS * 12, smem4 = PT_TILE * 4 + (PT_MAX_PER + 1) * PT_THREADS * 12;
     if (!attr_set) {
         cudaFuncSetAttribute(partition_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
         cudaFuncSetAttribute(partition_kernel<PT_MAX_PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4);
@@ -449,12 +538,12 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
         attr_set = true;
     }
     if (n_buckets <= PT_THREADS)
-        partition_kernel<1><<<g2, PT_THREADS, smem1, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.counts, p.off, p.chunk_base, p.suffixes, p.ticket);
+        partition_kernel<1><<<g2, PT_THREADS, smem1, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_base, p.suffixes, p.ticket);
     else
-        partition_kernel<PT_MAX_PER><<<g2, PT_THREADS, smem4, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, p.counts, p.off, p.chunk_base, p.suffixes, p.ticket);
+        partition_kernel<PT_MAX_PER><<<g2, PT_THREADS, smem4, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_base, p.suffixes, p.ticket);
     if (step_events && step_events[1]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(step_events[1]), s);
-    const unsigned int g3 = (unsigned int)(n_buckets < 148 ? n_buckets : 148);
-    bucket_count_kernel<<<g3, BC_THREADS, BC_WORDS * 4, s>>>(p.suffixes, p.base, n_buckets, table);
+    const unsigned int g3 = (unsigned int)(n_all < 148 ? n_all : 148);
+    bucket_count_kernel<<<g3, BC_THREADS, BC_WORDS * 4, s>>>(p.suffixes, p.base, n_buckets, n_all, table, route ? tt.t[k - 1] : nullptr);
     return kmap_check_launch("count_partitioned");
 }
 

@@ -21,7 +21,7 @@ __device__ __forceinline__ uint32_t window_mask(uint32_t v0, uint32_t v1, int k)
     return (uint32_t)m;
 }
 
-struct TileWords { uint32_t fresh, w0, w1, w2; };
+struct TileWords { uint32_t fresh, w0, w1, w2, corr; };       // corr: windows of exactly k-1 valid bases (routed run-end corrections)
 struct RawWords { uint32_t v0, v1, h, w0, w1, w2; };
 
 // this thread's 32 positions of tile `tile`: validity (+ one word of look-ahead), hidden windows, the three packed
@@ -39,9 +39,13 @@ __device__ __forceinline__ RawWords load_raw_words(const uint32_t* __restrict__ 
     }
     return r;
 }
-__device__ __forceinline__ TileWords cook(const RawWords& r, int k) {
+// route: also flag the windows that have exactly k-1 valid bases in front of a run end -- the "+1 at level k-1" corrections,
+// when they travel through the partition as extra buckets instead of being scattered REDs (partition.cu)
+__device__ __forceinline__ TileWords cook(const RawWords& r, int k, bool route = false) {
     TileWords t;
-    t.fresh = window_mask(r.v0, r.v1, k) & ~r.h;
+    const uint32_t full = window_mask(r.v0, r.v1, k);
+    t.fresh = full & ~r.h;
+    t.corr = route ? (window_mask(r.v0, r.v1, k - 1) & ~full & ~r.h) : 0u;
     t.w0 = r.w0; t.w1 = r.w1; t.w2 = r.w2;
     return t;
 }
