@@ -74,10 +74,22 @@ def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterabl
     Inputs larger than `chunk_positions` are streamed through the device in chunks of whole reads: the host-to-device copy
     of chunk i+1 (copy stream, from pinned memory) overlaps packing and counting of chunk i (`count_tables_streamed`)."""
     out: Dict[int, Tuple[np.ndarray, np.ndarray]] = {}
-    ks = sorted(set(int(k) for k in k_list))
+    ks_all = sorted(set(int(k) for k in k_list))
+    wide = [k for k in ks_all if k >= 16]          # uint64 hashes, no dense table: sort / run-length path (csrc/sorted.cu)
+    ks = [k for k in ks_all if k < 16]
+    if wide:
+        if table_allreduce is not None:
+            raise KmapError("count_kmers: k >= 16 has no dense table to all-reduce; count those k on one rank")
+        dev = upload_reads(seq_np_arr, boarder_mat, validate)
+        for k in wide:
+            kh, cnt = dev.count_sorted(k, dedup=not rep_mode)
+            if revcom_mode:
+                kh, cnt = E.merge_revcom_sorted(kh, cnt, k)
+            out[k] = (E.to_host(kh, np.uint64), E.to_host(cnt, np.int64))
+        del dev
     if not ks:
         return out
-    contiguous = ks == list(range(ks[0], ks[-1] + 1)) and ks[-1] <= 15
+    contiguous = ks == list(range(ks[0], ks[-1] + 1))
     bounds = _chunk_bounds(seq_np_arr, boarder_mat, chunk_positions) if contiguous else None
     flat = None
     if bounds is not None and len(bounds) > 2:

@@ -37,5 +37,10 @@ def testfa():
 
 
 @pytest.fixture(scope="session")
+def testfa_stock_k():
+    return _load("testfa_stock_k.pkl")
+
+
+@pytest.fixture(scope="session")
 def motif_def_file():
     return str(ROOT / "kmap_b200" / "default_motif_def_table.csv")

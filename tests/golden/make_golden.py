@@ -361,6 +361,52 @@ def gen_testfa():
     print("test.fa goldens written; final conseqs:", finals)
 
 
+def gen_testfa_stock_k():
+    """The same README workflow with the STOCK k range of default_config.toml (min_k = 6, max_k = 16): k = 16 runs the
+    reference's uint64 / int64 code paths.  Only what the driver writes is kept (text files, sample, distance matrix,
+    k{k}.pkl payloads of k = 15, 16)."""
+    import tomllib
+    import tomli_w
+    res_dir = Path(tempfile.mkdtemp()) / "res"
+    res_dir.mkdir()
+    with open("/root/reference/src/kmap/default_config.toml", "rb") as fh:
+        cfg = tomllib.load(fh)
+    assert cfg["kmer_count"]["min_k"] == 6 and cfg["kmer_count"]["max_k"] == 16
+    cfg["motif_discovery"]["motif_pos_density_flag"] = False     # float KDE + plots: out of scope
+    cfg["motif_discovery"]["motif_co_occurence_flag"] = False    # plots: out of scope
+    cfg["motif_discovery"]["n_total_sample"] = 400               # keeps the committed matrix small
+    cfg["motif_discovery"]["n_motif_sample"] = 200
+    cfg["general"]["input_fasta_file"] = TEST_FA
+    cfg["general"]["res_dir"] = str(res_dir)
+    with open(res_dir / "config.toml", "wb") as fh:
+        tomli_w.dump(cfg, fh)
+    t = time.time()
+    kc._preproc(TEST_FA, str(res_dir))
+    np.random.seed(20240415)
+    md._scan_motif(str(res_dir))
+    print(f"stock-k scan_motif {time.time()-t:.1f}s", flush=True)
+    out = {}
+    text = {}
+    for p in sorted(res_dir.rglob("*")):
+        if p.suffix in (".csv", ".txt", ".tsv", ".toml"):
+            text[str(p.relative_to(res_dir))] = p.read_text()
+    out["text_files"] = text
+    out["kmer_count"] = {}
+    for k in (15, 16):
+        with open(res_dir / "kmer_count" / f"k{k}.pkl", "rb") as fh:
+            kk, ukh, ucnt = pickle.load(fh)
+        out["kmer_count"][k] = dict(uniq_kh=ukh, uniq_cnt=ucnt)
+    with open(res_dir / "sample_kmers.pkl", "rb") as fh:
+        out["sample_kmers"] = pickle.load(fh)
+    with open(res_dir / "sample_kmer_hamdist_mat.pkl", "rb") as fh:
+        kk, mat, lab = pickle.load(fh)
+    assert mat.max() < 256
+    out["hamdist"] = dict(k=kk, mat=mat.astype(np.uint8), ref_dtype=str(mat.dtype), labels=lab)
+    with gzip.open(HERE / "testfa_stock_k.pkl.gz", "wb") as fh:
+        pickle.dump(out, fh, protocol=4)
+    print("stock-k goldens written; final conseqs:", text["final_conseq.txt"].split(), "sample k =", kk)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["unit", "small", "testfa"]
     if "unit" in what:
@@ -369,3 +415,5 @@ if __name__ == "__main__":
         gen_small()
     if "testfa" in what:
         gen_testfa()
+    if "stock" in what:
+        gen_testfa_stock_k()

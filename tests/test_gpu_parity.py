@@ -636,3 +636,64 @@ def test_label_kmers_vs_oracle(MD, K, motif_def_file, k, conseqs):
         assert got_kh.dtype == want_kh.dtype and np.array_equal(got_kh, want_kh), (k, revcom)
         assert np.array_equal(got_label, want_label), (k, revcom)
         assert len(set(got_label.tolist())) >= 2
+
+
+def test_count_kmers_api_mixed_dense_and_wide_k(ENG):
+    """api.count_kmers across the dense / sorted boundary: k = 14, 15 from dense tables, k = 16, 17 from the sort path,
+    every list equal to the oracle's first-round (merged) counts with the reference's dtypes"""
+    from kmap_b200 import api
+    rng = np.random.default_rng(99)
+    reads, seq, borders = rand_reads(rng, 800, 0, 120, p_n=0.01, special=["A" * 70, "ACGTACGTTTGCA" * 9, "GAATTC" * 12])
+    for rep_mode in (False, True):
+        got = api.count_kmers(seq, borders, [14, 15, 16, 17], rep_mode=rep_mode)
+        for k in (14, 15, 16, 17):
+            u, c = _oracle_counts(seq, borders, k, not rep_mode)
+            wu, wc = O.merge_revcom(u, c, k)
+            assert got[k][0].dtype == wu.dtype and got[k][1].dtype == wc.dtype, k
+            assert np.array_equal(got[k][0], wu) and np.array_equal(got[k][1], wc), (k, rep_mode)
+
+
+def test_scan_motif_workflow_stock_k_range(MD, K, testfa, testfa_stock_k, tmp_path):
+    """README workflow with the STOCK k range of default_config.toml (6..16): k = 15 on the 4 GiB dense table, k = 16 through
+    the uint64 sort path (three accepted consensus sequences, so mask + recount run there too); every text output, the
+    k15 / k16 pickles, the sample and its distance matrix equal the unmodified reference's."""
+    import pickle
+    import tomli_w
+    import tomllib
+    g = testfa_stock_k
+    seq, borders = testfa["input_bin"], testfa["borders"]
+    fa = tmp_path / "test.fa"
+    with open(fa, "w") as fh:
+        for i, (st, en) in enumerate(borders):
+            fh.write(f">r{i}\n{K.arr2dna(seq[st:en])}\n")
+    res_dir = tmp_path / "res"
+    res_dir.mkdir()
+    cfg = tomllib.loads(g["text_files"]["config.toml"])
+    assert cfg["kmer_count"]["min_k"] == 6 and cfg["kmer_count"]["max_k"] == 16
+    cfg["general"]["input_fasta_file"] = str(fa)
+    cfg["general"]["res_dir"] = str(res_dir)
+    with open(res_dir / "config.toml", "wb") as fh:
+        tomli_w.dump(cfg, fh)
+    K._preproc(str(fa), str(res_dir))
+    np.random.seed(20240415)
+    MD._scan_motif(str(res_dir))
+    tf = g["text_files"]
+    for name in [n for n in tf if n.endswith((".txt", ".tsv")) or n.startswith("hamming_balls/") or n in
+                 ("candidate_conseq.csv", "final_conseq.info.csv", "motif_def_table.csv")]:
+        assert (res_dir / name).read_text() == tf[name], name
+    for name in [n for n in tf if n.endswith("motif_occurence.csv")]:
+        assert_occurrence_text_equal((res_dir / name).read_text().splitlines(), tf[name])
+    for k in (15, 16):
+        with open(res_dir / "kmer_count" / f"k{k}.pkl", "rb") as fh:
+            kk, ukh, ucnt = pickle.load(fh)
+        want = g["kmer_count"][k]
+        assert kk == k and ukh.dtype == want["uniq_kh"].dtype and ucnt.dtype == want["uniq_cnt"].dtype
+        assert np.array_equal(ukh, want["uniq_kh"]) and np.array_equal(ucnt, want["uniq_cnt"])
+    with open(res_dir / "sample_kmers.pkl", "rb") as fh:
+        skh, scnt, slab, sconseq = pickle.load(fh)
+    gkh, gcnt, glab, gconseq = g["sample_kmers"]
+    assert sconseq == gconseq and np.array_equal(skh, gkh) and np.array_equal(scnt, gcnt) and np.array_equal(slab, glab)
+    with open(res_dir / "sample_kmer_hamdist_mat.pkl", "rb") as fh:
+        kk, mat, lab = pickle.load(fh)
+    assert kk == g["hamdist"]["k"] and str(mat.dtype) == g["hamdist"]["ref_dtype"]
+    assert np.array_equal(mat, g["hamdist"]["mat"]) and np.array_equal(lab, g["hamdist"]["labels"])
