@@ -44,3 +44,19 @@ def test_chunk_bounds_declines_small_or_foreign_layouts():
     shifted = borders.copy()
     shifted[0, 0] = 1
     assert api._chunk_bounds(seq, shifted, len(seq) // 4) is None
+
+
+def test_read_fasta_bytes_starts_at_first_header(tmp_path):
+    """host side of the device FASTA ingest: the text handed to the parser starts at the first header line
+    (text before it is ignored like Bio.SeqIO does), plain and gzipped"""
+    import gzip
+    from kmap_b200 import engine as E
+    cases = {b">a\nACGT\n": b">a\nACGT\n", b"junk\n>a\nAC": b">a\nAC", b"x>y\r>b\nT": b">b\nT", b"no header": b"", b"": b"",
+             b"\n\n>": b">"}
+    for i, (raw, want) in enumerate(cases.items()):
+        p = tmp_path / f"c{i}.fa"
+        p.write_bytes(raw)
+        assert bytes(E.read_fasta_bytes(p)) == want
+        with gzip.open(tmp_path / f"c{i}.fa.gz", "wb") as fh:
+            fh.write(raw)
+        assert bytes(E.read_fasta_bytes(tmp_path / f"c{i}.fa.gz")) == want
