@@ -114,7 +114,9 @@ __device__ __forceinline__ ThreadCounts count_thread(const ThreadBytes& t) {
 
 // type of the line in progress at this thread's first byte: the last line started by an earlier thread of the tile, else
 // `carry` (the tile's own incoming type; FA_UNK in pass 1).  *tile_last = the same for the byte after the tile.
+// warp_last: FA_THREADS / 32 + 1 ints of shared memory (the cross-warp part is done once, by warp 0).
 __device__ __forceinline__ int incoming_type(int last, int carry, int* warp_last, int* tile_last) {
+    constexpr int NW = FA_THREADS / 32;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int incl = last;
 #pragma unroll
@@ -124,25 +126,40 @@ __device__ __forceinline__ int incoming_type(int last, int carry, int* warp_last
     }
     if (lane == 31) warp_last[w] = incl;
     __syncthreads();
-    int pre = carry;
-    for (int q = 0; q < w; ++q) if (warp_last[q] != FA_UNK) pre = warp_last[q];
-    int excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
-    if (lane == 0 || excl == FA_UNK) excl = pre;
-    int tl = carry;
-    for (int q = 0; q < FA_THREADS / 32; ++q) if (warp_last[q] != FA_UNK) tl = warp_last[q];
-    *tile_last = tl;
+    if (w == 0) {
+        // exclusive "last known" scan over the warps, seeded with the carry; slot NW = the whole tile
+        int v = lane < NW ? warp_last[lane] : FA_UNK;
+        int sc = v;
+#pragma unroll
+        for (int o = 1; o < NW; o <<= 1) {
+            const int y = __shfl_up_sync(0xFFFFFFFFu, sc, o);
+            if (lane >= o && sc == FA_UNK) sc = y;
+        }
+        int ex = __shfl_up_sync(0xFFFFFFFFu, sc, 1);
+        if (lane == 0 || ex == FA_UNK) ex = carry;
+        if (sc == FA_UNK) sc = carry;
+        __syncwarp();
+        if (lane < NW) warp_last[lane] = ex;
+        if (lane == NW - 1) warp_last[NW] = sc;
+    }
     __syncthreads();
+    int excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+    if (lane == 0 || excl == FA_UNK) excl = warp_last[w];
+    *tile_last = warp_last[NW];
     return excl;
 }
 
-__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* ws) {
+// sum over the block of three small counts packed into one 64-bit value (16 bits each would do; 21 are used); the
+// result is valid in thread 0 only.  ws: FA_THREADS / 32 words of shared memory.
+__device__ __forceinline__ unsigned long long block_sum3(uint32_t a, uint32_t b, uint32_t c, unsigned long long* ws) {
+    unsigned long long v = (unsigned long long)a | ((unsigned long long)b << 21) | ((unsigned long long)c << 42);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
     if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
     __syncthreads();
-    uint32_t t = 0;
-    for (int q = 0; q < FA_THREADS / 32; ++q) t += ws[q];
-    __syncthreads();
+    unsigned long long t = 0;
+    if (threadIdx.x == 0)
+        for (int q = 0; q < FA_THREADS / 32; ++q) t += ws[q];
     return t;
 }
 
@@ -151,18 +168,18 @@ struct TileSummary { uint32_t last, known_seq, pending, n_hdr; };
 
 __global__ void __launch_bounds__(FA_THREADS) fasta_tile_summary_kernel(const uint8_t* __restrict__ text, int64_t n, uint32_t carry_last_byte,
                                                                         TileSummary* __restrict__ summ) {
-    __shared__ int warp_last[FA_THREADS / 32];
-    __shared__ uint32_t ws[FA_THREADS / 32];
+    __shared__ int warp_last[FA_THREADS / 32 + 1];
+    __shared__ unsigned long long ws[FA_THREADS / 32];
     const ThreadBytes t = load_thread_bytes(text, n, blockIdx.x, carry_last_byte);
     const ThreadCounts c = count_thread(t);
     int tile_last;
     const int in_type = incoming_type(c.last, FA_UNK, warp_last, &tile_last);
-    const uint32_t known = block_sum_u32(c.known_seq + (in_type == FA_SEQ ? c.pending : 0u), ws);
-    const uint32_t pending = block_sum_u32(in_type == FA_UNK ? c.pending : 0u, ws);
-    const uint32_t n_hdr = block_sum_u32(__popc(t.hdr), ws);
+    const unsigned long long sums = block_sum3(c.known_seq + (in_type == FA_SEQ ? c.pending : 0u), in_type == FA_UNK ? c.pending : 0u,
+                                               __popc(t.hdr), ws);
     if (threadIdx.x == 0) {
         TileSummary s;
-        s.last = (uint32_t)tile_last; s.known_seq = known; s.pending = pending; s.n_hdr = n_hdr;
+        s.last = (uint32_t)tile_last;
+        s.known_seq = (uint32_t)(sums & 0x1FFFFFull); s.pending = (uint32_t)((sums >> 21) & 0x1FFFFFull); s.n_hdr = (uint32_t)(sums >> 42);
         summ[blockIdx.x] = s;
     }
 }
@@ -238,9 +255,10 @@ __global__ void __launch_bounds__(FA_THREADS) fasta_emit_kernel(const uint8_t* _
                                                                 const TileStart* __restrict__ starts, uint8_t* __restrict__ seq_out,
                                                                 long long seq_origin, long long* __restrict__ rec_start,
                                                                 unsigned long long hdr0) {
-    __shared__ int warp_last[FA_THREADS / 32];
-    __shared__ uint32_t wsum[FA_THREADS / 32];
+    __shared__ int warp_last[FA_THREADS / 32 + 1];
+    __shared__ uint32_t wsum[FA_THREADS / 32 + 1];
     __shared__ uint8_t stage[FA_TILE];
+    constexpr int NW = FA_THREADS / 32;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const ThreadBytes t = load_thread_bytes(text, n, blockIdx.x, carry_last_byte);
     const ThreadCounts c = count_thread(t);
@@ -249,7 +267,7 @@ __global__ void __launch_bounds__(FA_THREADS) fasta_emit_kernel(const uint8_t* _
     const int in_type = incoming_type(c.last, (int)(ts.seq_and_type & 3ull), warp_last, &tile_last);
     const uint32_t n_seq = c.known_seq + (in_type == FA_SEQ ? c.pending : 0u);
     const uint32_t n_hdr = __popc(t.hdr);
-    // exclusive scan of (outputs, headers) per thread; both fit 16 bits (a tile has 4096 bytes)
+    // exclusive scan of (outputs, headers) per thread; both fit 16 bits (a tile has 8192 bytes)
     const uint32_t v = (n_seq + n_hdr) | (n_hdr << 16);
     uint32_t incl = v;
 #pragma unroll
@@ -259,9 +277,21 @@ __global__ void __launch_bounds__(FA_THREADS) fasta_emit_kernel(const uint8_t* _
     }
     if (lane == 31) wsum[w] = incl;
     __syncthreads();
-    uint32_t pre = 0, total = 0;
-    for (int q = 0; q < FA_THREADS / 32; ++q) { if (q < w) pre += wsum[q]; total += wsum[q]; }
-    const uint32_t excl = pre + incl - v;
+    if (w == 0) {                                               // the cross-warp part once: exclusive prefixes, slot NW = total
+        const uint32_t mine = lane < NW ? wsum[lane] : 0u;
+        uint32_t sc = mine;
+#pragma unroll
+        for (int o = 1; o < NW; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, sc, o);
+            if (lane >= o) sc += y;
+        }
+        __syncwarp();
+        if (lane < NW) wsum[lane] = sc - mine;
+        if (lane == NW - 1) wsum[NW] = sc;
+    }
+    __syncthreads();
+    const uint32_t total = wsum[NW];
+    const uint32_t excl = wsum[w] + incl - v;
     uint32_t pos = excl & 0xFFFFu;                              // index among the tile's outputs
     unsigned long long rec = ts.n_hdr + (excl >> 16);           // global index of the next record to start
     // global position of the tile's output number i: first + i, where (sequence characters + separators) written before the
