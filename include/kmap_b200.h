@@ -198,6 +198,15 @@ int kmap_occurrence_fill(const uint32_t* packed, const uint32_t* valid, const in
                          int k, uint32_t conseq, int d, int revcom, const uint8_t* min_dist, const int64_t* offsets,
                          int32_t* pos_out, void* stream);
 
+/* The rows of a *.motif_occurence.csv (gen_motif_occurence_file, motif_discovery.py:1409-1418; cell format :1472-1475)
+ * from the results of the occurrence scan, formatted natively: for every read r in [r0, r1) with at least one hit, the
+ * line "r;cell_0;...;cell_{m-1};seq_len[r]\n", cell_j = pos_host[j][offsets_host[j][r] .. offsets_host[j][r+1]) joined
+ * by ','.  ALL pointers are HOST pointers (offsets_host / pos_host: m pointers each); no device work.  The file is
+ * created (append == 0) or appended to.  Returns the number of rows written, or a negative KMAP_ERR_*.
+ * (Cells with more than 20 positions need the reference's random pick, :1467-1469: the Python caller formats those rows.) */
+int64_t kmap_write_occurrence_rows(const char* path_host, int append, int m, const int64_t* const* offsets_host,
+                                   const int32_t* const* pos_host, const int64_t* seq_len_host, int64_t r0, int64_t r1);
+
 /* cal_samp_kmer_hamdist_mat (motif_discovery.py:777-803): rows [row0, row1) of the n x n distance matrix of
  * kh[] at k bases; pairs whose labels are equal and have head_len[label] < k use only the first head_len bases.
  * head_len = int32[n_labels] (k for labels without override).  out = uint8[(row1-row0) * n] row-major. */

@@ -303,17 +303,60 @@ def motif_occurence_lines(dev: E.SeqOnDevice, borders: np.ndarray, conseq_list, 
     return lines
 
 
+def write_motif_occurence_file(per_conseq, borders: np.ndarray, conseq_list, output_file) -> List[Tuple[int, int]]:
+    """The *.motif_occurence.csv of :1409-1418 from the scan results, rows formatted natively (kmap_write_occurrence_rows;
+    ~5 us per row in Python is what scan_motif would otherwise wait for).  A read with more than 20 positions in some cell
+    needs the reference's random pick (:1467-1469, numpy's global RNG): those rows go through the Python formatter, in read
+    order, so the RNG stream is consumed exactly as the reference consumes it.  Returns per consensus
+    (reads with the motif, listed positions) -- what get_motif_seq_num parses back out of the file."""
+    import ctypes
+    L = lib()
+    with open(output_file, "w+") as fh:
+        fh.write("seq_ind;" + ";".join(f"motif_{i}_{conseq_list[i]}" for i in range(len(conseq_list))) + ";seq_len\n")
+    m = len(per_conseq)
+    if m == 0:
+        return []
+    n_seq = len(borders)
+    lens = np.ascontiguousarray(borders[:, 1] - borders[:, 0], dtype=np.int64)
+    offs = [np.ascontiguousarray(o, dtype=np.int64) for _, o, _ in per_conseq]
+    poss = [np.ascontiguousarray(p_, dtype=np.int32) for _, _, p_ in per_conseq]
+    counts = [np.diff(o) for o in offs]
+    over = np.zeros(n_seq, dtype=bool)
+    for c in counts:
+        over |= c > 20
+    off_ptrs = (ctypes.c_void_p * m)(*[o.ctypes.data for o in offs])
+    pos_ptrs = (ctypes.c_void_p * m)(*[p_.ctypes.data if len(p_) else None for p_ in poss])
+    path = str(output_file).encode()
+
+    def native_rows(r0, r1):
+        if r1 > r0:
+            rc = L.kmap_write_occurrence_rows(path, 1, m, off_ptrs, pos_ptrs, lens.ctypes.data, r0, r1)
+            if rc < 0:
+                check(int(rc), "kmap_write_occurrence_rows")
+    r = 0
+    for f in np.flatnonzero(over):
+        native_rows(r, int(f))
+        _, cells = _cells_for_read(per_conseq, int(f))
+        with open(output_file, "a") as fh:
+            fh.write(f"{int(f)};{cells};{lens[f]}\n")
+        r = int(f) + 1
+    native_rows(r, n_seq)
+    return [(int(np.count_nonzero(c)), int(np.minimum(c, 20).sum())) for c in counts]
+
+
 def gen_motif_occurence_file(conseq_list: List[str], motif_def_dict: dict, input_fasta_file: Path, output_file: Path,
                              revcom_mode=True, _dev_cache=None):
     """:1396-1419.  The reference re-parses the FASTA file per call; the encoded arrays are identical to input.bin
-    (same upper-casing and code table), so a cached device copy may be passed by the driver."""
+    (same upper-casing and code table), so a cached device copy may be passed by the driver.  Returns per consensus
+    (reads with the motif, listed positions)."""
     assert Path(input_fasta_file).exists()
     if _dev_cache is not None:
         dev, borders = _dev_cache
     else:
         dev = E.SeqOnDevice.from_fasta(input_fasta_file)
         borders = E.to_host(dev.borders, np.int64).reshape(-1, 2)
-    write_lines(motif_occurence_lines(dev, borders, conseq_list, motif_def_dict, revcom_mode), output_file)
+    per_conseq = motif_occurence_table(dev, conseq_list, motif_def_dict, revcom_mode)
+    return write_motif_occurence_file(per_conseq, borders, conseq_list, output_file)
 
 
 def get_motif_seq_num(occurence_file_path: Path, motif_index: int) -> Tuple[int, int]:
@@ -565,16 +608,17 @@ def _scan_motif(res_dir: str, debug=False):
                 with open(kmer_cnt_file, "wb") as fh:
                     pickle.dump([kmer_len, first[0], first[1]], fh)
             tmp_candidate_conseq_list = [hash2kmer(kh, kmer_len) for kh in consensus_kh_dict]
+            occ_stats = []
             if store_flag:
                 tmp_occurence_file = kmer_count_dir / f"k{kmer_len}.motif_occurence.csv"
-                gen_motif_occurence_file(tmp_candidate_conseq_list, motif_def_dict, input_fasta_file, tmp_occurence_file,
-                                         revcom_mode, _dev_cache=occurrence_dev())
+                occ_stats = gen_motif_occurence_file(tmp_candidate_conseq_list, motif_def_dict, input_fasta_file,
+                                                     tmp_occurence_file, revcom_mode, _dev_cache=occurrence_dev())
             for i, kmer_seq in enumerate(tmp_candidate_conseq_list):
                 kh = kmer2hash(kmer_seq)
                 prop, ratio, log10_p_value = consensus_kh_dict[kh]
                 n_motif_seq, n_motif_occurrence = -n_all_seq, -n_all_seq
                 if store_flag:
-                    n_motif_seq, n_motif_occurrence = get_motif_seq_num(tmp_occurence_file, i)
+                    n_motif_seq, n_motif_occurrence = occ_stats[i]      # == get_motif_seq_num(tmp_occurence_file, i) (:1345-1393)
                 motif_seq_prop = float(n_motif_seq) / n_all_seq
                 motif_per_motif_seq = float(n_motif_occurrence) / n_motif_seq
                 row = (f"{kmer_len},{kh},{kmer_seq},{reverse_complement(kmer_seq)},{prop:0.8f},"

@@ -60,3 +60,38 @@ def test_read_fasta_bytes_starts_at_first_header(tmp_path):
         with gzip.open(tmp_path / f"c{i}.fa.gz", "wb") as fh:
             fh.write(raw)
         assert bytes(E.read_fasta_bytes(tmp_path / f"c{i}.fa.gz")) == want
+
+
+def test_native_occurrence_writer_equals_python_formatter(tmp_path):
+    """kmap_write_occurrence_rows (host-only C++) writes the *.motif_occurence.csv rows exactly as the per-read Python
+    formatter (reference motif_discovery.py:1409-1418, 1472-1475), including the rows whose > 20 hits need the random
+    pick from numpy's global RNG (same stream consumption), and the returned counts equal get_motif_seq_num of the file"""
+    from kmap_b200 import motif_discovery as MD
+    rng = np.random.default_rng(0)
+    n_seq, m = 3000, 3
+    lens = rng.integers(0, 200, n_seq)
+    ends = np.cumsum(lens + 1)
+    borders = np.stack([ends - lens - 1, ends - 1], axis=1).astype(np.int64)
+    per = []
+    for j in range(m):
+        cnt = rng.integers(0, 4, n_seq) * (rng.random(n_seq) < 0.3)
+        if j == 1:
+            cnt[[5, 700, 2999]] = 25
+        off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+        pos = np.concatenate([np.sort(rng.choice(300, c, replace=False)) for c in cnt]).astype(np.int32)
+        per.append((None, off, pos))
+    conseqs = ["ACG", "TTGA", "CC"]
+    np.random.seed(7)
+    lines = ["seq_ind;" + ";".join(f"motif_{i}_{conseqs[i]}" for i in range(m)) + ";seq_len"]
+    has = np.zeros(n_seq, bool)
+    for _, o, _p in per:
+        has |= np.diff(o) > 0
+    for r in np.flatnonzero(has):
+        _, cells = MD._cells_for_read(per, r)
+        lines.append(f"{r};{cells};{lens[r]}")
+    np.random.seed(7)
+    stats = MD.write_motif_occurence_file(per, borders, conseqs, tmp_path / "o.csv")
+    assert (tmp_path / "o.csv").read_text() == "\n".join(lines) + "\n"
+    assert stats == [MD.get_motif_seq_num(tmp_path / "o.csv", i) for i in range(m)]
+    assert MD.write_motif_occurence_file([], borders, [], tmp_path / "e.csv") == []
+    assert (tmp_path / "e.csv").read_text() == "seq_ind;;seq_len\n"
