@@ -63,6 +63,11 @@ int kmap_ham_dist_tail_u64(const uint64_t* kh, int64_t n, uint64_t target, int k
 /* revcom_hash_kernel_uint32/64 (taichi_core.py:181-224) behind get_revcom_hash_arr (kmer_count.py:613-623) */
 int kmap_revcom_u32(const uint32_t* in, int64_t n, int k, uint32_t* out, void* stream);
 int kmap_revcom_u64(const uint64_t* in, int64_t n, int k, uint64_t* out, void* stream);
+/* candidates for find_motif's top-k selection (np.argpartition(cnt, -top_k)[-top_k:], motif_discovery.py:657): each of the
+ * n_blocks blocks writes its kk (<= 8) largest (count, index) pairs, ordered by (count descending, index ascending), to
+ * out_val / out_idx [n_blocks * kk] (index -1 = fewer than kk elements seen).  The host merges the candidates. */
+int kmap_topk_candidates_i32(const int32_t* cnt, int64_t n, int kk, int32_t* out_val, int64_t* out_idx, int n_blocks, void* stream);
+int kmap_topk_candidates_i64(const int64_t* cnt, int64_t n, int kk, int64_t* out_val, int64_t* out_idx, int n_blocks, void* stream);
 /* the labelling step of sample_disp_kmer (motif_discovery.py:849-892) for all unique k-mers at once: label[i] = index of
  * the nearest consensus (head distance over the first conseq_len[c] bases to conseq[c], or -- revcom != 0 -- tail distance
  * over the last conseq_len[c] bases to rc_conseq[c]; a consensus farther than dmax[c] counts as distance k; ties keep

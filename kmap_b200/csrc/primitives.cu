@@ -111,6 +111,73 @@ __global__ void __launch_bounds__(256) label_kmers_kernel(H* __restrict__ kh, in
     }
 }
 
+// Top-kk candidates of a count array for find_motif's `np.argpartition(cnt, -top_k)[-top_k:]` (motif_discovery.py:657):
+// every block emits its kk largest (value, index) pairs, ordered by (value descending, index ascending); the host merges
+// blocks x kk candidates.  The caller asks for top_k + 1 and uses the result only when the boundary is strict (see
+// motif_discovery.find_motif_on_device): which of several equal values numpy's introselect keeps is not reproducible.
+constexpr int TOPK_MAX = 8;
+constexpr int TOPK_BLOCK = 256;
+template <typename T>
+__global__ void __launch_bounds__(TOPK_BLOCK) topk_candidates_kernel(const T* __restrict__ cnt, int64_t n, int kk, T* __restrict__ out_val,
+                                                                     long long* __restrict__ out_idx) {
+    __shared__ T s_val[TOPK_BLOCK / 32];
+    __shared__ long long s_idx[TOPK_BLOCK / 32];
+    __shared__ int s_owner[TOPK_BLOCK / 32];
+    __shared__ int winner;
+    T val[TOPK_MAX];
+    long long idx[TOPK_MAX];
+#pragma unroll
+    for (int j = 0; j < TOPK_MAX; ++j) { val[j] = 0; idx[j] = -1; }          // idx < 0: empty slot
+    auto better = [](T av, long long ai, T bv, long long bi) {              // a before b?  (empty slots last)
+        if (bi < 0) return ai >= 0;
+        if (ai < 0) return false;
+        return av > bv || (av == bv && ai < bi);
+    };
+    for (int64_t i = (int64_t)blockIdx.x * TOPK_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * TOPK_BLOCK) {
+        const T v = __ldg(cnt + i);
+        if (!better(v, i, val[TOPK_MAX - 1], idx[TOPK_MAX - 1])) continue;
+        T cv = v;
+        long long ci = i;
+#pragma unroll
+        for (int j = 0; j < TOPK_MAX; ++j) {                                 // insertion into the sorted list
+            if (better(cv, ci, val[j], idx[j])) { const T tv = val[j]; const long long ti = idx[j]; val[j] = cv; idx[j] = ci; cv = tv; ci = ti; }
+        }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int head = 0;                                                            // next unused entry of this thread's list
+    for (int r = 0; r < kk; ++r) {
+        T hv = 0;
+        long long hi = -1;
+#pragma unroll
+        for (int j = 0; j < TOPK_MAX; ++j) if (j == head) { hv = val[j]; hi = idx[j]; }
+        T bv = hv;
+        long long bi = hi;
+        int owner = threadIdx.x;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const T ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+            const long long oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+            const int oo = __shfl_xor_sync(0xFFFFFFFFu, owner, o);
+            if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; owner = oo; }
+        }
+        if (lane == 0) { s_val[w] = bv; s_idx[w] = bi; s_owner[w] = owner; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            T gv = s_val[0];
+            long long gi = s_idx[0];
+            int go = s_owner[0];
+            for (int q = 1; q < TOPK_BLOCK / 32; ++q)
+                if (better(s_val[q], s_idx[q], gv, gi)) { gv = s_val[q]; gi = s_idx[q]; go = s_owner[q]; }
+            out_val[(size_t)blockIdx.x * kk + r] = gv;
+            out_idx[(size_t)blockIdx.x * kk + r] = gi;
+            winner = gi >= 0 ? go : -1;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x == winner) ++head;
+        __syncthreads();
+    }
+}
+
 // remove_duplicate_hash_per_seq (kmer_count.py:743-760): one block per read; a shared-memory map
 // hash -> smallest position (open addressing), filled in passes when the read has more distinct hashes than the
 // map holds (pass p owns the hashes with mix(h) % n_pass == p).  Any position that is not the first occurrence
@@ -168,6 +235,14 @@ int launch_label(H* kh, int64_t n, int k, const H* conseq, const H* rc_conseq, c
     label_kmers_kernel<H><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(kh, n, k, conseq, rc_conseq, conseq_len, dmax, n_conseq, dmax_k,
                                                                           revcom, label);
     return kmap_check_launch("label_kmers");
+}
+
+template <typename T>
+int launch_topk(const T* cnt, int64_t n, int kk, T* out_val, int64_t* out_idx, int n_blocks, void* stream) {
+    KMAP_REQUIRE(n >= 0 && kk >= 1 && kk <= TOPK_MAX && n_blocks >= 1, "bad argument (kk <= 8)");
+    KMAP_REQUIRE(out_val && out_idx && (cnt || n == 0), "null pointer");
+    topk_candidates_kernel<T><<<(unsigned int)n_blocks, TOPK_BLOCK, 0, as_stream(stream)>>>(cnt, n, kk, out_val, reinterpret_cast<long long*>(out_idx));
+    return kmap_check_launch("topk_candidates");
 }
 
 template <typename H>
@@ -238,6 +313,12 @@ int kmap_label_kmers_u32(uint32_t* kh, int64_t n, int k, const uint32_t* conseq,
 int kmap_label_kmers_u64(uint64_t* kh, int64_t n, int k, const uint64_t* conseq, const uint64_t* rc_conseq, const int32_t* conseq_len,
                          const int32_t* dmax, int n_conseq, int dmax_k, int revcom, int32_t* label, void* stream) {
     return launch_label<uint64_t>(kh, n, k, conseq, rc_conseq, conseq_len, dmax, n_conseq, dmax_k, revcom, label, stream, 31);
+}
+int kmap_topk_candidates_i32(const int32_t* cnt, int64_t n, int kk, int32_t* out_val, int64_t* out_idx, int n_blocks, void* stream) {
+    return launch_topk<int32_t>(cnt, n, kk, out_val, out_idx, n_blocks, stream);
+}
+int kmap_topk_candidates_i64(const int64_t* cnt, int64_t n, int kk, int64_t* out_val, int64_t* out_idx, int n_blocks, void* stream) {
+    return launch_topk<long long>(reinterpret_cast<const long long*>(cnt), n, kk, reinterpret_cast<long long*>(out_val), out_idx, n_blocks, stream);
 }
 int kmap_dedup_hash_per_read_u32(uint32_t* hash, int64_t n, const int64_t* borders, int64_t n_seq, void* stream) {
     KMAP_REQUIRE(n >= 0 && n_seq >= 0, "negative size");

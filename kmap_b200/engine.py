@@ -365,6 +365,24 @@ def hamball_sums_list(kh: torch.Tensor, cnt: torch.Tensor, k: int, cand: Sequenc
     return out
 
 
+def topk_candidates(cnt: torch.Tensor, kk: int) -> Tuple[np.ndarray, np.ndarray]:
+    """(values, indices) of the kk largest counts of a device list (int32 or int64), ordered by (value descending, index
+    ascending); fewer than kk when the list is shorter.  Blocks of kmap_topk_candidates_* merged on the host."""
+    L = lib()
+    n = int(cnt.numel())
+    n_blocks = max(1, min(148 * 4, (n + 255) // 256))
+    wide = cnt.dtype == torch.int64
+    out_val = empty(n_blocks * kk, torch.int64 if wide else torch.int32)
+    out_idx = empty(n_blocks * kk, torch.int64)
+    fn = L.kmap_topk_candidates_i64 if wide else L.kmap_topk_candidates_i32
+    check(fn(_ptr(cnt), n, int(kk), _ptr(out_val), _ptr(out_idx), n_blocks, _stream_ptr()), "kmap_topk_candidates")
+    val, idx = out_val.cpu().numpy(), out_idx.cpu().numpy()
+    keep = idx >= 0
+    val, idx = val[keep], idx[keep]
+    order = np.lexsort((idx, -val.astype(np.int64)))[:kk]
+    return val[order], idx[order]
+
+
 def exclusive_scan_u32(counts: torch.Tensor) -> torch.Tensor:
     L = lib()
     n = int(counts.numel())

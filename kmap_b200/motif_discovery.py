@@ -33,15 +33,37 @@ def write_lines(str_list: List, outfile):
 # ======================================================================================================================
 class _CountState:
     """Counts of the current (possibly masked) sequence: dense forward table on the device (k <= 15) or 64-bit merged
-    lists from the sort path (k >= 16), + the reference's merged lists on the host (np.argpartition has to see exactly
-    those arrays)."""
+    lists from the sort path (k >= 16), + the reference's merged lists.  The host copies of the lists are fetched lazily:
+    the first round needs them (k{k}.pkl, n_total_kmer), a later round only when numpy itself has to make the top-k
+    selection (np.argpartition has to see exactly those arrays)."""
 
     def __init__(self, k, revcom, table=None, kh_dev=None, cnt_dev=None, wide=False):
         self.k, self.revcom, self.table, self.kh_dev, self.cnt_dev, self.wide = k, revcom, table, kh_dev, cnt_dev, wide
-        self.kh = self.cnt = None
-        if kh_dev is not None:
-            self.kh = E.to_host(kh_dev, np.uint64 if wide else np.uint32).astype(get_hash_dtype(k), copy=False)
-            self.cnt = E.to_host(cnt_dev, np.int64 if wide else np.int32).astype(get_cnt_dtype(k), copy=False)
+        self._kh = self._cnt = None
+
+    @property
+    def n(self) -> int:
+        return int(self.kh_dev.numel()) if self._kh is None else len(self._kh)
+
+    @property
+    def kh(self) -> np.ndarray:
+        if self._kh is None:
+            self._kh = E.to_host(self.kh_dev, np.uint64 if self.wide else np.uint32).astype(get_hash_dtype(self.k), copy=False)
+        return self._kh
+
+    @property
+    def cnt(self) -> np.ndarray:
+        if self._cnt is None:
+            self._cnt = E.to_host(self.cnt_dev, np.int64 if self.wide else np.int32).astype(get_cnt_dtype(self.k), copy=False)
+        return self._cnt
+
+    def kh_at(self, inds) -> np.ndarray:
+        """the hashes at a few list positions (without bringing the whole list to the host)"""
+        if self._kh is not None:
+            return self._kh[inds]
+        hd = np.uint64 if self.wide else np.uint32
+        vals = [E.to_host(self.kh_dev[int(i):int(i) + 1], hd)[0] for i in inds]
+        return np.array(vals, dtype=hd).astype(get_hash_dtype(self.k), copy=False)
 
     @classmethod
     def from_table(cls, table, k, revcom):
@@ -59,9 +81,9 @@ class _CountState:
     def from_lists(cls, kh, cnt, k, revcom):
         wide = k >= 16
         st = cls(k, revcom, wide=wide)
-        st.kh, st.cnt = np.asarray(kh), np.asarray(cnt)
-        st.kh_dev = E.to_device(st.kh.astype(np.uint64 if wide else np.uint32, copy=False))
-        st.cnt_dev = E.to_device(st.cnt.astype(np.int64 if wide else np.int32, copy=False))
+        st._kh, st._cnt = np.asarray(kh), np.asarray(cnt)
+        st.kh_dev = E.to_device(st._kh.astype(np.uint64 if wide else np.uint32, copy=False))
+        st.cnt_dev = E.to_device(st._cnt.astype(np.int64 if wide else np.int32, copy=False))
         return st
 
     def ball_sums(self, cand, d):
@@ -72,9 +94,25 @@ class _CountState:
         return E.hamball_sums_list(self.kh_dev, self.cnt_dev, self.k, cand, d, self.revcom)
 
 
+def _top_k_indices(state: "_CountState", top_k: int):
+    """(indices, unambiguous): the top_k entries of state.cnt that `np.argpartition(cnt, -top_k)[-top_k:]` selects (:657).
+    On a long list the selection runs on the device (kmap_topk_candidates_*; numpy's introselect over 1.7e7 counts is 0.2 s
+    per trial and was 58 % of scan_motif at 1e6 reads).  The device result is used only when it cannot differ from
+    numpy's as a SET: the top_k-th count must be strictly larger than the next one (which of several equal counts
+    introselect keeps is not reproducible); the ORDER numpy would return only matters when two candidates tie on their
+    ball sums, which the caller checks (unambiguous=True asks for that check)."""
+    n = state.n if hasattr(state, "n") else len(state.cnt)
+    if state.cnt_dev is not None and n >= (1 << 16) and top_k + 1 <= 8 and int(state.cnt_dev.numel()) == n:
+        val, idx = E.topk_candidates(state.cnt_dev, top_k + 1)
+        if len(val) == top_k + 1 and val[top_k - 1] > val[top_k]:
+            return idx[:top_k].astype(np.intp), True
+    return np.array(np.argpartition(state.cnt, -top_k)[-top_k:]), False
+
+
 def find_motif_on_device(dev: E.SeqOnDevice, kmer_len: int, max_ham_dist, p_unif, ratio_mu, ratio_std, ratio_cutoff,
                          top_k=5, n_trial=10, merge_revcom_mode=True, rep_mode=False, first_lists=None,
-                         first_table: Optional[torch.Tensor] = None, debug=False, sorted_path: Optional[bool] = None):
+                         first_table: Optional[torch.Tensor] = None, debug=False, sorted_path: Optional[bool] = None,
+                         table_buffer: Optional[torch.Tensor] = None):
     """Core of find_motif on a device-resident sequence (mutates dev.valid).  Returns (result dict, (uniq_kh, uniq_cnt)
     of the first round).  `first_lists` plays the role of a pre-existing k{k}.pkl (:621-624); `first_table` lets a
     caller that counted every k in one pass hand in the forward table.  sorted_path: count by sorting 64-bit keys
@@ -87,25 +125,34 @@ def find_motif_on_device(dev: E.SeqOnDevice, kmer_len: int, max_ham_dist, p_unif
     elif use_sorted:
         state = _CountState.from_sorted(dev, k, merge_revcom_mode, dedup=not rep_mode)
     else:
-        table = first_table if first_table is not None else dev.count(k, dedup=not rep_mode)
+        if first_table is not None:
+            table = first_table
+        else:       # (table_buffer: a caller that walks several k re-uses one allocation of at least 4^k cells)
+            buf = table_buffer[:1 << (2 * k)] if table_buffer is not None and table_buffer.numel() >= (1 << (2 * k)) else None
+            table = dev.count(k, dedup=not rep_mode, table=buf)
         state = _CountState.from_table(table, k, merge_revcom_mode)
     first = (state.kh, state.cnt)
     n_total_kmer = int(np.sum(state.cnt, dtype=np.int64))       # exact
 
     found = {}
     for i_trial in range(n_trial):
-        if top_k > len(state.cnt):
+        if top_k > state.n:
             break
-        top_k_inds = np.array(np.argpartition(state.cnt, -top_k)[-top_k:])
+        top_k_inds, unambiguous = _top_k_indices(state, top_k)
         if len(top_k_inds) == 0:
             break
-        cand = state.kh[top_k_inds]
+        cand = state.kh_at(top_k_inds)
         hamball_cnt_arr = np.zeros(top_k)
         hamball_cnt_arr[:] = state.ball_sums(cand, max_ham_dist)
+        if unambiguous and np.count_nonzero(hamball_cnt_arr == hamball_cnt_arr.max()) > 1:
+            # equal ball sums: the winner is the first one in numpy's own order of the top-k (np.argmax below)
+            top_k_inds = np.array(np.argpartition(state.cnt, -top_k)[-top_k:])
+            cand = state.kh_at(top_k_inds)
+            hamball_cnt_arr[:] = state.ball_sums(cand, max_ham_dist)
         if debug:
             print(f"{i_trial= }")
         best = np.argmax(hamball_cnt_arr)
-        consensus_kh = state.kh[top_k_inds[best]]
+        consensus_kh = cand[best]
         hamball_proportion = (hamball_cnt_arr[best] + 0.0) / n_total_kmer
         hamball_ratio = hamball_proportion / p_unif
         if not hamball_ratio > ratio_cutoff:
@@ -490,7 +537,7 @@ def sample_disp_kmer(conseq_list: List[str], kmer_len: int, motif_def_dict: dict
     for c in range(n_conseq + 1):
         c_inds = np.where(label_arr == c)[0]
         ws = uniq_kh_cnt_arr[c_inds]
-        ws = ws / sum(ws)
+        ws = ws / np.sum(ws, dtype=np.int64)       # (:908 uses the builtin sum: the same integer, 0.1 s per 1e7 counts slower)
         tmpcnts = np.random.multinomial(sample_cnt_arr[c], ws, size=1).squeeze()
         samp_inds.append(c_inds[tmpcnts > 0])
         samp_cnts.append(tmpcnts[tmpcnts > 0])
@@ -591,6 +638,8 @@ def _scan_motif(res_dir: str, debug=False):
         if store_flag:
             header += ",n_motif_reads,n_all_reads,motif_reads_prop,motif_occurrence,motif_occurrence_per_motif_read"
         rows = [header]
+        k_dense = min(max_k, 15)
+        table_buffer = E.empty(1 << (2 * k_dense), torch.int32) if k_dense >= min_k else None     # one table allocation for every k
         for kmer_len in range(min_k, max_k + 1):
             dev.restore_valid()
             m = motif_def_dict[kmer_len]
@@ -603,7 +652,7 @@ def _scan_motif(res_dir: str, debug=False):
                 first_lists = (kh0, cnt0)
             consensus_kh_dict, first = find_motif_on_device(dev, kmer_len, m.max_ham_dist, m.p_uniform, m.ratio_mu,
                                                             m.ratio_std, m.ratio_cutoff, top_k, n_trial, revcom_mode,
-                                                            rep_mode, first_lists, None, debug)
+                                                            rep_mode, first_lists, None, debug, table_buffer=table_buffer)
             if save_kmer_cnt_flag and not kmer_cnt_file.exists():
                 with open(kmer_cnt_file, "wb") as fh:
                     pickle.dump([kmer_len, first[0], first[1]], fh)

@@ -697,3 +697,31 @@ def test_scan_motif_workflow_stock_k_range(MD, K, testfa, testfa_stock_k, tmp_pa
         kk, mat, lab = pickle.load(fh)
     assert kk == g["hamdist"]["k"] and str(mat.dtype) == g["hamdist"]["ref_dtype"]
     assert np.array_equal(mat, g["hamdist"]["mat"]) and np.array_equal(lab, g["hamdist"]["labels"])
+
+
+def test_topk_candidates_and_find_motif_selection(ENG, MD):
+    """the device top-k candidates == the k largest counts (value descending, index ascending), for int32 and int64 lists, and
+    _top_k_indices falls back to numpy's own selection whenever the boundary is tied"""
+    import torch
+    rng = np.random.default_rng(5)
+    for dtype, n in [(np.int32, 10), (np.int32, 70000), (np.int32, 3_000_000), (np.int64, 200_000)]:
+        cnt = rng.integers(0, 1000, n).astype(dtype)
+        cnt[rng.integers(0, n, 4)] += 5000
+        for kk in (1, 6, 8):
+            val, idx = ENG.topk_candidates(ENG.to_device(cnt), kk)
+            order = np.lexsort((np.arange(n), -cnt.astype(np.int64)))[:kk]
+            assert np.array_equal(idx, order) and np.array_equal(val, cnt[order]), (dtype, n, kk)
+
+    class S:       # what _top_k_indices reads of a _CountState
+        pass
+    st = S()
+    st.cnt = rng.integers(0, 50, 100000).astype(np.int32)
+    st.cnt[[7, 99, 5000, 77777, 1234]] = [900, 800, 700, 600, 500]
+    st.cnt_dev = ENG.to_device(st.cnt)
+    inds, unambiguous = MD._top_k_indices(st, 5)
+    assert unambiguous and sorted(inds.tolist()) == sorted([7, 99, 5000, 77777, 1234])
+    assert sorted(inds.tolist()) == sorted(np.argpartition(st.cnt, -5)[-5:].tolist())
+    st.cnt[4321] = 500                       # a tie at the boundary: numpy decides
+    st.cnt_dev = ENG.to_device(st.cnt)
+    inds, unambiguous = MD._top_k_indices(st, 5)
+    assert not unambiguous and np.array_equal(inds, np.argpartition(st.cnt, -5)[-5:])
