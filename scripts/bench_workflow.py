@@ -56,6 +56,17 @@ def main():
     out["scan_motif_s"] = time.perf_counter() - t
     s = io.StringIO()
     pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(28)
+    # CPU leg: the oracle port of find_motif (per-read Python de-duplication, np.unique, list scans, Python mask loop) for ONE
+    # k on a sample of the same reads; the reference's drivers repeat it for 7 values of k and add per-read occurrence scans
+    from oracle import kmap_oracle as O
+    n_cpu = min(n_reads, 20000)
+    s_np, b_np = synth.generate_numpy(spec, 0, n_cpu)
+    mdd = K.init_motif_def_dict(ROOT / "kmap_b200" / "default_motif_def_table.csv")
+    m = mdd[10]
+    t = time.perf_counter()
+    O.find_motif(s_np.copy(), 10, m.max_ham_dist, m.p_uniform, m.ratio_mu, m.ratio_std, m.ratio_cutoff, boarder_mat=b_np)
+    out["cpu_oracle_find_motif_k10_s"] = time.perf_counter() - t
+    out["cpu_sample_reads"] = n_cpu
     out["final_conseq"] = (res / "final_conseq.txt").read_text().split()
     out["candidate_rows"] = len((res / "candidate_conseq.csv").read_text().splitlines()) - 1
     Path("gpurun_out").mkdir(exist_ok=True)
