@@ -12,7 +12,7 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 HEADER = _PKG.parent / "include" / "kmap_b200.h"
-LIB_PATH = _PKG / "libkmap_b200.so"
+LIB_PATH = Path(os.environ.get("KMAP_B200_LIB", _PKG / "libkmap_b200.so"))      # (the override is for tuning sweeps)
 
 _CTYPES = {
     "int": ctypes.c_int, "int64_t": ctypes.c_int64, "uint32_t": ctypes.c_uint32, "uint64_t": ctypes.c_uint64,

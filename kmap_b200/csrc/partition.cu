@@ -24,7 +24,10 @@ constexpr int PT_TILE = PT_THREADS * 32;          // positions (= staged entries
 constexpr int PT_MAX_BUCKETS = 4096;              // k <= 14
 constexpr int PT_MAX_PER = PT_MAX_BUCKETS / PT_THREADS;
 constexpr int PT_MAX_ALL = PT_MAX_BUCKETS + PT_MAX_BUCKETS / 4;      // + the buckets of the routed level k-1 (one per thread at most)
-constexpr int PT_WU = 8;                          // write-out entries in flight per thread
+#ifndef KMAP_PT_WU
+#define KMAP_PT_WU 8
+#endif
+constexpr int PT_WU = KMAP_PT_WU;                // write-out entries in flight per thread
 
 // extra_base: index of the first extra bucket (= n_buckets).  A routed correction is the (k-1)-mer at a position with
 // exactly k-1 valid bases: bucket extra_base + (its key >> 16), suffix = its low 16 bits.
@@ -361,7 +364,10 @@ __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t
 constexpr int BC_THREADS = 1024;
 constexpr int BC_CELLS = 65536;
 constexpr int BC_WORDS = BC_CELLS / 2;            // two 16-bit counters per word
-constexpr int BC_UNROLL = 4;                      // 128-bit loads in flight per thread
+#ifndef KMAP_BC_UNROLL
+#define KMAP_BC_UNROLL 4
+#endif
+constexpr int BC_UNROLL = KMAP_BC_UNROLL;         // 128-bit loads in flight per thread
 
 // A half-word counter that reaches 0x8000 is folded into the global cell at once (the fold happens long before the
 // half could carry into its neighbour: at most BC_THREADS increments are in flight).
