@@ -203,6 +203,15 @@ int kmap_occurrence_fill(const uint32_t* packed, const uint32_t* valid, const in
                          int k, uint32_t conseq, int d, int revcom, const uint8_t* min_dist, const int64_t* offsets,
                          int32_t* pos_out, void* stream);
 
+/* the same three for 64-bit hashes (17 <= k <= 31; any k <= 31 is accepted): plain one-thread-per-position flag kernel */
+int kmap_mask_u64(const uint32_t* packed, const uint32_t* valid_pre, uint32_t* valid, int64_t n, int k, const uint64_t* cons,
+                  const int32_t* d, int m, uint32_t* flag_scratch, void* stream);
+int kmap_occurrence_count_u64(const uint32_t* packed, const uint32_t* valid, const int64_t* borders, int64_t n_seq, int k,
+                              uint64_t conseq, int d, int revcom, uint8_t* min_dist, uint32_t* n_hit, void* stream);
+int kmap_occurrence_fill_u64(const uint32_t* packed, const uint32_t* valid, const int64_t* borders, int64_t n_seq, int k,
+                             uint64_t conseq, int d, int revcom, const uint8_t* min_dist, const int64_t* offsets,
+                             int32_t* pos_out, void* stream);
+
 /* The rows of a *.motif_occurence.csv (gen_motif_occurence_file, motif_discovery.py:1409-1418; cell format :1472-1475)
  * from the results of the occurrence scan, formatted natively: for every read r in [r0, r1) with at least one hit, the
  * line "r;cell_0;...;cell_{m-1};seq_len[r]\n", cell_j = pos_host[j][offsets_host[j][r] .. offsets_host[j][r+1]) joined

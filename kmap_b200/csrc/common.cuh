@@ -60,6 +60,13 @@ __device__ __forceinline__ uint32_t window16(const uint32_t* __restrict__ packed
 __device__ __forceinline__ uint32_t window_hash(const uint32_t* __restrict__ packed, int64_t p, int k) {
     return window16(packed, p) >> (32 - 2 * k);
 }
+// 32 bases starting at position p, first base in the most significant bits (windows of 17..31 bases: 64-bit hashes)
+__device__ __forceinline__ uint64_t window32(const uint32_t* __restrict__ packed, int64_t p) {
+    const int64_t w = p >> 4;
+    const uint32_t s = ((uint32_t)p & 15u) * 2u;
+    const uint32_t a = __ldg(packed + w), b = __ldg(packed + w + 1), c = __ldg(packed + w + 2);
+    return ((uint64_t)__funnelshift_l(b, a, s) << 32) | __funnelshift_l(c, b, s);
+}
 // validity bits of positions p .. p+31 (bit i = position p+i)
 __device__ __forceinline__ uint32_t valid32(const uint32_t* __restrict__ valid, int64_t p) {
     const int64_t w = p >> 5;

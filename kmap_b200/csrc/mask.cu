@@ -167,20 +167,35 @@ __device__ __forceinline__ int64_t occurrence_n_pos(int64_t L, int k) {
     return L + m > 0 ? L + m : 0;
 }
 
-template <bool FILL>
+// hash-width helpers: uint32 for k <= 16 (one 16-base fetch), uint64 for 17 <= k <= 31
+template <typename H> struct HashOps;
+template <> struct HashOps<uint32_t> {
+    static __device__ __forceinline__ uint32_t low(int k) { return lowmask32(k); }
+    static __device__ __forceinline__ uint32_t key(const uint32_t* __restrict__ packed, int64_t p, int k) { return window16(packed, p) >> (32 - 2 * k); }
+    static __device__ __forceinline__ uint32_t dist(uint32_t x, uint32_t low) { return nz_groups32(x, low); }
+    static __device__ __forceinline__ uint32_t rc(uint32_t h, int k) { return revcom32(h, k); }
+};
+template <> struct HashOps<uint64_t> {
+    static __device__ __forceinline__ uint64_t low(int k) { return lowmask64(k); }
+    static __device__ __forceinline__ uint64_t key(const uint32_t* __restrict__ packed, int64_t p, int k) { return window32(packed, p) >> (64 - 2 * k); }
+    static __device__ __forceinline__ uint32_t dist(uint64_t x, uint64_t low) { return nz_groups64(x, low); }
+    static __device__ __forceinline__ uint64_t rc(uint64_t h, int k) { return revcom64(h, k); }
+};
+
+template <bool FILL, typename H>
 __global__ void __launch_bounds__(MK_BLOCK) occurrence_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
-                                                              const int64_t* __restrict__ borders, int64_t n_seq, int k, uint32_t conseq,
+                                                              const int64_t* __restrict__ borders, int64_t n_seq, int k, H conseq,
                                                               int d, int revcom, uint8_t* __restrict__ min_dist, uint32_t* __restrict__ n_hit,
                                                               const int64_t* __restrict__ offsets, int32_t* __restrict__ pos_out) {
+    typedef HashOps<H> Ops;
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * MK_BLOCK + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * MK_BLOCK) >> 5;
-    const uint32_t low = lowmask32(k);
-    const uint32_t c = conseq & low, rc = revcom32(c, k);
-    const uint32_t km = (1u << k) - 1u;
-    const int sh = 32 - 2 * k;
-    uint32_t inv_d = nz_groups32(0xFFFFFFFFu ^ c, low);
-    if (revcom) { const uint32_t r = nz_groups32(0xFFFFFFFFu ^ rc, low); inv_d = r < inv_d ? r : inv_d; }
+    const H low = Ops::low(k);
+    const H c = conseq & low, rc = Ops::rc(c, k);
+    const uint32_t km = (k >= 32) ? 0xFFFFFFFFu : ((1u << k) - 1u);
+    uint32_t inv_d = Ops::dist((H)~(H)0 ^ c, low);
+    if (revcom) { const uint32_t r = Ops::dist((H)~(H)0 ^ rc, low); inv_d = r < inv_d ? r : inv_d; }
 
     for (int64_t r = warp0; r < n_seq; r += n_warps) {
         const int64_t st = __ldg(borders + 2 * r), en = __ldg(borders + 2 * r + 1);
@@ -196,9 +211,9 @@ __global__ void __launch_bounds__(MK_BLOCK) occurrence_kernel(const uint32_t* __
                 const int64_t p = st + i;
                 const bool ok = (L >= k) && ((valid32(valid, p) & km) == km);
                 if (ok) {
-                    const uint32_t h = window16(packed, p) >> sh;
-                    dist = nz_groups32(h ^ c, low);
-                    if (revcom) { const uint32_t rd = nz_groups32(h ^ rc, low); dist = rd < dist ? rd : dist; }
+                    const H h = Ops::key(packed, p, k);
+                    dist = Ops::dist(h ^ c, low);
+                    if (revcom) { const uint32_t rd = Ops::dist(h ^ rc, low); dist = rd < dist ? rd : dist; }
                 } else {
                     dist = inv_d;
                 }
@@ -218,6 +233,27 @@ __global__ void __launch_bounds__(MK_BLOCK) occurrence_kernel(const uint32_t* __
         }
         if (!FILL && lane == 0) { min_dist[r] = (uint8_t)best; n_hit[r] = hits; }
     }
+}
+
+// ---- mask for 17 <= k <= 31 (64-bit hashes): one thread = one position, one flag word per warp ----------------------------------
+// Same rule as mask_flag_kernel: flag <=> some consensus within d of the PRE-mask window, an invalid window comparing like
+// the all-ones hash (T..T).  These k are beyond the stock motif_def_table's accepted range, so this is the plain version.
+__global__ void __launch_bounds__(MK_BLOCK) mask_flag_wide_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
+                                                                  int64_t n, int k, const uint64_t* __restrict__ cons,
+                                                                  const int32_t* __restrict__ dmax, int m, uint32_t* __restrict__ flags) {
+    __shared__ uint64_t sc[MK_MAXM];
+    __shared__ int sd[MK_MAXM];
+    const uint64_t low = lowmask64(k);
+    if (threadIdx.x < m) { sc[threadIdx.x] = cons[threadIdx.x] & low; sd[threadIdx.x] = dmax[threadIdx.x]; }
+    __syncthreads();
+    const int64_t p = (int64_t)blockIdx.x * MK_BLOCK + threadIdx.x;            // (whole warps run past n: the ballot needs them)
+    bool hit = false;
+    if (p < n) {
+        const uint64_t h = window_ok(valid, p, k) ? (window32(packed, p) >> (64 - 2 * k)) : low;
+        for (int j = 0; j < m; ++j) hit = hit || (int)nz_groups64(h ^ sc[j], low) <= sd[j];
+    }
+    const uint32_t word = __ballot_sync(0xFFFFFFFFu, hit);
+    if ((threadIdx.x & 31) == 0 && (p >> 5) < (n + 31) / 32) flags[p >> 5] = word;
 }
 
 }  // namespace
@@ -247,7 +283,7 @@ int kmap_occurrence_count(const uint32_t* packed, const uint32_t* valid, const i
     KMAP_REQUIRE(n_seq >= 0 && k >= 1 && k <= 16, "bad argument (k <= 16)");
     if (n_seq == 0) return KMAP_OK;
     KMAP_REQUIRE(packed && valid && borders && min_dist && n_hit, "null pointer");
-    occurrence_kernel<false><<<occurrence_grid(n_seq), MK_BLOCK, 0, as_stream(stream)>>>(
+    occurrence_kernel<false, uint32_t><<<occurrence_grid(n_seq), MK_BLOCK, 0, as_stream(stream)>>>(
         packed, valid, borders, n_seq, k, conseq, d, revcom, min_dist, n_hit, nullptr, nullptr);
     return kmap_check_launch("occurrence_count");
 }
@@ -258,9 +294,43 @@ int kmap_occurrence_fill(const uint32_t* packed, const uint32_t* valid, const in
     KMAP_REQUIRE(n_seq >= 0 && k >= 1 && k <= 16, "bad argument (k <= 16)");
     if (n_seq == 0) return KMAP_OK;
     KMAP_REQUIRE(packed && valid && borders && min_dist && offsets && pos_out, "null pointer");
-    occurrence_kernel<true><<<occurrence_grid(n_seq), MK_BLOCK, 0, as_stream(stream)>>>(
+    occurrence_kernel<true, uint32_t><<<occurrence_grid(n_seq), MK_BLOCK, 0, as_stream(stream)>>>(
         packed, valid, borders, n_seq, k, conseq, d, revcom, const_cast<uint8_t*>(min_dist), nullptr, offsets, pos_out);
     return kmap_check_launch("occurrence_fill");
+}
+
+// ---- 64-bit hashes (17 <= k <= 31; any 1 <= k <= 31 is accepted) -------------------------------------------------------------------
+int kmap_mask_u64(const uint32_t* packed, const uint32_t* valid_pre, uint32_t* valid, int64_t n, int k, const uint64_t* cons,
+                  const int32_t* d, int m, uint32_t* flag_scratch, void* stream) {
+    KMAP_REQUIRE(n >= 0 && k >= 1 && k <= 31 && m >= 0 && m <= MK_MAXM, "bad argument (k <= 31, m <= 16)");
+    if (n == 0 || m == 0) return KMAP_OK;
+    KMAP_REQUIRE(packed && valid_pre && valid && cons && d && flag_scratch, "null pointer");
+    cudaStream_t s = as_stream(stream);
+    const int64_t n_words = (n + 31) / 32;
+    mask_flag_wide_kernel<<<grid_for(n_words * 32, MK_BLOCK), MK_BLOCK, 0, s>>>(packed, valid_pre, n, k, cons, d, m, flag_scratch);
+    mask_dilate_kernel<<<grid_for(n_words, MK_BLOCK), MK_BLOCK, 0, s>>>(flag_scratch, n_words, k, valid);
+    return kmap_check_launch("mask_u64");
+}
+
+int kmap_occurrence_count_u64(const uint32_t* packed, const uint32_t* valid, const int64_t* borders, int64_t n_seq, int k,
+                              uint64_t conseq, int d, int revcom, uint8_t* min_dist, uint32_t* n_hit, void* stream) {
+    KMAP_REQUIRE(n_seq >= 0 && k >= 1 && k <= 31, "bad argument (k <= 31)");
+    if (n_seq == 0) return KMAP_OK;
+    KMAP_REQUIRE(packed && valid && borders && min_dist && n_hit, "null pointer");
+    occurrence_kernel<false, uint64_t><<<occurrence_grid(n_seq), MK_BLOCK, 0, as_stream(stream)>>>(
+        packed, valid, borders, n_seq, k, conseq, d, revcom, min_dist, n_hit, nullptr, nullptr);
+    return kmap_check_launch("occurrence_count_u64");
+}
+
+int kmap_occurrence_fill_u64(const uint32_t* packed, const uint32_t* valid, const int64_t* borders, int64_t n_seq, int k,
+                             uint64_t conseq, int d, int revcom, const uint8_t* min_dist, const int64_t* offsets, int32_t* pos_out,
+                             void* stream) {
+    KMAP_REQUIRE(n_seq >= 0 && k >= 1 && k <= 31, "bad argument (k <= 31)");
+    if (n_seq == 0) return KMAP_OK;
+    KMAP_REQUIRE(packed && valid && borders && min_dist && offsets && pos_out, "null pointer");
+    occurrence_kernel<true, uint64_t><<<occurrence_grid(n_seq), MK_BLOCK, 0, as_stream(stream)>>>(
+        packed, valid, borders, n_seq, k, conseq, d, revcom, const_cast<uint8_t*>(min_dist), nullptr, offsets, pos_out);
+    return kmap_check_launch("occurrence_fill_u64");
 }
 
 }  // extern "C"

@@ -30,14 +30,6 @@ __device__ __forceinline__ u64 mix64(u64 z) {
     return z ^ (z >> 31);
 }
 
-// 32 bases starting at position p, first base in the most significant bits
-__device__ __forceinline__ u64 window32(const uint32_t* __restrict__ packed, int64_t p) {
-    const int64_t w = p >> 4;
-    const uint32_t s = ((uint32_t)p & 15u) * 2u;
-    const uint32_t a = __ldg(packed + w), b = __ldg(packed + w + 1), c = __ldg(packed + w + 2);
-    return ((u64)__funnelshift_l(b, a, s) << 32) | __funnelshift_l(c, b, s);
-}
-
 // ---- keys -----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) window_keys_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
                                                           int64_t n, int k, u64* __restrict__ keys) {

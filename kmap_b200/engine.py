@@ -281,17 +281,22 @@ class SeqOnDevice:
         m = len(consensus_kh)
         if m == 0 or self.n == 0:
             return
-        if not 1 <= k <= 16:
-            raise KmapError(f"mask_input on the device covers k <= 16 (got {k})")
-        cons = to_device(np.asarray([int(c) & 0xFFFFFFFF for c in consensus_kh], dtype=np.uint32))
+        if not 1 <= k <= 31:
+            raise KmapError(f"mask_input: 1 <= k <= 31 (got {k})")
+        wide = k > 16                               # 64-bit hashes: the plain kernel (csrc/mask.cu, kmap_mask_u64)
+        if wide:
+            cons = to_device(np.asarray([int(c) for c in consensus_kh], dtype=np.uint64))
+        else:
+            cons = to_device(np.asarray([int(c) & 0xFFFFFFFF for c in consensus_kh], dtype=np.uint32))
         d = to_device(np.asarray([int(x) for x in max_dist], dtype=np.int32))
         if self._flag_scratch is None:
             self._flag_scratch = empty(self.valid.numel(), torch.int32)
         pre = self.valid if m <= 16 else self.valid.clone()   # every consensus is compared on the pre-mask windows
+        fn = L.kmap_mask_u64 if wide else L.kmap_mask
         for i in range(0, m, 16):
             mm = min(16, m - i)
-            check(L.kmap_mask(_ptr(self.packed), _ptr(pre), _ptr(self.valid), self.n, k, cons[i:].data_ptr(),
-                              d[i:].data_ptr(), mm, _ptr(self._flag_scratch), _stream_ptr()), "kmap_mask")
+            check(fn(_ptr(self.packed), _ptr(pre), _ptr(self.valid), self.n, k, cons[i:].data_ptr(),
+                     d[i:].data_ptr(), mm, _ptr(self._flag_scratch), _stream_ptr()), "kmap_mask")
 
     def masked_seq_to_numpy(self, out: np.ndarray):
         """write the masking state into `out` (the caller's seq_np_arr): 255 wherever a base is no longer valid."""
@@ -398,15 +403,16 @@ def occurrence_scan(seq: SeqOnDevice, k: int, conseq_kh: int, d: int, revcom: bo
     n_seq = seq.n_seq
     min_dist = empty(n_seq, torch.uint8)
     n_hit = empty(n_seq, torch.int32)
-    check(L.kmap_occurrence_count(_ptr(seq.packed), _ptr(seq.valid), _ptr(seq.borders), n_seq, k, int(conseq_kh), int(d),
-                                  int(revcom), _ptr(min_dist), _ptr(n_hit), _stream_ptr()), "kmap_occurrence_count")
+    f_count, f_fill = (L.kmap_occurrence_count_u64, L.kmap_occurrence_fill_u64) if k > 16 else \
+                      (L.kmap_occurrence_count, L.kmap_occurrence_fill)
+    check(f_count(_ptr(seq.packed), _ptr(seq.valid), _ptr(seq.borders), n_seq, k, int(conseq_kh), int(d),
+                  int(revcom), _ptr(min_dist), _ptr(n_hit), _stream_ptr()), "kmap_occurrence_count")
     offsets = exclusive_scan_u32(n_hit)
     total = int(offsets[-1].item()) if n_seq else 0
     pos = empty(total, torch.int32)
     if total:
-        check(L.kmap_occurrence_fill(_ptr(seq.packed), _ptr(seq.valid), _ptr(seq.borders), n_seq, k, int(conseq_kh), int(d),
-                                     int(revcom), _ptr(min_dist), _ptr(offsets), _ptr(pos), _stream_ptr()),
-              "kmap_occurrence_fill")
+        check(f_fill(_ptr(seq.packed), _ptr(seq.valid), _ptr(seq.borders), n_seq, k, int(conseq_kh), int(d),
+                     int(revcom), _ptr(min_dist), _ptr(offsets), _ptr(pos), _stream_ptr()), "kmap_occurrence_fill")
     return min_dist.cpu().numpy(), offsets.cpu().numpy(), pos.cpu().numpy()
 
 

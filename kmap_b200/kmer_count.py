@@ -277,8 +277,8 @@ def merge_revcom(uniq_kmer_hash_arr: np.ndarray, uniq_kh_cnt_arr: np.ndarray, km
 def mask_input(seq_np_arr: np.ndarray, kmer_len: int, consensus_kh_arr: np.ndarray, max_hamball_dist_arr: np.ndarray):
     """:580-610.  Mutates seq_np_arr in place and returns it.  Windows are compared on the PRE-mask array for every
     consensus; invalid windows behave like T..T (the reference compares their all-ones hash)."""
-    if not 1 <= kmer_len <= 16:
-        raise KmapError(f"mask_input: the device kernel covers k <= 16 (got {kmer_len})")
+    if not 1 <= kmer_len <= 31:
+        raise KmapError(f"mask_input: 1 <= k <= 31 (got {kmer_len})")
     if len(seq_np_arr) == 0 or len(consensus_kh_arr) == 0:
         return seq_np_arr
     dev = E.SeqOnDevice.from_numpy(seq_np_arr, None, keep_u8=True)

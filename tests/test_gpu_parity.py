@@ -725,3 +725,61 @@ def test_topk_candidates_and_find_motif_selection(ENG, MD):
     st.cnt_dev = ENG.to_device(st.cnt)
     inds, unambiguous = MD._top_k_indices(st, 5)
     assert not unambiguous and np.array_equal(inds, np.argpartition(st.cnt, -5)[-5:])
+
+
+@pytest.mark.parametrize("k", [17, 20, 31])
+def test_wide_k_mask_occurrence_and_find_motif_vs_oracle(ENG, MD, K, k):
+    """17 <= k <= 31 (64-bit hashes end to end): mask_input, the occurrence scan and the whole find_motif loop (count by
+    sorting, ball sums on lists, mask, recount) == the oracle; the motif definition is made up (the stock table has no
+    accepted k there), so that consensus sequences ARE accepted and masked"""
+    rng = np.random.default_rng(1000 + k)
+    motif = "".join("ACGT"[b] for b in rng.integers(0, 4, k))
+    reads = []
+    for _ in range(1200):
+        L = int(rng.integers(0, 90))
+        s = rng.integers(0, 4, L).astype(np.uint8)
+        s[rng.random(L) < 0.01] = 255
+        r = O.arr2dna(s)
+        if rng.random() < 0.5 and L > k + 2:
+            mm = list(motif)
+            for j in rng.choice(k, int(rng.integers(0, 3)), replace=False):
+                mm[j] = "ACGT"[int(rng.integers(0, 4))]
+            mm = "".join(mm) if rng.random() < 0.5 else O.reverse_complement("".join(mm))
+            off = int(rng.integers(0, L - k))
+            r = r[:off] + mm + r[off + k:]
+        reads.append(r)
+    reads += ["T" * 60, "A" * 50, "N" * 5, ""]
+    arrs = [O.dna2arr(r) for r in reads]
+    seq = np.concatenate(arrs)
+    lens = np.array([len(a) for a in arrs])
+    ends = np.cumsum(lens)
+    borders = np.stack([ends - lens, ends - 1], axis=1).astype(np.int64)
+    ckh = O.kmer2hash(motif)
+    cons = np.array([ckh, O.revcom_hash(ckh, k), O.kmer2hash("T" * (k - 1) + "G")], dtype=np.uint64)
+    ds = np.array([2, 2, 1])
+    want = O.mask_input(seq.copy(), k, cons, ds)
+    got = K.mask_input(seq.copy(), k, cons, ds)
+    assert np.array_equal(got, want) and (want != seq).any()
+    # occurrence scan: every read, consensus of length k
+    m_def = K.MotifDef(kmer_len=k, p_uniform=1e-6, max_ham_dist=2, ratio_mu=1.0, ratio_std=0.1, ratio_cutoff=1.5)
+    mdd = {k: m_def}
+    dev = ENG.SeqOnDevice.from_numpy(seq, borders)
+    cmin = motif if ckh <= O.revcom_hash(ckh, k) else O.reverse_complement(motif)
+    lines = MD.motif_occurence_lines(dev, borders, [cmin], mdd, True)
+    np.random.seed(3)
+    want_lines = O.motif_occurence_lines(reads, [cmin], mdd, True)
+    assert_occurrence_text_equal(lines, "\n".join(want_lines))
+    # the whole find_motif loop
+    for rep in (False, True):
+        work = seq.copy()
+        want_found, want_first = O.find_motif(work, k, 2, m_def.p_uniform, m_def.ratio_mu, m_def.ratio_std, m_def.ratio_cutoff,
+                                              boarder_mat=borders, rep_mode=rep)
+        dev = ENG.SeqOnDevice.from_numpy(seq, borders, keep_u8=True)
+        found, first = MD.find_motif_on_device(dev, k, 2, m_def.p_uniform, m_def.ratio_mu, m_def.ratio_std, m_def.ratio_cutoff,
+                                               rep_mode=rep)
+        assert len(want_found) >= 1 and [int(x) for x in found] == [int(x) for x in want_found]
+        assert all(found[a] == want_found[b] for a, b in zip(found, want_found))
+        assert np.array_equal(first[0], want_first[0]) and np.array_equal(first[1], want_first[1])
+        out = seq.copy()
+        dev.masked_seq_to_numpy(out)
+        assert np.array_equal(out, work)
