@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--partitions", type=int, default=0, help="key-range passes for the k=14 table (0 = auto)")
     ap.add_argument("--cpu-sample-reads", type=int, default=40000)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-crosscheck", action="store_true", help="skip the full-size all-k vs direct per-k table comparison")
     ap.add_argument("--no-hamdist", action="store_true", help="skip the distance-matrix leg (10 GB / n_gpus of output per GPU)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--extras", action="store_true", help="also time compaction / Hamming-ball / mask / distance-matrix kernels")
@@ -259,6 +260,13 @@ def main():
     checks = {}
     tot14 = int(tables[KMAX].to(torch.int64).sum().item())
     checks["sum_table_k14"] = tot14
+    if args.algo == "allk" and world == 1 and not args.no_crosscheck:
+        # full-size parity property: the tables the all-k algorithm DERIVES (level 14 -> 13 -> .. -> 8, with the run-end and
+        # repeat corrections of every level on the way) equal independent direct counts by the per-k kernels
+        for kc in (KMIN, KMAX - 1):
+            direct = dev.count(kc, dedup=dedup)
+            checks[f"allk_table_k{kc}_equals_direct_count"] = bool(torch.equal(direct, tables[kc]))
+            del direct
 
     # ---- roofline of the dominant kernel (the counting kernel), measured live with CUDA events ----------------------
     peaks_file = ROOT / "MEASURED_PEAKS.json"
