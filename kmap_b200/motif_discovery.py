@@ -421,6 +421,127 @@ def get_motif_seq_num(occurence_file_path: Path, motif_index: int) -> Tuple[int,
 
 
 # ======================================================================================================================
+# consumers of final.motif_occurence.csv that write DATA files (:1189-1343): co-occurrence matrices / distances and the
+# motif position densities.  Host functions like the reference's (they parse the CSV this path writes); the plots the
+# reference draws from the same numbers stay in the reference package.
+# ======================================================================================================================
+def _occurrence_rows(occurence_file_path: Path, n_cols: Optional[int] = None):
+    with open(occurence_file_path, "r", newline="") as fh:
+        header = next(fh).rstrip("\r\n").split(";")
+        if n_cols is not None:
+            assert len(header) == n_cols
+        for line in fh:
+            yield line.rstrip("\r\n").split(";")
+
+
+def get_motif_co_occurence_mat(occurence_file_path: Path, n_conseq: int):
+    """:1189-1254.  (co-occurrence counts int[n, n] with the per-motif read counts on the diagonal, median |distance|
+    matrix float[n, n] (1e6 where two motifs never share a read), {(i, j): [median position of j - median position of i
+    per shared read, in file order]})."""
+    assert n_conseq > 0
+    res_mat = np.zeros((n_conseq, n_conseq), dtype=int)
+    dist_mat = np.zeros((n_conseq, n_conseq), dtype=float)
+    individual_counts = np.zeros(n_conseq, dtype=int)
+    dist_dict = {(i, j): [] for i in range(n_conseq) for j in range(i + 1, n_conseq)}
+    for row in _occurrence_rows(occurence_file_path, n_conseq + 2):
+        motif_inds = [i for i, e in enumerate(row[1:-1]) if e.strip() != ""]
+        for i in motif_inds:
+            individual_counts[i] += 1
+        if len(motif_inds) <= 1:
+            continue
+        med = {}
+        for i in motif_inds:
+            v = sorted(int(x) for x in row[i + 1].split(","))
+            h = len(v) // 2
+            med[i] = float(v[h]) if len(v) % 2 else (v[h - 1] + v[h]) / 2.0          # np.median of the positions
+        for a in range(len(motif_inds)):
+            for b in range(a + 1, len(motif_inds)):
+                ii, jj = motif_inds[a], motif_inds[b]
+                res_mat[ii, jj] += 1
+                res_mat[jj, ii] += 1
+                dist_dict[(ii, jj)].append(med[jj] - med[ii])
+    np.fill_diagonal(res_mat, individual_counts)
+    for i in range(n_conseq):
+        for j in range(i + 1, n_conseq):
+            dist_mat[i, j] = dist_mat[j, i] = 1e6 if len(dist_dict[(i, j)]) == 0 else np.median(np.abs(dist_dict[(i, j)]))
+    return res_mat, dist_mat, dist_dict
+
+
+def write_co_occurence_dist_arr(output_file: Path, dist_dict, conseq_list: List[str]):
+    """:1147-1163"""
+    names = [f"m{i}_{s}_{reverse_complement(s)}" for i, s in enumerate(conseq_list)]
+    with open(output_file, "w") as fh:
+        for i, j in dist_dict:
+            vals = dist_dict[(i, j)]
+            if len(vals) == 0:
+                continue
+            fh.write(names[i] + "-" + names[j] + "\n")
+            fh.write("\t".join(f"{n:.2f}" for n in vals) + "\n")
+
+
+def write_co_occurence_mat(output_file: Path, dist_mat: np.ndarray, conseq_list: List[str]):
+    """:1166-1187"""
+    assert len(conseq_list) == len(dist_mat)
+    rc_names = [f"m{i}_{reverse_complement(s)}" for i, s in enumerate(conseq_list)]
+    names = [f"m{i}_{s}" for i, s in enumerate(conseq_list)]
+    with open(output_file, "w") as fh:
+        fh.write("\t".join(["RC"] + names) + "\n")
+        for i, arr in enumerate(dist_mat):
+            arr = np.around(arr, decimals=2)
+            fh.write(rc_names[i] + "\t" + "\t".join([str(x) for x in arr]) + "\n")
+
+
+def get_motif_pos_density(occurence_file_path: Path, motif_index: int, kmer_len: int, x_step=0.01, x_arr=None):
+    """:1256-1343.  (reads with the motif, listed positions, density over x_arr): every read adds the mean of normal
+    densities (sd = x_step) centred at its relative motif positions loc / (seq_len - k + 1).  Same arithmetic, in the same
+    order, as the reference's `sum(norm(xi, scale=x_step).pdf(x_arr) for xi in ...) / len(...)` accumulated read by read
+    (scipy's pdf is exp(-y^2 / 2) / sqrt(2 pi) / scale with y = (x - loc) / scale); only the exponentials are batched."""
+    if x_arr is None:
+        x_arr = np.arange(0, 1, x_step)
+    x_arr = np.asarray(x_arr)
+    density = np.zeros_like(x_arr)
+    norm_c = np.sqrt(2 * np.pi)
+    lines_with_motif = total_occurrences = 0
+    batch_pos, batch_len = [], []
+
+    def flush():
+        nonlocal density
+        if not batch_pos:
+            return
+        counts = np.array([len(p_) for p_ in batch_pos])
+        width = int(counts.max())
+        centres = np.zeros((len(batch_pos), width))
+        for r, p_ in enumerate(batch_pos):
+            centres[r, :len(p_)] = p_
+        acc = None
+        for j in range(width):                      # left to right inside a read, like sum() over the generator
+            y = (x_arr[None, :] - centres[:, j:j + 1]) / x_step
+            pdf = np.exp(-y ** 2 / 2.0) / norm_c / x_step
+            if acc is None:
+                acc = 0 + pdf
+            else:
+                acc = np.where((counts > j)[:, None], acc + pdf, acc)
+        acc = acc / counts[:, None]
+        for row in acc:                             # read by read, like `density +=`
+            density += row
+        batch_pos.clear()
+
+    for row in _occurrence_rows(occurence_file_path):
+        cell = row[motif_index + 1].strip()
+        if cell == "":
+            continue
+        seq_len = float(row[-1].strip())
+        locs = [int(n) for n in cell.split(",")]
+        batch_pos.append([(loc + 0.0) / (seq_len - kmer_len + 1) for loc in locs])
+        lines_with_motif += 1
+        total_occurrences += len(locs)
+        if len(batch_pos) >= 4096:
+            flush()
+    flush()
+    return lines_with_motif, total_occurrences, density
+
+
+# ======================================================================================================================
 # sampled k-mer distance matrix (:705-808)
 # ======================================================================================================================
 def _convert_to_block_mat(uniq_dist_mat: np.ndarray, block_size_arr: np.ndarray) -> np.ndarray:
@@ -714,9 +835,31 @@ def _scan_motif(res_dir: str, debug=False):
     gen_motif_occurence_file(final_conseq_list, motif_def_dict, input_fasta_file, occurence_file, revcom_mode,
                              _dev_cache=occurrence_dev())
 
-    if md_cfg["motif_pos_density_flag"] or md_cfg["motif_co_occurence_flag"]:
-        print("motif position density / co-occurrence plots are produced by the reference package from "
-              f"{occurence_file}; they are outside kmap_b200's scope.")
+    # the DATA files of the density / co-occurrence steps (:364-425); the pdf figures the reference draws from the same
+    # numbers (matplotlib) are not produced here
+    if md_cfg["motif_pos_density_flag"] and final_conseq_list:
+        x_step = 0.01
+        x_arr = np.arange(0, 1.0 + x_step, x_step)
+        dens = [get_motif_pos_density(occurence_file, i, len(conseq), x_step=x_step, x_arr=x_arr)[2]
+                for i, conseq in enumerate(final_conseq_list)]
+        with open(res / FileNameDict["motif_pos_density_file"], "wb") as fh:
+            pickle.dump([x_arr, np.vstack(dens)], fh)
+        print("motif position distribution generated (figures: reference package).")
+    if md_cfg["motif_co_occurence_flag"] and final_conseq_list:
+        co_occur_dir = res / FileNameDict["co_occur_dir"]
+        co_occur_dir.mkdir(exist_ok=True)
+        co_occur_mat_file = co_occur_dir / FileNameDict["co_occur_mat_file"]
+        if co_occur_mat_file.exists():
+            print(f"{co_occur_mat_file}, re-use it!")
+        else:
+            co_occur_mat, loc_dist_mat, loc_dist_dict = get_motif_co_occurence_mat(occurence_file, len(final_conseq_list))
+            co_sum_mat = np.diag(co_occur_mat) + np.diag(co_occur_mat).reshape((-1, 1))
+            co_occur_norm_mat = 2 * co_occur_mat / co_sum_mat
+            write_co_occurence_mat(co_occur_mat_file, co_occur_mat + 0.0, final_conseq_list)
+            write_co_occurence_mat(co_occur_dir / FileNameDict["co_occur_mat_norm_file"], co_occur_norm_mat, final_conseq_list)
+            write_co_occurence_mat(co_occur_dir / FileNameDict["co_occur_dist_mat_file"], loc_dist_mat, final_conseq_list)
+            write_co_occurence_dist_arr(co_occur_dir / FileNameDict["co_occur_dist_data_file"], loc_dist_dict, final_conseq_list)
+        print("motif co-occurence matrix generated (figures: reference package).")
 
     if md_cfg["sample_kmer_flag"] and not save_kmer_cnt_flag:
         print(f"kmers cannot be sampled when {save_kmer_cnt_flag=}, skip kmer sampling!")

@@ -407,6 +407,57 @@ def gen_testfa_stock_k():
     print("stock-k goldens written; final conseqs:", text["final_conseq.txt"].split(), "sample k =", kk)
 
 
+def gen_consumers():
+    """The data-producing consumers of final.motif_occurence.csv in the reference's scan_motif (motif_discovery.py:364-425):
+    get_motif_pos_density, get_motif_co_occurence_mat and the three writers, called directly (their plotting siblings are
+    not run) on the occurrence files recorded above and on a synthetic file with three motifs and empty / multi-hit cells."""
+    out = []
+    srcs = []
+    for name in ("testfa.pkl.gz", "testfa_stock_k.pkl.gz"):
+        with gzip.open(HERE / name, "rb") as fh:
+            g = pickle.load(fh)
+        finals = g["text_files"]["final_conseq.txt"].split()
+        srcs.append((name, g["text_files"]["final.motif_occurence.csv"], finals))
+    rng = np.random.default_rng(5)
+    conseqs = ["ACGTAC", "TTGACA", "GGATCC"]
+    lines = ["seq_ind;" + ";".join(f"motif_{i}_{c}" for i, c in enumerate(conseqs)) + ";seq_len"]
+    for r in range(400):
+        L = int(rng.integers(20, 120))
+        cells = []
+        for j in range(3):
+            n = int(rng.choice([0, 0, 1, 1, 2, 3, 5]))
+            cells.append(",".join(map(str, sorted(rng.choice(L - 6, n, replace=False).tolist()))) if n else "")
+        if any(cells):
+            lines.append(f"{r};" + ";".join(cells) + f";{L}")
+    srcs.append(("synthetic3", "\n".join(lines) + "\n", conseqs))
+    tmp = Path(tempfile.mkdtemp())
+    for name, text, finals in srcs:
+        f = tmp / "occ.csv"
+        f.write_text(text)
+        n = len(finals)
+        co_mat, dist_mat, dist_dict = md.get_motif_co_occurence_mat(f, n)
+        co_sum = np.diag(co_mat) + np.diag(co_mat).reshape((-1, 1))
+        norm = 2 * co_mat / co_sum
+        files = {}
+        for key, mat in (("co_occurence_mat.tsv", co_mat + 0.0), ("co_occurence_mat.norm.tsv", norm),
+                         ("co_occurence_motif_dist_mat.tsv", dist_mat)):
+            md.write_co_occurence_mat(tmp / key, mat, finals)
+            files[key] = (tmp / key).read_text()
+        md.write_co_occurence_dist_arr(tmp / "d.txt", dist_dict, finals)
+        files["co_occurence_motif_dist_data.txt"] = (tmp / "d.txt").read_text()
+        x_step = 0.01
+        x_arr = np.arange(0, 1.0 + x_step, x_step)
+        dens = []
+        for i, c in enumerate(finals):
+            dens.append(md.get_motif_pos_density(f, i, len(c), x_step=x_step, x_arr=x_arr))
+        out.append(dict(name=name, occurence_text=text, conseqs=finals, co_mat=co_mat, dist_mat=dist_mat,
+                        dist_dict={k: list(map(float, v)) for k, v in dist_dict.items()}, files=files, x_arr=x_arr,
+                        density=[(a, b, d) for a, b, d in dens]))
+        print(name, "co_mat", co_mat.tolist(), "density sums", [float(d[2].sum()) for d in dens])
+    with gzip.open(HERE / "consumers.pkl.gz", "wb") as fh:
+        pickle.dump(out, fh, protocol=4)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["unit", "small", "testfa"]
     if "unit" in what:
@@ -417,3 +468,5 @@ if __name__ == "__main__":
         gen_testfa()
     if "stock" in what:
         gen_testfa_stock_k()
+    if "consumers" in what:
+        gen_consumers()

@@ -5,8 +5,12 @@ Run on the B200 box:  python -m pytest tests -m gpu -x -q
 import numpy as np
 import pytest
 
+from pathlib import Path
+
 from helpers import assert_occurrence_text_equal
 from oracle import kmap_oracle as O
+
+GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
 
 pytestmark = pytest.mark.gpu
 
@@ -670,6 +674,8 @@ def test_scan_motif_workflow_stock_k_range(MD, K, testfa, testfa_stock_k, tmp_pa
     res_dir.mkdir()
     cfg = tomllib.loads(g["text_files"]["config.toml"])
     assert cfg["kmer_count"]["min_k"] == 6 and cfg["kmer_count"]["max_k"] == 16
+    cfg["motif_discovery"]["motif_pos_density_flag"] = True          # stock settings: the data files of these two steps
+    cfg["motif_discovery"]["motif_co_occurence_flag"] = True         # are compared with the reference functions' below
     cfg["general"]["input_fasta_file"] = str(fa)
     cfg["general"]["res_dir"] = str(res_dir)
     with open(res_dir / "config.toml", "wb") as fh:
@@ -697,6 +703,16 @@ def test_scan_motif_workflow_stock_k_range(MD, K, testfa, testfa_stock_k, tmp_pa
         kk, mat, lab = pickle.load(fh)
     assert kk == g["hamdist"]["k"] and str(mat.dtype) == g["hamdist"]["ref_dtype"]
     assert np.array_equal(mat, g["hamdist"]["mat"]) and np.array_equal(lab, g["hamdist"]["labels"])
+    # density / co-occurrence data files (reference motif_discovery.py:364-425) against what the reference's own functions
+    # returned for the same final.motif_occurence.csv (tests/golden/consumers.pkl.gz)
+    import gzip
+    with gzip.open(GOLDEN_DIR / "consumers.pkl.gz", "rb") as fh:
+        cons = next(c for c in pickle.load(fh) if c["name"] == "testfa_stock_k.pkl.gz")
+    for name, text in cons["files"].items():
+        assert (res_dir / "co_occurence" / name).read_text() == text, name
+    with open(res_dir / "motif_pos_density.np.pkl", "rb") as fh:
+        x_arr, dens = pickle.load(fh)
+    assert np.array_equal(x_arr, cons["x_arr"]) and np.array_equal(dens, np.vstack([d[2] for d in cons["density"]]))
 
 
 def test_topk_candidates_and_find_motif_selection(ENG, MD):
