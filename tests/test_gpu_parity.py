@@ -799,3 +799,33 @@ def test_wide_k_mask_occurrence_and_find_motif_vs_oracle(ENG, MD, K, k):
         out = seq.copy()
         dev.masked_seq_to_numpy(out)
         assert np.array_equal(out, work)
+
+
+def test_large_input_identities(ENG):
+    """size-independent identities on an input far beyond what the oracle can count (5e6 synthetic ChIP-like reads x 100 bp,
+    5.05e8 positions, generated on the device): repetitive mode -- every table sums to the number of windows of its level;
+    de-duplicated mode -- the derived tables of the all-k count (routed level 13, fused lower levels) equal direct per-k
+    counts, and a 4:1 fold of level k+1 never exceeds level k by more than the run-end windows; sort path at k = 16 --
+    counts sum to the windows, keys ascend"""
+    import torch
+    from kmap_b200 import synth
+    n_reads, L = 5_000_000, 100
+    seq_d, borders_d = synth.generate_device(synth.CFG3, 0, n_reads)
+    dev = ENG.SeqOnDevice.from_device_u8(seq_d, borders_d)
+    del seq_d
+    rep = dev.count_all(8, 14, dedup=False)
+    for k in range(8, 15):
+        assert int(rep[k].to(torch.int64).sum().item()) == n_reads * (L - k + 1), k
+    ded = dev.count_all(8, 14, dedup=True)
+    for k in (8, 11, 13):
+        direct = dev.count(k, dedup=True)
+        assert torch.equal(direct, ded[k]), k
+        del direct
+    for k in range(8, 14):
+        folded = ded[k + 1].view(-1, 4).sum(dim=1, dtype=torch.int64)
+        extra = ded[k].to(torch.int64) - folded            # +1 per read end, -1 per repeat whose extension is new
+        assert int(extra.sum().item()) <= n_reads and int(extra.abs().sum().item()) <= 2 * n_reads, k
+        assert int(ded[k].to(torch.int64).sum().item()) <= n_reads * (L - k + 1)
+    kh, cnt = dev.count_sorted(16, dedup=False)
+    assert int(cnt.sum().item()) == n_reads * (L - 16 + 1)
+    assert bool((kh[1:] > kh[:-1]).all().item()) and int(cnt.min().item()) >= 1
