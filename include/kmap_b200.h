@@ -114,7 +114,6 @@ int64_t kmap_dedup_work_words(int64_t n_seq);
  * only), after the partition pass (instrumentation for bench.py).  Synchronises the stream once when dedup != 0. */
 #define KMAP_KMAX_PREFIX_PASSES 0    /* global atomics in n_partitions key-prefix passes (no scratch) */
 #define KMAP_KMAX_SORTED 1           /* csrc/partition.cu, scratch = kmap_partition_scratch_bytes(n, kmax) */
-#define KMAP_KMAX_SLOTTED 2          /* csrc/slots.cu, scratch = kmap_slot_scratch_bytes(n, kmax) */
 int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
                      int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
                      uint32_t* bitmap, int n_partitions, int scheme, void* part_scratch, int64_t part_scratch_bytes,
@@ -129,15 +128,6 @@ int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, int64_t n, c
 int kmap_count_dense_partitioned(const uint32_t* packed, const uint32_t* valid, int64_t n, int k, uint32_t* table,
                                  void* scratch, int64_t scratch_bytes, void* stream);
 int64_t kmap_partition_scratch_bytes(int64_t n, int k);
-
-/* The same count (12 <= k <= 14) by slotted partitioning (csrc/slots.cu): bucket = top 12 bits of the key, and every
- * (bucket, tile of 32768 positions) pair owns one 32-byte sector of the scratch (a 16-bit count + up to 15 suffixes), so
- * no histogram pass and no per-tile sort are needed; a window that finds its sector full is counted with a global atomic
- * instead.  table[h] += count: the caller zeroes the table first.  scratch = kmap_slot_scratch_bytes(n, k) bytes
- * (4 bytes per position).  kmap_count_all_k: scheme = KMAP_KMAX_SLOTTED. */
-int kmap_count_dense_slotted(const uint32_t* packed, const uint32_t* valid, int64_t n, int k, uint32_t* table,
-                             void* scratch, int64_t scratch_bytes, void* stream);
-int64_t kmap_slot_scratch_bytes(int64_t n, int k);
 
 int kmap_fill_u32(uint32_t* p, int64_t n_words, uint32_t value, void* stream);
 /* dst[i] += src[i]: merges the tables of one chunk of reads into the running totals when the reads are streamed through
@@ -158,7 +148,7 @@ int kmap_list_add_rc_counts(const uint32_t* kh, int32_t* cnt, int64_t n, int k, 
 
 /* count_uniq_hash + merge_revcom (kmer_count.py:476-491, 643-685) from the dense forward table, in the
  * reference's exact output order (ascending forward hash of the surviving entries; value = min(h, rc h) when
- * revcom; palindromes doubled).  scratch = uint64[kmap_compact_scratch_words(k)] (256-byte aligned; for k >= 13 it
+ * revcom == 1, max(h, rc h) when revcom == 2 -- merge_revcom's keep_lower_hash_flag=False --; palindromes doubled).  scratch = uint64[kmap_compact_scratch_words(k)] (256-byte aligned; for k >= 13 it
  * also holds a permuted copy of the table, G[h] = F[rc h], so that the merge reads its partner cell without a gather).
  * Two-step: call with capacity 0 (out pointers may be NULL) to get *n_out_host, then with buffers.
  * Synchronises the stream. */
@@ -256,11 +246,12 @@ int64_t kmap_sort_scratch_words(int64_t n);
 int kmap_rle_u64(const uint64_t* sorted_keys, int64_t n, uint64_t* scratch, int64_t* pos_scratch, uint64_t* kh_out,
                  int64_t* cnt_out, int64_t capacity, void* stream);
 /* merge_revcom (kmer_count.py:643-685) on an ASCENDING unique list: survivors in list order, value min(h, rc h), count
- * cnt[h] + cnt[rc h] (a palindrome is its own partner: doubled).  Two-step like kmap_compact_merge (capacity 0 = size
+ * cnt[h] + cnt[rc h] (a palindrome is its own partner: doubled); keep_higher != 0 is keep_lower_hash_flag=False
+ * (kmer_count.py:671, 682: the higher hash of a pair survives, value max(h, rc h)).  Two-step like kmap_compact_merge (capacity 0 = size
  * query).  summed_cnt (may be NULL, must not alias cnt) = int64[n]: cnt[i] + cnt[partner of i] for every i, what the
  * reference leaves in the caller's count array (kmer_count.py:661).
  * scratch = uint64[kmap_merge_sorted_scratch_words(n)].  Synchronises. */
-int kmap_merge_revcom_sorted_u64(const uint64_t* kh, const int64_t* cnt, int64_t n, int k, uint64_t* scratch, uint64_t* kh_out,
+int kmap_merge_revcom_sorted_u64(const uint64_t* kh, const int64_t* cnt, int64_t n, int k, int keep_higher, uint64_t* scratch, uint64_t* kh_out,
                                  int64_t* cnt_out, int64_t capacity, int64_t* n_out_host, int64_t* summed_cnt, void* stream);
 int64_t kmap_merge_sorted_scratch_words(int64_t n);
 /* kmap_hamball_sum_list / kmap_hamball_extract for uint64 hashes and int64 counts (k <= 31) */

@@ -30,6 +30,12 @@ class TableAllReduce:
         self.dist.all_reduce(table, op=self.dist.ReduceOp.SUM, group=self.group)
         return table
 
+    def sum_int(self, value: int, device=None) -> int:
+        """sum of one host integer over the ranks (e.g. the window count that bounds the merged lists)"""
+        t = torch.tensor([int(value)], dtype=torch.int64, device=device if device is not None else "cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return int(t.item())
+
     @property
     def rank(self) -> int:
         return self.dist.get_rank(self.group)
@@ -111,6 +117,8 @@ def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterabl
         else:
             for k in ks:
                 table_allreduce(tables[k])
+        # the merged table holds the distinct k-mers of EVERY shard: the capacity bound is the total window count
+        n_total = table_allreduce.sum_int(n_total, device=tables[ks[0]].device)
         if lists_on is not None and table_allreduce.rank != lists_on:
             return out
     # compaction of table k+1 overlaps the device-to-host copy of the lists of k (copy stream + pinned buffers)

@@ -78,12 +78,13 @@ __global__ void __launch_bounds__(256) revcom_permute_kernel(const uint32_t* __r
 
 // ---- merged-entry rule on the forward table F (SURVEY Q6 recipe; kmer_count.py:656-683) ------------------
 // h survives iff F[h] > 0 and not (rc(h) present and h > rc(h)); value = min(h, rc h); count = F[h] + F[rc h]
-// (a palindrome is its own partner, so its count doubles).  frc = F[rc h].
-__device__ __forceinline__ bool merged_entry(uint32_t h, uint32_t fh, uint32_t frc, int k, uint32_t* value, uint32_t* count) {
+// (a palindrome is its own partner, so its count doubles).  frc = F[rc h].  keep_higher = merge_revcom's
+// keep_lower_hash_flag=False (kmer_count.py:671, 682): the comparisons turn around, value = max(h, rc h).
+__device__ __forceinline__ bool merged_entry(uint32_t h, uint32_t fh, uint32_t frc, int k, bool keep_higher, uint32_t* value, uint32_t* count) {
     if (fh == 0) return false;
     const uint32_t rc = revcom32(h, k);
-    if (frc > 0 && h > rc) return false;
-    *value = h < rc ? h : rc;
+    if (frc > 0 && (keep_higher ? h < rc : h > rc)) return false;
+    *value = (h < rc) != keep_higher ? h : rc;
     *count = fh + frc;
     return true;
 }
@@ -113,7 +114,7 @@ __device__ __forceinline__ void load_items(const uint32_t* __restrict__ F, const
 
 __device__ __forceinline__ bool item_entry(uint32_t h, uint32_t fh, uint32_t frc, int k, int revcom, uint32_t* value, uint32_t* count) {
     if (!revcom) { *value = h; *count = fh; return fh != 0; }
-    return merged_entry(h, fh, frc, k, value, count);
+    return merged_entry(h, fh, frc, k, revcom == 2, value, count);
 }
 
 __global__ void __launch_bounds__(CP_BLOCK) table_tile_count_kernel(const uint32_t* __restrict__ F, const uint32_t* __restrict__ G,

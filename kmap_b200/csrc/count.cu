@@ -224,11 +224,8 @@ int kmap_count_long_reads(const uint32_t* packed, const uint32_t* valid, int64_t
     cudaError_t e = cudaSuccess;
     int rc;
     if (counts[0]) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(count_dedup_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_BLOCK_SLOTS * 4);
-            attr_set = true;
-        }
+        // (per-device attribute: set on every call, not once per process)
+        cudaFuncSetAttribute(count_dedup_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_BLOCK_SLOTS * 4);
         const unsigned int g = counts[0] < 148u * 3u ? counts[0] : 148u * 3u;
         count_dedup_block_kernel<<<g, 256, DD_BLOCK_SLOTS * 4, s>>>(packed, valid, n, borders, n_seq, k, table, work);
         rc = kmap_check_launch("count_dedup_block");

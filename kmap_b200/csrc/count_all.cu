@@ -345,9 +345,6 @@ int kmap_count_long_reads(const uint32_t* packed, const uint32_t* valid, int64_t
 // implemented in partition.cu: level-k count through key partitioning + shared-memory counters
 int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const uint32_t* hide, int64_t n, int k, uint32_t* table,
                            void* scratch, const KmapTableSet* terminal_tabs, int kmin, void* const* step_events, cudaStream_t s);
-// implemented in slots.cu: level-k count through slotted key partitioning (one sector per bucket and tile)
-int kmap_count_slotted(const uint32_t* packed, const uint32_t* valid, const uint32_t* hide, int64_t n, int k, uint32_t* table,
-                       void* scratch, const KmapTableSet* terminal_tabs, int kmin, void* const* step_events, cudaStream_t s);
 
 extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
                                 int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
@@ -389,7 +386,7 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
         else
             dedup_scan_kernel<false><<<(unsigned int)blocks, AK_WARPS * 32, 0, s>>>(packed, valid, n, borders, n_seq, kmin, kmax, tabs, dupmask, work);
     }
-    KMAP_REQUIRE(scheme >= KMAP_KMAX_PREFIX_PASSES && scheme <= KMAP_KMAX_SLOTTED, "unknown scheme");
+    KMAP_REQUIRE(scheme >= KMAP_KMAX_PREFIX_PASSES && scheme <= KMAP_KMAX_SORTED, "unknown scheme");
     const bool use_partition = scheme != KMAP_KMAX_PREFIX_PASSES && part_scratch && kmax >= 12 && kmax <= 14;
     if (!use_partition) {          // (the partitioned count does these corrections inside its histogram pass)
         const int64_t n_groups = (n_words + 3) / 4;
@@ -421,11 +418,7 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
     const uint32_t* hide = dedup ? dupmask : nullptr;
     if (use_partition) {
         // level kmax through key partitioning + shared-memory counters (partition.cu)
-        if (scheme == KMAP_KMAX_SLOTTED) {
-            KMAP_REQUIRE(part_scratch_bytes >= kmap_slot_scratch_bytes(n, kmax), "slot scratch too small");
-            rc = kmap_count_slotted(packed, valid, hide, n, kmax, tabs.t[kmax], part_scratch, kmin < kmax ? &tabs : nullptr, kmin,
-                                    phase_events ? phase_events + 5 : nullptr, s);
-        } else {
+        {
             KMAP_REQUIRE(part_scratch_bytes >= kmap_partition_scratch_bytes(n, kmax), "partition scratch too small");
             // (run-end corrections: fused into the histogram pass, except that a level whose table is beyond L2 -- level 13
             // under k = 14 -- travels through the partition itself as extra buckets; see partition.cu)

@@ -535,14 +535,11 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
     cudaMemsetAsync(p.ticket, 0, 8, s);
     if (step_events && step_events[0]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(step_events[0]), s);
     const unsigned int g2 = (unsigned int)(n_tiles < 148 ? n_tiles : 148);
-    static bool attr_set = false;
     const int smem1 = PT_TILE * 4 + 2 * PT_THREADS * 12, smem4 = PT_TILE * 4 + (PT_MAX_PER + 1) * PT_THREADS * 12;
-    if (!attr_set) {
-        cudaFuncSetAttribute(partition_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
-        cudaFuncSetAttribute(partition_kernel<PT_MAX_PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4);
-        cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_WORDS * 4);
-        attr_set = true;
-    }
+    // (function attributes are per device: set on every call -- it is a host-side table write -- rather than once per process)
+    cudaFuncSetAttribute(partition_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    cudaFuncSetAttribute(partition_kernel<PT_MAX_PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4);
+    cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_WORDS * 4);
     if (n_buckets <= PT_THREADS)
         partition_kernel<1><<<g2, PT_THREADS, smem1, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_base, p.suffixes, p.ticket);
     else

@@ -419,8 +419,8 @@ __device__ __forceinline__ int64_t find_key(const u64* __restrict__ kh, int64_t 
 
 // partner[i] = index of rc(kh[i]) in the list or -1; tile_counts = survivors per tile
 // (entry i is dropped iff its partner is present and kh[i] > rc(kh[i]), kmer_count.py:668-676)
-__global__ void __launch_bounds__(RL_BLOCK) merge_plan_kernel(const u64* __restrict__ kh, int64_t n, int k, long long* __restrict__ partner,
-                                                              uint64_t* __restrict__ tile_counts) {
+__global__ void __launch_bounds__(RL_BLOCK) merge_plan_kernel(const u64* __restrict__ kh, int64_t n, int k, bool keep_higher,
+                                                              long long* __restrict__ partner, uint64_t* __restrict__ tile_counts) {
     const int64_t base = (int64_t)blockIdx.x * RL_TILE + (int64_t)threadIdx.x * RL_ITEMS;
     uint32_t c = 0;
     for (int j = 0; j < RL_ITEMS; ++j) {
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(RL_BLOCK) merge_plan_kernel(const u64* __restr
             const u64 h = __ldg(kh + i), rc = revcom64(h, k);
             const int64_t p = find_key(kh, n, rc);
             partner[i] = p;
-            c += !(p >= 0 && h > rc);
+            c += !(p >= 0 && (keep_higher ? h < rc : h > rc));
         }
     }
     uint32_t total;
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(RL_BLOCK) merge_plan_kernel(const u64* __restr
 // survivors in list order: (min(h, rc h), cnt[h] + cnt[rc h]); summed (may be NULL) gets cnt[i] + cnt[partner] for EVERY i,
 // which is what the reference leaves in the caller's count array (kmer_count.py:661)
 __global__ void __launch_bounds__(RL_BLOCK) merge_write_kernel(const u64* __restrict__ kh, const long long* __restrict__ cnt, int64_t n, int k,
-                                                               const long long* __restrict__ partner, const uint64_t* __restrict__ tile_offsets,
+                                                               bool keep_higher, const long long* __restrict__ partner, const uint64_t* __restrict__ tile_offsets,
                                                                u64* __restrict__ kh_out, long long* __restrict__ cnt_out,
                                                                long long* __restrict__ summed) {
     const int64_t base = (int64_t)blockIdx.x * RL_TILE + (int64_t)threadIdx.x * RL_ITEMS;
@@ -455,8 +455,8 @@ __global__ void __launch_bounds__(RL_BLOCK) merge_write_kernel(const u64* __rest
             const u64 h = __ldg(kh + i), rc = revcom64(h, k);
             const long long p = partner[i];
             sum[j] = cnt[i] + (p >= 0 ? cnt[p] : 0ll);
-            val[j] = h < rc ? h : rc;
-            if (!(p >= 0 && h > rc)) { keep |= 1u << j; ++c; }
+            val[j] = (h < rc) != keep_higher ? h : rc;
+            if (!(p >= 0 && (keep_higher ? h < rc : h > rc))) { keep |= 1u << j; ++c; }
         }
     }
     uint32_t total;
@@ -692,7 +692,7 @@ int kmap_rle_u64(const uint64_t* sorted_keys, int64_t n, uint64_t* scratch, int6
 
 int64_t kmap_merge_sorted_scratch_words(int64_t n) { return n < 0 ? 0 : n + rl_tiles(n) + 2; }
 
-int kmap_merge_revcom_sorted_u64(const uint64_t* kh, const int64_t* cnt, int64_t n, int k, uint64_t* scratch, uint64_t* kh_out,
+int kmap_merge_revcom_sorted_u64(const uint64_t* kh, const int64_t* cnt, int64_t n, int k, int keep_higher, uint64_t* scratch, uint64_t* kh_out,
                                  int64_t* cnt_out, int64_t capacity, int64_t* n_out_host, int64_t* summed_cnt, void* stream) {
     KMAP_REQUIRE(n >= 0 && k >= 1 && k <= 31 && n_out_host, "bad argument (1 <= k <= 31)");
     *n_out_host = 0;
@@ -703,7 +703,7 @@ int kmap_merge_revcom_sorted_u64(const uint64_t* kh, const int64_t* cnt, int64_t
     long long* partner = reinterpret_cast<long long*>(scratch);
     uint64_t* tile_counts = scratch + n;
     const u64* khp = reinterpret_cast<const u64*>(kh);
-    merge_plan_kernel<<<(unsigned int)tiles, RL_BLOCK, 0, s>>>(khp, n, k, partner, tile_counts);
+    merge_plan_kernel<<<(unsigned int)tiles, RL_BLOCK, 0, s>>>(khp, n, k, keep_higher != 0, partner, tile_counts);
     scan_tiles64_kernel<<<1, 1024, 0, s>>>(tile_counts, tiles);
     int rc = kmap_check_launch("merge_revcom_sorted(plan)");
     if (rc) return rc;
@@ -714,7 +714,7 @@ int kmap_merge_revcom_sorted_u64(const uint64_t* kh, const int64_t* cnt, int64_t
         kmap_set_error("merge_revcom_sorted: capacity %lld < %lld", (long long)capacity, (long long)*n_out_host);
         return KMAP_ERR_CAPACITY;
     }
-    merge_write_kernel<<<(unsigned int)tiles, RL_BLOCK, 0, s>>>(khp, reinterpret_cast<const long long*>(cnt), n, k, partner, tile_counts,
+    merge_write_kernel<<<(unsigned int)tiles, RL_BLOCK, 0, s>>>(khp, reinterpret_cast<const long long*>(cnt), n, k, keep_higher != 0, partner, tile_counts,
                                                                reinterpret_cast<u64*>(kh_out), reinterpret_cast<long long*>(cnt_out),
                                                                reinterpret_cast<long long*>(summed_cnt));
     return kmap_check_launch("merge_revcom_sorted(write)");

@@ -1,4 +1,4 @@
-// Tile helpers shared by the level-k partition kernels (partition.cu, slots.cu): a CTA walks the packed reads in tiles
+// Tile helpers shared by the level-k partition kernels (partition.cu): a CTA walks the packed reads in tiles
 // of blockDim.x validity words, one word (32 window positions) per thread.
 #pragma once
 #include "common.cuh"

@@ -103,10 +103,10 @@ class SeqOnDevice:
     PARTITION_MIN_K = 13
 
     # schemes for a level-k table beyond L2 (include/kmap_b200.h)
-    PREFIX_PASSES, SORTED, SLOTTED = 0, 1, 2
+    PREFIX_PASSES, SORTED = 0, 1
 
     def _part_scratch(self, k: int, scheme: int = 1) -> torch.Tensor:
-        need = lib().kmap_slot_scratch_bytes(self.n, k) if scheme == self.SLOTTED else lib().kmap_partition_scratch_bytes(self.n, k)
+        need = lib().kmap_partition_scratch_bytes(self.n, k)
         if self._part is None or self._part.numel() < need:
             self._part = None                      # release before growing
             self._part = empty(need, torch.uint8)
@@ -167,12 +167,10 @@ class SeqOnDevice:
     def count(self, k: int, dedup: bool, table: Optional[torch.Tensor] = None, zero: bool = True,
               partitioned: Optional[bool] = None, scheme: Optional[int] = None) -> torch.Tensor:
         """dense forward table uint32[4^k] (held as int32 bits).  dedup=True fuses remove_duplicate_hash_per_seq.
-        partitioned: None = choose by k (PARTITION_MIN_K), True/False = force (plain counts with 9 <= k <= 14 only);
-        scheme: SORTED (default) or SLOTTED (12 <= k <= 14)."""
+        partitioned: None = choose by k (PARTITION_MIN_K), True/False = force (plain counts with 9 <= k <= 14 only)."""
         L = lib()
         if not 1 <= k <= 15:
-            raise KmapError(f"dense counting supports 1 <= k <= 15 (got {k}); k >= 16 uses 64-bit hashes "
-                            "(sort path, not built yet)")
+            raise KmapError(f"dense counting supports 1 <= k <= 15 (got {k}); k >= 16 uses 64-bit hashes: count_sorted")
         n_cells = 1 << (2 * k)
         if table is None:
             table = zeros(n_cells, torch.int32)
@@ -194,10 +192,6 @@ class SeqOnDevice:
                 rc = L.kmap_count_dense_dedup(_ptr(self.packed), _ptr(self.valid), self.n, _ptr(self.borders), self.n_seq,
                                               k, _ptr(table), _ptr(self._work), _ptr(bitmap), _stream_ptr())
             check(rc, "kmap_count_dense_dedup")
-        elif scheme == self.SLOTTED and 12 <= k <= 14 and zero:
-            scratch = self._part_scratch(k, self.SLOTTED)
-            check(L.kmap_count_dense_slotted(_ptr(self.packed), _ptr(self.valid), self.n, k, _ptr(table), _ptr(scratch),
-                                             scratch.numel(), _stream_ptr()), "kmap_count_dense_slotted")
         elif (partitioned if partitioned is not None else k >= self.PARTITION_MIN_K) and 9 <= k <= 14 and zero:
             scratch = self._part_scratch(k)
             check(L.kmap_count_dense_partitioned(_ptr(self.packed), _ptr(self.valid), self.n, k, _ptr(table), _ptr(scratch),
@@ -212,7 +206,7 @@ class SeqOnDevice:
                   scheme: Optional[int] = None) -> dict:
         """Dense forward tables for every k in [kmin, kmax] from ONE update per window at level kmax (csrc/count_all.cu);
         identical to {k: self.count(k, dedup)}.  Returns {k: int32-bit-pattern tensor of 4^k cells}.
-        scheme: how the level-kmax table is built when 12 <= kmax <= 14 -- SORTED (default: measured fastest), SLOTTED,
+        scheme: how the level-kmax table is built when 12 <= kmax <= 14 -- SORTED (default: measured fastest)
         or PREFIX_PASSES (global atomics in n_partitions key-prefix passes; also what `partitioned=False` /
         n_partitions > 0 select)."""
         L = lib()
@@ -435,7 +429,7 @@ def sort_count_keys(keys: torch.Tensor, key_bits: int) -> Tuple[torch.Tensor, to
     return kh, cnt
 
 
-def merge_revcom_sorted(kh: torch.Tensor, cnt: torch.Tensor, k: int, want_summed: bool = False):
+def merge_revcom_sorted(kh: torch.Tensor, cnt: torch.Tensor, k: int, want_summed: bool = False, keep_higher: bool = False):
     """merge_revcom (kmer_count.py:643-685) on an ascending unique (uint64 kh, int64 cnt) device list -> (kh, cnt) in the
     reference's order [, the summed counts the reference leaves in the caller's array]."""
     L = lib()
@@ -446,7 +440,7 @@ def merge_revcom_sorted(kh: torch.Tensor, cnt: torch.Tensor, k: int, want_summed
     n_out = ctypes.c_int64(0)
     out_kh, out_cnt = empty(n, torch.int64), empty(n, torch.int64)      # survivors <= n: one call
     summed = empty(n, torch.int64) if want_summed else None
-    check(L.kmap_merge_revcom_sorted_u64(_ptr(kh), _ptr(cnt), n, k, _ptr(scratch), _ptr(out_kh), _ptr(out_cnt), n, ctypes.byref(n_out),
+    check(L.kmap_merge_revcom_sorted_u64(_ptr(kh), _ptr(cnt), n, k, int(keep_higher), _ptr(scratch), _ptr(out_kh), _ptr(out_cnt), n, ctypes.byref(n_out),
                                          _ptr(summed), _stream_ptr()), "kmap_merge_revcom_sorted_u64")
     out = (out_kh[:n_out.value], out_cnt[:n_out.value])
     return out + (summed,) if want_summed else out

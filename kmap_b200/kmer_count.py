@@ -243,10 +243,9 @@ def count_uniq_hash(hash_arr: np.ndarray, kmer_len):
 
 def merge_revcom(uniq_kmer_hash_arr: np.ndarray, uniq_kh_cnt_arr: np.ndarray, kmer_len: int, keep_lower_hash_flag=True) -> Tuple:
     """:643-685.  Sums the counts of reverse-complement pairs (a palindrome is its own partner: doubled), keeps the
-    lower hash of a pair, relabels lone k-mers to min(h, rc h); result order = ascending forward hash of the survivors.
+    lower hash of a pair (the higher one with keep_lower_hash_flag=False), relabels lone k-mers to min (max) of (h, rc h);
+    result order = ascending forward hash of the survivors.
     Like the reference it also updates the caller's count array in place (the `+=` at :661)."""
-    if not keep_lower_hash_flag:
-        raise KmapError("merge_revcom(keep_lower_hash_flag=False) is never used by scan_motif and is not built")
     kh = np.asarray(uniq_kmer_hash_arr)
     n = len(kh)
     if n == 0:
@@ -256,7 +255,7 @@ def merge_revcom(uniq_kmer_hash_arr: np.ndarray, uniq_kh_cnt_arr: np.ndarray, km
             raise KmapError("merge_revcom for k >= 16 expects the ascending unique hashes count_uniq_hash returns")
         out_kh, out_cnt, summed = E.merge_revcom_sorted(E.to_device(kh.astype(np.uint64, copy=False)),
                                                         E.to_device(np.asarray(uniq_kh_cnt_arr).astype(np.int64, copy=False)),
-                                                        kmer_len, want_summed=True)
+                                                        kmer_len, want_summed=True, keep_higher=not keep_lower_hash_flag)
         uniq_kh_cnt_arr[:] = E.to_host(summed, np.int64).astype(uniq_kh_cnt_arr.dtype, copy=False)
         return (E.to_host(out_kh, np.uint64).astype(kh.dtype, copy=False),
                 E.to_host(out_cnt, np.int64).astype(uniq_kh_cnt_arr.dtype, copy=False))
@@ -266,7 +265,7 @@ def merge_revcom(uniq_kmer_hash_arr: np.ndarray, uniq_kh_cnt_arr: np.ndarray, km
     cnt_d = E.to_device(np.asarray(uniq_kh_cnt_arr).astype(np.int32, copy=False))
     table = E.zeros(1 << (2 * kmer_len), torch.int32)
     check(L.kmap_scatter_counts(kh_d.data_ptr(), cnt_d.data_ptr(), n, kmer_len, table.data_ptr(), _stream()), "kmap_scatter_counts")
-    out_kh, out_cnt = E.compact_merge(table, kmer_len, revcom=True)
+    out_kh, out_cnt = E.compact_merge(table, kmer_len, revcom=1 if keep_lower_hash_flag else 2)
     check(L.kmap_list_add_rc_counts(kh_d.data_ptr(), cnt_d.data_ptr(), n, kmer_len, table.data_ptr(), _stream()),
           "kmap_list_add_rc_counts")
     uniq_kh_cnt_arr[:] = E.to_host(cnt_d, np.int32).astype(uniq_kh_cnt_arr.dtype, copy=False)

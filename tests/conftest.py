@@ -42,5 +42,10 @@ def testfa_stock_k():
 
 
 @pytest.fixture(scope="session")
+def r2_vectors():
+    return _load("r2_vectors.pkl")
+
+
+@pytest.fixture(scope="session")
 def motif_def_file():
     return str(ROOT / "kmap_b200" / "default_motif_def_table.csv")

@@ -124,6 +124,16 @@ def test_merge_revcom_vectors(K, unit_vectors):
             assert np.array_equal(cnt, g["mutated_cnt"])
 
 
+def test_merge_revcom_keep_higher_flag(K, r2_vectors):
+    """keep_lower_hash_flag=False (kmer_count.py:668-683) on the dense (k < 16) and the sorted-list (k >= 16) path"""
+    for g in r2_vectors["merge_revcom_flag"]:
+        kh, cnt = g["kh"].copy(), g["cnt"].copy()
+        mk, mc = K.merge_revcom(kh, cnt, g["k"], keep_lower_hash_flag=g["keep_lower"])
+        assert np.array_equal(mk, g["out_kh"]) and np.array_equal(mc, g["out_cnt"]), (g["k"], g["keep_lower"])
+        assert mk.dtype == g["out_kh"].dtype and mc.dtype == g["out_cnt"].dtype
+        assert np.array_equal(cnt, g["mutated_cnt"]), (g["k"], g["keep_lower"])
+
+
 def test_mask_known_answers(K, unit_vectors, motif_def_file):
     g = unit_vectors["mask_ham_ball"]
     mdd = K.init_motif_def_dict(motif_def_file)
@@ -164,9 +174,6 @@ def test_partitioned_count_equals_direct_count(ENG, k):
     got = ENG.to_host(dev.count(k, dedup=False, partitioned=True, scheme=ENG.SeqOnDevice.SORTED), np.uint32)
     direct = ENG.to_host(dev.count(k, dedup=False, partitioned=False), np.uint32)
     assert np.array_equal(got, direct), (k, int(np.abs(got.astype(np.int64) - direct.astype(np.int64)).sum()))
-    if k >= 12:     # the slotted scheme: most sectors overflow here (homopolymers), so the direct-count path is exercised too
-        slotted = ENG.to_host(dev.count(k, dedup=False, partitioned=True, scheme=ENG.SeqOnDevice.SLOTTED), np.uint32)
-        assert np.array_equal(slotted, direct), (k, int(np.abs(slotted.astype(np.int64) - direct.astype(np.int64)).sum()))
     assert np.array_equal(got, dense_table_from_oracle(seq, borders, k, False))
     assert got[0] >= 69000 and got[4 ** k - 1] >= 39000
     # a second call re-uses the scratch and must not depend on its previous content
@@ -183,9 +190,8 @@ def test_partitioned_count_tiny_and_empty(ENG):
         borders = np.stack([ends - lens, ends - 1], axis=1).astype(np.int64)
         dev = ENG.SeqOnDevice.from_numpy(seq, borders)
         for k in (9, 14):
-            for scheme in (ENG.SeqOnDevice.SORTED, ENG.SeqOnDevice.SLOTTED):
-                got = ENG.to_host(dev.count(k, dedup=False, partitioned=True, scheme=scheme), np.uint32)
-                assert np.array_equal(got, dense_table_from_oracle(seq, borders, k, False))
+            got = ENG.to_host(dev.count(k, dedup=False, partitioned=True), np.uint32)
+            assert np.array_equal(got, dense_table_from_oracle(seq, borders, k, False))
 
 
 @pytest.mark.parametrize("kmin,kmax,parts", [(8, 14, 0), (8, 14, 3), (1, 6, 0), (5, 5, 1), (11, 15, 5), (3, 9, 2), (9, 13, 0),
@@ -202,7 +208,7 @@ def test_count_all_k_equals_per_k_counts(ENG, kmin, kmax, parts):
     borders = np.concatenate([borders, borders2 + borders[-1, 1] + 1])
     # tandem repeats so that k-mers repeat inside reads with different extensions
     dev = ENG.SeqOnDevice.from_numpy(seq, borders)
-    for dedup, scheme in ((True, None), (False, None), (True, ENG.SeqOnDevice.SLOTTED)):
+    for dedup, scheme in ((True, None), (False, None), (True, ENG.SeqOnDevice.PREFIX_PASSES)):
         tabs = dev.count_all(kmin, kmax, dedup, n_partitions=parts, scheme=scheme)
         for k in range(kmin, kmax + 1):
             got = ENG.to_host(tabs[k], np.uint32)
