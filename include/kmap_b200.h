@@ -245,6 +245,11 @@ int64_t kmap_sort_scratch_words(int64_t n);
  * (capacity >= the number of distinct keys).  scratch as above, pos_scratch = int64[capacity].  Synchronises. */
 int kmap_rle_u64(const uint64_t* sorted_keys, int64_t n, uint64_t* scratch, int64_t* pos_scratch, uint64_t* kh_out,
                  int64_t* cnt_out, int64_t capacity, void* stream);
+/* count_uniq_hash (kmer_count.py:476-491) of a sharded input = the per-shard (hash, count) lists added up:
+ * cnt_out[j] += cnt[i] where uniq[j] == kh[i] (uniq ascending and distinct: the sorted union of the shards' hashes; an
+ * absent hash is skipped).  The caller zeroes cnt_out and calls this once per shard list. */
+int kmap_list_add_counts_u64(const uint64_t* uniq, int64_t n_uniq, const uint64_t* kh, const int64_t* cnt, int64_t n, int64_t* cnt_out,
+                             void* stream);
 /* merge_revcom (kmer_count.py:643-685) on an ASCENDING unique list: survivors in list order, value min(h, rc h), count
  * cnt[h] + cnt[rc h] (a palindrome is its own partner: doubled); keep_higher != 0 is keep_lower_hash_flag=False
  * (kmer_count.py:671, 682: the higher hash of a pair survives, value max(h, rc h)).  Two-step like kmap_compact_merge (capacity 0 = size

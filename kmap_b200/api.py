@@ -41,6 +41,110 @@ class TableAllReduce:
         return self.dist.get_rank(self.group)
 
 
+class DistContext:
+    """One process per GPU (launched by `python -m torch.distributed.run ... -m kmap_b200 scan_motif ...`): what the
+    reference-shaped drivers need from the process group.  Reads shard by contiguous ranges (reads are the independent
+    units of the counting path, kmer_count.py:755-759), dense tables merge by an integer all-reduce, per-read results are
+    gathered on rank 0, which alone writes files.  With one process everything is a no-op."""
+
+    def __init__(self, dist=None, group=None):
+        self.dist, self.group = dist, group
+        self.rank = dist.get_rank(group) if dist is not None else 0
+        self.world = dist.get_world_size(group) if dist is not None else 1
+        self.table_allreduce = TableAllReduce(group) if self.world > 1 else None
+
+    @classmethod
+    def from_env(cls) -> "DistContext":
+        """WORLD_SIZE > 1 in the environment (torchrun): join (or create, backend nccl when CUDA is there, else gloo) the
+        default process group and bind this process to cuda:LOCAL_RANK."""
+        import os
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return cls(dist) if dist.get_world_size() > 1 else cls()
+        if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+            return cls()
+        if torch.cuda.is_available():
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
+        return cls(dist)
+
+    @property
+    def is_root(self) -> bool:
+        return self.rank == 0
+
+    def allreduce(self, table: torch.Tensor) -> torch.Tensor:
+        return table if self.table_allreduce is None else self.table_allreduce(table)
+
+    def agree(self, obj):
+        """rank 0's value on every rank (decisions that depend on files rank 0 may be writing)"""
+        if self.world == 1:
+            return obj
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=0, group=self.group)
+        return box[0]
+
+    def gather(self, obj):
+        """[obj of rank 0, obj of rank 1, ...] on rank 0, None elsewhere"""
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world if self.rank == 0 else None
+        self.dist.gather_object(obj, out, dst=0, group=self.group)
+        return out
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+
+
+def concat_occurrence_shards(parts):
+    """per-shard results of the occurrence scan, in rank order -> the result for all reads:
+    parts[r] = (min_dist uint8[n_r], offsets int64[n_r + 1], positions int32[t_r]) (engine.occurrence_scan)."""
+    min_dist = np.concatenate([p_[0] for p_ in parts])
+    offs, base = [np.zeros(1, dtype=np.int64)], 0
+    for _, o, _ in parts:
+        o = np.asarray(o, dtype=np.int64)
+        offs.append(o[1:] + base)
+        base += int(o[-1]) if len(o) else 0
+    return min_dist, np.concatenate(offs), np.concatenate([np.asarray(p_[2], dtype=np.int32) for p_ in parts])
+
+
+def merge_sorted_counts_over_ranks(kh: torch.Tensor, cnt: torch.Tensor, ctx: DistContext, key_bits: int = 64):
+    """k >= 16 has no dense table to all-reduce (kmer_count.py:359-365: uint64 hashes): every rank sorts and run-length
+    encodes its own reads (SeqOnDevice.count_sorted), the (hash, count) lists are all-gathered, and every rank builds the
+    same merged list: distinct hashes of all ranks ascending, counts added up -- what count_uniq_hash returns for the
+    whole input (kmer_count.py:476-491)."""
+    if ctx.world == 1:
+        return kh, cnt
+    L = _lib()
+    dist = ctx.dist
+    n_local = torch.tensor([int(kh.numel())], dtype=torch.int64, device=kh.device)
+    sizes = [torch.zeros_like(n_local) for _ in range(ctx.world)]
+    dist.all_gather(sizes, n_local, group=ctx.group)
+    sizes = [int(x.item()) for x in sizes]
+    cap = max(max(sizes), 1)
+    pad_kh, pad_cnt = torch.zeros(cap, dtype=torch.int64, device=kh.device), torch.zeros(cap, dtype=torch.int64, device=kh.device)
+    pad_kh[:kh.numel()] = kh
+    pad_cnt[:cnt.numel()] = cnt
+    all_kh = [torch.empty_like(pad_kh) for _ in range(ctx.world)]
+    all_cnt = [torch.empty_like(pad_cnt) for _ in range(ctx.world)]
+    dist.all_gather(all_kh, pad_kh, group=ctx.group)
+    dist.all_gather(all_cnt, pad_cnt, group=ctx.group)
+    lists = [(a[:m], c[:m]) for a, c, m in zip(all_kh, all_cnt, sizes) if m]
+    if not lists:
+        return kh[:0], cnt[:0]
+    uniq, _ = E.sort_count_keys(torch.cat([a for a, _ in lists]), key_bits)     # distinct hashes of all ranks, ascending
+    total = torch.zeros(uniq.numel(), dtype=torch.int64, device=kh.device)
+    stream = torch.cuda.current_stream().cuda_stream
+    for a, c in lists:
+        a, c = a.contiguous(), c.contiguous()
+        _check(L.kmap_list_add_counts_u64(uniq.data_ptr(), uniq.numel(), a.data_ptr(), c.data_ptr(), a.numel(), total.data_ptr(), stream),
+               "kmap_list_add_counts_u64")
+    return uniq, total
+
+
 def _pinned_like(t: torch.Tensor) -> torch.Tensor:
     return torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
 

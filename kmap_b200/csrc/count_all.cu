@@ -26,71 +26,233 @@ typedef KmapTableSet TableSet;            // t[k] = dense table of level k (only
 __device__ __forceinline__ int run_length(uint32_t vb) { return vb == 0xFFFFFFFFu ? 32 : __ffs(~vb) - 1; }
 
 // ---- A: per-read duplicate analysis at level kmin, corrections for kmin..kmax-1, duplicate mask for level kmax -------
-// One warp = one read.  Lane j owns the C = ceil(n_pos / 32) consecutive windows j*C .. j*C+C-1 (C <= 8): it fetches its
-// stretch of the packed read and of the validity mask once (two funnel shifts each) and rolls through its windows with
-// compile-time shifts.  Windows are visited in rounds (round t = window t of every lane); "earlier" below means an
-// earlier (round, lane) pair -- any fixed total order gives the same tables.
+// A warp works on R = 32 / G reads at a time, G lanes per read (G = 8 when every read of the batch has at most 128
+// windows at level kmin, else 16): the cost of the scan is instructions per ROUND (one window of every lane), not per
+// window, so four 100-bp reads side by side in one warp take about the rounds one read used to take with a warp of its
+// own (206 -> ~75 warp instructions per read).  Lane j of a group owns the C = ceil(n_pos / G) consecutive windows
+// j*C .. j*C+C-1 of its read (C <= 16): it fetches its stretch of the packed read and of the validity mask once (two
+// funnel shifts each) and rolls through its windows with compile-time shifts.  Windows are visited in rounds
+// (round t = window t of every lane); "earlier" below means an earlier (round, lane) pair of the SAME read -- any
+// fixed total order gives the same tables.
 // Repeats inside a read are rare, so the common path is a filter, not a set: every warp owns a bitmap of AK_BM_BITS
-// bits in shared memory, indexed by the window's kmin-mer (exact for kmin <= 8, hashed to 16 bits above).  One
-// ATOMS.OR per window sets the bit and returns whether it was already set; set bits are cleared again (plain stores
-// of zero words) when the read is done, so there are no epochs and no probing.  A window that found its bit set MAY
-// repeat an earlier one: the warp then compares it with every earlier window of the read -- all still in registers --
-// and gets the exact repeat depth.  When several lanes of one round share a bit, the lane that won the atomic need
-// not be the lowest one; every flagged lane therefore also broadcasts its window to the HIGHER lanes of its round,
-// which is how an unflagged winner learns about the earlier windows it repeats.
-constexpr int AK_BM_BITS = 65536;
+// bits in shared memory, indexed by a hash of (group, kmin-mer).  One ATOMS.OR per window sets the bit and returns
+// whether it was already set; set bits are cleared again (plain stores of zero words) when the reads are done, so
+// there are no epochs and no probing.  A window that found its bit set MAY repeat an earlier one (or collide with
+// another window: ~0.3 % of the windows of a 100-bp read): a cheap exact test on the kmin-mers of the group decides
+// whether anything repeats at all, and only then the warp compares the window with every earlier window of the read
+// -- all still in registers -- and gets the exact repeat depth.  When several lanes of one round share a bit, the
+// lane that won the atomic need not be the lowest one; every flagged lane therefore also broadcasts its window to the
+// HIGHER lanes of its group and round, which is how an unflagged winner learns about the earlier windows it repeats.
+#ifndef KMAP_AK_BM_BITS
+#define KMAP_AK_BM_BITS 65536
+#endif
+constexpr int AK_BM_BITS = KMAP_AK_BM_BITS;      // per warp; 16 index bits are hashed, the low ones are used
 constexpr int AK_BM_WORDS = AK_BM_BITS / 32;
-constexpr int AK_MAXC = AK_WARP_MAX / 32;
+constexpr int AK_MAXC = 16;               // windows per lane
 
 __device__ __forceinline__ int common_prefix(uint32_t a, uint32_t b) {       // equal leading bases of two 16-base words
     const uint32_t diff = a ^ b;
     return diff ? (__clz(diff) >> 1) : 16;
 }
 
-template <bool HASHED>                                              // 4^kmin > AK_BM_BITS: fold the key to 16 bits
+__device__ __forceinline__ uint32_t bm_index(uint32_t key, int grp) {        // 16-bit slot of (group, kmin-mer)
+    return (((key + ((uint32_t)grp << 28)) * 0x9E3779B1u) >> 16) & (uint32_t)(AK_BM_BITS - 1);
+}
+
+struct DedupStaged { uint32_t st_lo, st_hi; int L; uint32_t va, vb, w0, w1, w2; };
+
+struct DedupCtx {
+    const uint32_t* __restrict__ packed;
+    const uint32_t* __restrict__ valid;
+    uint32_t* __restrict__ dupmask;
+    uint32_t* __restrict__ work;
+    uint32_t* const* stab;
+    uint32_t* bm;
+    uint32_t* xs;
+    uint32_t* medium_ids;
+    uint32_t* long_ids;
+    int kmin, kmax, lane;
+};
+
+// raw words of this lane's stretch of read `jj` of the batch (no use yet: the loads overlap the work on the previous reads)
+template <int GS>
+__device__ __forceinline__ void dedup_stage(const DedupCtx& c, uint32_t stlo_lane, uint32_t sthi_lane, int L_lane, int n_in, int pass,
+                                            DedupStaged& g) {
+    constexpr int G = 1 << GS, R = 32 >> GS;
+    const int rr = pass * R + (c.lane >> GS);                     // read of the batch this lane's group works on
+    const int src = rr & 31;
+    g.st_lo = __shfl_sync(0xFFFFFFFFu, stlo_lane, src);
+    g.st_hi = __shfl_sync(0xFFFFFFFFu, sthi_lane, src);
+    const int len = __shfl_sync(0xFFFFFFFFu, L_lane, src);
+    g.L = (rr < n_in && pass * R < 32) ? len : 0;                 // (words that are not loaded keep stale values: never looked at)
+    const int n_pos = g.L - c.kmin + 1;
+    if (n_pos <= 0 || n_pos > AK_WARP_MAX) return;
+    const int C = (n_pos + G - 1) >> GS;
+    const int base = (c.lane & (G - 1)) * C;
+    if (base >= n_pos) return;
+    // word indices fit 32 bits (the host side checks n < 2^36)
+    const uint32_t bv = (g.st_lo & 31u) + (uint32_t)base;
+    const uint32_t* vd = c.valid + (__funnelshift_r(g.st_lo, g.st_hi, 5) + (bv >> 5));
+    g.va = __ldg(vd); g.vb = __ldg(vd + 1);
+    const uint32_t bp = (g.st_lo & 15u) + (uint32_t)base;
+    const uint32_t* pk = c.packed + (__funnelshift_r(g.st_lo, g.st_hi, 4) + (bp >> 4));
+    g.w0 = __ldg(pk); g.w1 = __ldg(pk + 1); g.w2 = __ldg(pk + 2);
+}
+
+// everything that happens to the R reads of one pass
+template <int GS>
+__device__ __forceinline__ void dedup_process(const DedupCtx& c, const DedupStaged& g, int64_t batch, int n_in, int pass, int64_t en_lane) {
+    constexpr int G = 1 << GS, R = 32 >> GS;
+    const int lane = c.lane, kmin = c.kmin, kmax = c.kmax;
+    const int grp = lane >> GS, j = lane & (G - 1);
+    const int rr = pass * R + grp;
+    const int64_t st = (int64_t)(((uint64_t)g.st_hi << 32) | g.st_lo);
+    const int n_pos = g.L - kmin + 1;
+    const int64_t en_grp = __shfl_sync(0xFFFFFFFFu, en_lane, rr & 31);
+    if (n_pos > AK_WARP_MAX) {
+        // too long for the on-chip path: hide the read from the masked count and queue it for the direct kernels
+        const int64_t r = batch + rr;
+        const int64_t L64 = en_grp - st;
+        for (int64_t w = (st >> 5) + j; w <= ((en_grp - 1) >> 5); w += G) {
+            const int64_t lo = w << 5;
+            uint32_t bits = 0xFFFFFFFFu;
+            if (lo < st) bits &= 0xFFFFFFFFu << (st - lo);
+            if (lo + 32 > en_grp) bits &= 0xFFFFFFFFu >> (lo + 32 - en_grp);
+            atomicOr(c.dupmask + w, bits);
+        }
+        if (j == 0) {
+            if (L64 - kmin + 1 <= AK_BLOCK_MAX) c.medium_ids[atomicAdd(&c.work[0], 1u)] = (uint32_t)r;
+            else c.long_ids[atomicAdd(&c.work[1], 1u)] = (uint32_t)r;
+        }
+    }
+    // this lane's stretch of its read, in 32-bit arithmetic relative to the read start
+    const int C = (n_pos > 0 && n_pos <= AK_WARP_MAX) ? (n_pos + G - 1) >> GS : 0;      // windows per lane of this group, 0..16
+    const int Cmax = __reduce_max_sync(0xFFFFFFFFu, C);
+    if (Cmax == 0) return;
+    const int base = j * C;
+    const int mine = min(max(n_pos - base, 0), C);              // windows this lane really has
+    uint32_t vbits = 0, hi = 0, lo = 0;
+    if (mine > 0) {
+        vbits = __funnelshift_r(g.va, g.vb, ((int)(g.st_lo & 31u) + base) & 31);
+        const int room = g.L - base;                            // positions of the read from `base` on
+        if (room < 32) vbits &= (1u << room) - 1u;              // never look past the read end
+        const int sh = ((int)(g.st_lo & 15u) + base) & 15;
+        hi = __funnelshift_l(g.w1, g.w0, 2 * sh);               // bases base .. base+15
+        lo = __funnelshift_l(g.w2, g.w1, 2 * sh);               // bases base+16 .. base+31
+    }
+    // (a window that would leave the read has fewer than kmin valid bits left: `room` above already excludes it)
+    const int key_shift = 32 - 2 * kmin;
+    const uint32_t kmin_mask = (1u << kmin) - 1u;
+    // the 16-base words of the windows already visited live in shared memory (xs[round][lane]: conflict-free), so that the
+    // round loop stays rolled: unrolled it keeps 16 words per lane in registers and replicates the repeat analysis 16 times
+    // (164 registers, 12 warps per SM)
+    uint32_t* xs = c.xs + lane;
+#pragma unroll 1
+    for (int t = 0; t < Cmax; ++t) {
+        const uint32_t vb = vbits >> t;
+        const uint32_t x = __funnelshift_l(lo, hi, 2 * t);      // 16 bases from window base+t
+        const bool ok = t < C && (vb & kmin_mask) == kmin_mask;
+        const uint32_t idx = bm_index(x >> key_shift, grp);
+        const uint32_t bit = 1u << (idx & 31u);
+        // (a lane without a window ORs nothing in: one unconditional ATOMS is cheaper than a branch around it)
+        const uint32_t old = atomicOr(c.bm + (idx >> 5), ok ? bit : 0u);
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, ok && (old & bit) != 0);
+        if (todo) {
+            // rare: exact depth dd of the longest repeat with an earlier window of the read (order: round, then lane)
+            const int vlen = ok ? run_length(vb) : 0;           // windows shorter than kmin never match anything
+            int dd = 0;
+            do {
+                const int b = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t xi = __shfl_sync(0xFFFFFFFFu, x, b);
+                const bool same_read = (b >> GS) == grp;
+                // quick exact test: does any window of this read -- an earlier round, or this round -- start with the same
+                // kmin bases?  (validity ignored: conservative).  Most flagged windows are bitmap collisions and stop here.
+                bool hit = (lane != b) && ((x ^ xi) >> key_shift) == 0u;
+                for (int u = 0; u < t; ++u) hit |= ((xs[32 * u] ^ xi) >> key_shift) == 0u;
+                if (!__any_sync(0xFFFFFFFFu, hit && same_read)) continue;
+                const int vi = min(__shfl_sync(0xFFFFFFFFu, vlen, b), kmax);
+                int best = 0;
+                if (same_read) {
+                    for (int u = 0; u < t; ++u) {
+                        const uint32_t vu = vbits >> u;
+                        const int lu = (vu & kmin_mask) == kmin_mask ? run_length(vu) : 0;
+                        best = max(best, min(common_prefix(xs[32 * u], xi), min(lu, vi)));
+                    }
+                    const int same = min(common_prefix(x, xi), min(vlen, vi));
+                    if (lane < b) best = max(best, same);
+                    else if (lane > b && same >= kmin) dd = max(dd, same);      // b precedes this lane in the round
+                }
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));   // (stays inside the group)
+                if (lane == b) dd = max(dd, best);
+            } while (todo);
+            // fresh_k(i) = [k <= vlen][k > dd]: the window is hidden from level kmax when it repeats at every level;
+            // otherwise level dd loses one count (this cancels either the count its extension brings up from level
+            // dd+1, or -- when dd == vlen -- the +1 the run-end corrections add for a window that ends its run)
+            if (dd >= kmin) {
+                if (dd >= kmax) {
+                    const int64_t p = st + base + t;
+                    atomicOr(c.dupmask + (p >> 5), 1u << (p & 31));
+                } else {
+                    atomicAdd(c.stab[dd] + (x >> (32 - 2 * dd)), 0xFFFFFFFFu);
+                }
+            }
+        }
+        xs[32 * t] = x;
+    }
+    // give the bitmap back: every bit set above lives in the word of one of this lane's windows
+    __syncwarp();
+#pragma unroll 1
+    for (int t = 0; t < C; ++t) c.bm[bm_index(xs[32 * t] >> key_shift, grp) >> 5] = 0;
+    __syncwarp();
+}
+
+template <int GS>
+__device__ __forceinline__ void dedup_batch(const DedupCtx& c, uint32_t stlo_lane, uint32_t sthi_lane, int L_lane, int64_t en_lane,
+                                            int64_t batch, int n_in) {
+    constexpr int R = 32 >> GS;
+    // two staging register sets alternate, so that the software pipeline needs no register moves
+    DedupStaged sa, sb;
+    sa.st_lo = sa.st_hi = 0; sa.L = 0; sa.va = sa.vb = sa.w0 = sa.w1 = sa.w2 = 0;
+    sb = sa;
+    const int n_pass = (n_in + R - 1) / R;
+    dedup_stage<GS>(c, stlo_lane, sthi_lane, L_lane, n_in, 0, sa);
+#pragma unroll 1
+    for (int p = 0; p < n_pass; p += 2) {
+        dedup_stage<GS>(c, stlo_lane, sthi_lane, L_lane, n_in, p + 1, sb);
+        dedup_process<GS>(c, sa, batch, n_in, p, en_lane);
+        dedup_stage<GS>(c, stlo_lane, sthi_lane, L_lane, n_in, p + 2, sa);
+        dedup_process<GS>(c, sb, batch, n_in, p + 1, en_lane);
+    }
+}
+
 __global__ void __launch_bounds__(AK_WARPS * 32) dedup_scan_kernel(
     const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid, int64_t n, const int64_t* __restrict__ borders,
     int64_t n_seq, int kmin, int kmax, TableSet tabs, uint32_t* __restrict__ dupmask, uint32_t* __restrict__ work) {
     __shared__ __align__(16) uint32_t bm_all[AK_WARPS][AK_BM_WORDS];
+    __shared__ uint32_t xs_all[AK_WARPS][AK_MAXC * 32];
     __shared__ uint32_t* stab[16];
     if (threadIdx.x < 16) stab[threadIdx.x] = tabs.t[threadIdx.x];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint32_t* bm = bm_all[wib];
     {
-        uint4* b4 = reinterpret_cast<uint4*>(bm);
+        uint4* b4 = reinterpret_cast<uint4*>(bm_all[wib]);
 #pragma unroll
         for (int j = 0; j < AK_BM_WORDS / 4 / 32; ++j) b4[lane + 32 * j] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
     const int64_t warp0 = (int64_t)blockIdx.x * AK_WARPS + wib;
     const int64_t n_warps = (int64_t)gridDim.x * AK_WARPS;
-    const int key_shift = 32 - 2 * kmin;
-    const uint32_t kmin_mask = (1u << kmin) - 1u;
-    uint32_t* medium_ids = work + 4;
-    uint32_t* long_ids = work + 4 + n_seq;
+    DedupCtx c;
+    c.packed = packed; c.valid = valid; c.dupmask = dupmask; c.work = work; c.stab = stab; c.bm = bm_all[wib]; c.xs = xs_all[wib];
+    c.medium_ids = work + 4; c.long_ids = work + 4 + n_seq;
+    c.kmin = kmin; c.kmax = kmax; c.lane = lane;
 
     // A warp takes 32 consecutive reads at a time: lane j fetches and clamps the borders of read j (one coalesced 16-byte
-    // load per read, the 64-bit arithmetic done once per lane instead of once per lane and read), then the warp walks the 32
-    // reads, getting (start, length) of each by shuffles.  The words of read j+1 are requested before read j is processed
-    // (nothing consumes them until the next iteration), so their DRAM latency overlaps the work on read j.
-    struct Staged { uint32_t st_lo, st_hi; int L; uint32_t va, vb, w0, w1, w2; };
-    auto stage_words = [&](uint32_t st_lo, uint32_t st_hi, int L, Staged& g) {      // raw words of this lane's stretch (no use yet)
-        g.st_lo = st_lo; g.st_hi = st_hi; g.L = L;            // (words that are not loaded keep stale values: never looked at)
-        const int n_pos = L - kmin + 1;
-        if (n_pos <= 0 || n_pos > AK_WARP_MAX) return;
-        const int C = (n_pos + 31) >> 5;
-        const int base = lane * C;
-        if (base >= n_pos) return;
-        // word indices fit 32 bits (the host side checks n < 2^36)
-        const uint32_t bv = (st_lo & 31u) + (uint32_t)base;
-        const uint32_t* vd = valid + (__funnelshift_r(st_lo, st_hi, 5) + (bv >> 5));
-        g.va = __ldg(vd); g.vb = __ldg(vd + 1);
-        const uint32_t bp = (st_lo & 15u) + (uint32_t)base;
-        const uint32_t* pk = packed + (__funnelshift_r(st_lo, st_hi, 4) + (bp >> 4));
-        g.w0 = __ldg(pk); g.w1 = __ldg(pk + 1); g.w2 = __ldg(pk + 2);
-    };
+    // load per read, the 64-bit arithmetic done once per lane instead of once per lane and read), then walks them R at a
+    // time, getting (start, length) of each by shuffles.  The words of the next R reads are requested before the current
+    // ones are processed (nothing consumes them until the next iteration), so their DRAM latency overlaps the work.
     const longlong2* borders2 = reinterpret_cast<const longlong2*>(borders);
-
     for (int64_t batch = warp0 * 32; batch < n_seq; batch += n_warps * 32) {
         const int64_t r_lane = batch + lane;
         const longlong2 be = r_lane < n_seq ? __ldg(borders2 + r_lane) : make_longlong2(0, 0);
@@ -99,123 +261,10 @@ __global__ void __launch_bounds__(AK_WARPS * 32) dedup_scan_kernel(
         const int L_lane = (int)(len_lane < 0 ? 0 : (len_lane > 0x3FFFFFFF ? 0x3FFFFFFF : len_lane));
         const uint32_t stlo_lane = (uint32_t)st_lane, sthi_lane = (uint32_t)((uint64_t)st_lane >> 32);
         const int n_in = (int)(n_seq - batch < 32 ? n_seq - batch : 32);
-        // read j of the batch -> g (reads past the end of the batch get length 0: nothing is loaded, nothing is done)
-        auto stage_at = [&](int j, Staged& g) {
-            const int jj = j < 31 ? j : 31;
-            const uint32_t a = __shfl_sync(0xFFFFFFFFu, stlo_lane, jj), b = __shfl_sync(0xFFFFFFFFu, sthi_lane, jj);
-            const int len = __shfl_sync(0xFFFFFFFFu, L_lane, jj);
-            stage_words(a, b, j < n_in ? len : 0, g);
-        };
-        // everything that happens to one read; two copies of it alternate on two staging registers sets below, so that the
-        // software pipeline needs no register moves
-        auto process = [&](const Staged& g, const int jr) {
-        const int64_t st = (int64_t)(((uint64_t)g.st_hi << 32) | g.st_lo);
-        if (g.L - kmin + 1 <= 0) return;
-        if (g.L - kmin + 1 > AK_WARP_MAX) {
-            // too long for the on-chip path: hide the read from the masked count and queue it for the direct kernels
-            const int64_t r = batch + jr;
-            const int64_t en = __shfl_sync(0xFFFFFFFFu, en_lane, jr);
-            const int64_t L64 = en - st;
-            for (int64_t w = (st >> 5) + lane; w <= ((en - 1) >> 5); w += 32) {
-                const int64_t lo = w << 5;
-                uint32_t bits = 0xFFFFFFFFu;
-                if (lo < st) bits &= 0xFFFFFFFFu << (st - lo);
-                if (lo + 32 > en) bits &= 0xFFFFFFFFu >> (lo + 32 - en);
-                atomicOr(dupmask + w, bits);
-            }
-            if (lane == 0) {
-                if (L64 - kmin + 1 <= AK_BLOCK_MAX) medium_ids[atomicAdd(&work[0], 1u)] = (uint32_t)r;
-                else long_ids[atomicAdd(&work[1], 1u)] = (uint32_t)r;
-            }
-            return;
-        }
-        const int L = g.L;
-        // this lane's stretch of the read, in 32-bit arithmetic relative to the read start
-        const int n_pos = L - kmin + 1;
-        const int C = (n_pos + 31) >> 5;                            // windows per lane, 1..8
-        const int base = lane * C;
-        const int mine = min(max(n_pos - base, 0), C);              // windows this lane really has
-        uint32_t vbits = 0, hi = 0, lo = 0;
-        if (mine > 0) {
-            vbits = __funnelshift_r(g.va, g.vb, ((int)(st & 31) + base) & 31);
-            const int room = L - base;                              // positions of the read from `base` on
-            if (room < 32) vbits &= (1u << room) - 1u;              // never look past the read end
-            const int sh = ((int)(st & 15) + base) & 15;
-            hi = __funnelshift_l(g.w1, g.w0, 2 * sh);               // bases base .. base+15
-            lo = __funnelshift_l(g.w2, g.w1, 2 * sh);               // bases base+16 .. base+31
-        }
-        // (a window that would leave the read has fewer than kmin valid bits left: `room` above already excludes it)
-        uint32_t xs[AK_MAXC];
-        uint32_t wd[AK_MAXC];
-#pragma unroll
-        for (int t = 0; t < AK_MAXC; ++t) {
-            if (t >= C) break;                                      // warp-uniform
-            const uint32_t vb = vbits >> t;
-            const uint32_t x = __funnelshift_l(lo, hi, 2 * t);     // 16 bases from window base+t
-            const bool ok = (vb & kmin_mask) == kmin_mask;
-            const uint32_t key = x >> key_shift;
-            const uint32_t idx = HASHED ? (key * 0x9E3779B1u) >> 16 : key;
-            const uint32_t bit = 1u << (idx & 31u);
-            wd[t] = idx >> 5;
-            // (a lane without a window ORs nothing in: one unconditional ATOMS is cheaper than a branch around it)
-            const uint32_t old = atomicOr(bm + wd[t], ok ? bit : 0u);
-            uint32_t todo = __ballot_sync(0xFFFFFFFFu, (old & bit) != 0);
-            if (todo) {
-                // rare: exact depth dd of the longest repeat with an earlier window of the read (order: round, then lane)
-                const int vlen = ok ? run_length(vb) : 0;           // windows shorter than kmin never match anything
-                int dd = 0;
-                do {
-                    const int b = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const uint32_t xi = __shfl_sync(0xFFFFFFFFu, x, b);
-                    const int vi = min(__shfl_sync(0xFFFFFFFFu, vlen, b), kmax);
-                    int best = 0;
-#pragma unroll
-                    for (int u = 0; u < t; ++u) {
-                        const uint32_t vu = vbits >> u;
-                        const int lu = (vu & kmin_mask) == kmin_mask ? run_length(vu) : 0;
-                        best = max(best, min(common_prefix(xs[u], xi), min(lu, vi)));
-                    }
-                    const int same = min(common_prefix(x, xi), min(vlen, vi));
-                    if (lane < b) best = max(best, same);
-                    else if (lane > b && same >= kmin) dd = max(dd, same);      // b precedes this lane in the round
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
-                    if (lane == b) dd = max(dd, best);
-                } while (todo);
-                // fresh_k(i) = [k <= vlen][k > dd]: the window is hidden from level kmax when it repeats at every level;
-                // otherwise level dd loses one count (this cancels either the count its extension brings up from level
-                // dd+1, or -- when dd == vlen -- the +1 terminal_corrections_kernel adds for a window that ends its run)
-                if (dd >= kmin) {
-                    if (dd >= kmax) {
-                        const int64_t p = st + base + t;
-                        atomicOr(dupmask + (p >> 5), 1u << (p & 31));
-                    } else {
-                        atomicAdd(stab[dd] + (x >> (32 - 2 * dd)), 0xFFFFFFFFu);
-                    }
-                }
-            }
-            xs[t] = x;
-        }
-        // give the bitmap back: every bit set above lives in one of the words wd[0..C)
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < AK_MAXC; ++t)
-            if (t < C) bm[wd[t]] = 0;
-        __syncwarp();
-        };      // process
-
-        Staged sa, sb;
-        sa.st_lo = sa.st_hi = 0; sa.L = 0; sa.va = sa.vb = sa.w0 = sa.w1 = sa.w2 = 0;
-        sb = sa;
-        stage_at(0, sa);
-#pragma unroll 1
-        for (int jr = 0; jr < n_in; jr += 2) {
-            stage_at(jr + 1, sb);
-            process(sa, jr);
-            stage_at(jr + 2, sa);
-            process(sb, jr + 1);
-        }
+        const int np_lane = L_lane - kmin + 1;
+        const int np_max = __reduce_max_sync(0xFFFFFFFFu, np_lane <= AK_WARP_MAX ? np_lane : 0);
+        if (np_max <= 8 * AK_MAXC) dedup_batch<3>(c, stlo_lane, sthi_lane, L_lane, en_lane, batch, n_in);
+        else dedup_batch<4>(c, stlo_lane, sthi_lane, L_lane, en_lane, batch, n_in);
     }
 }
 
@@ -381,10 +430,7 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
         if (e != cudaSuccess) { kmap_set_error("count_all_k: %s", cudaGetErrorString(e)); return (int)e; }
         int64_t blocks = (n_seq + 32 * AK_WARPS - 1) / (32 * AK_WARPS);          // a warp takes 32 reads at a time
         if (blocks > 148 * 7 * 8) blocks = 148 * 7 * 8;           // 7 blocks of 4 warps (32 KB of marks each) per SM
-        if (kmin > 8)
-            dedup_scan_kernel<true><<<(unsigned int)blocks, AK_WARPS * 32, 0, s>>>(packed, valid, n, borders, n_seq, kmin, kmax, tabs, dupmask, work);
-        else
-            dedup_scan_kernel<false><<<(unsigned int)blocks, AK_WARPS * 32, 0, s>>>(packed, valid, n, borders, n_seq, kmin, kmax, tabs, dupmask, work);
+        dedup_scan_kernel<<<(unsigned int)blocks, AK_WARPS * 32, 0, s>>>(packed, valid, n, borders, n_seq, kmin, kmax, tabs, dupmask, work);
     }
     KMAP_REQUIRE(scheme >= KMAP_KMAX_PREFIX_PASSES && scheme <= KMAP_KMAX_SORTED, "unknown scheme");
     const bool use_partition = scheme != KMAP_KMAX_PREFIX_PASSES && part_scratch && kmax >= 12 && kmax <= 14;

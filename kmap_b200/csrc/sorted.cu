@@ -417,6 +417,18 @@ __device__ __forceinline__ int64_t find_key(const u64* __restrict__ kh, int64_t 
     return (lo < n && __ldg(kh + lo) == x) ? lo : -1;
 }
 
+// cnt_out[index of kh[i] in uniq] += cnt[i]: sums the per-rank (hash, count) lists of a sharded count into the list of the
+// distinct hashes of all ranks (count_uniq_hash over the whole input = the per-shard results added up, kmer_count.py:476-491)
+__global__ void __launch_bounds__(256) list_add_counts_kernel(const u64* __restrict__ uniq, int64_t n_uniq, const u64* __restrict__ kh,
+                                                              const long long* __restrict__ cnt, int64_t n, unsigned long long* __restrict__ cnt_out) {
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (; i < n; i += stride) {
+        const int64_t j = find_key(uniq, n_uniq, __ldg(kh + i));
+        if (j >= 0) atomicAdd(cnt_out + j, (unsigned long long)__ldg(cnt + i));
+    }
+}
+
 // partner[i] = index of rc(kh[i]) in the list or -1; tile_counts = survivors per tile
 // (entry i is dropped iff its partner is present and kh[i] > rc(kh[i]), kmer_count.py:668-676)
 __global__ void __launch_bounds__(RL_BLOCK) merge_plan_kernel(const u64* __restrict__ kh, int64_t n, int k, bool keep_higher,
@@ -688,6 +700,19 @@ int kmap_rle_u64(const uint64_t* sorted_keys, int64_t n, uint64_t* scratch, int6
     run_length_kernel<<<grid_for(n_uniq, 256), 256, 0, s>>>(reinterpret_cast<const long long*>(pos_scratch), n_uniq, (long long)n,
                                                             reinterpret_cast<long long*>(cnt_out));
     return kmap_check_launch("rle(write)");
+}
+
+int kmap_list_add_counts_u64(const uint64_t* uniq, int64_t n_uniq, const uint64_t* kh, const int64_t* cnt, int64_t n, int64_t* cnt_out,
+                             void* stream) {
+    KMAP_REQUIRE(n >= 0 && n_uniq >= 0, "negative size");
+    if (n == 0 || n_uniq == 0) return KMAP_OK;
+    KMAP_REQUIRE(uniq && kh && cnt && cnt_out, "null pointer");
+    int64_t g = (n + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    list_add_counts_kernel<<<(unsigned int)g, 256, 0, as_stream(stream)>>>(reinterpret_cast<const u64*>(uniq), n_uniq, reinterpret_cast<const u64*>(kh),
+                                                                           reinterpret_cast<const long long*>(cnt), n,
+                                                                           reinterpret_cast<unsigned long long*>(cnt_out));
+    return kmap_check_launch("list_add_counts");
 }
 
 int64_t kmap_merge_sorted_scratch_words(int64_t n) { return n < 0 ? 0 : n + rl_tiles(n) + 2; }

@@ -101,6 +101,9 @@ class SeqOnDevice:
     # level-k counts of tables beyond L2 go through key partitioning (csrc/partition.cu); below this k the table is
     # L2 resident and direct atomics win (measured)
     PARTITION_MIN_K = 13
+    # de-duplicated level-k counts from this k on go through the per-read scan + hidden-window count of the all-k path
+    # (one filter atomic per window in shared memory) instead of one hash-set insertion + global RED per window
+    DEDUP_SCAN_MIN_K = 12
 
     # schemes for a level-k table beyond L2 (include/kmap_b200.h)
     PREFIX_PASSES, SORTED = 0, 1
@@ -151,10 +154,23 @@ class SeqOnDevice:
         return cls.from_device_u8(to_device(seq_np_arr), borders, keep_u8)
 
     @classmethod
-    def from_fasta(cls, fasta_file, keep_u8: bool = False) -> "SeqOnDevice":
-        """straight from the FASTA file: parsed, encoded and packed on the device, no host copy of input.bin"""
+    def from_fasta(cls, fasta_file, keep_u8: bool = False, rank: int = 0, world: int = 1) -> "SeqOnDevice":
+        """straight from the FASTA file: parsed, encoded and packed on the device, no host copy of input.bin.
+        world > 1: only the contiguous read range of `rank` is kept (borders rebased to it); `all_borders` then holds the
+        border matrix of the whole file."""
         seq, borders = fasta_to_device(fasta_file)
-        return cls.from_device_u8(seq, borders, keep_u8)
+        if world <= 1:
+            return cls.from_device_u8(seq, borders, keep_u8)
+        n_seq = int(borders.shape[0])
+        r0, r1 = n_seq * rank // world, n_seq * (rank + 1) // world
+        if r1 > r0:
+            ends = borders[[r0, r1 - 1]].cpu()
+            p0, p1 = int(ends[0, 0]), int(ends[1, 1]) + 1
+            shard = cls.from_device_u8(seq[p0:p1].clone(), borders[r0:r1] - p0, keep_u8)
+        else:
+            shard = cls.from_device_u8(seq[:0].clone(), borders[:0].clone(), keep_u8)
+        shard.all_borders = borders
+        return shard
 
     # ---- masking state ----------------------------------------------------------------------------------------
     def snapshot_valid(self):
@@ -167,16 +183,22 @@ class SeqOnDevice:
     def count(self, k: int, dedup: bool, table: Optional[torch.Tensor] = None, zero: bool = True,
               partitioned: Optional[bool] = None, scheme: Optional[int] = None) -> torch.Tensor:
         """dense forward table uint32[4^k] (held as int32 bits).  dedup=True fuses remove_duplicate_hash_per_seq.
-        partitioned: None = choose by k (PARTITION_MIN_K), True/False = force (plain counts with 9 <= k <= 14 only)."""
+        partitioned: None = choose by k (PARTITION_MIN_K / DEDUP_SCAN_MIN_K), True = force the partitioned count (plain counts
+        with 9 <= k <= 14), False = force the direct kernels (one global atomic per counted window)."""
         L = lib()
         if not 1 <= k <= 15:
             raise KmapError(f"dense counting supports 1 <= k <= 15 (got {k}); k >= 16 uses 64-bit hashes: count_sorted")
         n_cells = 1 << (2 * k)
+        via_scan = dedup and zero and partitioned is not False and k >= self.DEDUP_SCAN_MIN_K
         if table is None:
-            table = zeros(n_cells, torch.int32)
-        elif zero:
+            table = empty(n_cells, torch.int32) if via_scan else zeros(n_cells, torch.int32)
+        elif zero and not via_scan:
             check(L.kmap_fill_u32(_ptr(table), n_cells, 0, _stream_ptr()), "kmap_fill_u32")
-        if dedup:
+        if via_scan:
+            # per-read scan (dedup_scan_kernel) + level-k count with the repeats hidden: the kernels of the all-k count
+            # (csrc/count_all.cu, csrc/partition.cu) with kmin = kmax = k; count_all zeroes the table itself
+            self.count_all(k, k, True, tables={k: table})
+        elif dedup:
             if self.borders is None:
                 raise KmapError("per-read de-duplication needs the border matrix")
             need = L.kmap_dedup_work_words(self.n_seq)

@@ -17,6 +17,8 @@ import torch
 
 from . import engine as E
 from ._lib import KmapError, check, lib
+ALL_K_MAX = 14       # largest k whose first count comes out of the all-k pass (SeqOnDevice.count_all through csrc/partition.cu)
+
 from .kmer_count import (FileNameDict, MotifDef, cal_hamming_dist, cal_hamming_dist_head, cal_hamming_dist_tail,
                          dna2arr, gen_motif_def_dict, get_cnt_dtype, get_hash_dtype, get_revcom_hash_arr, hash2kmer,
                          init_motif_def_dict, kmer2hash, mask_ham_ball, reverse_complement, revcom_hash)
@@ -112,24 +114,40 @@ def _top_k_indices(state: "_CountState", top_k: int):
 def find_motif_on_device(dev: E.SeqOnDevice, kmer_len: int, max_ham_dist, p_unif, ratio_mu, ratio_std, ratio_cutoff,
                          top_k=5, n_trial=10, merge_revcom_mode=True, rep_mode=False, first_lists=None,
                          first_table: Optional[torch.Tensor] = None, debug=False, sorted_path: Optional[bool] = None,
-                         table_buffer: Optional[torch.Tensor] = None):
+                         table_buffer: Optional[torch.Tensor] = None, ctx=None):
     """Core of find_motif on a device-resident sequence (mutates dev.valid).  Returns (result dict, (uniq_kh, uniq_cnt)
     of the first round).  `first_lists` plays the role of a pre-existing k{k}.pkl (:621-624); `first_table` lets a
-    caller that counted every k in one pass hand in the forward table.  sorted_path: count by sorting 64-bit keys
-    (csrc/sorted.cu) instead of a dense table; None = only where there is no dense table (k >= 16)."""
+    caller that counted every k in one pass (SeqOnDevice.count_all) hand in the forward table -- already merged over the
+    ranks.  sorted_path: count by sorting 64-bit keys (csrc/sorted.cu) instead of a dense table; None = only where there
+    is no dense table (k >= 16).  ctx (api.DistContext): `dev` holds this rank's shard of the reads; every count is merged
+    over the ranks (dense tables: integer all-reduce; sorted lists: all-gather + merge), the selection, the ball sums and
+    the decisions are then replicated, and every rank masks its own reads."""
     from scipy.stats import norm
     k = kmer_len
     use_sorted = (k >= 16) if sorted_path is None else bool(sorted_path)
+    sharded = ctx is not None and ctx.world > 1
+
+    def count_sorted_state(dedup):
+        if not sharded:
+            return _CountState.from_sorted(dev, k, merge_revcom_mode, dedup=dedup)
+        from .api import merge_sorted_counts_over_ranks
+        kh_dev, cnt_dev = merge_sorted_counts_over_ranks(*dev.count_sorted(k, dedup), ctx)
+        if merge_revcom_mode:
+            kh_dev, cnt_dev = E.merge_revcom_sorted(kh_dev, cnt_dev, k)
+        return _CountState(k, merge_revcom_mode, None, kh_dev, cnt_dev, wide=True)
+
     if first_lists is not None:
         state = _CountState.from_lists(first_lists[0], first_lists[1], k, merge_revcom_mode)
     elif use_sorted:
-        state = _CountState.from_sorted(dev, k, merge_revcom_mode, dedup=not rep_mode)
+        state = count_sorted_state(dedup=not rep_mode)
     else:
         if first_table is not None:
             table = first_table
         else:       # (table_buffer: a caller that walks several k re-uses one allocation of at least 4^k cells)
             buf = table_buffer[:1 << (2 * k)] if table_buffer is not None and table_buffer.numel() >= (1 << (2 * k)) else None
             table = dev.count(k, dedup=not rep_mode, table=buf)
+            if sharded:
+                ctx.allreduce(table)
         state = _CountState.from_table(table, k, merge_revcom_mode)
     first = (state.kh, state.cnt)
     n_total_kmer = int(np.sum(state.cnt, dtype=np.int64))       # exact (SURVEY Q7)
@@ -164,9 +182,15 @@ def find_motif_on_device(dev: E.SeqOnDevice, kmer_len: int, max_ham_dist, p_unif
             cons.append(int(revcom_hash(consensus_kh, k)))
         dev.mask(k, cons, [max_ham_dist] * len(cons))
         if use_sorted:                                                # recounts are never de-duplicated (:695-696)
-            state = _CountState.from_sorted(dev, k, merge_revcom_mode, dedup=False)
+            state = count_sorted_state(dedup=False)
         else:
-            table = dev.count(k, dedup=False, table=state.table)
+            if state.table is None:         # the first round came from a k{k}.pkl: no table yet
+                buf = table_buffer[:1 << (2 * k)] if table_buffer is not None and table_buffer.numel() >= (1 << (2 * k)) else None
+                table = dev.count(k, dedup=False, table=buf)
+            else:
+                table = dev.count(k, dedup=False, table=state.table)
+            if sharded:
+                ctx.allreduce(table)
             state = _CountState.from_table(table, k, merge_revcom_mode)
     return found, first
 
@@ -392,10 +416,12 @@ def write_motif_occurence_file(per_conseq, borders: np.ndarray, conseq_list, out
 
 
 def gen_motif_occurence_file(conseq_list: List[str], motif_def_dict: dict, input_fasta_file: Path, output_file: Path,
-                             revcom_mode=True, _dev_cache=None):
+                             revcom_mode=True, _dev_cache=None, _ctx=None, _return_scan=False):
     """:1396-1419.  The reference re-parses the FASTA file per call; the encoded arrays are identical to input.bin
     (same upper-casing and code table), so a cached device copy may be passed by the driver.  Returns per consensus
-    (reads with the motif, listed positions)."""
+    (reads with the motif, listed positions) [, the scan results per consensus (min_dist, offsets, positions)].
+    _ctx (api.DistContext, world > 1): `_dev_cache` holds this rank's reads and the border matrix of the whole file; the
+    per-read results are gathered in rank order and rank 0 writes the file (the other ranks return ([], None))."""
     assert Path(input_fasta_file).exists()
     if _dev_cache is not None:
         dev, borders = _dev_cache
@@ -403,7 +429,14 @@ def gen_motif_occurence_file(conseq_list: List[str], motif_def_dict: dict, input
         dev = E.SeqOnDevice.from_fasta(input_fasta_file)
         borders = E.to_host(dev.borders, np.int64).reshape(-1, 2)
     per_conseq = motif_occurence_table(dev, conseq_list, motif_def_dict, revcom_mode)
-    return write_motif_occurence_file(per_conseq, borders, conseq_list, output_file)
+    if _ctx is not None and _ctx.world > 1:
+        from .api import concat_occurrence_shards
+        parts = _ctx.gather(per_conseq)
+        if not _ctx.is_root:
+            return ([], None) if _return_scan else []
+        per_conseq = [concat_occurrence_shards([parts[r][j] for r in range(_ctx.world)]) for j in range(len(conseq_list))]
+    stats = write_motif_occurence_file(per_conseq, borders, conseq_list, output_file)
+    return (stats, per_conseq) if _return_scan else stats
 
 
 def get_motif_seq_num(occurence_file_path: Path, motif_index: int) -> Tuple[int, int]:
@@ -720,6 +753,8 @@ def _scan_motif(res_dir: str, debug=False):
         assert Path(md_cfg["noise_kmer_file"]).exists()
         with open(Path(md_cfg["noise_kmer_file"]), "r") as fh:
             mask_noise_seq_list = [ln.strip() for ln in fh if ln.strip()]
+    from .api import DistContext, concat_occurrence_shards, shard_reads
+    ctx = DistContext.from_env()          # one process per GPU under torchrun; a single process otherwise
     with open(proc_fasta_file_path, "rb") as fh:
         seq_np_arr = pickle.load(fh)
     if mask_noise_seq_list:
@@ -728,12 +763,14 @@ def _scan_motif(res_dir: str, debug=False):
     with open(boarder_pkl_file, "rb") as fh:
         boarder_mat = pickle.load(fh)
     n_all_seq = len(boarder_mat)
+    if ctx.world > 1:                     # this rank's contiguous range of reads (reads are independent units)
+        seq_np_arr, boarder_mat = shard_reads(seq_np_arr, boarder_mat, ctx.rank, ctx.world)
 
     top_k, n_trial = md_cfg["top_k"], md_cfg["n_trial"]
     save_kmer_cnt_flag = md_cfg["save_kmer_cnt_flag"]
     candidate_conseq_list = []
     kmer_count_dir = res / FileNameDict["kmer_count_dir"]
-    if save_kmer_cnt_flag:
+    if save_kmer_cnt_flag and ctx.is_root:
         kmer_count_dir.mkdir(exist_ok=True)
     input_fasta_file = Path(config_dict["general"]["input_fasta_file"])
 
@@ -746,12 +783,13 @@ def _scan_motif(res_dir: str, debug=False):
         nonlocal occ_dev
         if occ_dev is None:
             assert input_fasta_file.exists()
-            fa_dev = E.SeqOnDevice.from_fasta(input_fasta_file)       # parsed on the device, never copied back
-            occ_dev = (fa_dev, E.to_host(fa_dev.borders, np.int64).reshape(-1, 2))
+            fa_dev = E.SeqOnDevice.from_fasta(input_fasta_file, rank=ctx.rank, world=ctx.world)   # parsed on the device
+            all_borders = getattr(fa_dev, "all_borders", fa_dev.borders)
+            occ_dev = (fa_dev, E.to_host(all_borders, np.int64).reshape(-1, 2) if ctx.is_root else None)
         return occ_dev
 
     candidate_conseq_file = res / FileNameDict["candidate_conseq_file"]
-    if candidate_conseq_file.exists():
+    if ctx.agree(candidate_conseq_file.exists()):
         print(f"{candidate_conseq_file} already exist, re-use it.")
     else:
         store_flag = md_cfg["store_conseq_occur_info_flag"]
@@ -759,22 +797,36 @@ def _scan_motif(res_dir: str, debug=False):
         if store_flag:
             header += ",n_motif_reads,n_all_reads,motif_reads_prop,motif_occurrence,motif_occurrence_per_motif_read"
         rows = [header]
-        k_dense = min(max_k, 15)
-        table_buffer = E.empty(1 << (2 * k_dense), torch.int32) if k_dense >= min_k else None     # one table allocation for every k
+        # k{k}.pkl files of an earlier run replace the first counts (:621-624); rank 0 looks, every rank follows
+        have_pkl = ctx.agree({k: bool(save_kmer_cnt_flag and (kmer_count_dir / f"k{k}.pkl").exists())
+                              for k in range(min_k, max_k + 1)})
+        # The first-round counts of every k with a dense table in ONE pass over the reads (:262-273 calls find_motif, and with
+        # it comp_kmer_hash + remove_duplicate_hash_per_seq + count_uniq_hash, once per k): SeqOnDevice.count_all updates
+        # only the table of the largest k per window and derives the smaller ones (csrc/count_all.cu, csrc/partition.cu).
+        # Under torchrun the tables of the shards are merged by one all-reduce of the flat buffer.
+        first_tables = {}
+        ks_first = [k for k in range(min_k, min(max_k, ALL_K_MAX) + 1) if not have_pkl[k]]
+        if ks_first:
+            flat, first_tables = E.alloc_tables(ks_first[0], ks_first[-1])
+            dev.count_all(ks_first[0], ks_first[-1], dedup=not rep_mode, tables=first_tables)
+            ctx.allreduce(flat)
+        k_single = [k for k in range(min_k, min(max_k, 15) + 1) if k not in first_tables]
+        table_buffer = E.empty(1 << (2 * max(k_single)), torch.int32) if k_single else None   # one allocation for those k
         for kmer_len in range(min_k, max_k + 1):
             dev.restore_valid()
             m = motif_def_dict[kmer_len]
             kmer_cnt_file = kmer_count_dir / f"k{kmer_len}.pkl"
             first_lists = None
-            if save_kmer_cnt_flag and kmer_cnt_file.exists():
+            if have_pkl[kmer_len]:
                 with open(kmer_cnt_file, "rb") as fh:
                     k_from_file, kh0, cnt0 = pickle.load(fh)
                     assert kmer_len == k_from_file
                 first_lists = (kh0, cnt0)
             consensus_kh_dict, first = find_motif_on_device(dev, kmer_len, m.max_ham_dist, m.p_uniform, m.ratio_mu,
                                                             m.ratio_std, m.ratio_cutoff, top_k, n_trial, revcom_mode,
-                                                            rep_mode, first_lists, None, debug, table_buffer=table_buffer)
-            if save_kmer_cnt_flag and not kmer_cnt_file.exists():
+                                                            rep_mode, first_lists, first_tables.get(kmer_len), debug,
+                                                            table_buffer=table_buffer, ctx=ctx)
+            if save_kmer_cnt_flag and not have_pkl[kmer_len] and ctx.is_root:
                 with open(kmer_cnt_file, "wb") as fh:
                     pickle.dump([kmer_len, first[0], first[1]], fh)
             tmp_candidate_conseq_list = [hash2kmer(kh, kmer_len) for kh in consensus_kh_dict]
@@ -782,8 +834,11 @@ def _scan_motif(res_dir: str, debug=False):
             if store_flag:
                 tmp_occurence_file = kmer_count_dir / f"k{kmer_len}.motif_occurence.csv"
                 occ_stats = gen_motif_occurence_file(tmp_candidate_conseq_list, motif_def_dict, input_fasta_file,
-                                                     tmp_occurence_file, revcom_mode, _dev_cache=occurrence_dev())
+                                                     tmp_occurence_file, revcom_mode, _dev_cache=occurrence_dev(), _ctx=ctx)
             for i, kmer_seq in enumerate(tmp_candidate_conseq_list):
+                candidate_conseq_list.append(kmer_seq)
+                if not ctx.is_root:
+                    continue
                 kh = kmer2hash(kmer_seq)
                 prop, ratio, log10_p_value = consensus_kh_dict[kh]
                 n_motif_seq, n_motif_occurrence = -n_all_seq, -n_all_seq
@@ -797,20 +852,25 @@ def _scan_motif(res_dir: str, debug=False):
                     row += (f",{n_motif_seq},{n_all_seq},{motif_seq_prop:0.4f},{n_motif_occurrence},"
                             f"{motif_per_motif_seq:0.2f}")
                 rows.append(row)
-                candidate_conseq_list.append(kmer_seq)
+        del first_tables, table_buffer
         print(f"kmer counting finished for k={min_k}...{max_k}. Candidate consensus sequences generated.")
-        write_lines(rows, candidate_conseq_file)
+        if ctx.is_root:
+            write_lines(rows, candidate_conseq_file)
+        ctx.barrier()
 
     final_conseq_file = res / FileNameDict["final_conseq_file"]
-    if final_conseq_file.exists():
-        final_conseq_list = final_conseq_file.read_text().splitlines()
+    if ctx.agree(final_conseq_file.exists()):
+        final_conseq_list = ctx.agree(final_conseq_file.read_text().splitlines() if ctx.is_root else None)
         print(f"{final_conseq_file} already exist, re-use it.")
     else:
-        final_conseq_list = merge_consensus_seqs(candidate_conseq_list)
-        write_lines(final_conseq_list, final_conseq_file)
+        final_conseq_list = ctx.agree(merge_consensus_seqs(candidate_conseq_list) if ctx.is_root else None)
+        if ctx.is_root:
+            write_lines(final_conseq_list, final_conseq_file)
 
     final_conseq_info_file = res / FileNameDict["final_conseq_info_file"]
-    if final_conseq_info_file.exists():
+    if not ctx.is_root:
+        pass
+    elif final_conseq_info_file.exists():
         print(f"{final_conseq_info_file} already exist, re-use it.")
     else:
         final_conseq_list = final_conseq_file.read_text().splitlines()
@@ -832,8 +892,11 @@ def _scan_motif(res_dir: str, debug=False):
         print("Final consensus sequences generated.")
 
     occurence_file = res / FileNameDict["motif_occurence_file"]
-    gen_motif_occurence_file(final_conseq_list, motif_def_dict, input_fasta_file, occurence_file, revcom_mode,
-                             _dev_cache=occurrence_dev())
+    final_scan = gen_motif_occurence_file(final_conseq_list, motif_def_dict, input_fasta_file, occurence_file, revcom_mode,
+                                          _dev_cache=occurrence_dev(), _ctx=ctx, _return_scan=True)
+    if not ctx.is_root:                   # everything below is host work on files: rank 0 alone
+        ctx.barrier()
+        return
 
     # the DATA files of the density / co-occurrence steps (:364-425); the pdf figures the reference draws from the same
     # numbers (matplotlib) are not produced here
@@ -898,3 +961,4 @@ def _scan_motif(res_dir: str, debug=False):
             _ex_hamball(res_dir, conseq, "matrix", output_cntmat_file, max_ham_dist=motif_def_dict[len(conseq)].max_ham_dist)
         print("Motif count matrix extracted (logos are drawn by the reference package's draw_logo).")
     print("All tasks of scan motif finished.")
+    ctx.barrier()
