@@ -107,6 +107,18 @@ def launches_per_step(args, dedup):
     return (1 if dedup else 0) + 5 + max(1, args.partitions) + derive      # + terminal-correction launches + prefix passes
 
 
+def table_checksum(table):
+    """sum over h of h * T[h] mod 2^64: a position-weighted checksum of a dense table.  Equal checksums on every level prove
+    what equal sums cannot: that the merged tables of 1, 2, 4 and 8 GPUs hold the same counts in the same cells."""
+    import torch
+    total, step = 0, 1 << 26
+    for lo in range(0, table.numel(), step):
+        t = table[lo:lo + step].view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+        idx = torch.arange(lo, lo + t.numel(), dtype=torch.int64, device=t.device)
+        total += int((t * idx).sum().item())
+    return total & 0xFFFFFFFFFFFFFFFF
+
+
 def n_kmers_total(n_reads, L):
     return sum(n_reads * max(0, L - k + 1) for k in range(KMIN, KMAX + 1))
 
@@ -260,6 +272,8 @@ def main():
     checks = {}
     tot14 = int(tables[KMAX].to(torch.int64).sum().item())
     checks["sum_table_k14"] = tot14
+    # per-level position-weighted checksums of the (merged) tables: identical for every number of GPUs iff the tables are
+    checks["table_checksums"] = {str(k): table_checksum(tables[k]) for k in range(KMIN, KMAX + 1)}
     if args.algo == "allk" and world == 1 and not args.no_crosscheck:
         # full-size parity property: the tables the all-k algorithm DERIVES (level 14 -> 13 -> .. -> 8, with the run-end and
         # repeat corrections of every level on the way) equal independent direct counts by the per-k kernels

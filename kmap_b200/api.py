@@ -188,11 +188,15 @@ def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterabl
     wide = [k for k in ks_all if k >= 16]          # uint64 hashes, no dense table: sort / run-length path (csrc/sorted.cu)
     ks = [k for k in ks_all if k < 16]
     if wide:
-        if table_allreduce is not None:
-            raise KmapError("count_kmers: k >= 16 has no dense table to all-reduce; count those k on one rank")
+        # no dense table to all-reduce: every rank sorts / run-length encodes its shard, the lists are merged over the ranks
+        ctx = DistContext(table_allreduce.dist, table_allreduce.group) if table_allreduce is not None else None
         dev = upload_reads(seq_np_arr, boarder_mat, validate)
         for k in wide:
             kh, cnt = dev.count_sorted(k, dedup=not rep_mode)
+            if ctx is not None:
+                kh, cnt = merge_sorted_counts_over_ranks(kh, cnt, ctx, 2 * k)
+            if lists_on is not None and ctx is not None and ctx.rank != lists_on:
+                continue
             if revcom_mode:
                 kh, cnt = E.merge_revcom_sorted(kh, cnt, k)
             out[k] = (E.to_host(kh, np.uint64), E.to_host(cnt, np.int64))

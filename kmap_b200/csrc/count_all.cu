@@ -48,15 +48,20 @@ __device__ __forceinline__ int run_length(uint32_t vb) { return vb == 0xFFFFFFFF
 #endif
 constexpr int AK_BM_BITS = KMAP_AK_BM_BITS;      // per warp; 16 index bits are hashed, the low ones are used
 constexpr int AK_BM_WORDS = AK_BM_BITS / 32;
-constexpr int AK_MAXC = 16;               // windows per lane
+constexpr int AK_BM_LOG_WORDS = AK_BM_BITS == 65536 ? 11 : AK_BM_BITS == 32768 ? 10 : AK_BM_BITS == 16384 ? 9 : 8;
+static_assert((1 << AK_BM_LOG_WORDS) == AK_BM_WORDS, "AK_BM_BITS must be 8192, 16384, 32768 or 65536");
+#ifndef KMAP_AK_BLOCKS
+#define KMAP_AK_BLOCKS 6
+#endif
+#ifndef KMAP_AK_PIPE
+#define KMAP_AK_PIPE 0
+#endif
+constexpr int AK_BLOCKS = KMAP_AK_BLOCKS;  // resident blocks per SM the scan is compiled for (register cap)
+constexpr int AK_MAXC = 12;               // windows per lane (even)
 
 __device__ __forceinline__ int common_prefix(uint32_t a, uint32_t b) {       // equal leading bases of two 16-base words
     const uint32_t diff = a ^ b;
     return diff ? (__clz(diff) >> 1) : 16;
-}
-
-__device__ __forceinline__ uint32_t bm_index(uint32_t key, int grp) {        // 16-bit slot of (group, kmin-mer)
-    return (((key + ((uint32_t)grp << 28)) * 0x9E3779B1u) >> 16) & (uint32_t)(AK_BM_BITS - 1);
 }
 
 struct DedupStaged { uint32_t st_lo, st_hi; int L; uint32_t va, vb, w0, w1, w2; };
@@ -68,9 +73,9 @@ struct DedupCtx {
     uint32_t* __restrict__ work;
     uint32_t* const* stab;
     uint32_t* bm;
-    uint32_t* xs;
-    uint32_t* medium_ids;
-    uint32_t* long_ids;
+    uint32_t dummy_off;                // byte offset (from bm) of this lane's dummy word
+    int64_t n_seq, n;
+    const int64_t* __restrict__ borders;
     int kmin, kmax, lane;
 };
 
@@ -99,30 +104,52 @@ __device__ __forceinline__ void dedup_stage(const DedupCtx& c, uint32_t stlo_lan
     g.w0 = __ldg(pk); g.w1 = __ldg(pk + 1); g.w2 = __ldg(pk + 2);
 }
 
-// everything that happens to the R reads of one pass
+// windows of k (<= 15) valid bases starting at bits 0..15 of v (bit i = position i; log-step run-length test)
+__device__ __forceinline__ uint32_t run_mask(uint32_t v, int k) {
+    const uint32_t r2 = v & (v >> 1), r4 = r2 & (r2 >> 2), r8 = r4 & (r4 >> 4);
+    uint32_t m = 0xFFFFFFFFu;
+    int off = 0;
+    if (k & 8) { m &= r8; off = 8; }
+    if (k & 4) { m &= r4 >> off; off += 4; }
+    if (k & 2) { m &= r2 >> off; off += 2; }
+    if (k & 1) { m &= v >> off; }
+    return m;
+}
+
+// everything that happens to the R reads of one pass.  Three phases:
+//   filter  every window of every lane sets its bit (rounds fully unrolled and independent of each other: the atomics of
+//           a pass are all in flight together, nothing is voted on per round); a lane remembers which of its windows
+//           found their bit set;
+//   exact   only for the rounds in which some lane was flagged (about one per pass: bitmap collisions and real repeats):
+//           the flagged windows are compared with the windows of their read, which are rebuilt from the two register
+//           words of every lane;
+//   clear   one store per window.
 template <int GS>
-__device__ __forceinline__ void dedup_process(const DedupCtx& c, const DedupStaged& g, int64_t batch, int n_in, int pass, int64_t en_lane) {
+__device__ __forceinline__ void dedup_process(const DedupCtx& c, const DedupStaged& g, int64_t batch, int n_in, int pass) {
     constexpr int G = 1 << GS, R = 32 >> GS;
     const int lane = c.lane, kmin = c.kmin, kmax = c.kmax;
     const int grp = lane >> GS, j = lane & (G - 1);
     const int rr = pass * R + grp;
     const int64_t st = (int64_t)(((uint64_t)g.st_hi << 32) | g.st_lo);
     const int n_pos = g.L - kmin + 1;
-    const int64_t en_grp = __shfl_sync(0xFFFFFFFFu, en_lane, rr & 31);
-    if (n_pos > AK_WARP_MAX) {
+    if (__any_sync(0xFFFFFFFFu, n_pos > AK_WARP_MAX)) {
         // too long for the on-chip path: hide the read from the masked count and queue it for the direct kernels
-        const int64_t r = batch + rr;
-        const int64_t L64 = en_grp - st;
-        for (int64_t w = (st >> 5) + j; w <= ((en_grp - 1) >> 5); w += G) {
-            const int64_t lo = w << 5;
-            uint32_t bits = 0xFFFFFFFFu;
-            if (lo < st) bits &= 0xFFFFFFFFu << (st - lo);
-            if (lo + 32 > en_grp) bits &= 0xFFFFFFFFu >> (lo + 32 - en_grp);
-            atomicOr(c.dupmask + w, bits);
-        }
-        if (j == 0) {
-            if (L64 - kmin + 1 <= AK_BLOCK_MAX) c.medium_ids[atomicAdd(&c.work[0], 1u)] = (uint32_t)r;
-            else c.long_ids[atomicAdd(&c.work[1], 1u)] = (uint32_t)r;
+        if (n_pos > AK_WARP_MAX) {
+            const int64_t en_raw = __ldg(c.borders + 2 * (batch + rr) + 1);      // (g.L is clamped; rare path: fetch the end again)
+            const int64_t en_grp = en_raw > c.n ? c.n : en_raw;
+            const int64_t r = batch + rr;
+            const int64_t L64 = en_grp - st;
+            for (int64_t w = (st >> 5) + j; w <= ((en_grp - 1) >> 5); w += G) {
+                const int64_t lo = w << 5;
+                uint32_t bits = 0xFFFFFFFFu;
+                if (lo < st) bits &= 0xFFFFFFFFu << (st - lo);
+                if (lo + 32 > en_grp) bits &= 0xFFFFFFFFu >> (lo + 32 - en_grp);
+                atomicOr(c.dupmask + w, bits);
+            }
+            if (j == 0) {
+                if (L64 - kmin + 1 <= AK_BLOCK_MAX) (c.work + 4)[atomicAdd(&c.work[0], 1u)] = (uint32_t)r;          // medium reads
+                else (c.work + 4 + c.n_seq)[atomicAdd(&c.work[1], 1u)] = (uint32_t)r;                               // long reads
+            }
         }
     }
     // this lane's stretch of its read, in 32-bit arithmetic relative to the read start
@@ -130,9 +157,8 @@ __device__ __forceinline__ void dedup_process(const DedupCtx& c, const DedupStag
     const int Cmax = __reduce_max_sync(0xFFFFFFFFu, C);
     if (Cmax == 0) return;
     const int base = j * C;
-    const int mine = min(max(n_pos - base, 0), C);              // windows this lane really has
     uint32_t vbits = 0, hi = 0, lo = 0;
-    if (mine > 0) {
+    if (base < n_pos) {                                         // (C > 0 here)
         vbits = __funnelshift_r(g.va, g.vb, ((int)(g.st_lo & 31u) + base) & 31);
         const int room = g.L - base;                            // positions of the read from `base` on
         if (room < 32) vbits &= (1u << room) - 1u;              // never look past the read end
@@ -140,76 +166,96 @@ __device__ __forceinline__ void dedup_process(const DedupCtx& c, const DedupStag
         hi = __funnelshift_l(g.w1, g.w0, 2 * sh);               // bases base .. base+15
         lo = __funnelshift_l(g.w2, g.w1, 2 * sh);               // bases base+16 .. base+31
     }
-    // (a window that would leave the read has fewer than kmin valid bits left: `room` above already excludes it)
+    // bit t: window base+t belongs to this lane and has kmin valid bases (a window that would leave the read has fewer
+    // than kmin valid bits left: `room` above already excludes it)
+    const uint32_t okm = run_mask(vbits, kmin) & ((1u << C) - 1u);
     const int key_shift = 32 - 2 * kmin;
-    const uint32_t kmin_mask = (1u << kmin) - 1u;
-    // the 16-base words of the windows already visited live in shared memory (xs[round][lane]: conflict-free), so that the
-    // round loop stays rolled: unrolled it keeps 16 words per lane in registers and replicates the repeat analysis 16 times
-    // (164 registers, 12 warps per SM)
-    uint32_t* xs = c.xs + lane;
-#pragma unroll 1
-    for (int t = 0; t < Cmax; ++t) {
-        const uint32_t vb = vbits >> t;
-        const uint32_t x = __funnelshift_l(lo, hi, 2 * t);      // 16 bases from window base+t
-        const bool ok = t < C && (vb & kmin_mask) == kmin_mask;
-        const uint32_t idx = bm_index(x >> key_shift, grp);
-        const uint32_t bit = 1u << (idx & 31u);
-        // (a lane without a window ORs nothing in: one unconditional ATOMS is cheaper than a branch around it)
-        const uint32_t old = atomicOr(c.bm + (idx >> 5), ok ? bit : 0u);
-        uint32_t todo = __ballot_sync(0xFFFFFFFFu, ok && (old & bit) != 0);
-        if (todo) {
-            // rare: exact depth dd of the longest repeat with an earlier window of the read (order: round, then lane)
-            const int vlen = ok ? run_length(vb) : 0;           // windows shorter than kmin never match anything
-            int dd = 0;
-            do {
-                const int b = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const uint32_t xi = __shfl_sync(0xFFFFFFFFu, x, b);
-                const bool same_read = (b >> GS) == grp;
-                // quick exact test: does any window of this read -- an earlier round, or this round -- start with the same
-                // kmin bases?  (validity ignored: conservative).  Most flagged windows are bitmap collisions and stop here.
-                bool hit = (lane != b) && ((x ^ xi) >> key_shift) == 0u;
-                for (int u = 0; u < t; ++u) hit |= ((xs[32 * u] ^ xi) >> key_shift) == 0u;
-                if (!__any_sync(0xFFFFFFFFu, hit && same_read)) continue;
-                const int vi = min(__shfl_sync(0xFFFFFFFFu, vlen, b), kmax);
-                int best = 0;
-                if (same_read) {
-                    for (int u = 0; u < t; ++u) {
-                        const uint32_t vu = vbits >> u;
-                        const int lu = (vu & kmin_mask) == kmin_mask ? run_length(vu) : 0;
-                        best = max(best, min(common_prefix(xs[32 * u], xi), min(lu, vi)));
-                    }
-                    const int same = min(common_prefix(x, xi), min(vlen, vi));
-                    if (lane < b) best = max(best, same);
-                    else if (lane > b && same >= kmin) dd = max(dd, same);      // b precedes this lane in the round
-                }
+    const uint32_t salt = (uint32_t)grp * 0x3C6EF372u;          // reads that share the warp's bitmap use different slots
+    uint8_t* const bm8 = reinterpret_cast<uint8_t*>(c.bm);
+
+    // ---- filter -------------------------------------------------------------------------------------------------------
+    // (a lane without a window at round t sends its atomic to a private dummy word instead: no branch, no operand select)
+    uint32_t woff2[AK_MAXC / 2];                                // byte offsets of the touched words, two per register
+    uint32_t flagged = 0;                                       // bit t: window t found its bit already set
 #pragma unroll
-                for (int o = G / 2; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));   // (stays inside the group)
-                if (lane == b) dd = max(dd, best);
-            } while (todo);
-            // fresh_k(i) = [k <= vlen][k > dd]: the window is hidden from level kmax when it repeats at every level;
-            // otherwise level dd loses one count (this cancels either the count its extension brings up from level
-            // dd+1, or -- when dd == vlen -- the +1 the run-end corrections add for a window that ends its run)
-            if (dd >= kmin) {
-                if (dd >= kmax) {
-                    const int64_t p = st + base + t;
-                    atomicOr(c.dupmask + (p >> 5), 1u << (p & 31));
-                } else {
-                    atomicAdd(c.stab[dd] + (x >> (32 - 2 * dd)), 0xFFFFFFFFu);
+    for (int t = 0; t < AK_MAXC; ++t) {
+        if ((t & 3) == 0 && t >= Cmax) break;                   // (warp-uniform, tested every fourth round)
+        const uint32_t x = __funnelshift_l(lo, hi, 2 * t);      // 16 bases from window base+t
+        const uint32_t h = (x >> key_shift) * 0x9E3779B1u + salt;
+        uint32_t wo = (h >> (32 - AK_BM_LOG_WORDS - 2)) & (uint32_t)((AK_BM_WORDS - 1) << 2);     // byte offset of the word
+        wo = ((okm >> t) & 1u) ? wo : c.dummy_off;
+        if (t & 1) woff2[t >> 1] |= wo << 16; else woff2[t >> 1] = wo;
+        const uint32_t bit = __funnelshift_l(0u, 1u, h);        // 1 << (h & 31): M is odd, so these are the low key bits mixed
+        const uint32_t old = atomicOr(reinterpret_cast<uint32_t*>(bm8 + wo), bit);
+        if (old & bit) flagged |= 1u << t;
+    }
+    flagged &= okm;
+
+    // ---- exact: the rounds with a flagged window -------------------------------------------------------------------------
+    uint32_t rounds = __reduce_or_sync(0xFFFFFFFFu, flagged);
+    while (rounds) {
+        const int t = __ffs(rounds) - 1;
+        rounds &= rounds - 1;
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, (flagged >> t) & 1u);
+        const uint32_t x = __funnelshift_l(lo, hi, 2 * t);
+        // depth dd of the longest repeat with an earlier window of the read (order: round, then lane)
+        const int vlen = ((okm >> t) & 1u) ? run_length(vbits >> t) : 0;     // windows shorter than kmin never match anything
+        int dd = 0;
+        do {
+            const int b = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t xi = __shfl_sync(0xFFFFFFFFu, x, b);
+            const bool same_read = (b >> GS) == grp;
+            // quick exact test: does any other window of this read -- an earlier round, or this round -- start with the same
+            // kmin bases?  (validity ignored: conservative).  Most flagged windows are bitmap collisions and stop here.
+            uint32_t m = 0;
+#pragma unroll
+            for (int u = 0; u < AK_MAXC; ++u)
+                if ((((__funnelshift_l(lo, hi, 2 * u) ^ xi) >> key_shift) == 0u)) m |= 1u << u;
+            m &= ((1u << C) - 1u) & ((2u << t) - 1u);           // this lane's own windows of the rounds up to t ...
+            if (lane == b) m &= ~(1u << t);                      // ... except the flagged window itself
+            const bool hit = m != 0u;
+            if (!__any_sync(0xFFFFFFFFu, hit && same_read)) continue;
+            const int vi = min(__shfl_sync(0xFFFFFFFFu, vlen, b), kmax);
+            int best = 0;
+            if (same_read) {
+                for (int u = 0; u < t; ++u) {
+                    const int lu = ((okm >> u) & 1u) ? run_length(vbits >> u) : 0;
+                    best = max(best, min(common_prefix(__funnelshift_l(lo, hi, 2 * u), xi), min(lu, vi)));
                 }
+                const int same = min(common_prefix(x, xi), min(vlen, vi));
+                if (lane < b) best = max(best, same);
+                else if (lane > b && same >= kmin) dd = max(dd, same);      // b precedes this lane in the round
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));   // (stays inside the group)
+            if (lane == b) dd = max(dd, best);
+        } while (todo);
+        // fresh_k(i) = [k <= vlen][k > dd]: the window is hidden from level kmax when it repeats at every level;
+        // otherwise level dd loses one count (this cancels either the count its extension brings up from level
+        // dd+1, or -- when dd == vlen -- the +1 the run-end corrections add for a window that ends its run)
+        if (dd >= kmin) {
+            if (dd >= kmax) {
+                const int64_t p = st + base + t;
+                atomicOr(c.dupmask + (p >> 5), 1u << (p & 31));
+            } else {
+                atomicAdd(c.stab[dd] + (x >> (32 - 2 * dd)), 0xFFFFFFFFu);
             }
         }
-        xs[32 * t] = x;
     }
-    // give the bitmap back: every bit set above lives in the word of one of this lane's windows
+
+    // ---- clear: give the bitmap back (every bit set above lives in the word of one of this lane's windows) ---------------
     __syncwarp();
-#pragma unroll 1
-    for (int t = 0; t < C; ++t) c.bm[bm_index(xs[32 * t] >> key_shift, grp) >> 5] = 0;
+#pragma unroll
+    for (int t = 0; t < AK_MAXC; ++t) {
+        if ((t & 3) == 0 && t >= Cmax) break;
+        *reinterpret_cast<uint32_t*>(bm8 + ((t & 1) ? woff2[t >> 1] >> 16 : woff2[t >> 1] & 0xFFFFu)) = 0u;
+    }
     __syncwarp();
 }
 
 template <int GS>
-__device__ __forceinline__ void dedup_batch(const DedupCtx& c, uint32_t stlo_lane, uint32_t sthi_lane, int L_lane, int64_t en_lane,
+__device__ __forceinline__ void dedup_batch(const DedupCtx& c, uint32_t stlo_lane, uint32_t sthi_lane, int L_lane,
                                             int64_t batch, int n_in) {
     constexpr int R = 32 >> GS;
     // two staging register sets alternate, so that the software pipeline needs no register moves
@@ -217,21 +263,28 @@ __device__ __forceinline__ void dedup_batch(const DedupCtx& c, uint32_t stlo_lan
     sa.st_lo = sa.st_hi = 0; sa.L = 0; sa.va = sa.vb = sa.w0 = sa.w1 = sa.w2 = 0;
     sb = sa;
     const int n_pass = (n_in + R - 1) / R;
+#if !KMAP_AK_PIPE
+#pragma unroll 1
+    for (int p = 0; p < n_pass; ++p) {
+        dedup_stage<GS>(c, stlo_lane, sthi_lane, L_lane, n_in, p, sa);
+        dedup_process<GS>(c, sa, batch, n_in, p);
+    }
+    return;
+#endif
     dedup_stage<GS>(c, stlo_lane, sthi_lane, L_lane, n_in, 0, sa);
 #pragma unroll 1
     for (int p = 0; p < n_pass; p += 2) {
         dedup_stage<GS>(c, stlo_lane, sthi_lane, L_lane, n_in, p + 1, sb);
-        dedup_process<GS>(c, sa, batch, n_in, p, en_lane);
+        dedup_process<GS>(c, sa, batch, n_in, p);
         dedup_stage<GS>(c, stlo_lane, sthi_lane, L_lane, n_in, p + 2, sa);
-        dedup_process<GS>(c, sb, batch, n_in, p + 1, en_lane);
+        dedup_process<GS>(c, sb, batch, n_in, p + 1);
     }
 }
 
-__global__ void __launch_bounds__(AK_WARPS * 32) dedup_scan_kernel(
+__global__ void __launch_bounds__(AK_WARPS * 32, AK_BLOCKS) dedup_scan_kernel(
     const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid, int64_t n, const int64_t* __restrict__ borders,
     int64_t n_seq, int kmin, int kmax, TableSet tabs, uint32_t* __restrict__ dupmask, uint32_t* __restrict__ work) {
-    __shared__ __align__(16) uint32_t bm_all[AK_WARPS][AK_BM_WORDS];
-    __shared__ uint32_t xs_all[AK_WARPS][AK_MAXC * 32];
+    __shared__ __align__(16) uint32_t bm_all[AK_WARPS][AK_BM_WORDS + 32];    // + one dummy word per lane
     __shared__ uint32_t* stab[16];
     if (threadIdx.x < 16) stab[threadIdx.x] = tabs.t[threadIdx.x];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -244,8 +297,9 @@ __global__ void __launch_bounds__(AK_WARPS * 32) dedup_scan_kernel(
     const int64_t warp0 = (int64_t)blockIdx.x * AK_WARPS + wib;
     const int64_t n_warps = (int64_t)gridDim.x * AK_WARPS;
     DedupCtx c;
-    c.packed = packed; c.valid = valid; c.dupmask = dupmask; c.work = work; c.stab = stab; c.bm = bm_all[wib]; c.xs = xs_all[wib];
-    c.medium_ids = work + 4; c.long_ids = work + 4 + n_seq;
+    c.packed = packed; c.valid = valid; c.dupmask = dupmask; c.work = work; c.stab = stab; c.bm = bm_all[wib];
+    c.dummy_off = (uint32_t)(AK_BM_WORDS + lane) * 4u;
+    c.n_seq = n_seq; c.n = n; c.borders = borders;
     c.kmin = kmin; c.kmax = kmax; c.lane = lane;
 
     // A warp takes 32 consecutive reads at a time: lane j fetches and clamps the borders of read j (one coalesced 16-byte
@@ -263,8 +317,10 @@ __global__ void __launch_bounds__(AK_WARPS * 32) dedup_scan_kernel(
         const int n_in = (int)(n_seq - batch < 32 ? n_seq - batch : 32);
         const int np_lane = L_lane - kmin + 1;
         const int np_max = __reduce_max_sync(0xFFFFFFFFu, np_lane <= AK_WARP_MAX ? np_lane : 0);
-        if (np_max <= 8 * AK_MAXC) dedup_batch<3>(c, stlo_lane, sthi_lane, L_lane, en_lane, batch, n_in);
-        else dedup_batch<4>(c, stlo_lane, sthi_lane, L_lane, en_lane, batch, n_in);
+        if (np_max <= 4 * AK_MAXC) dedup_batch<2>(c, stlo_lane, sthi_lane, L_lane, batch, n_in);
+        else if (np_max <= 8 * AK_MAXC) dedup_batch<3>(c, stlo_lane, sthi_lane, L_lane, batch, n_in);
+        else if (np_max <= 16 * AK_MAXC) dedup_batch<4>(c, stlo_lane, sthi_lane, L_lane, batch, n_in);
+        else dedup_batch<5>(c, stlo_lane, sthi_lane, L_lane, batch, n_in);
     }
 }
 
@@ -429,7 +485,7 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
         if (e == cudaSuccess) e = cudaMemsetAsync(work, 0, 16, s);
         if (e != cudaSuccess) { kmap_set_error("count_all_k: %s", cudaGetErrorString(e)); return (int)e; }
         int64_t blocks = (n_seq + 32 * AK_WARPS - 1) / (32 * AK_WARPS);          // a warp takes 32 reads at a time
-        if (blocks > 148 * 7 * 8) blocks = 148 * 7 * 8;           // 7 blocks of 4 warps (32 KB of marks each) per SM
+        if (blocks > 148 * AK_BLOCKS * 8) blocks = 148 * AK_BLOCKS * 8;           // AK_BLOCKS blocks of 4 warps (32 KB of marks each) per SM
         dedup_scan_kernel<<<(unsigned int)blocks, AK_WARPS * 32, 0, s>>>(packed, valid, n, borders, n_seq, kmin, kmax, tabs, dupmask, work);
     }
     KMAP_REQUIRE(scheme >= KMAP_KMAX_PREFIX_PASSES && scheme <= KMAP_KMAX_SORTED, "unknown scheme");

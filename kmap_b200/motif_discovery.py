@@ -131,7 +131,7 @@ def find_motif_on_device(dev: E.SeqOnDevice, kmer_len: int, max_ham_dist, p_unif
         if not sharded:
             return _CountState.from_sorted(dev, k, merge_revcom_mode, dedup=dedup)
         from .api import merge_sorted_counts_over_ranks
-        kh_dev, cnt_dev = merge_sorted_counts_over_ranks(*dev.count_sorted(k, dedup), ctx)
+        kh_dev, cnt_dev = merge_sorted_counts_over_ranks(*dev.count_sorted(k, dedup), ctx, 2 * k)
         if merge_revcom_mode:
             kh_dev, cnt_dev = E.merge_revcom_sorted(kh_dev, cnt_dev, k)
         return _CountState(k, merge_revcom_mode, None, kh_dev, cnt_dev, wide=True)

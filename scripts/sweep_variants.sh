@@ -8,7 +8,7 @@ import json,sys
 l=[x for x in open('gpurun_out/sweep_tmp.log') if x.startswith('{"metric')]
 if l:
     d=json.loads(l[-1]); p=d['roofline']['phases_ms']
-    print(sys.argv[1], round(d['ms_per_step'],2), {k:round(v,2) for k,v in p.items() if k in ('bucket_hist','partition','bucket_count')}, d['checks'])
+    print(sys.argv[1], round(d['ms_per_step'],2), {k:round(v,2) for k,v in p.items() if k in ('dedup_scan','bucket_hist','partition','bucket_count')}, d['checks'])
 else:
     print(sys.argv[1], "FAILED")
 PY

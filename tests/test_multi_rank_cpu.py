@@ -95,3 +95,51 @@ def test_more_ranks_than_reads():
     seq, borders = synth.generate_numpy(synth.CFG2, 0, 2)
     sizes = [len(api.shard_reads(seq, borders, r, 5)[1]) for r in range(5)]
     assert sum(sizes) == 2 and max(sizes) == 1
+
+
+def _ctx_worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from kmap_b200 import api
+    ctx = api.DistContext.from_env()                                  # no CUDA here: joins with gloo
+    try:
+        agreed = ctx.agree({"have": rank == 0, "k": [8, 9]})          # rank 0's view of the files wins
+        # per-shard occurrence-scan results (min_dist, offsets, positions) of ranks with 3 and 2 reads
+        part = (np.array([1, 255, 0], np.uint8), np.array([0, 2, 2, 3], np.int64), np.array([4, 9, 1], np.int32)) if rank == 0 else \
+               (np.array([255, 2], np.uint8), np.array([0, 0, 4], np.int64), np.array([0, 5, 6, 7], np.int32))
+        gathered = ctx.gather(part)
+        merged = api.concat_occurrence_shards(gathered) if ctx.is_root else None
+        ctx.barrier()
+        q.put((rank, ctx.world, ctx.is_root, agreed, merged))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dist_context_agree_gather_and_occurrence_concat_world2():
+    """host side of `torchrun ... -m kmap_b200 scan_motif`: rank 0's decisions are broadcast, per-read scan results of the
+    shards are concatenated in rank order with rebased offsets (occurrence scan shards by reads)"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ctx_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {r[0]: r for r in (q.get(timeout=120) for _ in procs)}
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert got[0][1] == got[1][1] == 2 and got[0][2] and not got[1][2]
+    assert got[0][3] == got[1][3] == {"have": True, "k": [8, 9]}
+    assert got[1][4] is None
+    md, off, pos = got[0][4]
+    assert md.tolist() == [1, 255, 0, 255, 2] and off.tolist() == [0, 2, 2, 3, 3, 7] and pos.tolist() == [4, 9, 1, 0, 5, 6, 7]
+
+
+def test_dist_context_single_process_is_a_noop():
+    from kmap_b200 import api
+    ctx = api.DistContext()
+    assert ctx.world == 1 and ctx.rank == 0 and ctx.is_root and ctx.table_allreduce is None
+    assert ctx.agree(5) == 5 and ctx.gather("x") == ["x"]
+    ctx.barrier()
