@@ -20,14 +20,22 @@
 namespace {
 
 constexpr int PT_THREADS = KMAP_TILE_THREADS;
-constexpr int PT_TILE = PT_THREADS * 32;          // positions (= staged entries) per tile
+constexpr int PT_TILE_WORDS = KMAP_TILE_WORDS;    // validity words per tile, two per thread (tile.cuh)
+constexpr int PT_TILE = PT_TILE_WORDS * 32;       // positions (= staged entries at most) per tile: 65 472
+constexpr int PT_SLOTS = 65536;                   // entries of the staging buffer (PT_TILE rounded up)
 constexpr int PT_MAX_BUCKETS = 4096;              // k <= 14
 constexpr int PT_MAX_PER = PT_MAX_BUCKETS / PT_THREADS;
-constexpr int PT_MAX_ALL = PT_MAX_BUCKETS + PT_MAX_BUCKETS / 4;      // + the buckets of the routed level k-1 (one per thread at most)
+constexpr int PT_MAX_X = PT_MAX_BUCKETS / 4;      // buckets of the routed level k-1 (one per thread at most)
+constexpr int PT_MAX_ALL = PT_MAX_BUCKETS + PT_MAX_X;
+constexpr int PT_XCAP = PT_TILE / 14 + 2;         // routed entries a tile can hold (each needs a run end: >= 14 positions apart)
 #ifndef KMAP_PT_WU
 #define KMAP_PT_WU 8
 #endif
 constexpr int PT_WU = KMAP_PT_WU;                // write-out entries in flight per thread
+
+__device__ __forceinline__ uint32_t base16_at(const TileWords& t, int i) {           // 16 bases from position i of the word
+    return (i < 16) ? __funnelshift_l(t.w1, t.w0, 2 * i) : __funnelshift_l(t.w2, t.w1, 2 * (i - 16));
+}
 
 // extra_base: index of the first extra bucket (= n_buckets).  A routed correction is the (k-1)-mer at a position with
 // exactly k-1 valid bases: bucket extra_base + (its key >> 16), suffix = its low 16 bits.
@@ -35,15 +43,14 @@ __device__ __forceinline__ void tile_hist(const TileWords& t, int sh, uint32_t* 
     if (t.fresh) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-            if ((t.fresh >> i) & 1u) atomicAdd(&cnt[key_at(t, i, sh) >> 16], 1u);
+            if ((t.fresh >> i) & 1u) atomicAdd(&cnt[base16_at(t, i) >> (sh + 16)], 1u);
     }
     if (t.corr) {                                   // about one per read
         uint32_t c = t.corr;
         do {
             const int i = __ffs(c) - 1;
             c &= c - 1;
-            const uint32_t x = (i < 16) ? __funnelshift_l(t.w1, t.w0, 2 * i) : __funnelshift_l(t.w2, t.w1, 2 * (i - 16));
-            atomicAdd(&cnt[extra_base + (x >> (sh + 18))], 1u);
+            atomicAdd(&cnt[extra_base + (base16_at(t, i) >> (sh + 18))], 1u);
         } while (c);
     }
 }
@@ -58,7 +65,7 @@ __device__ __forceinline__ void tile_hist(const TileWords& t, int sh, uint32_t* 
 // With TERMINAL, the pass also does what terminal_corrections_kernel (count_all.cu) does: "+1 at level v" for every
 // window with exactly v valid bases (kmin <= v < k) in front of a run end.  Those are scattered global REDs; issued from
 // this kernel they overlap its shared-memory-bound histogram work instead of costing passes of their own.
-constexpr int PT_HGRID = 296;                     // CTAs of the histogram pass (two resident per SM)
+constexpr int PT_HGRID = 296;                     // CTAs of the histogram pass
 
 __host__ __device__ __forceinline__ int64_t chunk_first_tile(int64_t n_tiles, int h) { return n_tiles * h / PT_HGRID; }
 
@@ -84,18 +91,25 @@ __global__ void __launch_bounds__(PT_THREADS) bucket_hist_kernel(const uint32_t*
     uint32_t runx = 0;
 #pragma unroll
     for (int j = 0; j < PER; ++j) run[j] = 0;
-    RawWords nxt = load_raw_words(packed, valid, hide, n_words, t0 < t1 ? t0 : n_tiles);
+    RawPair nxt = load_raw_pair(packed, valid, hide, n_words, t0 < t1 ? t0 : n_tiles);
     RawPrev nxt_prev;
     nxt_prev.vp = nxt_prev.hp = nxt_prev.wp = 0;
     if (TERMINAL) nxt_prev = load_raw_prev(packed, valid, hide, n_words, t0 < t1 ? t0 : n_tiles);
     for (int64_t tile = t0; tile < t1; ++tile) {
         uint32_t* cnt = cnt2[(tile - t0) & 1];
-        const RawWords r = nxt;
+        const RawPair r = nxt;
         const RawPrev rp = nxt_prev;
-        nxt = load_raw_words(packed, valid, hide, n_words, tile + 1 < t1 ? tile + 1 : n_tiles);      // (past the end: zeros)
+        nxt = load_raw_pair(packed, valid, hide, n_words, tile + 1 < t1 ? tile + 1 : n_tiles);       // (past the end: zeros)
         if (TERMINAL) nxt_prev = load_raw_prev(packed, valid, hide, n_words, tile + 1 < t1 ? tile + 1 : n_tiles);
-        tile_hist(cook(r, k, route), sh, cnt, n_buckets);
-        if (TERMINAL) run_end_corrections(r, rp, kmin, kcorr, stab);      // levels kmin .. kcorr-1
+        const RawWords ra = first_word(r), rb = second_word(r);
+        tile_hist(cook(ra, k, route), sh, cnt, n_buckets);
+        tile_hist(cook(rb, k, route), sh, cnt, n_buckets);
+        if (TERMINAL) {                                             // levels kmin .. kcorr-1
+            run_end_corrections(ra, rp, kmin, kcorr, stab);
+            RawPrev rq;
+            rq.vp = r.v0; rq.hp = r.h0; rq.wp = r.w1;
+            run_end_corrections(rb, rq, kmin, kcorr, stab);
+        }
         __syncthreads();       // this tile's counts are complete; the other buffer was zeroed before the previous barrier
         if (b0 < n_buckets) {
             uint32_t c[PER];
@@ -169,7 +183,7 @@ __global__ void __launch_bounds__(256) bucket_total_kernel(const uint32_t* __res
 __global__ void __launch_bounds__(PT_THREADS) bucket_scan_kernel(const unsigned long long* __restrict__ total, int n_buckets,
                                                                  unsigned long long* __restrict__ base) {
     __shared__ unsigned long long warp_sums[32];
-    const int per = (n_buckets + PT_THREADS - 1) / PT_THREADS;       // <= PT_MAX_PER
+    const int per = (n_buckets + PT_THREADS - 1) / PT_THREADS;       // <= PT_MAX_PER + 1
     const int lo = threadIdx.x * per, hi = min(lo + per, n_buckets);
     unsigned long long mine = 0;
     for (int b = lo; b < hi; ++b) mine += total[b];
@@ -191,15 +205,21 @@ __global__ void __launch_bounds__(256) chunk_base_kernel(const uint32_t* __restr
 }
 
 // ---- 2. partition -------------------------------------------------------------------------------------------------------
-// Per tile: (b) exclusive scan of the tile's bucket counts (read from pass 1) -> tile-local starts, (d) counting-sort
-// scatter of the keys into bucket order in shared memory (one shared-memory atomic per window), (e) write-out: entry i of
-// the sorted tile goes to gdelta[bucket] + i, so consecutive lanes write consecutive addresses inside a run.  Tiles are
-// dealt round-robin, so the tiles in flight are neighbours and so are their runs in every bucket.  The raw words and the
-// count / offset rows of the next tile are requested a tile ahead.
-// (Measured alternatives, 1e8 reads x 100 bp, k = 14: a tile histogram inside this pass + one global cursor atomic per
-// (tile, bucket) 40.1 ms -- ncu: 3.3k shared-memory wavefronts for the histogram and 4.1k sectors of cursor atomics of
-// 25k LSU cycles per tile; two resident CTAs of 512 threads with tiles of 16384 positions 66.6 ms; private per-CTA
-// destination ranges 51 ms, see the file header.)
+// Per tile of 65 472 positions (two validity words per thread): (b) exclusive scan of the tile's bucket counts (read from
+// pass 1) -> tile-local starts, (d) counting-sort scatter of the 16-bit key suffixes into bucket order in shared memory
+// (one shared-memory atomic per window), (e) write-out: entry i of the sorted tile goes to gd[run of i] + i, so consecutive
+// lanes write consecutive addresses inside a run.  The staging buffer holds ONLY the suffixes (2 bytes per entry, which is
+// what lets a tile be 64 K positions: a (tile, bucket) run is then ~14 suffixes = 28 bytes, about one 32-byte sector, where
+// the 32 K-position tiles of the first version wrote runs of ~7 = 7.4 sectors per store request, and the write-out was 19
+// of the kernel's 32.5 ms); the run an entry belongs to is recovered from a bitmap of run starts: run(i) = F[i / 32] +
+// popc(heads[i / 32] & bits 0..i%32), F[w] = the run that contains entry 32w - 1, and gd[] is indexed by run (non-empty
+// buckets in bucket order).  Tiles are dealt by an atomic ticket, so the tiles in flight are neighbours and so are their
+// runs in every bucket.  The raw words and the count / offset rows of the next tile are requested a tile ahead.
+// Routed corrections (n_extra > 0): the windows with exactly k-1 valid bases go to buckets n_buckets .. n_buckets + n_extra - 1
+// (bucket = n_buckets + the top bits of the (k-1)-mer, suffix = its low 16 bits).  In shared memory they are laid out from
+// the END of the staging buffer downwards, the ordinary entries from the start upwards (together at most one entry per
+// position), so that neither layout needs the other's total; they are few (about one per read), so each carries its bucket
+// in a side array instead of taking part in the run bitmap.
 template <int PER>
 struct TileRow { uint32_t c[PER]; uint32_t o[PER]; uint32_t cx, ox; };        // cx, ox: the thread's extra bucket (routed level k-1)
 
@@ -218,7 +238,7 @@ __device__ __forceinline__ TileRow<PER> load_tile_row(const uint16_t* __restrict
         if (PER == 4) {
             const uint2 c = __ldcs(reinterpret_cast<const uint2*>(crow));
             const uint4 o = __ldcs(reinterpret_cast<const uint4*>(orow));
-            r.c[0] = c.x & 0xFFFFu; r.c[1] = c.x >> 16; r.c[2 % PER] = c.y & 0xFFFFu; r.c[3 % PER] = c.y >> 16;
+            r.c[0] = c.x & 0xFFFFu; r.c[1 % PER] = c.x >> 16; r.c[2 % PER] = c.y & 0xFFFFu; r.c[3 % PER] = c.y >> 16;
             r.o[0] = o.x; r.o[1 % PER] = o.y; r.o[2 % PER] = o.z; r.o[3 % PER] = o.w;
         } else {
 #pragma unroll
@@ -232,10 +252,32 @@ __device__ __forceinline__ TileRow<PER> load_tile_row(const uint16_t* __restrict
     return r;
 }
 
-// Routed corrections (n_extra > 0): the windows with exactly k-1 valid bases go to buckets n_buckets .. n_buckets + n_extra - 1
-// (bucket = n_buckets + the top bits of the (k-1)-mer, suffix = its low 16 bits).  In shared memory they are laid out from
-// the END of the tile buffer downwards, the ordinary entries from the start upwards (together at most one entry per
-// position), so that neither layout needs the other's total; one 64-bit scan carries both running sums.
+// shared memory of partition_kernel (dynamic): staging buffer, per-bucket running offsets, per-run destinations, run-start
+// bitmap (double buffered) + F, bucket of every routed entry
+constexpr int PT_SMEM = PT_SLOTS * 2 + PT_MAX_ALL * 4 + PT_MAX_ALL * 8 + 2 * (PT_SLOTS / 32) * 4 + (PT_SLOTS / 32 + 2) * 2 + PT_XCAP * 2 + 64;
+
+__device__ __forceinline__ void scatter_word(const TileWords& t, int sh, int n_buckets, uint32_t* off, uint16_t* sorted, uint16_t* xbucket) {
+    if (t.fresh) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if ((t.fresh >> i) & 1u) {
+                const uint32_t key = base16_at(t, i) >> sh;
+                sorted[atomicAdd(&off[key >> 16], 1u)] = (uint16_t)key;
+            }
+    }
+    if (t.corr) {
+        uint32_t c = t.corr;
+        do {
+            const int i = __ffs(c) - 1;
+            c &= c - 1;
+            const uint32_t key = base16_at(t, i) >> (sh + 2);             // the (k-1)-mer
+            const uint32_t pos = atomicAdd(&off[n_buckets + (key >> 16)], 1u);
+            sorted[pos] = (uint16_t)key;
+            xbucket[PT_SLOTS - 1 - pos] = (uint16_t)(key >> 16);
+        } while (c);
+    }
+}
+
 template <int PER>       // buckets per thread in the scan step: n_buckets <= PER * PT_THREADS
 __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
                                                                   const uint32_t* __restrict__ hide, int64_t n_words, int64_t n_tiles,
@@ -244,9 +286,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t
                                                                   const unsigned long long* __restrict__ chunk_base,
                                                                   uint16_t* __restrict__ suffixes, unsigned long long* __restrict__ ticket) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint32_t* sorted = reinterpret_cast<uint32_t*>(smem_raw);                                  // PT_TILE keys, grouped by bucket
-    unsigned long long* gdelta = reinterpret_cast<unsigned long long*>(sorted + PT_TILE);     // global start - tile start, per bucket
-    uint32_t* off = reinterpret_cast<uint32_t*>(gdelta + (PER + 1) * PT_THREADS);             // running tile offsets
+    uint16_t* sorted = reinterpret_cast<uint16_t*>(smem_raw);                                  // PT_SLOTS suffixes, grouped by bucket
+    unsigned long long* gd = reinterpret_cast<unsigned long long*>(sorted + PT_SLOTS);        // global start - tile start: per RUN, then per extra bucket
+    uint32_t* off = reinterpret_cast<uint32_t*>(gd + PT_MAX_ALL);                             // running tile offsets per bucket
+    uint32_t* heads2 = off + PT_MAX_ALL;                                                      // 2 x run-start bitmap
+    uint16_t* F = reinterpret_cast<uint16_t*>(heads2 + 2 * (PT_SLOTS / 32));                  // run that contains entry 32w - 1
+    uint16_t* xbucket = F + (PT_SLOTS / 32 + 2);                                              // bucket of routed entry (from the end)
     __shared__ unsigned long long warp_sums[32];
     __shared__ uint32_t tile_total, tile_total_x;
     const int sh = 32 - 2 * k;
@@ -255,6 +300,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t
     const bool route = n_extra > 0;
     const bool has_x = (int)threadIdx.x < n_extra;
     const int bx = n_buckets + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     // Tiles are handed out in order by an atomic ticket: the tiles in flight are then always the ~148 most recent ones,
     // so a run written into a bucket gets its neighbours (the runs of the adjacent tiles) within a tile time and the
     // partial lines complete in L2.  (A static round-robin lets the CTAs drift apart: 4x the DRAM writes, measured.)
@@ -263,21 +309,23 @@ __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t
         s_ticket[0] = (long long)atomicAdd(ticket, 1ull);
         s_ticket[1] = (long long)atomicAdd(ticket, 1ull);
     }
+    for (int w = threadIdx.x; w < 2 * (PT_SLOTS / 32); w += PT_THREADS) heads2[w] = 0;
     __syncthreads();
     int64_t tile = s_ticket[0], tile_next = s_ticket[1];
     __syncthreads();
-    RawWords raw = load_raw_words(packed, valid, hide, n_words, tile);
+    RawPair raw = load_raw_pair(packed, valid, hide, n_words, tile);
     TileRow<PER> row = load_tile_row<PER>(counts, off_rows, n_tiles, tile, n_buckets, n_extra);
     int h = -1;                                        // range of pass 1 that holds the current tile
     unsigned long long cb[PER];
     unsigned long long cbx = 0;
 #pragma unroll
     for (int j = 0; j < PER; ++j) cb[j] = 0;
+    int parity = 0;
     while (tile < n_tiles) {
         if (threadIdx.x == 0) s_ticket[0] = (long long)atomicAdd(ticket, 1ull);       // the tile after the next one
-        const TileWords cur = cook(raw, k, route);
+        const TileWords cur_a = cook(first_word(raw), k, route), cur_b = cook(second_word(raw), k, route);
         const TileRow<PER> tr = row;
-        raw = load_raw_words(packed, valid, hide, n_words, tile_next);
+        raw = load_raw_pair(packed, valid, hide, n_words, tile_next);
         row = load_tile_row<PER>(counts, off_rows, n_tiles, tile_next, n_buckets, n_extra);
         int hh = (int)((tile * PT_HGRID) / n_tiles);
         while (hh + 1 < PT_HGRID && chunk_first_tile(n_tiles, hh + 1) <= tile) ++hh;
@@ -288,75 +336,75 @@ __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t
             for (int j = 0; j < PER; ++j) cb[j] = b0 + j < n_buckets ? __ldg(chunk_base + (size_t)h * n_all + b0 + j) : 0ull;
             cbx = has_x ? __ldg(chunk_base + (size_t)h * n_all + bx) : 0ull;
         }
-        // (b) exclusive scan over the buckets; thread owns buckets [PER*tid, PER*tid + PER) and extra bucket n_buckets + tid;
-        // low half of the scanned value = ordinary entries, high half = routed ones
-        uint32_t mine = 0;
+        // (b) exclusive scan over the buckets; thread owns buckets [PER*tid, PER*tid + PER) and extra bucket n_buckets + tid.
+        // One 64-bit scan carries three running sums: ordinary entries (bits 0..19), routed entries (20..39), non-empty
+        // ordinary buckets = runs (40..59)
+        uint32_t mine = 0, mine_runs = 0;
 #pragma unroll
-        for (int j = 0; j < PER; ++j) mine += tr.c[j];
-        const unsigned long long both = (unsigned long long)mine | ((unsigned long long)tr.cx << 32);
+        for (int j = 0; j < PER; ++j) { mine += tr.c[j]; mine_runs += tr.c[j] ? 1u : 0u; }
+        const unsigned long long both = (unsigned long long)mine | ((unsigned long long)tr.cx << 20) | ((unsigned long long)mine_runs << 40);
         const unsigned long long excl = block_scan_excl<unsigned long long>(both, warp_sums);   // (its barriers also fence the previous write-out)
-        uint32_t run = (uint32_t)excl;
-        const uint32_t runx = (uint32_t)(excl >> 32);
+        uint32_t run = (uint32_t)excl & 0xFFFFFu;
+        const uint32_t runx = (uint32_t)(excl >> 20) & 0xFFFFFu;
+        uint32_t rid = (uint32_t)(excl >> 40);
         const int64_t tile_after = s_ticket[0];                      // (thread 0 writes it again only after two more barriers)
         if (threadIdx.x == PT_THREADS - 1) { tile_total = run + mine; tile_total_x = runx + tr.cx; }
+        uint32_t* heads = heads2 + parity * (PT_SLOTS / 32);         // (zeroed while the previous tile was scattered)
+        if (threadIdx.x == 0) F[0] = 0xFFFFu;                        // "run -1" precedes entry 0
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
-            off[b0 + j] = run;
-            gdelta[b0 + j] = cb[j] + tr.o[j] - run;
-            run += tr.c[j];
+            if (b0 + j < n_buckets) off[b0 + j] = run;
+            const uint32_t c = tr.c[j];
+            if (c) {
+                const uint32_t end = run + c;
+                gd[rid] = cb[j] + tr.o[j] - run;
+                atomicOr(&heads[run >> 5], 1u << (run & 31u));
+                for (uint32_t w = (run >> 5) + 1; w <= (end >> 5); ++w) F[w] = (uint16_t)rid;      // entry 32w - 1 lies in this run
+                ++rid;
+                run = end;
+            }
         }
         if (has_x) {
-            const uint32_t start = (uint32_t)PT_TILE - runx - tr.cx;  // this bucket's entries: sorted[start .. start + cx)
+            const uint32_t start = (uint32_t)PT_SLOTS - runx - tr.cx;  // this bucket's entries: sorted[start .. start + cx)
             off[bx] = start;
-            gdelta[bx] = cbx + tr.ox - start;
+            gd[PT_MAX_BUCKETS + threadIdx.x] = cbx + tr.ox - start;
         }
         __syncthreads();
-        // (d) scatter the keys into bucket order
-        if (cur.fresh) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if ((cur.fresh >> i) & 1u) {
-                    const uint32_t key = key_at(cur, i, sh);
-                    sorted[atomicAdd(&off[key >> 16], 1u)] = key;
-                }
+        {   // the bitmap of the next tile: nobody reads it any more (its last readers wrote out the previous tile)
+            uint32_t* hn = heads2 + (parity ^ 1) * (PT_SLOTS / 32);
+            hn[2 * threadIdx.x] = 0; hn[2 * threadIdx.x + 1] = 0;
         }
-        if (cur.corr) {
-            uint32_t c = cur.corr;
-            do {
-                const int i = __ffs(c) - 1;
-                c &= c - 1;
-                const uint32_t x = (i < 16) ? __funnelshift_l(cur.w1, cur.w0, 2 * i) : __funnelshift_l(cur.w2, cur.w1, 2 * (i - 16));
-                const uint32_t key = ((uint32_t)n_buckets << 16) + (x >> (sh + 2));       // bucket << 16 | suffix
-                sorted[atomicAdd(&off[key >> 16], 1u)] = key;
-            } while (c);
-        }
+        // (d) scatter the suffixes into bucket order
+        scatter_word(cur_a, sh, n_buckets, off, sorted, xbucket);
+        scatter_word(cur_b, sh, n_buckets, off, sorted, xbucket);
         __syncthreads();
         const uint32_t total = tile_total;
         // (e) write-out
         for (uint32_t i0 = threadIdx.x; i0 < total; i0 += PT_WU * PT_THREADS) {
-            uint32_t key[PT_WU];
+            uint32_t sfx[PT_WU], rr[PT_WU];
 #pragma unroll
             for (int u = 0; u < PT_WU; ++u) {
-                const uint32_t i = i0 + u * PT_THREADS;
-                key[u] = i < total ? sorted[i] : 0u;
+                const uint32_t i = i0 + u * PT_THREADS;              // (i >> 5 is the same for the lanes of a warp)
+                const uint32_t w = (i >> 5) & (PT_SLOTS / 32 - 1);   // (an index beyond `total` stays inside the arrays)
+                sfx[u] = sorted[i & (PT_SLOTS - 1)];
+                rr[u] = ((uint32_t)F[w] + __popc(heads[w] & (0xFFFFFFFFu >> (31 - lane)))) & 0xFFFFu;
             }
             unsigned long long d[PT_WU];
 #pragma unroll
-            for (int u = 0; u < PT_WU; ++u) d[u] = gdelta[key[u] >> 16];
+            for (int u = 0; u < PT_WU; ++u) d[u] = gd[rr[u] & (PT_MAX_BUCKETS - 1)];
 #pragma unroll
             for (int u = 0; u < PT_WU; ++u) {
                 const uint32_t i = i0 + u * PT_THREADS;
-                if (i < total) suffixes[d[u] + i] = (uint16_t)key[u];
+                if (i < total) suffixes[d[u] + i] = (uint16_t)sfx[u];
             }
         }
         if (route) {
-            for (uint32_t i = (uint32_t)PT_TILE - tile_total_x + threadIdx.x; i < (uint32_t)PT_TILE; i += PT_THREADS) {
-                const uint32_t key = sorted[i];
-                suffixes[gdelta[key >> 16] + i] = (uint16_t)key;
-            }
+            for (uint32_t i = (uint32_t)PT_SLOTS - tile_total_x + threadIdx.x; i < (uint32_t)PT_SLOTS; i += PT_THREADS)
+                suffixes[gd[PT_MAX_BUCKETS + xbucket[PT_SLOTS - 1 - i]] + i] = sorted[i];
         }
         tile = tile_next;
         tile_next = tile_after;
+        parity ^= 1;
     }
 }
 
@@ -468,7 +516,7 @@ static int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 // sized for n_buckets + n_buckets / 4 rows entries whether or not the corrections of level k-1 are routed
 static int64_t carve(void* scratch, int n_buckets, int64_t n, PartScratch* p) {
     const int64_t n_words = (n + 31) / 32;
-    const int64_t n_tiles = (n_words + PT_THREADS - 1) / PT_THREADS;
+    const int64_t n_tiles = (n_words + PT_TILE_WORDS - 1) / PT_TILE_WORDS;
     const int64_t n_all = n_buckets + n_buckets / 4;
     uint8_t* q = reinterpret_cast<uint8_t*>(scratch);
     int64_t o = 0;
@@ -518,7 +566,7 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
     PartScratch p;
     carve(scratch, n_buckets, n, &p);
     const int64_t n_words = (n + 31) / 32;
-    const int64_t n_tiles = (n_words + PT_THREADS - 1) / PT_THREADS;
+    const int64_t n_tiles = (n_words + PT_TILE_WORDS - 1) / PT_TILE_WORDS;
     const KmapTableSet none = KmapTableSet();
     const KmapTableSet& tt = terminal_tabs ? *terminal_tabs : none;
     const int km = terminal_tabs ? kmin : k;
@@ -535,7 +583,7 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
     cudaMemsetAsync(p.ticket, 0, 8, s);
     if (step_events && step_events[0]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(step_events[0]), s);
     const unsigned int g2 = (unsigned int)(n_tiles < 148 ? n_tiles : 148);
-    const int smem1 = PT_TILE * 4 + 2 * PT_THREADS * 12, smem4 = PT_TILE * 4 + (PT_MAX_PER + 1) * PT_THREADS * 12;
+    const int smem1 = PT_SMEM, smem4 = PT_SMEM;
     // (function attributes are per device: set on every call -- it is a host-side table write -- rather than once per process)
     cudaFuncSetAttribute(partition_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
     cudaFuncSetAttribute(partition_kernel<PT_MAX_PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4);

@@ -60,6 +60,31 @@ __device__ __forceinline__ uint32_t key_at(const TileWords& t, int i, int sh) { 
 }
 
 
+// ---- two validity words (64 window positions) per thread: the tiles of the partition kernels --------------------------------
+// A tile is KMAP_TILE_WORDS = 2046 validity words (65 472 positions): thread t owns words 2t and 2t+1 (thread 1023 idles), so
+// that no (tile, bucket) count can exceed 65 535 (the rows of pass 1 hold them as uint16) and every thread's first word index
+// is even (128-bit loads of the packed words).
+#define KMAP_TILE_WORDS 2046
+struct RawPair { uint32_t v0, v1, v2, h0, h1, w0, w1, w2, w3, w4; };
+
+__device__ __forceinline__ RawPair load_raw_pair(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid,
+                                                 const uint32_t* __restrict__ hide, int64_t n_words, int64_t tile) {
+    RawPair r;
+    r.v0 = r.v1 = r.v2 = r.h0 = r.h1 = r.w0 = r.w1 = r.w2 = r.w3 = r.w4 = 0;
+    const int64_t w = tile * KMAP_TILE_WORDS + 2 * threadIdx.x;           // even
+    if (2 * threadIdx.x < KMAP_TILE_WORDS && w < n_words) {               // (the arrays carry KMAP_PAD_WORDS zero words of padding)
+        const uint2 v = __ldcs(reinterpret_cast<const uint2*>(valid + w));
+        r.v0 = v.x; r.v1 = v.y; r.v2 = __ldcs(valid + w + 2);
+        if (hide) { const uint2 h = __ldcs(reinterpret_cast<const uint2*>(hide + w)); r.h0 = h.x; r.h1 = h.y; }
+        const uint4 p = __ldcs(reinterpret_cast<const uint4*>(packed + 2 * w));
+        r.w0 = p.x; r.w1 = p.y; r.w2 = p.z; r.w3 = p.w; r.w4 = __ldcs(packed + 2 * w + 4);
+    }
+    return r;
+}
+__device__ __forceinline__ RawWords first_word(const RawPair& r) { RawWords a; a.v0 = r.v0; a.v1 = r.v1; a.h = r.h0; a.w0 = r.w0; a.w1 = r.w1; a.w2 = r.w2; return a; }
+__device__ __forceinline__ RawWords second_word(const RawPair& r) { RawWords a; a.v0 = r.v1; a.v1 = r.v2; a.h = r.h1; a.w0 = r.w2; a.w1 = r.w3; a.w2 = r.w4; return a; }
+
+
 // what run_end_corrections needs beyond RawWords: the validity / hidden bits of the 32 positions before this thread's
 // word and the packed word before its first one.  Loaded together with the tile (no dependent loads later).
 struct RawPrev { uint32_t vp, hp, wp; };
@@ -68,8 +93,8 @@ __device__ __forceinline__ RawPrev load_raw_prev(const uint32_t* __restrict__ pa
                                                  const uint32_t* __restrict__ hide, int64_t n_words, int64_t tile) {
     RawPrev r;
     r.vp = r.hp = r.wp = 0;
-    const int64_t w = tile * blockDim.x + threadIdx.x;
-    if (w < n_words && w > 0) {
+    const int64_t w = tile * KMAP_TILE_WORDS + 2 * threadIdx.x;             // the first word of this thread's pair
+    if (2 * threadIdx.x < KMAP_TILE_WORDS && w < n_words && w > 0) {
         r.vp = __ldcs(valid + w - 1);
         if (hide) r.hp = __ldcs(hide + w - 1);
         r.wp = __ldcs(packed + 2 * w - 1);
