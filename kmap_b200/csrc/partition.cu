@@ -29,7 +29,7 @@ constexpr int PT_MAX_X = PT_MAX_BUCKETS / 4;      // buckets of the routed level
 constexpr int PT_MAX_ALL = PT_MAX_BUCKETS + PT_MAX_X;
 constexpr int PT_XCAP = PT_TILE / 14 + 2;         // routed entries a tile can hold (each needs a run end: >= 14 positions apart)
 #ifndef KMAP_PT_WU
-#define KMAP_PT_WU 8
+#define KMAP_PT_WU 4
 #endif
 constexpr int PT_WU = KMAP_PT_WU;                // write-out entries in flight per thread
 
@@ -379,7 +379,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t
         scatter_word(cur_b, sh, n_buckets, off, sorted, xbucket);
         __syncthreads();
         const uint32_t total = tile_total;
-        // (e) write-out
+        // (e) write-out.  Measured (skipping phases): loads + scan 3.6 ms, scatter 10.0 ms, write-out 15.2 ms of 28.8 ms at 1e8
+        // reads.  The write-out costs ~4.7 cycles per (store instruction, 128-byte line) pair -- 32 consecutive entries touch
+        // ~3.3 runs -- so its cost follows the number of runs, not bytes or instructions: a variant in which a lane took two
+        // neighbouring entries (32-bit store when aligned, else two 16-bit stores) issued fewer instructions but visited every
+        // line from up to three of them and took 38 ms.
         for (uint32_t i0 = threadIdx.x; i0 < total; i0 += PT_WU * PT_THREADS) {
             uint32_t sfx[PT_WU], rr[PT_WU];
 #pragma unroll
