@@ -206,6 +206,7 @@ def main():
 
     count_events = []
     phase_events = []
+    merge_comm = api.TableAllReduce() if world > 1 else None
 
     def step(record=False):
         if args.algo == "allk":
@@ -216,13 +217,12 @@ def main():
                 for e in ph:
                     e.record()                      # creates the cudaEvent_t handles the library re-records
                 e0.record()
-            dev.count_all(KMIN, KMAX, dedup, tables, n_partitions=args.partitions, phase_events=ph)
+            # N > 1: the tables are all-reduced from inside the count as they become final (kmap_count_all_k_sharded)
+            dev.count_all(KMIN, KMAX, dedup, tables, n_partitions=args.partitions, phase_events=ph, merge=merge_comm)
             if record:
                 e1.record()
                 count_events.append(("all", e0, e1))
                 phase_events.append((e0, ph, e1))
-            if world > 1:
-                dist.all_reduce(flat_tables)
             return
         for k in range(KMIN, KMAX + 1):
             if record:
@@ -233,7 +233,7 @@ def main():
                 e1.record()
                 count_events.append((k, e0, e1))
             if world > 1:
-                dist.all_reduce(tables[k])
+                merge_comm(tables[k])
 
     def barrier():
         if world > 1:
@@ -401,7 +401,7 @@ def main():
         del seq_d
         dev.seq_u8 = None
         seq_np, borders_np = seq_host.numpy(), borders_host.numpy()
-        comm = api.TableAllReduce() if world > 1 else None
+        comm = merge_comm
 
         def e2e_step():
             res = api.count_kmers(seq_np, borders_np, range(KMIN, KMAX + 1), rep_mode=not dedup, revcom_mode=True, validate=False,

@@ -36,6 +36,7 @@ extern "C" {
 #define KMAP_ERR_BAD_ARG (-1)
 #define KMAP_ERR_CAPACITY (-2)      /* output buffer too small; the required size was written to the *_host out-param */
 #define KMAP_ERR_NEED_SCRATCH (-3)  /* a read longer than the on-chip paths needs the caller-provided bitmap scratch */
+#define KMAP_ERR_COMM (-4)          /* the exchange step failed (no NCCL library in the process, or an NCCL error) */
 
 const char* kmap_last_error(void);
 int kmap_version(void);
@@ -118,6 +119,31 @@ int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, int64_t n, c
                      int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
                      uint32_t* bitmap, int n_partitions, int scheme, void* part_scratch, int64_t part_scratch_bytes,
                      void* const* phase_events, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU, reads sharded by contiguous ranges (the reference has no such path; reads are its
+ * independent units, kmer_count.py:755-759).  The one exchange step is an integer all-reduce of the dense tables over
+ * NVLink / NVSwitch (NCCL, bound at run time from the library the process already carries).  The communicator is made
+ * from a 128-byte unique id: rank 0 calls kmap_comm_unique_id and the host plumbing (torch.distributed) broadcasts the
+ * bytes; every rank then calls kmap_comm_init on ITS device.  The handle is owned by the caller (kmap_comm_destroy).
+ * ---------------------------------------------------------------------------------------------------------- */
+int kmap_comm_available(void);
+int kmap_comm_unique_id(uint8_t* id_out_host);                                     /* 128 bytes, HOST */
+int kmap_comm_init(const uint8_t* id_host, int rank, int world, void** comm_out_host);
+int kmap_comm_destroy(void* comm);
+/* table[i] = sum over the ranks of table[i], in place (uint32, modular): count_uniq_hash of the whole input from the
+ * per-shard tables.  Asynchronous on `stream`. */
+int kmap_table_allreduce(uint32_t* table, int64_t n_cells, void* comm, void* stream);
+/* kmap_count_all_k on this rank's shard of the reads with the tables MERGED over the ranks of `comm` on return (every rank
+ * gets the tables of the whole input).  The all-reduces are issued on `comm_stream` as the buffers become final -- the
+ * corrections of the small levels during the partition pass, the slices of the level-kmax table while the per-bucket
+ * count is still running -- and the 4:1 reductions run on the merged buffers.  Every rank must call it with the same
+ * kmin, kmax, dedup, scheme and with tables laid out the same way (one buffer, largest level first); an empty shard
+ * (n = 0) takes part in the collectives only.  `stream` waits for the exchange before the reductions. */
+int kmap_count_all_k_sharded(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
+                             int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
+                             uint32_t* bitmap, int n_partitions, int scheme, void* part_scratch, int64_t part_scratch_bytes,
+                             void* const* phase_events, void* stream, void* comm, void* comm_stream);
 
 /* kmap_count_dense for tables beyond L2 (9 <= k <= 14) without one global atomic per window: windows are partitioned
  * by the top bits of their key into 4^(k-8) buckets of 16-bit suffixes (scratch), then every bucket is counted in

@@ -18,16 +18,52 @@ from ._lib import KmapError, check as _check, lib as _lib
 
 class TableAllReduce:
     """In-place sum of a dense count table over all ranks.  uint32 counts travel as their int32 bit patterns: two's
-    complement addition is the same modular sum, so the merged table is bit-identical for any number of ranks."""
+    complement addition is the same modular sum, so the merged table is bit-identical for any number of ranks.
+    Device tensors go through the library's own exchange step (`kmap_table_allreduce`, include/kmap_b200.h: an NCCL
+    communicator created from a unique id that torch.distributed broadcasts -- the process group is plumbing only); host
+    tensors (the gloo tests of the host logic) through torch.distributed."""
 
     def __init__(self, group=None):
         import torch.distributed as dist
         if not dist.is_initialized():
             raise KmapError("TableAllReduce needs an initialised torch.distributed process group")
         self.dist, self.group = dist, group
+        self._comm = None
+        self._stream = None
+
+    # ---- the native communicator (lazy: the first device tensor creates it; collective over the group) ----------------
+    def native(self):
+        """(comm handle, exchange stream) of libkmap_b200 on the current device"""
+        if self._comm is None:
+            import ctypes
+            L = _lib()
+            rank, world = self.dist.get_rank(self.group), self.dist.get_world_size(self.group)
+            ident = (ctypes.c_uint8 * 128)()
+            if rank == 0:
+                _check(L.kmap_comm_unique_id(ident), "kmap_comm_unique_id")
+            box = [bytes(ident)]
+            self.dist.broadcast_object_list(box, src=self.dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                                            group=self.group)
+            ident = (ctypes.c_uint8 * 128).from_buffer_copy(box[0])
+            comm = ctypes.c_void_p()
+            _check(L.kmap_comm_init(ident, rank, world, ctypes.byref(comm)), "kmap_comm_init")
+            self._comm = comm
+            self._stream = torch.cuda.Stream()
+        return self._comm, self._stream
+
+    def close(self):
+        if self._comm is not None:
+            torch.cuda.synchronize()
+            _check(_lib().kmap_comm_destroy(self._comm), "kmap_comm_destroy")
+            self._comm = None
 
     def __call__(self, table: torch.Tensor) -> torch.Tensor:
-        self.dist.all_reduce(table, op=self.dist.ReduceOp.SUM, group=self.group)
+        if table.is_cuda:
+            comm, _ = self.native()
+            _check(_lib().kmap_table_allreduce(table.data_ptr(), table.numel(), comm, torch.cuda.current_stream().cuda_stream),
+                   "kmap_table_allreduce")
+        else:
+            self.dist.all_reduce(table, op=self.dist.ReduceOp.SUM, group=self.group)
         return table
 
     def sum_int(self, value: int, device=None) -> int:
@@ -39,6 +75,10 @@ class TableAllReduce:
     @property
     def rank(self) -> int:
         return self.dist.get_rank(self.group)
+
+    @property
+    def world(self) -> int:
+        return self.dist.get_world_size(self.group)
 
 
 class DistContext:
@@ -206,6 +246,7 @@ def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterabl
     contiguous = ks == list(range(ks[0], ks[-1] + 1))
     bounds = _chunk_bounds(seq_np_arr, boarder_mat, chunk_positions) if contiguous else None
     flat = None
+    merged_inside = False
     if bounds is not None and len(bounds) > 2:
         if validate:
             E.check_borders_tile(np.asarray(boarder_mat).reshape(-1, 2), len(seq_np_arr))
@@ -215,13 +256,16 @@ def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterabl
         n_total = dev.n
         if contiguous:
             flat, tables = E.alloc_tables(ks[0], ks[-1])
-            dev.count_all(ks[0], ks[-1], dedup=not rep_mode, tables=tables)   # one update per window at kmax, the rest derived
+            # one update per window at kmax, the rest derived; sharded: merged over the ranks from inside the count
+            dev.count_all(ks[0], ks[-1], dedup=not rep_mode, tables=tables, merge=table_allreduce)
+            merged_inside = table_allreduce is not None
         else:
             tables = {k: dev.count(k, dedup=not rep_mode) for k in ks}
         del dev
     if table_allreduce is not None:
         if flat is not None:
-            table_allreduce(flat)                                  # every level in one call
+            if not merged_inside:
+                table_allreduce(flat)                              # every level in one call
         else:
             for k in ks:
                 table_allreduce(tables[k])

@@ -1,0 +1,111 @@
+// The exchange step of the sharded counting path: integer all-reduce of dense count tables over the ranks of one node
+// (`ncclAllReduce(sum, ncclUint32, 4^k)` over NVLink / NVSwitch; the reference has no multi-process
+// path -- reads are its independent units, kmer_count.py:755-759).  NCCL is bound at run time (dlopen of the libnccl the
+// process already carries -- PyTorch's -- else the system one), so the library loads and exports every symbol on a box
+// without NCCL; the calls then fail loudly.  The communicator is created from a 128-byte unique id that the host plumbing
+// (torch.distributed) broadcasts; it is owned by the caller and passed to every call: the library keeps no communicator.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <mutex>
+#include "common.cuh"
+
+namespace {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;      // (optional)
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+// (the symbol table of the NCCL library: process-wide by nature, immutable once resolved)
+const NcclApi& nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { api.handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD); if (api.handle) break; }       // already in the process
+        if (!api.handle) for (const char* n : names) { api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.handle) break; }
+        if (!api.handle) return;
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.handle, "ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.handle, "ncclCommInitRank"));
+        api.CommInitRankConfig = reinterpret_cast<decltype(api.CommInitRankConfig)>(dlsym(api.handle, "ncclCommInitRankConfig"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.handle, "ncclCommDestroy"));
+        api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.handle, "ncclAllReduce"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+    });
+    return api;
+}
+
+int nccl_fail(const char* what, ncclResult_t r) {
+    kmap_set_error("%s: %s", what, nccl_api().GetErrorString ? nccl_api().GetErrorString(r) : "NCCL error");
+    return KMAP_ERR_COMM;
+}
+
+}  // namespace
+
+// used by count_all.cu / partition.cu for the merges they overlap with counting
+int kmap_allreduce_u32_on(uint32_t* buf, int64_t n, void* comm, cudaStream_t s) {
+    if (n == 0) return KMAP_OK;
+    const NcclApi& api = nccl_api();
+    if (!api.ok) { kmap_set_error("table_allreduce: no NCCL library in this process"); return KMAP_ERR_COMM; }
+    const ncclResult_t r = api.AllReduce(buf, buf, (size_t)n, ncclUint32, ncclSum, reinterpret_cast<ncclComm_t>(comm), s);
+    return r == ncclSuccess ? KMAP_OK : nccl_fail("table_allreduce", r);
+}
+
+extern "C" {
+
+int kmap_comm_available(void) { return nccl_api().ok ? 1 : 0; }
+
+int kmap_comm_unique_id(uint8_t* id_out) {
+    KMAP_REQUIRE(id_out, "null pointer");
+    const NcclApi& api = nccl_api();
+    if (!api.ok) { kmap_set_error("comm_unique_id: no NCCL library in this process"); return KMAP_ERR_COMM; }
+    ncclUniqueId id;
+    const ncclResult_t r = api.GetUniqueId(&id);
+    if (r != ncclSuccess) return nccl_fail("comm_unique_id", r);
+    memcpy(id_out, id.internal, NCCL_UNIQUE_ID_BYTES);
+    return KMAP_OK;
+}
+
+int kmap_comm_init(const uint8_t* id_in, int rank, int world, void** comm_out) {
+    KMAP_REQUIRE(id_in && comm_out && world >= 1 && rank >= 0 && rank < world, "bad argument");
+    const NcclApi& api = nccl_api();
+    if (!api.ok) { kmap_set_error("comm_init: no NCCL library in this process"); return KMAP_ERR_COMM; }
+    ncclUniqueId id;
+    memcpy(id.internal, id_in, NCCL_UNIQUE_ID_BYTES);
+    ncclComm_t comm = nullptr;
+    // The exchange runs BESIDE the counting kernels (count_all.cu / partition.cu leave KMAP_COMM_CTAS SMs free for it), so
+    // the collective is capped at that many CTAs: one that wants more would wait for whole waves of the counting kernel.
+    ncclResult_t r;
+    if (api.CommInitRankConfig) {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.maxCTAs = KMAP_COMM_CTAS;
+        r = api.CommInitRankConfig(&comm, world, id, rank, &cfg);              // binds to the current CUDA device
+    } else {
+        r = api.CommInitRank(&comm, world, id, rank);
+    }
+    if (r != ncclSuccess) return nccl_fail("comm_init", r);
+    *comm_out = comm;
+    return KMAP_OK;
+}
+
+int kmap_comm_destroy(void* comm) {
+    if (!comm) return KMAP_OK;
+    const NcclApi& api = nccl_api();
+    if (!api.ok) return KMAP_OK;
+    const ncclResult_t r = api.CommDestroy(reinterpret_cast<ncclComm_t>(comm));
+    return r == ncclSuccess ? KMAP_OK : nccl_fail("comm_destroy", r);
+}
+
+int kmap_table_allreduce(uint32_t* table, int64_t n_cells, void* comm, void* stream) {
+    KMAP_REQUIRE(n_cells >= 0 && (table || n_cells == 0) && comm, "bad argument");
+    return kmap_allreduce_u32_on(table, n_cells, comm, as_stream(stream));
+}
+
+}  // extern "C"

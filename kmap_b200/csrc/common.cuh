@@ -21,6 +21,11 @@ static inline unsigned int grid_for(int64_t n_threads, int block) {
     return (unsigned int)(g < 1 ? 1 : g);
 }
 
+// the exchange step of a sharded count (comm.cu): NCCL communicator + the stream the all-reduces are issued on
+struct KmapMerge { void* comm; cudaStream_t stream; };
+#define KMAP_COMM_CTAS 16         // CTAs the collective may use = SMs the counting kernels leave free while it runs
+int kmap_allreduce_u32_on(uint32_t* buf, int64_t n, void* comm, cudaStream_t s);
+
 // dense tables of several levels: t[k] = uint32[4^k] (only the levels a kernel uses are set); passed by value
 struct KmapTableSet { uint32_t* t[16]; };
 

@@ -449,16 +449,45 @@ int kmap_count_long_reads(const uint32_t* packed, const uint32_t* valid, int64_t
                           int k, uint32_t* table, uint32_t* work, uint32_t* bitmap, const uint32_t counts[2], cudaStream_t s);
 // implemented in partition.cu: level-k count through key partitioning + shared-memory counters
 int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const uint32_t* hide, int64_t n, int k, uint32_t* table,
-                           void* scratch, const KmapTableSet* terminal_tabs, int kmin, void* const* step_events, cudaStream_t s);
+                           void* scratch, const KmapTableSet* terminal_tabs, int kmin, void* const* step_events, cudaStream_t s,
+                           const KmapMerge* merge);
 
-extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
-                                int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
-                                uint32_t* bitmap, int n_partitions, int scheme, void* part_scratch, int64_t part_scratch_bytes,
-                                void* const* phase_events, void* stream) {
+// ---- the sharded form: this rank's reads, tables merged over the ranks -------------------------------------------------------
+// Every pre-derive buffer is linear in the reads (T_k = fold(T_k+1) + corrections_k, and the fold is linear), so the merged
+// tables are obtained by all-reducing the level-kmax table and the correction buffers of the lower levels and deriving
+// AFTERWARDS.  That lets the exchange start early: the corrections of the L2-resident levels are final after the histogram
+// pass (merged while the partition pass runs), the routed level and the slices of the level-kmax table are merged range by
+// range while the per-bucket count is still going (partition.cu).  Reads beyond the on-chip paths (counted by the direct
+// kernels after the reductions) are rare: whether ANY rank has some is learned from an 8-byte all-reduce of the queue
+// counters; if so their tables are built apart, merged and added.
+namespace {
+
+__global__ void __launch_bounds__(256) add_tables_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (; i < n; i += stride) dst[i] += src[i];
+}
+
+struct OneShotEvent {       // record on one stream, make another wait, release
+    static int chain(cudaStream_t from, cudaStream_t to) {
+        cudaEvent_t ev;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return kmap_check_launch("count_all_k(event)");
+        cudaEventRecord(ev, from);
+        cudaStreamWaitEvent(to, ev, 0);
+        cudaEventDestroy(ev);
+        return KMAP_OK;
+    }
+};
+
+int count_all_impl(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
+                   int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
+                   uint32_t* bitmap, int n_partitions, int scheme, void* part_scratch, int64_t part_scratch_bytes,
+                   void* const* phase_events, void* stream, const KmapMerge* merge) {
     KMAP_REQUIRE(n >= 0 && n_seq >= 0 && kmin >= 1 && kmin <= kmax && kmax <= 15, "need 1 <= kmin <= kmax <= 15");
     KMAP_REQUIRE(n_seq < (int64_t)0xFFFFFFFFll, "too many reads for one call (shard the input)");
     KMAP_REQUIRE(n < ((int64_t)1 << 36), "too many positions for one call (shard the input)");
     KMAP_REQUIRE(tables_host, "null pointer");
+    KMAP_REQUIRE(scheme >= KMAP_KMAX_PREFIX_PASSES && scheme <= KMAP_KMAX_SORTED, "unknown scheme");
     cudaStream_t s = as_stream(stream);
     TableSet tabs;
     for (int k = 0; k < 16; ++k) tabs.t[k] = nullptr;
@@ -468,29 +497,37 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
         cudaError_t e = cudaMemsetAsync(tabs.t[k], 0, ((size_t)1 << (2 * k)) * 4, s);
         if (e != cudaSuccess) { kmap_set_error("count_all_k: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    if (n == 0) return KMAP_OK;
-    KMAP_REQUIRE(packed && valid, "null pointer");
+    // an empty shard launches nothing of its own but still takes part in every collective of the sharded form
+    const bool local = n > 0 && (!dedup || n_seq > 0);
+    if (!local && !merge) return KMAP_OK;
+    KMAP_REQUIRE(!local || (packed && valid), "null pointer");
+    if (dedup) KMAP_REQUIRE(dupmask && work && (borders || !local), "de-duplication needs borders, dupmask and work scratch");
     // optional instrumentation (bench.py): 6 caller-owned cudaEvent_t recorded after zeroing, after the per-read scan,
     // after the level-kmax passes and after the table reductions; [4], [5] inside the partitioned level-kmax count: after
     // the bucket histogram (+ run-end corrections) and after the partition pass
     auto mark = [&](int i) { if (phase_events && phase_events[i]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(phase_events[i]), s); };
     mark(0);
     const int64_t n_words = (n + 31) / 32;
-    uint32_t counts[2] = {0, 0};
     cudaError_t e = cudaSuccess;
+    int rc = KMAP_OK;
     if (dedup) {
-        KMAP_REQUIRE(borders && dupmask && work, "de-duplication needs borders, dupmask and work scratch");
-        if (n_seq == 0) return KMAP_OK;
-        e = cudaMemsetAsync(dupmask, 0, (size_t)kmap_valid_words(n) * 4, s);
-        if (e == cudaSuccess) e = cudaMemsetAsync(work, 0, 16, s);
+        e = cudaMemsetAsync(work, 0, 16, s);
+        if (e == cudaSuccess && local) e = cudaMemsetAsync(dupmask, 0, (size_t)kmap_valid_words(n) * 4, s);
         if (e != cudaSuccess) { kmap_set_error("count_all_k: %s", cudaGetErrorString(e)); return (int)e; }
-        int64_t blocks = (n_seq + 32 * AK_WARPS - 1) / (32 * AK_WARPS);          // a warp takes 32 reads at a time
-        if (blocks > 148 * AK_BLOCKS * 8) blocks = 148 * AK_BLOCKS * 8;           // AK_BLOCKS blocks of 4 warps (32 KB of marks each) per SM
-        dedup_scan_kernel<<<(unsigned int)blocks, AK_WARPS * 32, 0, s>>>(packed, valid, n, borders, n_seq, kmin, kmax, tabs, dupmask, work);
+        if (local) {
+            int64_t blocks = (n_seq + 32 * AK_WARPS - 1) / (32 * AK_WARPS);          // a warp takes 32 reads at a time
+            if (blocks > 148 * AK_BLOCKS * 8) blocks = 148 * AK_BLOCKS * 8;           // AK_BLOCKS blocks of 4 warps (32 KB of marks each) per SM
+            dedup_scan_kernel<<<(unsigned int)blocks, AK_WARPS * 32, 0, s>>>(packed, valid, n, borders, n_seq, kmin, kmax, tabs, dupmask, work);
+        }
+        if (merge) {               // work[2..3] = the queue counters of all ranks: does ANY rank hold reads for the direct kernels?
+            e = cudaMemcpyAsync(work + 2, work, 8, cudaMemcpyDeviceToDevice, s);
+            if (e != cudaSuccess) { kmap_set_error("count_all_k: %s", cudaGetErrorString(e)); return (int)e; }
+            if ((rc = OneShotEvent::chain(s, merge->stream))) return rc;
+            if ((rc = kmap_allreduce_u32_on(work + 2, 2, merge->comm, merge->stream))) return rc;
+        }
     }
-    KMAP_REQUIRE(scheme >= KMAP_KMAX_PREFIX_PASSES && scheme <= KMAP_KMAX_SORTED, "unknown scheme");
     const bool use_partition = scheme != KMAP_KMAX_PREFIX_PASSES && part_scratch && kmax >= 12 && kmax <= 14;
-    if (!use_partition) {          // (the partitioned count does these corrections inside its histogram pass)
+    if (!use_partition && local) {          // (the partitioned count does these corrections inside its histogram pass)
         const int64_t n_groups = (n_words + 3) / 4;
         int64_t tb = (n_groups + 255) / 256;
         if (tb > 148 * 16) tb = 148 * 16;
@@ -514,38 +551,42 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
             v = hi + 1;
         }
     }
-    int rc = kmap_check_launch("count_all_k(scan)");
+    rc = kmap_check_launch("count_all_k(scan)");
     if (rc) return rc;
     mark(1);
     const uint32_t* hide = dedup ? dupmask : nullptr;
     if (use_partition) {
-        // level kmax through key partitioning + shared-memory counters (partition.cu)
-        {
-            KMAP_REQUIRE(part_scratch_bytes >= kmap_partition_scratch_bytes(n, kmax), "partition scratch too small");
-            // (run-end corrections: fused into the histogram pass, except that a level whose table is beyond L2 -- level 13
-            // under k = 14 -- travels through the partition itself as extra buckets; see partition.cu)
-            rc = kmap_count_partitioned(packed, valid, hide, n, kmax, tabs.t[kmax], part_scratch, kmin < kmax ? &tabs : nullptr, kmin,
-                                        phase_events ? phase_events + 4 : nullptr, s);
-        }
+        // level kmax through key partitioning + shared-memory counters (partition.cu).  Run-end corrections: fused into the
+        // histogram pass, except that a level whose table is beyond L2 -- level 13 under k = 14 -- travels through the
+        // partition itself as extra buckets.  With `merge`, the tables are all-reduced from inside, as they become final.
+        KMAP_REQUIRE(part_scratch_bytes >= kmap_partition_scratch_bytes(n, kmax), "partition scratch too small");
+        rc = kmap_count_partitioned(packed, valid, hide, local ? n : 0, kmax, tabs.t[kmax], part_scratch, kmin < kmax ? &tabs : nullptr, kmin,
+                                    phase_events ? phase_events + 4 : nullptr, s, merge);
         if (rc) return rc;
     } else {
-    // level kmax in key-prefix passes: 4^PB passes, each updating a 4^(kmax-PB)-cell slice that stays in L2
-    int PB = 0;
-    if (n_partitions <= 0) { while (PB < 3 && PB < kmax && (((size_t)4 << (2 * kmax)) >> (2 * PB)) > ((size_t)96 << 20)) ++PB; }
-    else { while (PB < 3 && PB < kmax && (1 << (2 * PB)) < n_partitions) ++PB; }
-    const int64_t n_groups = (n_words + 3) / 4;
-    const unsigned int gB = grid_for(n_groups, 256);
-    for (uint32_t prefix = 0; prefix < (1u << (2 * PB)); ++prefix) {
-        switch (PB) {
-            case 0: count_prefix_kernel<0><<<gB, 256, 0, s>>>(packed, valid, hide, n_groups, kmax, tabs.t[kmax], prefix); break;
-            case 1: count_prefix_kernel<1><<<gB, 256, 0, s>>>(packed, valid, hide, n_groups, kmax, tabs.t[kmax], prefix); break;
-            case 2: count_prefix_kernel<2><<<gB, 256, 0, s>>>(packed, valid, hide, n_groups, kmax, tabs.t[kmax], prefix); break;
-            default: count_prefix_kernel<3><<<gB, 256, 0, s>>>(packed, valid, hide, n_groups, kmax, tabs.t[kmax], prefix); break;
+        // level kmax in key-prefix passes: 4^PB passes, each updating a 4^(kmax-PB)-cell slice that stays in L2
+        int PB = 0;
+        if (n_partitions <= 0) { while (PB < 3 && PB < kmax && (((size_t)4 << (2 * kmax)) >> (2 * PB)) > ((size_t)96 << 20)) ++PB; }
+        else { while (PB < 3 && PB < kmax && (1 << (2 * PB)) < n_partitions) ++PB; }
+        const int64_t n_groups = (n_words + 3) / 4;
+        const unsigned int gB = grid_for(n_groups, 256);
+        for (uint32_t prefix = 0; local && prefix < (1u << (2 * PB)); ++prefix) {
+            switch (PB) {
+                case 0: count_prefix_kernel<0><<<gB, 256, 0, s>>>(packed, valid, hide, n_groups, kmax, tabs.t[kmax], prefix); break;
+                case 1: count_prefix_kernel<1><<<gB, 256, 0, s>>>(packed, valid, hide, n_groups, kmax, tabs.t[kmax], prefix); break;
+                case 2: count_prefix_kernel<2><<<gB, 256, 0, s>>>(packed, valid, hide, n_groups, kmax, tabs.t[kmax], prefix); break;
+                default: count_prefix_kernel<3><<<gB, 256, 0, s>>>(packed, valid, hide, n_groups, kmax, tabs.t[kmax], prefix); break;
+            }
+        }
+        rc = kmap_check_launch("count_all_k(count)");
+        if (rc) return rc;
+        if (merge) {               // no early slices on this path: every pre-derive buffer after the count
+            if ((rc = OneShotEvent::chain(s, merge->stream))) return rc;
+            for (int k = kmax; k >= kmin && !rc; --k) rc = kmap_allreduce_u32_on(tabs.t[k], (int64_t)1 << (2 * k), merge->comm, merge->stream);
+            if (rc) return rc;
         }
     }
-    rc = kmap_check_launch("count_all_k(count)");
-    if (rc) return rc;
-    }
+    if (merge && (rc = OneShotEvent::chain(merge->stream, s))) return rc;        // the reductions read merged buffers
     mark(2);
     for (int k = kmax - 1; k >= kmin; --k) {
         const int64_t cells = (int64_t)1 << (2 * k);
@@ -557,15 +598,68 @@ extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, i
     if (rc) return rc;
     mark(3);
     if (dedup) {
-        e = cudaMemcpyAsync(counts, work, 8, cudaMemcpyDeviceToHost, s);
+        uint32_t counts[4] = {0, 0, 0, 0};
+        e = cudaMemcpyAsync(counts, work, 16, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) { kmap_set_error("count_all_k: %s", cudaGetErrorString(e)); return (int)e; }
-        if (counts[0] || counts[1]) {
-            for (int k = kmin; k <= kmax; ++k) {
+        const bool mine = counts[0] || counts[1];
+        if (!merge) {
+            for (int k = kmin; mine && k <= kmax; ++k) {
                 rc = kmap_count_long_reads(packed, valid, n, borders, n_seq, k, tabs.t[k], work, bitmap, counts, s);
                 if (rc) return rc;
             }
+        } else if (counts[2] || counts[3]) {
+            // some rank holds long reads: their per-level counts go into tables of their own, which are merged and added
+            size_t total = 0;
+            for (int k = kmin; k <= kmax; ++k) total += (size_t)1 << (2 * k);
+            uint32_t* delta = nullptr;
+            e = cudaMallocAsync(reinterpret_cast<void**>(&delta), total * 4, s);
+            if (e == cudaSuccess) e = cudaMemsetAsync(delta, 0, total * 4, s);
+            if (e != cudaSuccess) { kmap_set_error("count_all_k(long reads of a sharded input): %s", cudaGetErrorString(e)); return (int)e; }
+            size_t o = 0;
+            for (int k = kmin; k <= kmax; ++k) {
+                if (mine) {
+                    rc = kmap_count_long_reads(packed, valid, n, borders, n_seq, k, delta + o, work, bitmap, counts, s);
+                    if (rc) break;
+                }
+                o += (size_t)1 << (2 * k);
+            }
+            if (!rc) rc = OneShotEvent::chain(s, merge->stream);
+            if (!rc) rc = kmap_allreduce_u32_on(delta, (int64_t)total, merge->comm, merge->stream);
+            if (!rc) rc = OneShotEvent::chain(merge->stream, s);
+            o = 0;
+            for (int k = kmin; k <= kmax && !rc; ++k) {
+                const int64_t cells = (int64_t)1 << (2 * k);
+                int64_t g = (cells + 255) / 256;
+                if (g > 148 * 32) g = 148 * 32;
+                add_tables_kernel<<<(unsigned int)g, 256, 0, s>>>(tabs.t[k], delta + o, cells);
+                o += (size_t)cells;
+            }
+            cudaFreeAsync(delta, s);
+            if (rc) return rc;
+            rc = kmap_check_launch("count_all_k(long reads)");
+            if (rc) return rc;
         }
     }
     return KMAP_OK;
+}
+
+}  // namespace
+
+extern "C" int kmap_count_all_k(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
+                                int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
+                                uint32_t* bitmap, int n_partitions, int scheme, void* part_scratch, int64_t part_scratch_bytes,
+                                void* const* phase_events, void* stream) {
+    return count_all_impl(packed, valid, n, borders, n_seq, kmin, kmax, dedup, tables_host, dupmask, work, bitmap, n_partitions, scheme,
+                          part_scratch, part_scratch_bytes, phase_events, stream, nullptr);
+}
+
+extern "C" int kmap_count_all_k_sharded(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
+                                        int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
+                                        uint32_t* bitmap, int n_partitions, int scheme, void* part_scratch, int64_t part_scratch_bytes,
+                                        void* const* phase_events, void* stream, void* comm, void* comm_stream) {
+    KMAP_REQUIRE(comm && comm_stream, "the sharded count needs a communicator and a stream for the exchange");
+    const KmapMerge merge = {comm, as_stream(comm_stream)};
+    return count_all_impl(packed, valid, n, borders, n_seq, kmin, kmax, dedup, tables_host, dupmask, work, bitmap, n_partitions, scheme,
+                          part_scratch, part_scratch_bytes, phase_events, stream, &merge);
 }

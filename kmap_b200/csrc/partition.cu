@@ -14,6 +14,8 @@
 //   3. bucket_count_kernel  one CTA per bucket: 65536 cells as packed 16-bit counters in shared memory (128 KB),
 //                           suffixes stream in with 128-bit loads, the table slice is written once, coalesced.
 // The result is identical to kmap_count_dense (integer sums are order independent).
+#include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 #include "tile.cuh"
 
@@ -416,6 +418,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) partition_kernel(const uint32_t
 constexpr int BC_THREADS = 1024;
 constexpr int BC_CELLS = 65536;
 constexpr int BC_WORDS = BC_CELLS / 2;            // two 16-bit counters per word
+constexpr int BC_QUEUES = 8;                      // per-bucket count launches of one call (ranges of a sharded count)
 #ifndef KMAP_BC_UNROLL
 #define KMAP_BC_UNROLL 4
 #endif
@@ -433,74 +436,119 @@ __device__ __forceinline__ void bump(uint32_t* sm, uint32_t s, uint32_t* __restr
     }
 }
 
+// One segment [lo, hi) of a bucket's suffixes -> the bucket's slice of the table.  shared_slice: other CTAs add to the same
+// slice right now (a bucket cut into segments), so the counters leave through atomics; else this CTA is the only writer:
+// plain stores into a zeroed slice, or (add_mode: routed level k-1, whose slice already carries the -1 corrections of the
+// per-read scan) a plain read-modify-write.
+__device__ __forceinline__ void count_segment(const uint16_t* __restrict__ suffixes, unsigned long long lo, unsigned long long hi,
+                                              uint32_t* __restrict__ slice, bool add_mode, bool shared_slice, uint32_t* sm, int* spilled) {
+    for (int w = threadIdx.x; w < BC_WORDS; w += BC_THREADS) sm[w] = 0;
+    if (threadIdx.x == 0) *spilled = 0;
+    __syncthreads();
+    // head up to a 16-byte boundary, 8 suffixes per 128-bit load, tail
+    unsigned long long a0 = (lo + 7ull) & ~7ull;
+    if (a0 > hi) a0 = hi;
+    const unsigned long long a1 = a0 + ((hi - a0) & ~7ull);
+    int my_spill = 0;
+    for (unsigned long long i = lo + threadIdx.x; i < a0; i += BC_THREADS) bump(sm, suffixes[i], slice, &my_spill);
+    const uint4* v = reinterpret_cast<const uint4*>(suffixes + a0);
+    const unsigned long long n_vec = (a1 - a0) >> 3;
+    for (unsigned long long i = threadIdx.x; i < n_vec; i += BC_UNROLL * BC_THREADS) {
+        uint4 q[BC_UNROLL];
+#pragma unroll
+        for (int u = 0; u < BC_UNROLL; ++u) {
+            const unsigned long long iu = i + (unsigned long long)u * BC_THREADS;
+            q[u] = iu < n_vec ? __ldcs(v + iu) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < BC_UNROLL; ++u) {
+            if (i + (unsigned long long)u * BC_THREADS >= n_vec) break;
+            const uint32_t ws[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                bump(sm, ws[j] & 0xFFFFu, slice, &my_spill);
+                bump(sm, ws[j] >> 16, slice, &my_spill);
+            }
+        }
+    }
+    for (unsigned long long i = a1 + threadIdx.x; i < hi; i += BC_THREADS) bump(sm, suffixes[i], slice, &my_spill);
+    if (my_spill) *spilled = 1;
+    __syncthreads();
+    const bool atomics = shared_slice || *spilled;           // (folded 0x8000s already sit in some cells: add on top)
+    if (atomics) {
+        for (int w = threadIdx.x; w < BC_WORDS; w += BC_THREADS) {
+            const uint32_t p = sm[w];
+            if (p & 0xFFFFu) atomicAdd(slice + 2 * w, p & 0xFFFFu);
+            if (p >> 16) atomicAdd(slice + 2 * w + 1, p >> 16);
+        }
+    } else if (add_mode) {
+        uint4* out = reinterpret_cast<uint4*>(slice);
+        for (int w = threadIdx.x; w < BC_WORDS / 2; w += BC_THREADS) {
+            const uint2 p = reinterpret_cast<const uint2*>(sm)[w];
+            if (p.x | p.y) {
+                uint4 v4 = out[w];
+                v4.x += p.x & 0xFFFFu; v4.y += p.x >> 16; v4.z += p.y & 0xFFFFu; v4.w += p.y >> 16;
+                out[w] = v4;
+            }
+        }
+    } else {
+        uint4* out = reinterpret_cast<uint4*>(slice);
+        for (int w = threadIdx.x; w < BC_WORDS / 2; w += BC_THREADS) {
+            const uint2 p = reinterpret_cast<const uint2*>(sm)[w];
+            out[w] = make_uint4(p.x & 0xFFFFu, p.x >> 16, p.y & 0xFFFFu, p.y >> 16);
+        }
+    }
+    __syncthreads();
+}
+
 // Buckets n_buckets .. n_all-1 hold the routed run-end corrections of level k-1: their counters are ADDED to the slice of
-// `lower` (the level k-1 table, which already carries the -1 corrections of the per-read scan).
+// `lower` (the level k-1 table).  A bucket with more than seg_len suffixes (a heavy hitter: the cells of a planted motif
+// collect millions of windows, and same-address shared-memory atomics serialise) is cut into segments: this kernel counts
+// the first one and queues the others for bucket_segments_kernel, so that one bucket never holds up a whole launch
+// (measured: the bucket of the planted 14-mer of cfg3 took 16x the time of an average one).
+// queue[0] = items pushed, queue[1] = items taken, queue[2..] = items (bucket | segment << 13).
 __global__ void __launch_bounds__(BC_THREADS, 1) bucket_count_kernel(const uint16_t* __restrict__ suffixes,
                                                                      const unsigned long long* __restrict__ base, int n_buckets,
-                                                                     int n_all, uint32_t* __restrict__ table, uint32_t* __restrict__ lower) {
+                                                                     int b_lo, int b_hi, uint32_t* __restrict__ table, uint32_t* __restrict__ lower,
+                                                                     unsigned long long seg_len, uint32_t* __restrict__ queue) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* sm = reinterpret_cast<uint32_t*>(smem_raw);
     __shared__ int spilled;
-    for (int b = blockIdx.x; b < n_all; b += gridDim.x) {
-        for (int w = threadIdx.x; w < BC_WORDS; w += BC_THREADS) sm[w] = 0;
-        if (threadIdx.x == 0) spilled = 0;
-        __syncthreads();
+    for (int b = b_lo + blockIdx.x; b < b_hi; b += gridDim.x) {
         const bool add_mode = b >= n_buckets;
         uint32_t* slice = add_mode ? lower + (size_t)(b - n_buckets) * BC_CELLS : table + (size_t)b * BC_CELLS;
         const unsigned long long lo = base[b], hi = base[b + 1];
-        // head up to a 16-byte boundary, 8 suffixes per 128-bit load, tail
-        unsigned long long a0 = (lo + 7ull) & ~7ull;
-        if (a0 > hi) a0 = hi;
-        const unsigned long long a1 = a0 + ((hi - a0) & ~7ull);
-        int my_spill = 0;
-        for (unsigned long long i = lo + threadIdx.x; i < a0; i += BC_THREADS) bump(sm, suffixes[i], slice, &my_spill);
-        const uint4* v = reinterpret_cast<const uint4*>(suffixes + a0);
-        const unsigned long long n_vec = (a1 - a0) >> 3;
-        for (unsigned long long i = threadIdx.x; i < n_vec; i += BC_UNROLL * BC_THREADS) {
-            uint4 q[BC_UNROLL];
-#pragma unroll
-            for (int u = 0; u < BC_UNROLL; ++u) {
-                const unsigned long long iu = i + (unsigned long long)u * BC_THREADS;
-                q[u] = iu < n_vec ? __ldcs(v + iu) : make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int u = 0; u < BC_UNROLL; ++u) {
-                if (i + (unsigned long long)u * BC_THREADS >= n_vec) break;
-                const uint32_t ws[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    bump(sm, ws[j] & 0xFFFFu, slice, &my_spill);
-                    bump(sm, ws[j] >> 16, slice, &my_spill);
-                }
-            }
+        const unsigned long long n_seg = hi > lo ? (hi - lo + seg_len - 1) / seg_len : 1;
+        if (n_seg > 1 && threadIdx.x == 0) {
+            const uint32_t at = atomicAdd(&queue[0], (uint32_t)(n_seg - 1));
+            for (uint32_t j = 1; j < (uint32_t)n_seg; ++j) queue[2 + at + j - 1] = (uint32_t)b | (j << 13);
         }
-        for (unsigned long long i = a1 + threadIdx.x; i < hi; i += BC_THREADS) bump(sm, suffixes[i], slice, &my_spill);
-        if (my_spill) spilled = 1;
+        count_segment(suffixes, lo, n_seg > 1 ? lo + seg_len : hi, slice, add_mode, n_seg > 1, sm, &spilled);
+    }
+}
+
+__global__ void __launch_bounds__(BC_THREADS, 1) bucket_segments_kernel(const uint16_t* __restrict__ suffixes,
+                                                                        const unsigned long long* __restrict__ base, int n_buckets,
+                                                                        uint32_t* __restrict__ table, uint32_t* __restrict__ lower,
+                                                                        unsigned long long seg_len, uint32_t* __restrict__ queue) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t* sm = reinterpret_cast<uint32_t*>(smem_raw);
+    __shared__ int spilled;
+    __shared__ uint32_t item;
+    const uint32_t n_items = queue[0];                      // (complete: the kernel that pushes them has finished)
+    for (;;) {
+        if (threadIdx.x == 0) item = atomicAdd(&queue[1], 1u);
         __syncthreads();
-        if (add_mode && !spilled) {   // this CTA is the only writer of the slice right now: plain read-modify-write
-            uint4* out = reinterpret_cast<uint4*>(slice);
-            for (int w = threadIdx.x; w < BC_WORDS / 2; w += BC_THREADS) {
-                const uint2 p = reinterpret_cast<const uint2*>(sm)[w];
-                if (p.x | p.y) {
-                    uint4 v = out[w];
-                    v.x += p.x & 0xFFFFu; v.y += p.x >> 16; v.z += p.y & 0xFFFFu; v.w += p.y >> 16;
-                    out[w] = v;
-                }
-            }
-        } else if (!spilled) {        // the slice was zero: plain coalesced stores
-            uint4* out = reinterpret_cast<uint4*>(slice);
-            for (int w = threadIdx.x; w < BC_WORDS / 2; w += BC_THREADS) {
-                const uint2 p = reinterpret_cast<const uint2*>(sm)[w];
-                out[w] = make_uint4(p.x & 0xFFFFu, p.x >> 16, p.y & 0xFFFFu, p.y >> 16);
-            }
-        } else {                      // some cells already hold folded 0x8000s: add on top
-            for (int w = threadIdx.x; w < BC_WORDS; w += BC_THREADS) {
-                const uint32_t p = sm[w];
-                if (p & 0xFFFFu) atomicAdd(slice + 2 * w, p & 0xFFFFu);
-                if (p >> 16) atomicAdd(slice + 2 * w + 1, p >> 16);
-            }
-        }
+        const uint32_t it = item;
         __syncthreads();
+        if (it >= n_items) return;
+        const uint32_t e = queue[2 + it];
+        const int b = (int)(e & 0x1FFFu);
+        const unsigned long long j = e >> 13;
+        const bool add_mode = b >= n_buckets;
+        uint32_t* slice = add_mode ? lower + (size_t)(b - n_buckets) * BC_CELLS : table + (size_t)b * BC_CELLS;
+        const unsigned long long lo = base[b] + j * seg_len, end = base[b + 1];
+        count_segment(suffixes, lo, lo + seg_len < end ? lo + seg_len : end, slice, add_mode, true, sm, &spilled);
     }
 }
 
@@ -513,6 +561,7 @@ struct PartScratch {
     uint16_t* suffixes;               // one per counted window (+ one per routed correction: never the same position)
     unsigned long long* ticket;       // tile dispenser of the partition pass
     unsigned long long* total;        // [n_all]
+    uint32_t* queues;                 // BC_QUEUES x (2 + n_all) words: segment queues of the per-bucket count launches
 };
 
 static int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -533,6 +582,7 @@ static int64_t carve(void* scratch, int n_buckets, int64_t n, PartScratch* p) {
     uint8_t* a5 = take(2 * n + 64);
     uint8_t* a6 = take(8);
     uint8_t* a7 = take((int64_t)n_all * 8);
+    uint8_t* a8 = take((int64_t)BC_QUEUES * (2 + n_all) * 4);
     if (p) {
         p->chunk_total = reinterpret_cast<uint32_t*>(a0);
         p->base = reinterpret_cast<unsigned long long*>(a1);
@@ -542,6 +592,7 @@ static int64_t carve(void* scratch, int n_buckets, int64_t n, PartScratch* p) {
         p->suffixes = reinterpret_cast<uint16_t*>(a5);
         p->ticket = reinterpret_cast<unsigned long long*>(a6);
         p->total = reinterpret_cast<unsigned long long*>(a7);
+        p->queues = reinterpret_cast<uint32_t*>(a8);
     }
     return o + 256;
 }
@@ -561,7 +612,8 @@ extern "C" int64_t kmap_partition_scratch_bytes(int64_t n, int k) {
 // added to the table by the per-bucket count (a scattered RED into a DRAM-resident table costs a sector read-modify-write:
 // 22 G/s against 187 G/s in L2, profiles/r01_red_rate_microbench.txt; measured 4.7 ms of the 13.6 ms histogram pass).
 int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const uint32_t* hide, int64_t n, int k, uint32_t* table,
-                           void* scratch, const KmapTableSet* terminal_tabs, int kmin, void* const* step_events, cudaStream_t s) {
+                           void* scratch, const KmapTableSet* terminal_tabs, int kmin, void* const* step_events, cudaStream_t s,
+                           const KmapMerge* merge) {
     const int n_buckets = 1 << (2 * (k - 8));
     const bool route = terminal_tabs && k - 1 >= kmin && k - 1 > 12;
     const int n_extra = route ? n_buckets / 4 : 0;
@@ -574,31 +626,121 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
     const KmapTableSet none = KmapTableSet();
     const KmapTableSet& tt = terminal_tabs ? *terminal_tabs : none;
     const int km = terminal_tabs ? kmin : k;
-    if (n_buckets <= PT_THREADS) {
-        if (terminal_tabs) bucket_hist_kernel<true, 1><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, tt, km, kcorr);
-        else bucket_hist_kernel<false, 1><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, tt, km, kcorr);
-    } else {
-        if (terminal_tabs) bucket_hist_kernel<true, PT_MAX_PER><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, tt, km, kcorr);
-        else bucket_hist_kernel<false, PT_MAX_PER><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, tt, km, kcorr);
+    const bool local = n > 0;                           // (an empty shard of a sharded count: collectives only)
+    if (local) {
+        if (n_buckets <= PT_THREADS) {
+            if (terminal_tabs) bucket_hist_kernel<true, 1><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, tt, km, kcorr);
+            else bucket_hist_kernel<false, 1><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, tt, km, kcorr);
+        } else {
+            if (terminal_tabs) bucket_hist_kernel<true, PT_MAX_PER><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, tt, km, kcorr);
+            else bucket_hist_kernel<false, PT_MAX_PER><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, tt, km, kcorr);
+        }
+        bucket_total_kernel<<<(n_all + 255) / 256, 256, 0, s>>>(p.chunk_total, n_all, p.total);
+        bucket_scan_kernel<<<1, PT_THREADS, 0, s>>>(p.total, n_all, p.base);
+        chunk_base_kernel<<<(n_all + 255) / 256, 256, 0, s>>>(p.chunk_total, n_all, p.base, p.chunk_base);
+        if (step_events && step_events[0]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(step_events[0]), s);
     }
-    bucket_total_kernel<<<(n_all + 255) / 256, 256, 0, s>>>(p.chunk_total, n_all, p.total);
-    bucket_scan_kernel<<<1, PT_THREADS, 0, s>>>(p.total, n_all, p.base);
-    chunk_base_kernel<<<(n_all + 255) / 256, 256, 0, s>>>(p.chunk_total, n_all, p.base, p.chunk_base);
-    cudaMemsetAsync(p.ticket, 0, 8, s);
-    if (step_events && step_events[0]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(step_events[0]), s);
-    const unsigned int g2 = (unsigned int)(n_tiles < 148 ? n_tiles : 148);
-    const int smem1 = PT_SMEM, smem4 = PT_SMEM;
-    // (function attributes are per device: set on every call -- it is a host-side table write -- rather than once per process)
-    cudaFuncSetAttribute(partition_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
-    cudaFuncSetAttribute(partition_kernel<PT_MAX_PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4);
-    cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_WORDS * 4);
-    if (n_buckets <= PT_THREADS)
-        partition_kernel<1><<<g2, PT_THREADS, smem1, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_base, p.suffixes, p.ticket);
-    else
-        partition_kernel<PT_MAX_PER><<<g2, PT_THREADS, smem4, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_base, p.suffixes, p.ticket);
-    if (step_events && step_events[1]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(step_events[1]), s);
-    const unsigned int g3 = (unsigned int)(n_all < 148 ? n_all : 148);
-    bucket_count_kernel<<<g3, BC_THREADS, BC_WORDS * 4, s>>>(p.suffixes, p.base, n_buckets, n_all, table, route ? tt.t[k - 1] : nullptr);
+    if (merge && merge->comm && terminal_tabs) {
+        // the corrections of levels kmin .. kcorr-1 are complete (per-read scan + the REDs of the histogram pass): merge them
+        // over the ranks while the partition pass runs.  Neighbouring tables (engine.alloc_tables lays them out largest first
+        // in one buffer, identically on every rank) go in one call.
+        cudaEvent_t ev;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return kmap_check_launch("count_partitioned(event)");
+        cudaEventRecord(ev, s);                        // (the partition pass is queued behind it)
+        int v = kcorr - 1;
+        bool first = true;
+        while (v >= kmin) {
+            uint32_t* lo = tt.t[v];
+            int64_t cells = (int64_t)1 << (2 * v);
+            int u = v - 1;
+            while (u >= kmin && tt.t[u] == lo + cells) { cells += (int64_t)1 << (2 * u); --u; }
+            if (first) { cudaStreamWaitEvent(merge->stream, ev, 0); first = false; }
+            const int rcm = kmap_allreduce_u32_on(lo, cells, merge->comm, merge->stream);
+            if (rcm) { cudaEventDestroy(ev); return rcm; }
+            v = u;
+        }
+        cudaEventDestroy(ev);
+    }
+    if (local) {
+        cudaMemsetAsync(p.ticket, 0, 8, s);
+        cudaMemsetAsync(p.queues, 0, (size_t)BC_QUEUES * (2 + n_all) * 4, s);
+        const unsigned int g2 = (unsigned int)(n_tiles < 148 ? n_tiles : 148);
+        const int smem1 = PT_SMEM, smem4 = PT_SMEM;
+        // (function attributes are per device: set on every call -- it is a host-side table write -- rather than once per process)
+        cudaFuncSetAttribute(partition_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+        cudaFuncSetAttribute(partition_kernel<PT_MAX_PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4);
+        cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_WORDS * 4);
+        cudaFuncSetAttribute(bucket_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_WORDS * 4);
+        if (n_buckets <= PT_THREADS)
+            partition_kernel<1><<<g2, PT_THREADS, smem1, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_base, p.suffixes, p.ticket);
+        else
+            partition_kernel<PT_MAX_PER><<<g2, PT_THREADS, smem4, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_base, p.suffixes, p.ticket);
+        if (step_events && step_events[1]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(step_events[1]), s);
+    }
+    // A CTA of the per-bucket count fills an SM.  With an exchange running beside it, KMAP_COMM_CTAS SMs are left to the
+    // collective's kernels (comm.cu caps them at that many CTAs) and the grid is one CTA per bucket instead of one persistent
+    // CTA per SM, so that SMs change hands at bucket granularity (measured at 2 GPUs with persistent CTAs: the collective got
+    // its SMs only between launches and the counting launches lost theirs to it: 6.9 ms instead of 4.4).
+    const bool beside = merge && merge->comm;
+    const int bc_grid = beside ? n_all : 148;
+    // segments: 1.25 x the average bucket (no bucket of a uniform input is cut), at least 2^17 suffixes, a multiple of 8
+    unsigned long long seg_len = (unsigned long long)(n / n_buckets + 1) * 5 / 4;
+    if (seg_len < (1ull << 17)) seg_len = 1ull << 17;
+    seg_len = (seg_len + 7ull) & ~7ull;
+    int n_launch = 0;
+    auto count_range = [&](int b_lo, int b_hi) {
+        const int nb = b_hi - b_lo;
+        if (nb <= 0 || !local) return;
+        uint32_t* q = p.queues + (size_t)(n_launch++ % BC_QUEUES) * (2 + n_all);
+        bucket_count_kernel<<<(unsigned int)(nb < bc_grid ? nb : bc_grid), BC_THREADS, BC_WORDS * 4, s>>>(p.suffixes, p.base, n_buckets, b_lo, b_hi, table,
+                                                                                                        route ? tt.t[k - 1] : nullptr, seg_len, q);
+        bucket_segments_kernel<<<beside ? 148 - KMAP_COMM_CTAS : 148, BC_THREADS, BC_WORDS * 4, s>>>(p.suffixes, p.base, n_buckets, table,
+                                                                                                       route ? tt.t[k - 1] : nullptr, seg_len, q);
+    };
+    if (!merge || !merge->comm) {
+        count_range(0, n_all);
+        return kmap_check_launch("count_partitioned");
+    }
+    // Sharded input: the slices of the table are final as soon as their buckets are counted, so the all-reduce over the
+    // ranks runs range by range on the merge stream while the next range is being counted (the routed buckets first: they
+    // complete the level k-1 corrections, which are merged as a whole).
+    cudaEvent_t ev;
+    int rc = KMAP_OK;
+    const bool trace = getenv("KMAP_MERGE_TRACE") != nullptr;                          // (debugging aid: timeline of the overlap)
+    cudaEvent_t t0 = nullptr, tc[8], tm[8];
+    int nt = 0;
+    if (trace) { cudaEventCreate(&t0); cudaEventRecord(t0, s); }
+    auto merge_after = [&](uint32_t* buf, int64_t cells) {
+        if (rc) return;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { rc = kmap_check_launch("count_partitioned(event)"); return; }
+        cudaEventRecord(ev, s);
+        cudaStreamWaitEvent(merge->stream, ev, 0);
+        cudaEventDestroy(ev);                          // (released once the wait has been satisfied)
+        if (trace) { cudaEventCreate(&tc[nt]); cudaEventRecord(tc[nt], s); }
+        rc = kmap_allreduce_u32_on(buf, cells, merge->comm, merge->stream);
+        if (trace) { cudaEventCreate(&tm[nt]); cudaEventRecord(tm[nt], merge->stream); ++nt; }
+    };
+    if (route) {
+        count_range(n_buckets, n_all);
+        merge_after(tt.t[k - 1], (int64_t)1 << (2 * (k - 1)));
+    }
+    const int n_chunks = n_buckets >= 1024 ? 4 : 1;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int b_lo = n_buckets * c / n_chunks, b_hi = n_buckets * (c + 1) / n_chunks;
+        count_range(b_lo, b_hi);
+        merge_after(table + (size_t)b_lo * BC_CELLS, (int64_t)(b_hi - b_lo) * BC_CELLS);
+    }
+    if (trace) {
+        cudaStreamSynchronize(s); cudaStreamSynchronize(merge->stream);
+        for (int i = 0; i < nt; ++i) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, t0, tc[i]); cudaEventElapsedTime(&b, t0, tm[i]);
+            fprintf(stderr, "[merge trace] range %d: counted at %.3f ms, merged at %.3f ms\n", i, a, b);
+            cudaEventDestroy(tc[i]); cudaEventDestroy(tm[i]);
+        }
+        cudaEventDestroy(t0);
+    }
+    if (rc) return rc;
     return kmap_check_launch("count_partitioned");
 }
 
@@ -608,5 +750,5 @@ extern "C" int kmap_count_dense_partitioned(const uint32_t* packed, const uint32
     if (n == 0) return KMAP_OK;
     KMAP_REQUIRE(packed && valid && table && scratch, "null pointer");
     KMAP_REQUIRE(scratch_bytes >= kmap_partition_scratch_bytes(n, k), "scratch too small (kmap_partition_scratch_bytes)");
-    return kmap_count_partitioned(packed, valid, nullptr, n, k, table, scratch, nullptr, k, nullptr, as_stream(stream));
+    return kmap_count_partitioned(packed, valid, nullptr, n, k, table, scratch, nullptr, k, nullptr, as_stream(stream), nullptr);
 }

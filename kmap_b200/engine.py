@@ -225,12 +225,14 @@ class SeqOnDevice:
 
     def count_all(self, kmin: int, kmax: int, dedup: bool, tables: Optional[dict] = None, n_partitions: int = 0,
                   phase_events: Optional[Sequence[torch.cuda.Event]] = None, partitioned: Optional[bool] = None,
-                  scheme: Optional[int] = None) -> dict:
+                  scheme: Optional[int] = None, merge=None) -> dict:
         """Dense forward tables for every k in [kmin, kmax] from ONE update per window at level kmax (csrc/count_all.cu);
         identical to {k: self.count(k, dedup)}.  Returns {k: int32-bit-pattern tensor of 4^k cells}.
         scheme: how the level-kmax table is built when 12 <= kmax <= 14 -- SORTED (default: measured fastest)
         or PREFIX_PASSES (global atomics in n_partitions key-prefix passes; also what `partitioned=False` /
-        n_partitions > 0 select)."""
+        n_partitions > 0 select).
+        merge (api.TableAllReduce): this object holds ONE RANK's shard of the reads; the tables returned are those of the
+        whole input, all-reduced over the ranks from inside the count as they become final (kmap_count_all_k_sharded)."""
         L = lib()
         if not (1 <= kmin <= kmax <= 15):
             raise KmapError("count_all needs 1 <= kmin <= kmax <= 15")
@@ -263,14 +265,19 @@ class SeqOnDevice:
             if len(phase_events) != 6:
                 raise KmapError("phase_events must hold 6 events")
             ev = (ctypes.c_void_p * 6)(*[e.cuda_event for e in phase_events])
-        rc = L.kmap_count_all_k(_ptr(self.packed), _ptr(self.valid), self.n, _ptr(self.borders), self.n_seq, kmin, kmax,
-                                int(dedup), ptrs, _ptr(dupmask), _ptr(work), None, int(n_partitions), int(scheme), _ptr(part), part_bytes,
-                                ev, _stream_ptr())
-        if rc == -3:   # a read beyond the block path: rerun with the bitmap scratch (tables are re-zeroed by the call)
+        def call(bm):
+            args = (_ptr(self.packed), _ptr(self.valid), self.n, _ptr(self.borders), self.n_seq, kmin, kmax, int(dedup), ptrs,
+                    _ptr(dupmask), _ptr(work), _ptr(bm), int(n_partitions), int(scheme), _ptr(part), part_bytes, ev, _stream_ptr())
+            if merge is None:
+                return L.kmap_count_all_k(*args)
+            comm, comm_stream = merge.native()
+            return L.kmap_count_all_k_sharded(*args, comm, comm_stream.cuda_stream)
+        if merge is not None and dedup:    # (a retry on one rank would leave the others waiting in a collective: give the bitmap upfront)
             bitmap = zeros(max((1 << (2 * kmax)) // 32, 1), torch.int32)
-            rc = L.kmap_count_all_k(_ptr(self.packed), _ptr(self.valid), self.n, _ptr(self.borders), self.n_seq, kmin, kmax,
-                                    int(dedup), ptrs, _ptr(dupmask), _ptr(work), _ptr(bitmap), int(n_partitions), int(scheme),
-                                    _ptr(part), part_bytes, ev, _stream_ptr())
+        rc = call(bitmap)
+        if rc == -3 and merge is None:   # a read beyond the block path: rerun with the bitmap scratch (tables are re-zeroed by the call)
+            bitmap = zeros(max((1 << (2 * kmax)) // 32, 1), torch.int32)
+            rc = call(bitmap)
         check(rc, "kmap_count_all_k")
         return tables
 

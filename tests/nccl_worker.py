@@ -29,8 +29,18 @@ def main():
     if mode == "count":
         from oracle import kmap_oracle as O
         n_reads = int(sys.argv[3])
-        for spec, L in ((synth.CFG3, 100), (synth.CFG2_N, 40)):
-            seq, borders = synth.generate_numpy(spec, 0, n_reads)
+        def with_long_reads():
+            """reads of every path of the per-read scan (warp / block / bitmap) in ONE of the two shards only: the rank without
+            them must still take part in the exchange of their tables"""
+            rng = np.random.default_rng(99)
+            reads = ["A" * 80, "CA" * 60, "ACGTTGCA" * 150, ("ACGTAGCTAGCTAGGATCGAT" * 1500)[:30000], "ACGTTGCAAC" * 40, "", "N"]
+            reads += [O.arr2dna(rng.integers(0, 4, int(rng.integers(0, 130))).astype(np.uint8)) for _ in range(2500)]
+            arrs = [O.dna2arr(r) for r in reads]
+            lens = np.array([len(a) for a in arrs])
+            ends = np.cumsum(lens)
+            return np.concatenate(arrs), np.stack([ends - lens, ends - 1], axis=1).astype(np.int64)
+        inputs = [synth.generate_numpy(synth.CFG3, 0, n_reads), synth.generate_numpy(synth.CFG2_N, 0, n_reads), with_long_reads()]
+        for seq, borders in inputs:
             s, b = api.shard_reads(seq, borders, rank, world)
             for rep_mode in (False, True):
                 ks = [8, 11, 13, 14]
