@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-crosscheck", action="store_true", help="skip the full-size all-k vs direct per-k table comparison")
     ap.add_argument("--no-hamdist", action="store_true", help="skip the distance-matrix leg (10 GB / n_gpus of output per GPU)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-piece2", action="store_true", help="skip the Hamming-ball / compaction / mask / find_motif leg")
+    ap.add_argument("--no-workflow", action="store_true", help="skip the cfg2 preproc + scan_motif wall-clock leg")
     ap.add_argument("--extras", action="store_true", help="also time compaction / Hamming-ball / mask / distance-matrix kernels")
     return ap.parse_args()
 
@@ -169,6 +171,55 @@ def run_reference_arm(args):
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def run_workflow_cfg2(n_reads=1_000_000):
+    """BASELINE config 2 through the reference-shaped drivers: 1e6 synthetic HT-SELEX-like reads x 40 bp as a FASTA file ->
+    `kmap preproc` -> `kmap scan_motif` (k = 8..14, stock settings otherwise); wall clock per stage."""
+    import shutil
+    import tempfile
+    try:
+        import tomli_w
+        import torch
+        from kmap_b200 import kmer_count as K, motif_discovery as MD, synth
+        spec = synth.CFG2
+        seq, _ = synth.generate_numpy(spec, 0, n_reads)
+        Lr = spec.read_len
+        body = np.frombuffer(b"ACGT", dtype=np.uint8)[np.minimum(seq.reshape(-1, Lr + 1)[:, :Lr], 3)]
+        rec = np.concatenate([np.full((n_reads, 1), ord(">"), np.uint8), np.full((n_reads, 1), ord("r"), np.uint8),
+                              np.full((n_reads, 1), 10, np.uint8), body, np.full((n_reads, 1), 10, np.uint8)], axis=1)
+        tmp = Path(tempfile.mkdtemp())
+        fa = tmp / "reads.fa"
+        rec.reshape(-1).tofile(fa)
+        res = tmp / "res"
+        res.mkdir()
+        cfg = K.read_default_config_file()
+        cfg["kmer_count"]["min_k"], cfg["kmer_count"]["max_k"] = 8, 14
+        cfg["motif_discovery"]["motif_pos_density_flag"] = False
+        cfg["motif_discovery"]["motif_co_occurence_flag"] = False
+        cfg["general"]["input_fasta_file"] = str(fa)
+        cfg["general"]["res_dir"] = str(res)
+        with open(res / "config.toml", "wb") as fh:
+            tomli_w.dump(cfg, fh)
+        out = {"reads": n_reads, "read_len": Lr, "fasta_MB": fa.stat().st_size / 1e6}
+        t = time.perf_counter()
+        K._preproc(str(fa), str(res))
+        torch.cuda.synchronize()
+        out["preproc_s"] = time.perf_counter() - t
+        np.random.seed(1)
+        import contextlib
+        import io
+        t = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            MD._scan_motif(str(res))
+        torch.cuda.synchronize()
+        out["scan_motif_s"] = time.perf_counter() - t
+        out["final_conseq"] = (res / "final_conseq.txt").read_text().split()
+        out["candidate_rows"] = len((res / "candidate_conseq.csv").read_text().splitlines()) - 1
+        shutil.rmtree(tmp, ignore_errors=True)
+        return out
+    except Exception as exc:
+        return {"error": f"{type(exc).__name__}: {exc}"[:400]}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -405,7 +456,7 @@ def main():
 
         def e2e_step():
             res = api.count_kmers(seq_np, borders_np, range(KMIN, KMAX + 1), rep_mode=not dedup, revcom_mode=True, validate=False,
-                                  table_allreduce=comm, lists_on=0)
+                                  table_allreduce=comm, lists_on="sharded" if world > 1 else None)
             return sum(a.nbytes + b.nbytes for a, b in res.values()) if res else 0
 
         e2e_step()
@@ -421,10 +472,32 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
+        io_bytes = torch.tensor([seq_np.nbytes + borders_np.nbytes, d2h], device="cuda", dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(io_bytes)                  # bytes copied by all ranks together
         e2e = {"value": n_total * L * (KMAX - KMIN + 1) / dt / 1e9, "unit": "Gbases/s",
-               "h2d_bytes_per_step": int(seq_np.nbytes + borders_np.nbytes), "d2h_bytes_per_step": int(d2h),
+               "h2d_bytes_per_step": int(io_bytes[0].item()), "d2h_bytes_per_step": int(io_bytes[1].item()),
                "ms_per_step": dt * 1e3, "steps": n_e2e,
-               "api": "kmap_b200.api.count_kmers(seq_np_arr, boarder_mat, k=8..14) -> {k: (uniq_kh_arr, uniq_kh_cnt_arr)}"}
+               "api": "kmap_b200.api.count_kmers(seq_np_arr, boarder_mat, k=8..14) -> {k: (uniq_kh_arr, uniq_kh_cnt_arr)}"
+                      + ("; every rank uploads its shard of the reads and returns the key-range slice of every merged list "
+                         "(lists_on='sharded': the slices of ranks 0..N-1 concatenate to the reference's list); "
+                         "h2d / d2h bytes = sums over the ranks" if world > 1 else "")}
+
+    # ---- piece 2 (Hamming-ball aggregation, compaction, mask, occurrence scan, find_motif) on the same resident workload ----
+    piece2 = None
+    if rank == 0 and not args.no_piece2 and L == 100 and n_local * 8 >= n_total:
+        from bench_extras import fill_rate_gbs, run_piece2
+        try:
+            piece2 = run_piece2(dev, tables, n_local, L, peak)
+            if hamdist is not None:
+                gbs, ms_fill = fill_rate_gbs()
+                hamdist["fill_rate_GBs"] = gbs
+                hamdist["frac_of_fill_rate"] = hamdist["write_GBs_per_gpu"] / gbs
+        except Exception as exc:                                   # a secondary measurement must never break the headline line
+            piece2 = {"error": f"{type(exc).__name__}: {exc}"[:400]}
+    workflow = None
+    if rank == 0 and world == 1 and not args.no_workflow:
+        workflow = run_workflow_cfg2()
 
     extras = None
     if args.extras and rank == 0:
@@ -452,7 +525,8 @@ def main():
                        "l2": "inputs larger than L2 (packed reads + borders = %.1f GB per GPU)" % ((dev.packed.numel() * 4 + dev.valid.numel() * 4 + n_local * 16) / 1e9),
                        "parallelism": f"reads x{n_gpus}"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (launches_per_step(args, dedup)),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "hamdist": hamdist, "checks": checks,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "hamdist": hamdist, "hamball": piece2, "workflow_cfg2": workflow,
+            "checks": checks,
         }
         if extras:
             out["extras"] = extras

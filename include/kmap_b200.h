@@ -180,6 +180,11 @@ int kmap_list_add_rc_counts(const uint32_t* kh, int32_t* cnt, int64_t n, int k, 
  * Synchronises the stream. */
 int kmap_compact_merge(const uint32_t* table, int k, int revcom, uint64_t* scratch, uint32_t* kh_out,
                        int32_t* cnt_out, int64_t capacity, int64_t* n_out_host, void* stream);
+/* The same for the forward hashes in [cell_lo, cell_hi) only (multiples of 2048; cell_hi may be 4^k): the entries of the
+ * merged list whose forward hash lies in the range, in list order -- the lists of consecutive ranges concatenate to the
+ * whole list, so the ranks of a sharded count can each compact and ship one key range. */
+int kmap_compact_merge_range(const uint32_t* table, int k, int revcom, int64_t cell_lo, int64_t cell_hi, uint64_t* scratch, uint32_t* kh_out,
+                             int32_t* cnt_out, int64_t capacity, int64_t* n_out_host, void* stream);
 int64_t kmap_compact_scratch_words(int k);
 
 /* Hamming-ball count of find_motif (motif_discovery.py:666-673) for m candidate consensus hashes, evaluated by

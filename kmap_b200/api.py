@@ -220,7 +220,9 @@ def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterabl
     """First-round counts of find_motif for every k (reference motif_discovery.py:627-640): per k the
     `(uniq_kh_arr uint32, uniq_kh_cnt_arr int32)` pair that the reference pickles into kmer_count/k{k}.pkl, in the
     reference's order.  With `table_allreduce` each rank passes ITS shard of the reads and the tables are merged before
-    compaction; `lists_on=r` returns the lists on rank r only (others get {}).
+    compaction; `lists_on=r` returns the lists on rank r only (others get {}); `lists_on="sharded"` returns on every rank the
+    slice of each list whose forward hashes fall into the rank's key range (`engine.key_range`): the slices of ranks 0, 1, ..
+    concatenate to the whole list, and compaction and the device-to-host copies run on all ranks at once.
     Inputs larger than `chunk_positions` are streamed through the device in chunks of whole reads: the host-to-device copy
     of chunk i+1 (copy stream, from pinned memory) overlaps packing and counting of chunk i (`count_tables_streamed`)."""
     out: Dict[int, Tuple[np.ndarray, np.ndarray]] = {}
@@ -235,7 +237,7 @@ def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterabl
             kh, cnt = dev.count_sorted(k, dedup=not rep_mode)
             if ctx is not None:
                 kh, cnt = merge_sorted_counts_over_ranks(kh, cnt, ctx, 2 * k)
-            if lists_on is not None and ctx is not None and ctx.rank != lists_on:
+            if lists_on is not None and ctx is not None and ctx.rank != (0 if lists_on == "sharded" else lists_on):
                 continue
             if revcom_mode:
                 kh, cnt = E.merge_revcom_sorted(kh, cnt, k)
@@ -271,13 +273,15 @@ def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterabl
                 table_allreduce(tables[k])
         # the merged table holds the distinct k-mers of EVERY shard: the capacity bound is the total window count
         n_total = table_allreduce.sum_int(n_total, device=tables[ks[0]].device)
-        if lists_on is not None and table_allreduce.rank != lists_on:
+        if lists_on is not None and lists_on != "sharded" and table_allreduce.rank != lists_on:
             return out
+    sharded_lists = table_allreduce is not None and lists_on == "sharded"
     # compaction of table k+1 overlaps the device-to-host copy of the lists of k (copy stream + pinned buffers)
     copy_stream = _copy_stream()
     pending = []
     for k in ks:
-        kh, cnt = E.compact_merge(tables[k], k, revcom_mode, upper_bound=_upper_bound(n_total, k))
+        cells = E.key_range(k, table_allreduce.rank, table_allreduce.world) if sharded_lists else None
+        kh, cnt = E.compact_merge(tables[k], k, revcom_mode, upper_bound=_upper_bound(n_total, k), cell_range=cells)
         done = torch.cuda.Event()
         done.record()
         with torch.cuda.stream(copy_stream):

@@ -119,8 +119,8 @@ __device__ __forceinline__ bool item_entry(uint32_t h, uint32_t fh, uint32_t frc
 
 __global__ void __launch_bounds__(CP_BLOCK) table_tile_count_kernel(const uint32_t* __restrict__ F, const uint32_t* __restrict__ G,
                                                                     int64_t n_cells, int k, int revcom,
-                                                                    uint64_t* __restrict__ tile_counts) {
-    const int64_t base = (int64_t)blockIdx.x * CP_TILE + (int64_t)threadIdx.x * CP_ITEMS;
+                                                                    uint64_t* __restrict__ tile_counts, int64_t tile0) {
+    const int64_t base = (tile0 + blockIdx.x) * CP_TILE + (int64_t)threadIdx.x * CP_ITEMS;
     uint32_t fh[CP_ITEMS], frc[CP_ITEMS];
     load_items(F, G, n_cells, k, revcom, base, fh, frc);
     uint32_t c = 0;
@@ -137,9 +137,9 @@ __global__ void __launch_bounds__(CP_BLOCK) table_tile_count_kernel(const uint32
 __global__ void __launch_bounds__(CP_BLOCK) table_tile_write_kernel(const uint32_t* __restrict__ F, const uint32_t* __restrict__ G,
                                                                     int64_t n_cells, int k, int revcom,
                                                                     const uint64_t* __restrict__ tile_offsets,
-                                                                    uint32_t* __restrict__ kh_out, int32_t* __restrict__ cnt_out) {
+                                                                    uint32_t* __restrict__ kh_out, int32_t* __restrict__ cnt_out, int64_t tile0) {
     __shared__ uint32_t svals[CP_TILE], scnts[CP_TILE];           // the tile's entries in order: coalesced write-out
-    const int64_t base = (int64_t)blockIdx.x * CP_TILE + (int64_t)threadIdx.x * CP_ITEMS;
+    const int64_t base = (tile0 + blockIdx.x) * CP_TILE + (int64_t)threadIdx.x * CP_ITEMS;
     uint32_t fh[CP_ITEMS], frc[CP_ITEMS];
     load_items(F, G, n_cells, k, revcom, base, fh, frc);
     uint32_t vals[CP_ITEMS], cnts[CP_ITEMS];
@@ -298,19 +298,24 @@ int64_t kmap_compact_scratch_words(int k) {
     return k >= 13 ? ((tiles + 31) & ~(int64_t)31) + ((int64_t)1 << (2 * k - 1)) : tiles;
 }
 
-int kmap_compact_merge(const uint32_t* table, int k, int revcom, uint64_t* scratch, uint32_t* kh_out, int32_t* cnt_out,
-                       int64_t capacity, int64_t* n_out_host, void* stream) {
+int kmap_compact_merge_range(const uint32_t* table, int k, int revcom, int64_t cell_lo, int64_t cell_hi, uint64_t* scratch, uint32_t* kh_out,
+                             int32_t* cnt_out, int64_t capacity, int64_t* n_out_host, void* stream) {
     KMAP_REQUIRE(k >= 1 && k <= 15, "dense tables support 1 <= k <= 15");
     KMAP_REQUIRE(table && scratch && n_out_host, "null pointer");
     cudaStream_t s = as_stream(stream);
     const int64_t n_cells = (int64_t)1 << (2 * k);
-    const int64_t n_tiles = (n_cells + CP_TILE - 1) / CP_TILE;
+    KMAP_REQUIRE(cell_lo >= 0 && cell_lo <= cell_hi && cell_hi <= n_cells && cell_lo % CP_TILE == 0 && (cell_hi % CP_TILE == 0 || cell_hi == n_cells),
+                 "the cell range must be aligned to 2048 cells");
+    const int64_t tile0 = cell_lo / CP_TILE;
+    const int64_t n_tiles = (cell_hi - cell_lo + CP_TILE - 1) / CP_TILE;
+    *n_out_host = 0;
+    if (n_tiles == 0) return KMAP_OK;
     uint32_t* G = nullptr;
     if (revcom && k >= 13) {
         G = reinterpret_cast<uint32_t*>(scratch + ((kmap_list_scratch_words(n_cells) + 31) & ~(int64_t)31));
         revcom_permute_kernel<<<1u << (2 * (k - 6)), 256, 0, s>>>(table, G, k);
     }
-    table_tile_count_kernel<<<(unsigned int)n_tiles, CP_BLOCK, 0, s>>>(table, G, n_cells, k, revcom, scratch);
+    table_tile_count_kernel<<<(unsigned int)n_tiles, CP_BLOCK, 0, s>>>(table, G, n_cells, k, revcom, scratch, tile0);
     scan_tiles_kernel<<<1, 1024, 0, s>>>(scratch, n_tiles);
     int rc = kmap_check_launch("compact_merge(count)");
     if (rc) return rc;
@@ -322,8 +327,14 @@ int kmap_compact_merge(const uint32_t* table, int k, int revcom, uint64_t* scrat
         return KMAP_ERR_CAPACITY;
     }
     if (*n_out_host == 0) return KMAP_OK;
-    table_tile_write_kernel<<<(unsigned int)n_tiles, CP_BLOCK, 0, s>>>(table, G, n_cells, k, revcom, scratch, kh_out, cnt_out);
+    table_tile_write_kernel<<<(unsigned int)n_tiles, CP_BLOCK, 0, s>>>(table, G, n_cells, k, revcom, scratch, kh_out, cnt_out, tile0);
     return kmap_check_launch("compact_merge(write)");
+}
+
+int kmap_compact_merge(const uint32_t* table, int k, int revcom, uint64_t* scratch, uint32_t* kh_out, int32_t* cnt_out,
+                       int64_t capacity, int64_t* n_out_host, void* stream) {
+    KMAP_REQUIRE(k >= 1 && k <= 15, "dense tables support 1 <= k <= 15");
+    return kmap_compact_merge_range(table, k, revcom, 0, (int64_t)1 << (2 * k), scratch, kh_out, cnt_out, capacity, n_out_host, stream);
 }
 
 int kmap_hamball_extract(const uint32_t* kh, const int32_t* cnt, int64_t n, int k, uint32_t conseq, int d, int revcom,

@@ -346,25 +346,40 @@ def _scratch(words: int) -> torch.Tensor:
     return t
 
 
-def compact_merge(table: torch.Tensor, k: int, revcom: bool, upper_bound: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+def key_range(k: int, rank: int, world: int) -> Tuple[int, int]:
+    """[cell_lo, cell_hi) of the level-k table that `rank` of `world` compacts: contiguous, aligned to the 2048-cell tiles of
+    the compaction kernels, tiling [0, 4^k)"""
+    n_cells = 1 << (2 * k)
+    n_tiles = (n_cells + 2047) // 2048
+    lo, hi = n_tiles * rank // world * 2048, n_tiles * (rank + 1) // world * 2048
+    return min(lo, n_cells), min(hi, n_cells)
+
+
+def compact_merge(table: torch.Tensor, k: int, revcom: bool, upper_bound: Optional[int] = None,
+                  cell_range: Optional[Tuple[int, int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """(kh uint32-bits, cnt int32) device tensors in the reference's order (kmer_count.py:476-491, 643-685).
-    With `upper_bound` (a safe capacity) the size query is skipped: one counting pass + one writing pass."""
+    With `upper_bound` (a safe capacity) the size query is skipped: one counting pass + one writing pass.
+    cell_range = (lo, hi): only the entries whose forward hash lies in [lo, hi) (`key_range`): the slices of consecutive
+    ranges concatenate to the whole list."""
     L = lib()
     scratch = _scratch(L.kmap_compact_scratch_words(k))
     n_out = ctypes.c_int64(0)
+    lo, hi = cell_range if cell_range is not None else (0, 1 << (2 * k))
+    if upper_bound is not None:
+        upper_bound = min(int(upper_bound), hi - lo)
     if upper_bound is not None and upper_bound <= (1 << 29):
         kh, cnt = empty(upper_bound, torch.int32), empty(upper_bound, torch.int32)
         if upper_bound > 0:
-            check(L.kmap_compact_merge(_ptr(table), k, int(revcom), _ptr(scratch), _ptr(kh), _ptr(cnt), upper_bound,
-                                       ctypes.byref(n_out), _stream_ptr()), "kmap_compact_merge")
+            check(L.kmap_compact_merge_range(_ptr(table), k, int(revcom), lo, hi, _ptr(scratch), _ptr(kh), _ptr(cnt), upper_bound,
+                                             ctypes.byref(n_out), _stream_ptr()), "kmap_compact_merge")
         return kh[:n_out.value], cnt[:n_out.value]
-    check(L.kmap_compact_merge(_ptr(table), k, int(revcom), _ptr(scratch), None, None, 0, ctypes.byref(n_out), _stream_ptr()),
+    check(L.kmap_compact_merge_range(_ptr(table), k, int(revcom), lo, hi, _ptr(scratch), None, None, 0, ctypes.byref(n_out), _stream_ptr()),
           "kmap_compact_merge(size)")
     n = n_out.value
     kh, cnt = empty(n, torch.int32), empty(n, torch.int32)
     if n:
-        check(L.kmap_compact_merge(_ptr(table), k, int(revcom), _ptr(scratch), _ptr(kh), _ptr(cnt), n, ctypes.byref(n_out),
-                                   _stream_ptr()), "kmap_compact_merge")
+        check(L.kmap_compact_merge_range(_ptr(table), k, int(revcom), lo, hi, _ptr(scratch), _ptr(kh), _ptr(cnt), n, ctypes.byref(n_out),
+                                         _stream_ptr()), "kmap_compact_merge")
     return kh, cnt
 
 

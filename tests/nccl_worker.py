@@ -45,9 +45,15 @@ def main():
             for rep_mode in (False, True):
                 ks = [8, 11, 13, 14]
                 got = api.count_kmers(s, b, list(range(8, 15)) + [16], rep_mode=rep_mode, table_allreduce=ctx.table_allreduce, lists_on=0)
+                # every rank compacts and returns one key range of every list: the slices concatenate to the whole list
+                part = api.count_kmers(s, b, range(8, 15), rep_mode=rep_mode, table_allreduce=ctx.table_allreduce, lists_on="sharded")
+                parts = ctx.gather(part)
                 if rank != 0:
                     assert got == {}
                     continue
+                for k in range(8, 15):
+                    for j in (0, 1):
+                        assert np.array_equal(np.concatenate([p_[k][j] for p_ in parts]), got[k][j]), (k, rep_mode, "sharded lists")
                 one = api.count_kmers(seq, borders, range(8, 15), rep_mode=rep_mode)
                 for k in range(8, 15):
                     assert np.array_equal(got[k][0], one[k][0]) and np.array_equal(got[k][1], one[k][1]), (k, rep_mode, "vs 1 GPU")
