@@ -254,6 +254,27 @@ int kmap_hamdist_matrix_u64(const uint64_t* kh, const int32_t* labels, int64_t n
 int kmap_exclusive_scan_u32(const uint32_t* in, int64_t n, int64_t* out, uint64_t* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Integer parts of the consumers of the occurrence scan (csrc/consumers.cu), from the scan results in device memory
+ * (offsets int64[n_seq + 1] and ascending positions int32[] per consensus, as kmap_occurrence_count / _fill + the scan
+ * produce them) instead of final.motif_occurence.csv parsed back.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* the `sum()` of find_motif (motif_discovery.py:648): *sum_out (device int64) = total of a count list */
+int kmap_sum_counts_i32(const int32_t* cnt, int64_t n, int64_t* sum_out, void* stream);
+int kmap_sum_counts_i64(const int64_t* cnt, int64_t n, int64_t* sum_out, void* stream);
+/* get_motif_co_occurence_mat (motif_discovery.py:1189-1254), m <= 31 motifs.  offsets_host / positions_host: HOST arrays of m
+ * device pointers.  present_out[r]: bit i = motif i is listed in read r, bit 31 = some cell of the read lists more than 20
+ * positions (the reference keeps a random 20 of them, :1467-1469: such reads are left to the host and are in no count).
+ * counts_out int64[m * m] (device): [i][i] = reads that list motif i, [i][j], i < j = reads that list both. */
+int kmap_cooc_reads(const int64_t* const* offsets_host, const int32_t* const* positions_host, int m, int64_t n_seq, uint32_t* present_out,
+                    int64_t* counts_out, void* stream);
+/* flags_out[r] = 1 iff read r lists motifs i and j (and is not left to the host); scan it with kmap_exclusive_scan_u32, then
+ * kmap_cooc_pair_fill writes, in read order, the read index and TWICE (median position of j - median position of i)
+ * (:1227-1240: np.median of the listed positions; the factor two keeps the .5 of an even count in an integer). */
+int kmap_cooc_pair_flags(const uint32_t* present, int64_t n_seq, int i, int j, uint32_t* flags_out, void* stream);
+int kmap_cooc_pair_fill(const int64_t* off_i, const int32_t* pos_i, const int64_t* off_j, const int32_t* pos_j, const uint32_t* flags,
+                        const int64_t* flag_offsets, int64_t n_seq, int64_t* read_out, int32_t* diff2_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * sort / run-length counting path (csrc/sorted.cu): the same pipeline for k-mers without a dense table
  * (16 <= k <= 31: uint64 hashes, int64 counts, kmer_count.py:351-365; any 1 <= k <= 31 is accepted so that the
  * two paths can be measured against each other).  It follows the reference's own flow: one hash per position ->

@@ -435,8 +435,8 @@ def exclusive_scan_u32(counts: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def occurrence_scan(seq: SeqOnDevice, k: int, conseq_kh: int, d: int, revcom: bool):
-    """per read: (min_dist uint8[n_seq] (255 = none), offsets int64[n_seq+1], positions int32[total]) on the host."""
+def occurrence_scan_device(seq: SeqOnDevice, k: int, conseq_kh: int, d: int, revcom: bool):
+    """per read: (min_dist uint8[n_seq] (255 = none), offsets int64[n_seq+1], positions int32[total]) as DEVICE tensors"""
     L = lib()
     n_seq = seq.n_seq
     min_dist = empty(n_seq, torch.uint8)
@@ -451,7 +451,57 @@ def occurrence_scan(seq: SeqOnDevice, k: int, conseq_kh: int, d: int, revcom: bo
     if total:
         check(f_fill(_ptr(seq.packed), _ptr(seq.valid), _ptr(seq.borders), n_seq, k, int(conseq_kh), int(d),
                      int(revcom), _ptr(min_dist), _ptr(offsets), _ptr(pos), _stream_ptr()), "kmap_occurrence_fill")
+    return min_dist, offsets, pos
+
+
+def occurrence_scan(seq: SeqOnDevice, k: int, conseq_kh: int, d: int, revcom: bool):
+    """per read: (min_dist uint8[n_seq] (255 = none), offsets int64[n_seq+1], positions int32[total]) on the host."""
+    min_dist, offsets, pos = occurrence_scan_device(seq, k, conseq_kh, d, revcom)
     return min_dist.cpu().numpy(), offsets.cpu().numpy(), pos.cpu().numpy()
+
+
+def sum_counts(cnt: torch.Tensor) -> int:
+    """exact total of a device count list (int32 or int64): the `sum()` of find_motif (motif_discovery.py:648)"""
+    L = lib()
+    out = empty(1, torch.int64)
+    fn = L.kmap_sum_counts_i64 if cnt.dtype == torch.int64 else L.kmap_sum_counts_i32
+    check(fn(_ptr(cnt), int(cnt.numel()), _ptr(out), _stream_ptr()), "kmap_sum_counts")
+    return int(out.item())
+
+
+COOC_MAX_MOTIFS = 31          # csrc/consumers.cu CO_MAX: one presence bit per motif, bit 31 flags a read left to the host
+
+
+def co_occurrence_scan(scan_dev):
+    """get_motif_co_occurence_mat's integer parts from the occurrence-scan results of m <= 31 consensus sequences on the device
+    (csrc/consumers.cu): (counts int64[m, m] -- [i][i] reads listing motif i, [i][j] (i < j) reads listing both --,
+    {(i, j): (read index int64[], twice the difference of the median positions int32[]) in read order},
+    reads left to the host int64[]: those with a cell of more than 20 positions, which are in none of the counts)."""
+    L = lib()
+    m = len(scan_dev)
+    n_seq = int(scan_dev[0][1].numel()) - 1
+    offs = (ctypes.c_void_p * m)(*[t[1].data_ptr() for t in scan_dev])
+    poss = (ctypes.c_void_p * m)(*[_ptr(t[2]) if t[2].numel() else None for t in scan_dev])
+    present = empty(n_seq, torch.int32)
+    counts_d = empty(m * m, torch.int64)
+    check(L.kmap_cooc_reads(offs, poss, m, n_seq, _ptr(present), _ptr(counts_d), _stream_ptr()), "kmap_cooc_reads")
+    counts = counts_d.cpu().numpy().reshape(m, m)
+    over = torch.nonzero(present < 0).flatten().cpu().numpy().astype(np.int64) if n_seq else np.zeros(0, dtype=np.int64)
+    pairs = {}
+    flags = empty(n_seq, torch.int32)
+    for i in range(m):
+        for j in range(i + 1, m):
+            c = int(counts[i, j])
+            if c == 0:
+                pairs[(i, j)] = (np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int32))
+                continue
+            check(L.kmap_cooc_pair_flags(_ptr(present), n_seq, i, j, _ptr(flags), _stream_ptr()), "kmap_cooc_pair_flags")
+            at = exclusive_scan_u32(flags)
+            reads, diff2 = empty(c, torch.int64), empty(c, torch.int32)
+            check(L.kmap_cooc_pair_fill(scan_dev[i][1].data_ptr(), _ptr(scan_dev[i][2]), scan_dev[j][1].data_ptr(), _ptr(scan_dev[j][2]),
+                                        _ptr(flags), _ptr(at), n_seq, _ptr(reads), _ptr(diff2), _stream_ptr()), "kmap_cooc_pair_fill")
+            pairs[(i, j)] = (reads.cpu().numpy(), diff2.cpu().numpy())
+    return counts, pairs, over
 
 
 # ---- sort / run-length path (csrc/sorted.cu): uint64 hashes, int64 counts ------------------------------------------------

@@ -114,9 +114,10 @@ def _top_k_indices(state: "_CountState", top_k: int):
 def find_motif_on_device(dev: E.SeqOnDevice, kmer_len: int, max_ham_dist, p_unif, ratio_mu, ratio_std, ratio_cutoff,
                          top_k=5, n_trial=10, merge_revcom_mode=True, rep_mode=False, first_lists=None,
                          first_table: Optional[torch.Tensor] = None, debug=False, sorted_path: Optional[bool] = None,
-                         table_buffer: Optional[torch.Tensor] = None, ctx=None):
+                         table_buffer: Optional[torch.Tensor] = None, ctx=None, want_first: bool = True):
     """Core of find_motif on a device-resident sequence (mutates dev.valid).  Returns (result dict, (uniq_kh, uniq_cnt)
-    of the first round).  `first_lists` plays the role of a pre-existing k{k}.pkl (:621-624); `first_table` lets a
+    of the first round, or None with want_first=False: the lists then stay on the device).  `first_lists` plays the role
+    of a pre-existing k{k}.pkl (:621-624); `first_table` lets a
     caller that counted every k in one pass (SeqOnDevice.count_all) hand in the forward table -- already merged over the
     ranks.  sorted_path: count by sorting 64-bit keys (csrc/sorted.cu) instead of a dense table; None = only where there
     is no dense table (k >= 16).  ctx (api.DistContext): `dev` holds this rank's shard of the reads; every count is merged
@@ -149,8 +150,9 @@ def find_motif_on_device(dev: E.SeqOnDevice, kmer_len: int, max_ham_dist, p_unif
             if sharded:
                 ctx.allreduce(table)
         state = _CountState.from_table(table, k, merge_revcom_mode)
-    first = (state.kh, state.cnt)
-    n_total_kmer = int(np.sum(state.cnt, dtype=np.int64))       # exact
+    first = (state.kh, state.cnt) if want_first else None
+    # exact total, summed where the counts are
+    n_total_kmer = E.sum_counts(state.cnt_dev) if state.cnt_dev is not None else int(np.sum(state.cnt, dtype=np.int64))
 
     found = {}
     for i_trial in range(n_trial):
@@ -326,14 +328,18 @@ def _ex_hamball(res_dir: str, conseq: str, return_type: str, output_file: str, m
 # ======================================================================================================================
 # motif occurrence (:1345-1477)
 # ======================================================================================================================
-def motif_occurence_table(dev: E.SeqOnDevice, conseq_list: Sequence[str], motif_def_dict: dict, revcom_mode=True):
+def motif_occurence_table(dev: E.SeqOnDevice, conseq_list: Sequence[str], motif_def_dict: dict, revcom_mode=True,
+                          keep_device: bool = False):
     """All reads x all consensus sequences in one device pass per consensus.  Returns a list (per consensus) of
-    (min_dist[n_seq], offsets[n_seq+1], positions[total])."""
-    out = []
+    (min_dist[n_seq], offsets[n_seq+1], positions[total]) on the host [, the same list as device tensors]."""
+    out, out_dev = [], []
     for conseq in conseq_list:
         k = len(conseq)
-        out.append(E.occurrence_scan(dev, k, int(kmer2hash(conseq)), motif_def_dict[k].max_ham_dist, revcom_mode))
-    return out
+        t = E.occurrence_scan_device(dev, k, int(kmer2hash(conseq)), motif_def_dict[k].max_ham_dist, revcom_mode)
+        out.append(tuple(x.cpu().numpy() for x in t))
+        if keep_device:
+            out_dev.append(t)
+    return (out, out_dev) if keep_device else out
 
 
 def _cells_for_read(per_conseq, r):
@@ -374,12 +380,15 @@ def motif_occurence_lines(dev: E.SeqOnDevice, borders: np.ndarray, conseq_list, 
     return lines
 
 
-def write_motif_occurence_file(per_conseq, borders: np.ndarray, conseq_list, output_file) -> List[Tuple[int, int]]:
+def write_motif_occurence_file(per_conseq, borders: np.ndarray, conseq_list, output_file,
+                               picked_rows: Optional[dict] = None) -> List[Tuple[int, int]]:
     """The *.motif_occurence.csv of :1409-1418 from the scan results, rows formatted natively (kmap_write_occurrence_rows;
     ~5 us per row in Python is what scan_motif would otherwise wait for).  A read with more than 20 positions in some cell
     needs the reference's random pick (:1467-1469, numpy's global RNG): those rows go through the Python formatter, in read
     order, so the RNG stream is consumed exactly as the reference consumes it.  Returns per consensus
-    (reads with the motif, listed positions) -- what get_motif_seq_num parses back out of the file."""
+    (reads with the motif, listed positions) -- what get_motif_seq_num parses back out of the file.
+    picked_rows (dict): filled with {read: [cell string per consensus]} for the rows that went through the random pick, for
+    the consumers that work from the scan results instead of the file (co_occurrence_from_scan, pos_density_from_scan)."""
     import ctypes
     L = lib()
     with open(output_file, "w+") as fh:
@@ -408,6 +417,8 @@ def write_motif_occurence_file(per_conseq, borders: np.ndarray, conseq_list, out
     for f in np.flatnonzero(over):
         native_rows(r, int(f))
         _, cells = _cells_for_read(per_conseq, int(f))
+        if picked_rows is not None:
+            picked_rows[int(f)] = cells.split(";")
         with open(output_file, "a") as fh:
             fh.write(f"{int(f)};{cells};{lens[f]}\n")
         r = int(f) + 1
@@ -419,7 +430,10 @@ def gen_motif_occurence_file(conseq_list: List[str], motif_def_dict: dict, input
                              revcom_mode=True, _dev_cache=None, _ctx=None, _return_scan=False):
     """:1396-1419.  The reference re-parses the FASTA file per call; the encoded arrays are identical to input.bin
     (same upper-casing and code table), so a cached device copy may be passed by the driver.  Returns per consensus
-    (reads with the motif, listed positions) [, the scan results per consensus (min_dist, offsets, positions)].
+    (reads with the motif, listed positions) [, with _return_scan a dict for the consumers of the file: `scan` = the scan
+    results per consensus (min_dist, offsets, positions) on the host, `lens` = read lengths, `picked_rows` = the rows
+    formatted with the random pick of 20 positions, `cooc` = the integer parts of the co-occurrence step computed on the
+    device from the scan results (engine.co_occurrence_scan), read indices in whole-file numbering].
     _ctx (api.DistContext, world > 1): `_dev_cache` holds this rank's reads and the border matrix of the whole file; the
     per-read results are gathered in rank order and rank 0 writes the file (the other ranks return ([], None))."""
     assert Path(input_fasta_file).exists()
@@ -428,15 +442,30 @@ def gen_motif_occurence_file(conseq_list: List[str], motif_def_dict: dict, input
     else:
         dev = E.SeqOnDevice.from_fasta(input_fasta_file)
         borders = E.to_host(dev.borders, np.int64).reshape(-1, 2)
-    per_conseq = motif_occurence_table(dev, conseq_list, motif_def_dict, revcom_mode)
-    if _ctx is not None and _ctx.world > 1:
+    per_conseq, per_conseq_dev = motif_occurence_table(dev, conseq_list, motif_def_dict, revcom_mode, keep_device=True)
+    world = _ctx.world if _ctx is not None else 1
+    cooc = None
+    if _return_scan and 1 <= len(conseq_list) <= E.COOC_MAX_MOTIFS:
+        cooc = [E.co_occurrence_scan(per_conseq_dev)]
+    del per_conseq_dev
+    if world > 1:
         from .api import concat_occurrence_shards
-        parts = _ctx.gather(per_conseq)
+        parts = _ctx.gather((per_conseq, cooc))
         if not _ctx.is_root:
             return ([], None) if _return_scan else []
-        per_conseq = [concat_occurrence_shards([parts[r][j] for r in range(_ctx.world)]) for j in range(len(conseq_list))]
-    stats = write_motif_occurence_file(per_conseq, borders, conseq_list, output_file)
-    return (stats, per_conseq) if _return_scan else stats
+        per_conseq = [concat_occurrence_shards([parts[r][0][j] for r in range(world)]) for j in range(len(conseq_list))]
+        if cooc is not None:                      # shard-local read indices -> whole-file numbering, in rank order
+            cooc, base = [], 0
+            for r in range(world):
+                counts, pairs, over = parts[r][1][0]
+                cooc.append((counts, {key: (reads + base, d2) for key, (reads, d2) in pairs.items()}, over + base))
+                base += len(parts[r][0][0][0]) if parts[r][0] else 0
+    picked_rows = {}
+    stats = write_motif_occurence_file(per_conseq, borders, conseq_list, output_file, picked_rows)
+    if not _return_scan:
+        return stats
+    lens = np.ascontiguousarray(borders[:, 1] - borders[:, 0], dtype=np.int64)
+    return stats, {"scan": per_conseq, "lens": lens, "picked_rows": picked_rows, "cooc": cooc}
 
 
 def get_motif_seq_num(occurence_file_path: Path, motif_index: int) -> Tuple[int, int]:
@@ -524,39 +553,43 @@ def write_co_occurence_mat(output_file: Path, dist_mat: np.ndarray, conseq_list:
             fh.write(rc_names[i] + "\t" + "\t".join([str(x) for x in arr]) + "\n")
 
 
+def _density_add_batch(density, counts, centres, x_arr, x_step):
+    """density += for every read of the batch, in order, the mean of the normal densities (sd = x_step) centred at
+    centres[r, :counts[r]]: the arithmetic of :1318-1326 (`sum(norm(xi, scale=x_step).pdf(x_arr) for xi in ...) / len(...)`
+    accumulated read by read; scipy's pdf is exp(-y^2 / 2) / sqrt(2 pi) / scale with y = (x - loc) / scale) in the same
+    order; only the exponentials are batched."""
+    norm_c = np.sqrt(2 * np.pi)
+    acc = None
+    for j in range(int(counts.max())):              # left to right inside a read, like sum() over the generator
+        y = (x_arr[None, :] - centres[:, j:j + 1]) / x_step
+        pdf = np.exp(-y ** 2 / 2.0) / norm_c / x_step
+        if acc is None:
+            acc = 0 + pdf
+        else:
+            acc = np.where((counts > j)[:, None], acc + pdf, acc)
+    acc = acc / counts[:, None]
+    for row in acc:                                 # read by read, like `density +=`
+        density += row
+
+
 def get_motif_pos_density(occurence_file_path: Path, motif_index: int, kmer_len: int, x_step=0.01, x_arr=None):
     """:1256-1343.  (reads with the motif, listed positions, density over x_arr): every read adds the mean of normal
-    densities (sd = x_step) centred at its relative motif positions loc / (seq_len - k + 1).  Same arithmetic, in the same
-    order, as the reference's `sum(norm(xi, scale=x_step).pdf(x_arr) for xi in ...) / len(...)` accumulated read by read
-    (scipy's pdf is exp(-y^2 / 2) / sqrt(2 pi) / scale with y = (x - loc) / scale); only the exponentials are batched."""
+    densities (sd = x_step) centred at its relative motif positions loc / (seq_len - k + 1)."""
     if x_arr is None:
         x_arr = np.arange(0, 1, x_step)
     x_arr = np.asarray(x_arr)
     density = np.zeros_like(x_arr)
-    norm_c = np.sqrt(2 * np.pi)
     lines_with_motif = total_occurrences = 0
-    batch_pos, batch_len = [], []
+    batch_pos = []
 
     def flush():
-        nonlocal density
         if not batch_pos:
             return
         counts = np.array([len(p_) for p_ in batch_pos])
-        width = int(counts.max())
-        centres = np.zeros((len(batch_pos), width))
+        centres = np.zeros((len(batch_pos), int(counts.max())))
         for r, p_ in enumerate(batch_pos):
             centres[r, :len(p_)] = p_
-        acc = None
-        for j in range(width):                      # left to right inside a read, like sum() over the generator
-            y = (x_arr[None, :] - centres[:, j:j + 1]) / x_step
-            pdf = np.exp(-y ** 2 / 2.0) / norm_c / x_step
-            if acc is None:
-                acc = 0 + pdf
-            else:
-                acc = np.where((counts > j)[:, None], acc + pdf, acc)
-        acc = acc / counts[:, None]
-        for row in acc:                             # read by read, like `density +=`
-            density += row
+        _density_add_batch(density, counts, centres, x_arr, x_step)
         batch_pos.clear()
 
     for row in _occurrence_rows(occurence_file_path):
@@ -572,6 +605,94 @@ def get_motif_pos_density(occurence_file_path: Path, motif_index: int, kmer_len:
             flush()
     flush()
     return lines_with_motif, total_occurrences, density
+
+
+def pos_density_from_scan(scan_info: dict, motif_index: int, kmer_len: int, x_step=0.01, x_arr=None):
+    """get_motif_pos_density (:1256-1343) from the results of the occurrence scan (the dict gen_motif_occurence_file returns
+    with _return_scan) instead of final.motif_occurence.csv parsed back: same three results, same float arithmetic in the
+    same order; the rows with more than 20 positions in a cell use the positions the file writer picked."""
+    if x_arr is None:
+        x_arr = np.arange(0, 1, x_step)
+    x_arr = np.asarray(x_arr)
+    density = np.zeros_like(x_arr)
+    _, offsets, pos = scan_info["scan"][motif_index]
+    lens, picked = scan_info["lens"], scan_info["picked_rows"]
+    cnt_all = np.diff(offsets)
+    reads = np.flatnonzero(cnt_all > 0)
+    lines_with_motif, total_occurrences = len(reads), 0
+    picked_reads = np.array(sorted(picked), dtype=np.int64)
+    for b0 in range(0, len(reads), 4096):
+        R = reads[b0:b0 + 4096]
+        counts = cnt_all[R].copy()
+        start = offsets[R]
+        denom = (lens[R] - kmer_len + 1).astype(np.float64)           # float(seq_len) - kmer_len + 1
+        swap = R[np.isin(R, picked_reads)] if len(picked_reads) else ()
+        for r in swap:                                                # random pick made while the file was written
+            counts[np.searchsorted(R, r)] = len(picked[int(r)][motif_index].split(","))
+        centres = np.zeros((len(R), int(counts.max())))
+        for j in range(centres.shape[1]):
+            sel = counts > j
+            centres[sel, j] = (pos[start[sel] + j] + 0.0) / denom[sel]
+        for r in swap:
+            at = int(np.searchsorted(R, r))
+            locs = [int(n) for n in picked[int(r)][motif_index].split(",")]
+            centres[at, :] = 0.0
+            centres[at, :len(locs)] = [(loc + 0.0) / denom[at] for loc in locs]
+        total_occurrences += int(counts.sum())
+        _density_add_batch(density, counts, centres, x_arr, x_step)
+    return lines_with_motif, total_occurrences, density
+
+
+def co_occurrence_from_scan(scan_info: dict, n_conseq: int):
+    """get_motif_co_occurence_mat (:1189-1254) from the results of the occurrence scan: the per-motif and per-pair read
+    counts, and for every pair the per-read difference of the median positions in read order, come from the device
+    (csrc/consumers.cu via engine.co_occurrence_scan); the reads whose row went through the random pick of 20 positions
+    are added from the picked rows.  Same three results as get_motif_co_occurence_mat on the file."""
+    assert n_conseq > 0
+    res_mat = np.zeros((n_conseq, n_conseq), dtype=int)
+    dist_mat = np.zeros((n_conseq, n_conseq), dtype=float)
+    individual_counts = np.zeros(n_conseq, dtype=int)
+    keys = [(i, j) for i in range(n_conseq) for j in range(i + 1, n_conseq)]
+    reads_of, vals_of = {key: [] for key in keys}, {key: [] for key in keys}
+    n_over = 0
+    for counts, pairs, over in scan_info["cooc"]:
+        individual_counts += np.diag(counts).astype(int)
+        res_mat += np.triu(counts, 1).astype(int)
+        n_over += len(over)
+        for key in keys:
+            reads_of[key].append(pairs[key][0])
+            vals_of[key].append(pairs[key][1] / 2.0)
+    picked = scan_info["picked_rows"]
+    assert n_over == len(picked)
+    extra = {key: ([], []) for key in keys}
+    for r in sorted(picked):
+        cells = picked[r]
+        motif_inds = [i for i, e in enumerate(cells) if e.strip() != ""]
+        for i in motif_inds:
+            individual_counts[i] += 1
+        med = {}
+        for i in motif_inds:
+            v = sorted(int(x) for x in cells[i].split(","))
+            h = len(v) // 2
+            med[i] = float(v[h]) if len(v) % 2 else (v[h - 1] + v[h]) / 2.0
+        for a_ in range(len(motif_inds)):
+            for b_ in range(a_ + 1, len(motif_inds)):
+                ii, jj = motif_inds[a_], motif_inds[b_]
+                res_mat[ii, jj] += 1
+                extra[(ii, jj)][0].append(r)
+                extra[(ii, jj)][1].append(med[jj] - med[ii])
+    res_mat = res_mat + res_mat.T
+    np.fill_diagonal(res_mat, individual_counts)
+    dist_dict = {}
+    for key in keys:
+        reads = np.concatenate(reads_of[key] + [np.asarray(extra[key][0], dtype=np.int64)])
+        vals = np.concatenate(vals_of[key] + [np.asarray(extra[key][1], dtype=np.float64)])
+        if len(extra[key][0]):
+            vals = vals[np.argsort(reads, kind="stable")]
+        dist_dict[key] = vals.tolist()
+        i, j = key
+        dist_mat[i, j] = dist_mat[j, i] = 1e6 if len(vals) == 0 else np.median(np.abs(dist_dict[key]))
+    return res_mat, dist_mat, dist_dict
 
 
 # ======================================================================================================================
@@ -824,7 +945,8 @@ def _scan_motif(res_dir: str, debug=False):
             consensus_kh_dict, first = find_motif_on_device(dev, kmer_len, m.max_ham_dist, m.p_uniform, m.ratio_mu,
                                                             m.ratio_std, m.ratio_cutoff, top_k, n_trial, revcom_mode,
                                                             rep_mode, first_lists, first_tables.get(kmer_len), debug,
-                                                            table_buffer=table_buffer, ctx=ctx)
+                                                            table_buffer=table_buffer, ctx=ctx,
+                                                            want_first=bool(save_kmer_cnt_flag and not have_pkl[kmer_len]))
             if save_kmer_cnt_flag and not have_pkl[kmer_len] and ctx.is_root:
                 with open(kmer_cnt_file, "wb") as fh:
                     pickle.dump([kmer_len, first[0], first[1]], fh)
@@ -891,8 +1013,8 @@ def _scan_motif(res_dir: str, debug=False):
         print("Final consensus sequences generated.")
 
     occurence_file = res / FileNameDict["motif_occurence_file"]
-    final_scan = gen_motif_occurence_file(final_conseq_list, motif_def_dict, input_fasta_file, occurence_file, revcom_mode,
-                                          _dev_cache=occurrence_dev(), _ctx=ctx, _return_scan=True)
+    _, final_scan = gen_motif_occurence_file(final_conseq_list, motif_def_dict, input_fasta_file, occurence_file, revcom_mode,
+                                             _dev_cache=occurrence_dev(), _ctx=ctx, _return_scan=True)
     if not ctx.is_root:                   # everything below is host work on files: rank 0 alone
         ctx.barrier()
         return
@@ -902,7 +1024,7 @@ def _scan_motif(res_dir: str, debug=False):
     if md_cfg["motif_pos_density_flag"] and final_conseq_list:
         x_step = 0.01
         x_arr = np.arange(0, 1.0 + x_step, x_step)
-        dens = [get_motif_pos_density(occurence_file, i, len(conseq), x_step=x_step, x_arr=x_arr)[2]
+        dens = [pos_density_from_scan(final_scan, i, len(conseq), x_step=x_step, x_arr=x_arr)[2]        # :1256-1343
                 for i, conseq in enumerate(final_conseq_list)]
         with open(res / FileNameDict["motif_pos_density_file"], "wb") as fh:
             pickle.dump([x_arr, np.vstack(dens)], fh)
@@ -914,7 +1036,10 @@ def _scan_motif(res_dir: str, debug=False):
         if co_occur_mat_file.exists():
             print(f"{co_occur_mat_file}, re-use it!")
         else:
-            co_occur_mat, loc_dist_mat, loc_dist_dict = get_motif_co_occurence_mat(occurence_file, len(final_conseq_list))
+            if final_scan["cooc"] is not None:     # integer parts on the device, from the scan results (csrc/consumers.cu)
+                co_occur_mat, loc_dist_mat, loc_dist_dict = co_occurrence_from_scan(final_scan, len(final_conseq_list))
+            else:                                  # more than 31 final motifs: the file, like the reference (:1189-1254)
+                co_occur_mat, loc_dist_mat, loc_dist_dict = get_motif_co_occurence_mat(occurence_file, len(final_conseq_list))
             co_sum_mat = np.diag(co_occur_mat) + np.diag(co_occur_mat).reshape((-1, 1))
             co_occur_norm_mat = 2 * co_occur_mat / co_sum_mat
             write_co_occurence_mat(co_occur_mat_file, co_occur_mat + 0.0, final_conseq_list)

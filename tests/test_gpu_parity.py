@@ -835,3 +835,52 @@ def test_large_input_identities(ENG):
     kh, cnt = dev.count_sorted(16, dedup=False)
     assert int(cnt.sum().item()) == n_reads * (L - 16 + 1)
     assert bool((kh[1:] > kh[:-1]).all().item()) and int(cnt.min().item()) >= 1
+
+
+def test_consumers_from_scan_equal_consumers_of_the_file(MD, K, motif_def_file, tmp_path):
+    """co-occurrence counts / per-read median differences (csrc/consumers.cu) and the position density computed from the
+    occurrence-scan results == the reference-shaped functions that parse final.motif_occurence.csv back
+    (motif_discovery.py:1189-1343; those are pinned to the reference's own outputs in test_oracle_golden.py).  Reads with
+    more than 20 positions in a cell (random pick, :1467-1469) take the host route: poly-A / CA-repeat reads force it."""
+    import kmap_b200.engine as E
+    rng = np.random.default_rng(11)
+    mdd = K.init_motif_def_dict(motif_def_file)
+    conseqs = ["ACGTACGT", "AAAAAAAA", "CACACACAC", "GGATCCGGATCC", "TTTTGGGGCCCC"]
+    special = ["A" * 60, "CA" * 40, "A" * 30 + "ACGTACGT" + "CA" * 20, "ACGTACGTTTTTGGGGCCCC", "ACGT", "ACGTACGTACGTACGT" + "A" * 12]
+    reads = list(special)
+    for _ in range(3000):
+        L = int(rng.integers(6, 90))
+        s = rng.integers(0, 4, L).astype(np.uint8)
+        for c in conseqs:                                     # plant (possibly mutated) copies so that motifs share reads
+            if rng.random() < 0.35 and L > len(c) + 2:
+                at = int(rng.integers(0, L - len(c)))
+                m = K.dna2arr(c, append_missing_val_flag=False).copy()
+                if rng.random() < 0.5:
+                    m[int(rng.integers(0, len(m)))] = int(rng.integers(0, 4))
+                s[at:at + len(m)] = m
+        reads.append(K.arr2dna(s))
+    fa = tmp_path / "in.fa"
+    with open(fa, "w") as fh:
+        for i, r in enumerate(reads):
+            fh.write(f">r{i}\n{r}\n")
+    for revcom in (True, False):
+        out = tmp_path / f"occ_{int(revcom)}.csv"
+        np.random.seed(5)
+        stats, info = MD.gen_motif_occurence_file(conseqs, mdd, fa, out, revcom, _return_scan=True)
+        assert len(info["picked_rows"]) >= 3 and info["cooc"] is not None
+        assert stats == [MD.get_motif_seq_num(out, i) for i in range(len(conseqs))]
+        co_f, dist_f, dd_f = MD.get_motif_co_occurence_mat(out, len(conseqs))
+        co_s, dist_s, dd_s = MD.co_occurrence_from_scan(info, len(conseqs))
+        assert co_s.dtype == co_f.dtype and np.array_equal(co_s, co_f)
+        assert np.array_equal(dist_s, dist_f)
+        assert dd_s == dd_f and any(len(v) for v in dd_f.values())
+        for i, c in enumerate(conseqs):
+            a = MD.get_motif_pos_density(out, i, len(c))
+            b = MD.pos_density_from_scan(info, i, len(c))
+            assert a[:2] == b[:2] and np.array_equal(a[2], b[2]), c
+    # the exact total of a count list (the `sum()` of find_motif, :648)
+    import torch
+    c32 = torch.randint(0, 2 ** 31 - 1, (1_000_003,), dtype=torch.int32, device="cuda")
+    assert E.sum_counts(c32) == int(c32.to(torch.int64).sum().item())
+    c64 = torch.randint(0, 2 ** 40, (77_777,), dtype=torch.int64, device="cuda")
+    assert E.sum_counts(c64) == int(c64.sum().item())

@@ -95,3 +95,66 @@ def test_native_occurrence_writer_equals_python_formatter(tmp_path):
     assert stats == [MD.get_motif_seq_num(tmp_path / "o.csv", i) for i in range(m)]
     assert MD.write_motif_occurence_file([], borders, [], tmp_path / "e.csv") == []
     assert (tmp_path / "e.csv").read_text() == "seq_ind;;seq_len\n"
+
+
+def _cooc_of_scan_numpy(per, m, n_seq):
+    """what engine.co_occurrence_scan returns (csrc/consumers.cu), restated with numpy for the host-side merge test"""
+    cnts = np.stack([np.diff(o) for _, o, _ in per])
+    over = np.flatnonzero((cnts > 20).any(axis=0)).astype(np.int64)
+    ok = ~(cnts > 20).any(axis=0)
+    counts = np.zeros((m, m), dtype=np.int64)
+    pairs = {}
+
+    def med2(j, r):
+        o, p = per[j][1], per[j][2]
+        v = p[o[r]:o[r + 1]]
+        h = len(v) // 2
+        return 2 * int(v[h]) if len(v) % 2 else int(v[h - 1]) + int(v[h])
+    for i in range(m):
+        counts[i, i] = np.count_nonzero((cnts[i] > 0) & ok)
+        for j in range(i + 1, m):
+            reads = np.flatnonzero((cnts[i] > 0) & (cnts[j] > 0) & ok).astype(np.int64)
+            counts[i, j] = len(reads)
+            pairs[(i, j)] = (reads, np.array([med2(j, r) - med2(i, r) for r in reads], dtype=np.int32))
+    return counts, pairs, over
+
+
+def test_consumers_from_scan_merge_logic(tmp_path):
+    """co_occurrence_from_scan / pos_density_from_scan (host side: device results + the rows of the random pick, one or
+    several shards) == the reference-shaped functions on the file the same scan results were written to"""
+    from kmap_b200 import motif_discovery as MD
+    rng = np.random.default_rng(3)
+    n_seq, m = 2500, 4
+    lens = rng.integers(30, 200, n_seq)
+    ends = np.cumsum(lens + 1)
+    borders = np.stack([ends - lens - 1, ends - 1], axis=1).astype(np.int64)
+    per = []
+    for j in range(m):
+        cnt = rng.integers(0, 5, n_seq) * (rng.random(n_seq) < 0.4)
+        if j in (1, 2):
+            cnt[[5 + j, 700, 2499]] = 23
+        off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+        pos = np.concatenate([np.sort(rng.choice(25, c, replace=False)) for c in cnt]).astype(np.int32)
+        per.append((None, off, pos))
+    conseqs = ["ACGT", "TTGA", "CCAGG", "GGGTTT"]
+    picked = {}
+    np.random.seed(9)
+    MD.write_motif_occurence_file(per, borders, conseqs, tmp_path / "o.csv", picked)
+    assert sorted(picked) == [6, 7, 700, 2499]
+    want = MD.get_motif_co_occurence_mat(tmp_path / "o.csv", m)
+    info = {"scan": per, "lens": (borders[:, 1] - borders[:, 0]).astype(np.int64), "picked_rows": picked}
+    # one shard, and three shards gathered in rank order
+    cuts = [0, 900, 901, n_seq]
+    shards = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        sub = [(None, o[a:b + 1] - o[a], p[o[a]:o[b]]) for _, o, p in per]
+        counts, pairs, over = _cooc_of_scan_numpy(sub, m, b - a)
+        shards.append((counts, {k_: (r + a, d) for k_, (r, d) in pairs.items()}, over + a))
+    for cooc in ([_cooc_of_scan_numpy(per, m, n_seq)], shards):
+        got = MD.co_occurrence_from_scan(dict(info, cooc=cooc), m)
+        assert got[0].dtype == want[0].dtype and np.array_equal(got[0], want[0])
+        assert np.array_equal(got[1], want[1]) and got[2] == want[2]
+    for i, c in enumerate(conseqs):
+        a = MD.get_motif_pos_density(tmp_path / "o.csv", i, len(c))
+        b = MD.pos_density_from_scan(info, i, len(c))
+        assert a[:2] == b[:2] and np.array_equal(a[2], b[2])
