@@ -163,6 +163,24 @@ int kmap_add_u32(uint32_t* dst, const uint32_t* src, int64_t n_words, void* stre
  * relative to the first position of the chunk */
 int kmap_rebase_borders(int64_t* borders, int64_t n_seq, int64_t offset, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Host side of the boundary (csrc/host_pack.cpp: plain C++, HOST pointers, no stream): the end-to-end call is bound by
+ * the PCIe link when input.bin travels at one byte per base (kmer_count.py:326-347 layout), so the host cores re-encode
+ * each chunk of reads into the packed form (0.375 B/position) in pinned staging memory while the previous chunk travels
+ * and is counted (kmap_b200/api.py count_tables_streamed).  Encoders only: nothing is hashed or counted on the host.
+ * ---------------------------------------------------------------------------------------------------------- */
+int kmap_host_threads(void);
+/* what kmap_pack2bit writes, from and to host memory; packed = uint32[kmap_packed_words(n)], valid = uint32[kmap_valid_words(n)];
+ * n_threads <= 0: all hardware threads */
+int kmap_host_pack2bit(const uint8_t* seq, int64_t n, uint32_t* packed, uint32_t* valid, int n_threads);
+/* rows of input.seqboarder.bin.pkl for reads laid out back to back from position `first` (kmer_count.py:335-343: st_0 = first,
+ * st_{i+1} = en_i + 1) -> strides_out[i] = en_i - st_i + 1 (uint32: 4 instead of 16 bytes per read over the link).
+ * KMAP_ERR_BAD_ARG if the rows are not back to back (the caller then ships the matrix itself). */
+int kmap_host_border_strides(const int64_t* borders, int64_t n_seq, int64_t first, uint32_t* strides_out, int n_threads);
+/* device: the border matrix (relative to the first read) back from the strides: offsets = int64[n_seq + 1] (exclusive prefix
+ * sums, kept), borders_out = int64[n_seq][2] = (offsets[i], offsets[i + 1] - 1); scratch = uint64[kmap_list_scratch_words(n_seq)] */
+int kmap_borders_from_strides(const uint32_t* strides, int64_t n_seq, int64_t* offsets, int64_t* borders_out, uint64_t* scratch, void* stream);
+
 /* count_uniq_hash (kmer_count.py:476-491) for callers that hold a materialised hash array: table[h] += 1 for every
  * h < 4^k (the invalid hash is skipped) */
 int kmap_count_hashes_u32(const uint32_t* hash, int64_t n, int k, uint32_t* table, void* stream);

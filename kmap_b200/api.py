@@ -216,15 +216,18 @@ def upload_reads(seq_np_arr: np.ndarray, boarder_mat: Optional[np.ndarray], vali
 
 def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterable[int], rep_mode: bool = False,
                 revcom_mode: bool = True, validate: bool = True, table_allreduce: Optional[TableAllReduce] = None,
-                lists_on: Optional[int] = None, chunk_positions: int = 1 << 29) -> Dict[int, Tuple[np.ndarray, np.ndarray]]:
+                lists_on: Optional[int] = None, chunk_positions: int = 1 << 28,
+                host_pack: Optional[bool] = None) -> Dict[int, Tuple[np.ndarray, np.ndarray]]:
     """First-round counts of find_motif for every k (reference motif_discovery.py:627-640): per k the
     `(uniq_kh_arr uint32, uniq_kh_cnt_arr int32)` pair that the reference pickles into kmer_count/k{k}.pkl, in the
     reference's order.  With `table_allreduce` each rank passes ITS shard of the reads and the tables are merged before
     compaction; `lists_on=r` returns the lists on rank r only (others get {}); `lists_on="sharded"` returns on every rank the
     slice of each list whose forward hashes fall into the rank's key range (`engine.key_range`): the slices of ranks 0, 1, ..
     concatenate to the whole list, and compaction and the device-to-host copies run on all ranks at once.
-    Inputs larger than `chunk_positions` are streamed through the device in chunks of whole reads: the host-to-device copy
-    of chunk i+1 (copy stream, from pinned memory) overlaps packing and counting of chunk i (`count_tables_streamed`)."""
+    Inputs larger than `chunk_positions` are streamed through the device in chunks of whole reads (`count_tables_streamed`):
+    the host cores re-encode chunks into the packed form the device works on (0.375 B/position over the link instead of 1)
+    while the copy engine ships other chunks as they are, and every chunk is counted while the next ones travel.
+    host_pack=False ships every chunk as it is (None: on unless KMAP_HOST_PACK=0)."""
     out: Dict[int, Tuple[np.ndarray, np.ndarray]] = {}
     ks_all = sorted(set(int(k) for k in k_list))
     wide = [k for k in ks_all if k >= 16]          # uint64 hashes, no dense table: sort / run-length path (csrc/sorted.cu)
@@ -252,7 +255,9 @@ def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterabl
     if bounds is not None and len(bounds) > 2:
         if validate:
             E.check_borders_tile(np.asarray(boarder_mat).reshape(-1, 2), len(seq_np_arr))
-        flat, tables, n_total = count_tables_streamed(seq_np_arr, boarder_mat, ks[0], ks[-1], rep_mode, bounds)
+        world_local = table_allreduce.world if table_allreduce is not None else 1
+        flat, tables, n_total = count_tables_streamed(seq_np_arr, boarder_mat, ks[0], ks[-1], rep_mode, bounds, host_pack,
+                                                      host_pack_threads(world_local))
     else:
         dev = upload_reads(seq_np_arr, boarder_mat, validate)
         n_total = dev.n
@@ -346,63 +351,217 @@ def _chunk_bounds(seq_np_arr: np.ndarray, boarder_mat, chunk_positions: int):
     return cuts
 
 
-def count_tables_streamed(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, kmin: int, kmax: int, rep_mode: bool, cuts):
+_staging = {}
+
+
+def _pinned_staging(tag: str, n: int, dtype: torch.dtype) -> torch.Tensor:
+    """pinned host staging buffer of at least n elements, kept between calls (pinning memory costs ~0.3 s per GB)"""
+    key = (tag, dtype)
+    buf = _staging.get(key)
+    if buf is None or buf.numel() < n:
+        _staging[key] = None
+        buf = _staging[key] = torch.empty(n, dtype=dtype, pin_memory=True)
+    return buf
+
+
+def host_pack_threads(world_local: int = 1) -> int:
+    """host threads one process may use for re-encoding (all hardware threads, shared by the ranks of the box)"""
+    import os
+    n = int(os.environ.get("KMAP_HOST_THREADS", "0")) or int(_lib().kmap_host_threads())
+    return max(1, n // max(1, world_local))
+
+
+def count_tables_streamed(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, kmin: int, kmax: int, rep_mode: bool, cuts,
+                          host_pack: Optional[bool] = None, n_threads: int = 0):
     """Dense forward tables of every k in [kmin, kmax] with the reads streamed through the device chunk by chunk.
     Reads are independent units (per-read de-duplication never crosses a read, kmer_count.py:755-759), so the table of the
-    whole input is the sum of the chunk tables: chunk i is packed and counted (SeqOnDevice.count_all) on the current
-    stream while chunk i+1 travels on the copy stream into the other half of a double buffer.
-    Returns (flat buffer, {k: table view}, n)."""
+    whole input is the sum of the chunk tables (SeqOnDevice.count_all per chunk + kmap_add_u32).
+    The call is bound by the host-to-device link when input.bin travels at one byte per base, so two feeders share the
+    chunks: a host thread re-encodes chunks from the FRONT into the packed form (csrc/host_pack.cpp, all host cores, 0.375
+    B/position, into pinned staging buffers) and ships them packed; the main thread ships chunks from the BACK as they are
+    (one raw copy in flight at a time; packed on the device) so that the link never waits for the encoder.  They meet
+    wherever the two rates put them.  The border rows travel as one uint32 stride per read (kmap_host_border_strides) and
+    are rebuilt on the device by a prefix sum.  host_pack=False: raw chunks only.  Returns (flat buffer, {k: table view}, n)."""
+    import queue
+    import threading
     E.require_cuda()
     L = _lib()
+    if host_pack is None:
+        import os
+        host_pack = os.environ.get("KMAP_HOST_PACK", "1") != "0"
     b = np.asarray(boarder_mat).reshape(-1, 2)
     if b.dtype != np.int64 or not b.flags.c_contiguous:
         b = np.ascontiguousarray(b, dtype=np.int64)
-    seq_t = torch.from_numpy(np.ascontiguousarray(seq_np_arr))
-    b_t = torch.from_numpy(b)
+    seq_np = np.ascontiguousarray(seq_np_arr)
+    seq_t = torch.from_numpy(seq_np)
+    n_threads = n_threads or host_pack_threads()
     spans = []
     for r0, r1 in zip(cuts[:-1], cuts[1:]):
         spans.append((r0, r1, int(b[r0, 0]), int(b[r1 - 1, 1]) + 1))
+    n_chunks = len(spans)
     max_pos = max(p1 - p0 for _, _, p0, p1 in spans)
     max_rows = max(r1 - r0 for r0, r1, _, _ in spans)
-    u8 = [E.empty(max_pos, torch.uint8) for _ in range(2)]
-    rows = [torch.empty((max_rows, 2), dtype=torch.int64, device="cuda") for _ in range(2)]
+    vw, pw = int(L.kmap_valid_words(max_pos)), int(L.kmap_packed_words(max_pos))
+    # device side: two slots, used in the order the chunks are enqueued
+    d_u8 = [None, None]
+    d_packed = [E.empty(pw, torch.int32) for _ in range(2)]
+    d_valid = [E.empty(vw, torch.int32) for _ in range(2)]
+    d_strides = [E.empty(max_rows, torch.int32) for _ in range(2)]
+    d_offsets = E.empty(max_rows + 1, torch.int64)
+    d_borders = torch.empty((max_rows, 2), dtype=torch.int64, device="cuda")
+    d_scan = E.empty(int(L.kmap_list_scratch_words(max_rows)), torch.int64)
+    # host side: two staging slots for the encoder, two stride slots for the raw feeder
+    h_packed = [_pinned_staging(f"packed{i}", pw, torch.int32) for i in range(2)]
+    h_valid = [_pinned_staging(f"valid{i}", vw, torch.int32) for i in range(2)]
+    h_strides = [_pinned_staging(f"strides{i}", max_rows, torch.int32) for i in range(4)]
     compute = torch.cuda.current_stream()
     copy = _copy_stream()
     copy.wait_stream(compute)
-    uploaded = [None] * len(spans)
-    released = [None] * len(spans)
-
-    def upload(i):
-        r0, r1, p0, p1 = spans[i]
-        with torch.cuda.stream(copy):
-            if i >= 2:
-                copy.wait_event(released[i - 2])
-            u8[i % 2][:p1 - p0].copy_(seq_t[p0:p1], non_blocking=True)
-            rows[i % 2][:r1 - r0].copy_(b_t[r0:r1], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy)
-            uploaded[i] = ev
-
     flat, totals = E.alloc_tables(kmin, kmax)
     part_flat, part = E.alloc_tables(kmin, kmax)
+
+    lock = threading.Lock()
+    nxt = {"front": 0, "back": n_chunks - 1}
+
+    def take(side):
+        with lock:
+            if nxt["front"] > nxt["back"]:
+                return None
+            i = nxt[side]
+            nxt[side] += 1 if side == "front" else -1
+            return i
+
+    def strides_of(i, out: torch.Tensor):
+        r0, r1, p0, _ = spans[i]
+        rc = L.kmap_host_border_strides(b.ctypes.data + 16 * r0, r1 - r0, p0, out.data_ptr(), n_threads)
+        if rc != 0:
+            raise KmapError("boarder_mat rows are not back to back inside a chunk (kmer_count.py:335-343 layout expected)")
+
+    ready = queue.Queue()
+    staged_free = [threading.Event(), threading.Event()]          # set once the copy out of the staging slot has finished
+    for e in staged_free:
+        e.set()
+    staged_copy_done = [None, None]
+    failed = []
+
+    def encoder():
+        try:
+            j = 0
+            while True:
+                slot = j % 2
+                staged_free[slot].wait()
+                if staged_copy_done[slot] is not None:
+                    staged_copy_done[slot].synchronize()
+                i = take("front")
+                if i is None:
+                    break
+                staged_free[slot].clear()
+                _, _, p0, p1 = spans[i]
+                _check(L.kmap_host_pack2bit(seq_np.ctypes.data + p0, p1 - p0, h_packed[slot].data_ptr(), h_valid[slot].data_ptr(), n_threads),
+                       "kmap_host_pack2bit")
+                strides_of(i, h_strides[slot])
+                ready.put((i, slot))
+                j += 1
+        except BaseException as exc:           # surfaced by the main thread
+            failed.append(exc)
+        finally:
+            ready.put(None)
+
+    enc = None
+    if host_pack:
+        enc = threading.Thread(target=encoder, name="kmap-host-pack", daemon=True)
+        enc.start()
+    else:
+        ready.put(None)
+
     chunk = None
-    upload(0)
-    for i, (r0, r1, p0, p1) in enumerate(spans):
-        if i + 1 < len(spans):
-            upload(i + 1)
-        compute.wait_event(uploaded[i])
-        borders_d = rows[i % 2][:r1 - r0]
-        _check(L.kmap_rebase_borders(borders_d.data_ptr(), r1 - r0, p0, compute.cuda_stream), "kmap_rebase_borders")
+    released = []                    # per enqueued chunk: event recorded when its count has finished (device slot free again)
+    raw_done = None                  # event behind the raw copy in flight
+    n_raw = 0
+    encoder_finished = False
+    counted = 0
+
+    def device_slot():
+        k_ = len(released)
+        if k_ >= 2:
+            copy.wait_event(released[k_ - 2])
+        return k_ % 2
+
+    def count_chunk(i, slot, uploaded):
+        nonlocal chunk, counted
+        r0, r1, p0, p1 = spans[i]
+        compute.wait_event(uploaded)
+        _check(L.kmap_borders_from_strides(d_strides[slot].data_ptr(), r1 - r0, d_offsets.data_ptr(), d_borders.data_ptr(),
+                                           d_scan.data_ptr(), compute.cuda_stream), "kmap_borders_from_strides")
+        borders_d = d_borders[:r1 - r0]
         if chunk is None:
-            chunk = E.SeqOnDevice.from_device_u8(u8[i % 2][:p1 - p0], borders_d, capacity=max_pos)
+            chunk = E.SeqOnDevice(p1 - p0, d_packed[slot], d_valid[slot], borders_d, r1 - r0)
         else:
-            chunk.rebind(u8[i % 2][:p1 - p0], borders_d)
-        chunk.count_all(kmin, kmax, dedup=not rep_mode, tables=totals if i == 0 else part)
-        if i > 0:
+            chunk.rebind_packed(p1 - p0, d_packed[slot], d_valid[slot], borders_d)
+        chunk.count_all(kmin, kmax, dedup=not rep_mode, tables=totals if counted == 0 else part)
+        if counted > 0:
             _check(L.kmap_add_u32(flat.data_ptr(), part_flat.data_ptr(), flat.numel(), compute.cuda_stream), "kmap_add_u32")
+        counted += 1
         ev = torch.cuda.Event()
         ev.record(compute)
-        released[i] = ev
+        released.append(ev)
+
+    import time
+    while True:
+        item = None
+        if encoder_finished and raw_done is not None and not raw_done.query():
+            time.sleep(0.0001)                              # nothing to do until the raw copy in flight has landed
+        if not encoder_finished:
+            try:
+                item = ready.get(timeout=0.0002) if (raw_done is not None and not raw_done.query()) or nxt["front"] > nxt["back"] \
+                    else ready.get_nowait()
+            except queue.Empty:
+                item = False
+            if item is None:
+                encoder_finished = True
+        if item:                                            # a chunk re-encoded by the host: ship it packed
+            i, hs = item
+            r0, r1, p0, p1 = spans[i]
+            slot = device_slot()
+            with torch.cuda.stream(copy):
+                n_vw = int(L.kmap_valid_words(p1 - p0))
+                d_packed[slot][:2 * n_vw].copy_(h_packed[hs][:2 * n_vw], non_blocking=True)
+                d_valid[slot][:n_vw].copy_(h_valid[hs][:n_vw], non_blocking=True)
+                d_strides[slot][:r1 - r0].copy_(h_strides[hs][:r1 - r0], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            staged_copy_done[hs] = ev
+            staged_free[hs].set()
+            count_chunk(i, slot, ev)
+            continue
+        if raw_done is None or raw_done.query():            # the link is free of raw copies: ship one chunk as it is
+            i = take("back")
+            if i is not None:
+                r0, r1, p0, p1 = spans[i]
+                hs = 2 + n_raw % 2
+                n_raw += 1
+                strides_of(i, h_strides[hs])
+                slot = device_slot()
+                if d_u8[slot] is None:
+                    d_u8[slot] = E.empty(max_pos, torch.uint8)
+                with torch.cuda.stream(copy):
+                    d_u8[slot][:p1 - p0].copy_(seq_t[p0:p1], non_blocking=True)
+                    d_strides[slot][:r1 - r0].copy_(h_strides[hs][:r1 - r0], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy)
+                raw_done = ev
+                compute.wait_event(ev)
+                _check(L.kmap_pack2bit(d_u8[slot].data_ptr(), p1 - p0, d_packed[slot].data_ptr(), d_valid[slot].data_ptr(),
+                                       compute.cuda_stream), "kmap_pack2bit")
+                count_chunk(i, slot, ev)
+                continue
+        if encoder_finished and nxt["front"] > nxt["back"]:
+            break
+    if enc is not None:
+        enc.join()
+    if failed:
+        raise failed[0]
+    assert counted == n_chunks
     return flat, totals, len(seq_np_arr)
 
 

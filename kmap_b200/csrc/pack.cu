@@ -92,9 +92,32 @@ __global__ void rebase_borders_kernel(int64_t* __restrict__ borders, int64_t n_v
     for (; i < n_values; i += stride) borders[i] -= offset;
 }
 
+// offsets[r] = sum of the strides of reads < r (int64[n_seq + 1]) -> rows [start, separator index] of the border matrix
+__global__ void borders_from_offsets_kernel(const int64_t* __restrict__ offsets, int64_t n_seq, int64_t* __restrict__ borders) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; r < n_seq; r += stride) {
+        const int64_t st = __ldg(offsets + r), nx = __ldg(offsets + r + 1);
+        reinterpret_cast<longlong2*>(borders)[r] = make_longlong2(st, nx - 1);
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int kmap_borders_from_strides(const uint32_t* strides, int64_t n_seq, int64_t* offsets, int64_t* borders_out, uint64_t* scratch, void* stream) {
+    KMAP_REQUIRE(n_seq >= 0, "negative size");
+    if (n_seq == 0) return KMAP_OK;
+    KMAP_REQUIRE(strides && offsets && borders_out && scratch, "null pointer");
+    KMAP_REQUIRE(((uintptr_t)borders_out & 15) == 0, "the border matrix must be 16-byte aligned");
+    int rc = kmap_exclusive_scan_u32(strides, n_seq, offsets, scratch, stream);
+    if (rc) return rc;
+    int64_t g = (n_seq + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    borders_from_offsets_kernel<<<(unsigned int)g, 256, 0, as_stream(stream)>>>(offsets, n_seq, borders_out);
+    return kmap_check_launch("borders_from_strides");
+}
 
 int kmap_add_u32(uint32_t* dst, const uint32_t* src, int64_t n_words, void* stream) {
     KMAP_REQUIRE(n_words >= 0, "negative size");

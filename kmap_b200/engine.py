@@ -139,6 +139,22 @@ class SeqOnDevice:
         self.n, self.borders, self.n_seq = n, borders, (0 if borders is None else int(borders.shape[0]))
         self.seq_u8, self._valid0 = None, None
 
+    def rebind_packed(self, n: int, packed: torch.Tensor, valid: torch.Tensor, borders: Optional[torch.Tensor]):
+        """re-use this object (every scratch buffer) for another chunk of at most the same size that is ALREADY in the packed
+        form (uploaded packed, or packed into these buffers by the caller)"""
+        L = lib()
+        if valid.numel() < L.kmap_valid_words(n) or packed.numel() < L.kmap_packed_words(n):
+            raise KmapError("rebind_packed: buffers too small for the chunk")
+        if self._dupmask_words() and valid.numel() > self._dupmask_words():
+            self._dupmask = None
+        self.n, self.packed, self.valid, self.borders = n, packed, valid, borders
+        self.n_seq = 0 if borders is None else int(borders.shape[0])
+        self.seq_u8, self._valid0 = None, None
+
+    def _dupmask_words(self) -> int:
+        d = getattr(self, "_dupmask", None)
+        return 0 if d is None else int(d.numel())
+
     @classmethod
     def from_numpy(cls, seq_np_arr: np.ndarray, boarder_mat: Optional[np.ndarray] = None, keep_u8: bool = False,
                    validate: bool = True) -> "SeqOnDevice":

@@ -419,8 +419,10 @@ def test_scan_motif_workflow_testfa(MD, K, testfa, tmp_path):
 
 
 def test_streamed_count_kmers_equals_single_upload(ENG):
-    """api.count_kmers with the reads streamed through the device in chunks (double-buffered H2D on a copy stream) returns
-    the same lists as one upload, in both modes; reads of every path (warp / block / bitmap) sit in different chunks"""
+    """api.count_kmers with the reads streamed through the device in chunks (some re-encoded by the host cores and shipped
+    packed, some shipped as they are and packed on the device, whichever feeder gets to them first; or all shipped as they
+    are) returns the same lists as one upload, in both modes; reads of every path (warp / block / bitmap) sit in different
+    chunks"""
     from kmap_b200 import api
     rng = np.random.default_rng(4242)
     special = ["A" * 80, "CA" * 60, "", "N", "ACGTTGCA" * 150, ("ACGTAGCTAGCTAGGATCGAT" * 1500)[:30000], "ACGTTGCAAC" * 40]
@@ -428,12 +430,45 @@ def test_streamed_count_kmers_equals_single_upload(ENG):
     for rep_mode in (False, True):
         one = api.count_kmers(seq, borders, range(8, 15), rep_mode=rep_mode, chunk_positions=1 << 40)
         many = api.count_kmers(seq, borders, range(8, 15), rep_mode=rep_mode, chunk_positions=len(seq) // 7)
+        raw = api.count_kmers(seq, borders, range(8, 15), rep_mode=rep_mode, chunk_positions=len(seq) // 23, host_pack=False)
         assert api._chunk_bounds(seq, borders, len(seq) // 7) is not None
         for k in range(8, 15):
             assert np.array_equal(one[k][0], many[k][0]) and np.array_equal(one[k][1], many[k][1]), (k, rep_mode)
+            assert np.array_equal(one[k][0], raw[k][0]) and np.array_equal(one[k][1], raw[k][1]), (k, rep_mode)
         want = O.merge_revcom(*O.count_uniq_hash(O.comp_kmer_hash(seq, 11) if rep_mode else
                                                  O.remove_duplicate_hash_per_seq(O.comp_kmer_hash(seq, 11), borders, np.uint32(0xFFFFFFFF)), 11), 11)
         assert np.array_equal(many[11][0], want[0]) and np.array_equal(many[11][1], want[1])
+
+
+def test_host_encoders_equal_device_pack(ENG):
+    """kmap_host_pack2bit (csrc/host_pack.cpp) writes the words kmap_pack2bit writes on the device, and the border matrix
+    rebuilt on the device from the per-read strides equals the matrix (kmer_count.py:335-343 layout)"""
+    import torch
+    from kmap_b200._lib import lib
+    L = lib()
+    rng = np.random.default_rng(8)
+    for n_reads in (0, 1, 700, 40000):
+        _, seq, borders = rand_reads(rng, n_reads, 0, 150, p_n=0.02, special=["ACGT"])
+        seq = seq.copy()
+        seq[rng.random(len(seq)) < 0.001] = 7                          # any byte above 3 is a missing value
+        n = len(seq)
+        dev = ENG.SeqOnDevice.from_numpy(seq, borders)
+        nw = int(L.kmap_valid_words(n))
+        packed, valid = np.zeros(2 * nw, np.uint32), np.zeros(nw, np.uint32)
+        for th in (1, 5):
+            assert L.kmap_host_pack2bit(seq.ctypes.data, n, packed.ctypes.data, valid.ctypes.data, th) == 0
+            assert np.array_equal(packed, ENG.to_host(dev.packed, np.uint32)[:2 * nw])
+            assert np.array_equal(valid, ENG.to_host(dev.valid, np.uint32)[:nw])
+        m = len(borders)
+        strides = np.zeros(m, np.uint32)
+        shifted = borders + 12345
+        assert L.kmap_host_border_strides(shifted.ctypes.data, m, 12345, strides.ctypes.data, 3) == 0
+        d_str = ENG.to_device(strides)
+        off = ENG.empty(m + 1, torch.int64)
+        out = torch.empty((m, 2), dtype=torch.int64, device="cuda")
+        scr = ENG.empty(int(L.kmap_list_scratch_words(m)), torch.int64)
+        ENG.check(L.kmap_borders_from_strides(d_str.data_ptr(), m, off.data_ptr(), out.data_ptr(), scr.data_ptr(), None), "borders_from_strides")
+        assert np.array_equal(out.cpu().numpy(), borders)
 
 
 # ---- preproc ingest (csrc/fasta.cu) -------------------------------------------------------------------------------------
