@@ -439,7 +439,31 @@ def main():
                    "frac_of_hbm_copy_peak": (row1 - row0) * n_h / ms_h / 1e6 / peak,
                    "note": "uint8 output, 1 B per pair; same-label pairs of the 12-base consensus use the head distance; includes the "
                            "H2D of the keys and labels; a B200 writes at most ~3.9 TB/s (the copy peak counts a read and a write)"}
-        del out_h
+        # the comparator BASELINE config 5 names: the same rows as an int8 one-hot GEMM on the tcgen05 tensor cores
+        # (csrc/hamdist_mma.cu, hand-written tcgen05.mma.kind::i8 + TMEM epilogue); the output must be bit-identical
+        from kmap_b200.motif_discovery import hamdist_matrix_onehot_mma
+        out_g = E.empty((row1 - row0) * n_h, torch.uint8)
+        hamdist_matrix_onehot_mma(khs, labels_h, [14, 12], k_h, row0, row1, out=out_g)     # warm-up
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            hamdist_matrix_onehot_mma(khs, labels_h, [14, 12], k_h, row0, row1, out=out_g)
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1) / 5], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        ms_g = float(tg.item())
+        same = bool(torch.equal(out_g, out_h))
+        checks["hamdist_onehot_gemm_equals_popcount"] = same
+        hamdist["onehot_tcgen05_gemm"] = {
+            "ms": ms_g, "pairs_per_s": n_h * n_h / ms_g * 1e3, "identical_output": same, "popcount_over_gemm_time": ms_h / ms_g,
+            "mma": "tcgen05.mma.cta_group::1.kind::i8, M=128 N=256 K=2x32 per 128x256 tile, S32 accumulators in TMEM (2 x 256 columns)",
+            "note": "one-hot A x complement-one-hot B^T gives the distance itself; 2 x 56 int8 MACs per pair = 1.1e12 MACs = under 0.3 ms "
+                    "of tensor time: both formulations are bound by the 1 B/pair store, so the simpler popcount kernel is kept "
+                    "(DESIGN.md section 4.7)"}
+        del out_h, out_g
 
     # ---- end-to-end through the public API with host buffers -------------------------------------------------------------
     e2e = None
@@ -472,12 +496,17 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        io_bytes = torch.tensor([seq_np.nbytes + borders_np.nbytes, d2h], device="cuda", dtype=torch.int64)
+        stats = api.last_stream_stats or {}
+        h2d = stats.get("h2d_bytes", seq_np.nbytes + borders_np.nbytes)     # bytes that crossed the link (chunks re-encoded by the host travel packed)
+        io_bytes = torch.tensor([h2d, d2h], device="cuda", dtype=torch.int64)
         if world > 1:
             dist.all_reduce(io_bytes)                  # bytes copied by all ranks together
         e2e = {"value": n_total * L * (KMAX - KMIN + 1) / dt / 1e9, "unit": "Gbases/s",
                "h2d_bytes_per_step": int(io_bytes[0].item()), "d2h_bytes_per_step": int(io_bytes[1].item()),
-               "ms_per_step": dt * 1e3, "steps": n_e2e,
+               "ms_per_step": dt * 1e3, "steps": n_e2e, "host_input_bytes": int(seq_np.nbytes + borders_np.nbytes) * world,
+               "feeders": {k_: stats.get(k_) for k_ in ("chunks", "raw_chunks")},
+               "transport": "chunks of reads re-encoded by the host cores into the packed form (0.375 B/position, csrc/host_pack.cpp) "
+                            "or shipped as they are, whichever feeder reaches them first; border rows as uint32 strides",
                "api": "kmap_b200.api.count_kmers(seq_np_arr, boarder_mat, k=8..14) -> {k: (uniq_kh_arr, uniq_kh_cnt_arr)}"
                       + ("; every rank uploads its shard of the reads and returns the key-range slice of every merged list "
                          "(lists_on='sharded': the slices of ranks 0..N-1 concatenate to the reference's list); "

@@ -267,6 +267,12 @@ int kmap_hamdist_matrix_u32(const uint32_t* kh, const int32_t* labels, int64_t n
                             int n_labels, int64_t row0, int64_t row1, uint8_t* out, void* stream);
 int kmap_hamdist_matrix_u64(const uint64_t* kh, const int32_t* labels, int64_t n, int k, const int32_t* head_len,
                             int n_labels, int64_t row0, int64_t row1, uint8_t* out, void* stream);
+/* The same matrix (k <= 16) computed as an int8 one-hot GEMM on the tcgen05 tensor cores (csrc/hamdist_mma.cu): the
+ * comparator the XOR/popcount kernel is benchmarked against (BASELINE north_star, config 5); bit-identical output.
+ * scratch = kmap_hamdist_mma_scratch_bytes(n) bytes of device memory, 256-byte aligned (the one-hot operands). */
+int64_t kmap_hamdist_mma_scratch_bytes(int64_t n);
+int kmap_hamdist_matrix_onehot_mma(const uint32_t* kh, const int32_t* labels, int64_t n, int k, const int32_t* head_len, int n_labels,
+                                   int64_t row0, int64_t row1, uint8_t* out, void* scratch, int64_t scratch_bytes, void* stream);
 
 /* exclusive prefix sum of uint32 counts into int64 offsets (out[n] = total); scratch = uint64[kmap_list_scratch_words(n)] */
 int kmap_exclusive_scan_u32(const uint32_t* in, int64_t n, int64_t* out, uint64_t* scratch, void* stream);

@@ -216,7 +216,7 @@ def upload_reads(seq_np_arr: np.ndarray, boarder_mat: Optional[np.ndarray], vali
 
 def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterable[int], rep_mode: bool = False,
                 revcom_mode: bool = True, validate: bool = True, table_allreduce: Optional[TableAllReduce] = None,
-                lists_on: Optional[int] = None, chunk_positions: int = 1 << 28,
+                lists_on: Optional[int] = None, chunk_positions: int = 1 << 29,
                 host_pack: Optional[bool] = None) -> Dict[int, Tuple[np.ndarray, np.ndarray]]:
     """First-round counts of find_motif for every k (reference motif_discovery.py:627-640): per k the
     `(uniq_kh_arr uint32, uniq_kh_cnt_arr int32)` pair that the reference pickles into kmer_count/k{k}.pkl, in the
@@ -304,11 +304,11 @@ def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterabl
 _copy_streams = {}
 
 
-def _copy_stream() -> torch.cuda.Stream:
-    dev = torch.cuda.current_device()
-    if dev not in _copy_streams:
-        _copy_streams[dev] = torch.cuda.Stream()
-    return _copy_streams[dev]
+def _copy_stream(which: int = 0) -> torch.cuda.Stream:
+    key = (torch.cuda.current_device(), which)
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream()
+    return _copy_streams[key]
 
 
 def _upper_bound(n: int, k: int) -> int:
@@ -354,6 +354,14 @@ def _chunk_bounds(seq_np_arr: np.ndarray, boarder_mat, chunk_positions: int):
 _staging = {}
 
 
+def _os_environ_get(key, default):
+    import os
+    return os.environ.get(key, default)
+
+last_stream_trace = None
+last_stream_stats = None
+
+
 def _pinned_staging(tag: str, n: int, dtype: torch.dtype) -> torch.Tensor:
     """pinned host staging buffer of at least n elements, kept between calls (pinning memory costs ~0.3 s per GB)"""
     key = (tag, dtype)
@@ -367,7 +375,9 @@ def _pinned_staging(tag: str, n: int, dtype: torch.dtype) -> torch.Tensor:
 def host_pack_threads(world_local: int = 1) -> int:
     """host threads one process may use for re-encoding (all hardware threads, shared by the ranks of the box)"""
     import os
-    n = int(os.environ.get("KMAP_HOST_THREADS", "0")) or int(_lib().kmap_host_threads())
+    n = int(os.environ.get("KMAP_HOST_THREADS", "0"))
+    if n <= 0:                       # all hardware threads but two: the feeder and the counting thread need to run too
+        n = max(1, int(_lib().kmap_host_threads()) - 2)
     return max(1, n // max(1, world_local))
 
 
@@ -402,26 +412,43 @@ def count_tables_streamed(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, kmin:
     max_pos = max(p1 - p0 for _, _, p0, p1 in spans)
     max_rows = max(r1 - r0 for r0, r1, _, _ in spans)
     vw, pw = int(L.kmap_valid_words(max_pos)), int(L.kmap_packed_words(max_pos))
-    # device side: two slots, used in the order the chunks are enqueued
-    d_u8 = [None, None]
-    d_packed = [E.empty(pw, torch.int32) for _ in range(2)]
-    d_valid = [E.empty(vw, torch.int32) for _ in range(2)]
-    d_strides = [E.empty(max_rows, torch.int32) for _ in range(2)]
+    # device side: slots used in the order the chunks are enqueued; enough of them that neither the link nor the count
+    # waits for the other over a few chunks (a slot is 0.375 B/position, + 1 B/position if a raw chunk ever lands in it)
+    n_slots = min(int(_os_environ_get('KMAP_STREAM_SLOTS', '6')), n_chunks)
+    d_u8 = [None] * n_slots
+    d_packed = [E.empty(pw, torch.int32) for _ in range(n_slots)]
+    d_valid = [E.empty(vw, torch.int32) for _ in range(n_slots)]
+    d_strides = [E.empty(max_rows, torch.int32) for _ in range(n_slots)]
     d_offsets = E.empty(max_rows + 1, torch.int64)
     d_borders = torch.empty((max_rows, 2), dtype=torch.int64, device="cuda")
     d_scan = E.empty(int(L.kmap_list_scratch_words(max_rows)), torch.int64)
     # host side: two staging slots for the encoder, two stride slots for the raw feeder
-    h_packed = [_pinned_staging(f"packed{i}", pw, torch.int32) for i in range(2)]
-    h_valid = [_pinned_staging(f"valid{i}", vw, torch.int32) for i in range(2)]
-    h_strides = [_pinned_staging(f"strides{i}", max_rows, torch.int32) for i in range(4)]
+    N_STAGED = 4
+    h_packed = [_pinned_staging(f"packed{i}", pw, torch.int32) for i in range(N_STAGED)]
+    h_valid = [_pinned_staging(f"valid{i}", vw, torch.int32) for i in range(N_STAGED)]
+    max_raw = int(_os_environ_get('KMAP_STREAM_MAX_RAW', '1')) if host_pack else 2      # raw copies queued on the link at a time
+    h_strides = [_pinned_staging(f"strides{i}", max_rows, torch.int32) for i in range(N_STAGED + max_raw + 1)]
     compute = torch.cuda.current_stream()
+    # two copy streams: the packed chunks do not queue behind the (2.7 x longer) raw copies, so the encoder gets its staging
+    # slots back as soon as the link has taken them
     copy = _copy_stream()
+    copy_packed = _copy_stream(1)
     copy.wait_stream(compute)
+    copy_packed.wait_stream(compute)
     flat, totals = E.alloc_tables(kmin, kmax)
     part_flat, part = E.alloc_tables(kmin, kmax)
 
     lock = threading.Lock()
     nxt = {"front": 0, "back": n_chunks - 1}
+    import os as _os
+    import time as _time
+    trace = [] if _os.environ.get("KMAP_STREAM_TRACE") else None       # (debugging aid: host-side timeline of the three threads)
+    t_origin = _time.perf_counter()
+
+    def mark(what, i=-1):
+        if trace is not None:
+            trace.append((round(1e3 * (_time.perf_counter() - t_origin), 2), threading.current_thread().name, what, i))
+    mark("setup done")
 
     def take(side):
         with lock:
@@ -438,17 +465,17 @@ def count_tables_streamed(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, kmin:
             raise KmapError("boarder_mat rows are not back to back inside a chunk (kmer_count.py:335-343 layout expected)")
 
     ready = queue.Queue()
-    staged_free = [threading.Event(), threading.Event()]          # set once the copy out of the staging slot has finished
+    staged_free = [threading.Event() for _ in range(N_STAGED)]    # set once the copy out of the staging slot has been queued
     for e in staged_free:
         e.set()
-    staged_copy_done = [None, None]
+    staged_copy_done = [None] * N_STAGED
     failed = []
 
     def encoder():
         try:
             j = 0
             while True:
-                slot = j % 2
+                slot = j % N_STAGED
                 staged_free[slot].wait()
                 if staged_copy_done[slot] is not None:
                     staged_copy_done[slot].synchronize()
@@ -457,9 +484,11 @@ def count_tables_streamed(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, kmin:
                     break
                 staged_free[slot].clear()
                 _, _, p0, p1 = spans[i]
+                mark("pack begin", i)
                 _check(L.kmap_host_pack2bit(seq_np.ctypes.data + p0, p1 - p0, h_packed[slot].data_ptr(), h_valid[slot].data_ptr(), n_threads),
                        "kmap_host_pack2bit")
                 strides_of(i, h_strides[slot])
+                mark("pack end", i)
                 ready.put((i, slot))
                 j += 1
         except BaseException as exc:           # surfaced by the main thread
@@ -474,93 +503,161 @@ def count_tables_streamed(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, kmin:
     else:
         ready.put(None)
 
-    chunk = None
+    # The count of a chunk ends with a host synchronisation (the per-read scan reports reads beyond its on-chip paths), so
+    # it runs on a thread of its own: this thread keeps the link busy meanwhile.
+    N_SLOTS = len(d_packed)
+    slots_free = threading.Semaphore(N_SLOTS)
     released = []                    # per enqueued chunk: event recorded when its count has finished (device slot free again)
-    raw_done = None                  # event behind the raw copy in flight
+    to_count = queue.Queue()
+    device_index = torch.cuda.current_device()
+
+    def counter():
+        chunk = None
+        counted = 0
+        try:
+            torch.cuda.set_device(device_index)
+            with torch.cuda.stream(compute):
+                while True:
+                    item = to_count.get()
+                    if item is None:
+                        break
+                    i, slot, uploaded, raw = item
+                    r0, r1, p0, p1 = spans[i]
+                    mark("count begin (host)", i)
+                    if trace is not None:
+                        uploaded.synchronize()
+                        mark("upload landed", i)
+                    compute.wait_event(uploaded)
+                    if raw:
+                        _check(L.kmap_pack2bit(d_u8[slot].data_ptr(), p1 - p0, d_packed[slot].data_ptr(), d_valid[slot].data_ptr(),
+                                               compute.cuda_stream), "kmap_pack2bit")
+                    _check(L.kmap_borders_from_strides(d_strides[slot].data_ptr(), r1 - r0, d_offsets.data_ptr(), d_borders.data_ptr(),
+                                                       d_scan.data_ptr(), compute.cuda_stream), "kmap_borders_from_strides")
+                    borders_d = d_borders[:r1 - r0]
+                    if chunk is None:
+                        chunk = E.SeqOnDevice(p1 - p0, d_packed[slot], d_valid[slot], borders_d, r1 - r0)
+                    else:
+                        chunk.rebind_packed(p1 - p0, d_packed[slot], d_valid[slot], borders_d)
+                    chunk.count_all(kmin, kmax, dedup=not rep_mode, tables=totals if counted == 0 else part)
+                    if counted > 0:
+                        _check(L.kmap_add_u32(flat.data_ptr(), part_flat.data_ptr(), flat.numel(), compute.cuda_stream), "kmap_add_u32")
+                    counted += 1
+                    ev = torch.cuda.Event()
+                    ev.record(compute)
+                    released.append(ev)
+                    slots_free.release()
+                    if trace is not None:
+                        ev.synchronize()
+                    mark("count end", i)
+        except BaseException as exc:
+            failed.append(exc)
+            for _ in range(n_chunks + N_SLOTS):          # let the feeder run to its end
+                slots_free.release()
+
+    cnt_thread = threading.Thread(target=counter, name="kmap-count", daemon=True)
+    cnt_thread.start()
+
+    n_enq = 0
+
+    def device_slot(stream):
+        nonlocal n_enq
+        slots_free.acquire()                                # the count that used this slot N_SLOTS chunks ago has been queued ...
+        if n_enq >= N_SLOTS and not failed:
+            stream.wait_event(released[n_enq - N_SLOTS])    # ... and the copy waits until it has finished
+        n_enq += 1
+        return (n_enq - 1) % N_SLOTS
+
+    raw_events = []                  # events behind the raw copies in flight
+    copy_events = []
     n_raw = 0
     encoder_finished = False
-    counted = 0
-
-    def device_slot():
-        k_ = len(released)
-        if k_ >= 2:
-            copy.wait_event(released[k_ - 2])
-        return k_ % 2
-
-    def count_chunk(i, slot, uploaded):
-        nonlocal chunk, counted
-        r0, r1, p0, p1 = spans[i]
-        compute.wait_event(uploaded)
-        _check(L.kmap_borders_from_strides(d_strides[slot].data_ptr(), r1 - r0, d_offsets.data_ptr(), d_borders.data_ptr(),
-                                           d_scan.data_ptr(), compute.cuda_stream), "kmap_borders_from_strides")
-        borders_d = d_borders[:r1 - r0]
-        if chunk is None:
-            chunk = E.SeqOnDevice(p1 - p0, d_packed[slot], d_valid[slot], borders_d, r1 - r0)
-        else:
-            chunk.rebind_packed(p1 - p0, d_packed[slot], d_valid[slot], borders_d)
-        chunk.count_all(kmin, kmax, dedup=not rep_mode, tables=totals if counted == 0 else part)
-        if counted > 0:
-            _check(L.kmap_add_u32(flat.data_ptr(), part_flat.data_ptr(), flat.numel(), compute.cuda_stream), "kmap_add_u32")
-        counted += 1
-        ev = torch.cuda.Event()
-        ev.record(compute)
-        released.append(ev)
-
     import time
-    while True:
-        item = None
-        if encoder_finished and raw_done is not None and not raw_done.query():
-            time.sleep(0.0001)                              # nothing to do until the raw copy in flight has landed
-        if not encoder_finished:
-            try:
-                item = ready.get(timeout=0.0002) if (raw_done is not None and not raw_done.query()) or nxt["front"] > nxt["back"] \
-                    else ready.get_nowait()
-            except queue.Empty:
-                item = False
-            if item is None:
-                encoder_finished = True
-        if item:                                            # a chunk re-encoded by the host: ship it packed
-            i, hs = item
-            r0, r1, p0, p1 = spans[i]
-            slot = device_slot()
-            with torch.cuda.stream(copy):
-                n_vw = int(L.kmap_valid_words(p1 - p0))
-                d_packed[slot][:2 * n_vw].copy_(h_packed[hs][:2 * n_vw], non_blocking=True)
-                d_valid[slot][:n_vw].copy_(h_valid[hs][:n_vw], non_blocking=True)
-                d_strides[slot][:r1 - r0].copy_(h_strides[hs][:r1 - r0], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy)
-            staged_copy_done[hs] = ev
-            staged_free[hs].set()
-            count_chunk(i, slot, ev)
-            continue
-        if raw_done is None or raw_done.query():            # the link is free of raw copies: ship one chunk as it is
-            i = take("back")
-            if i is not None:
+    try:
+        while not failed:
+            raw_events = [e for e in raw_events if not e.query()]
+            chunks_left = nxt["front"] <= nxt["back"]
+            can_raw = chunks_left and len(raw_events) < max_raw
+            item = False
+            if not encoder_finished:
+                try:
+                    item = ready.get_nowait() if can_raw else ready.get(timeout=0.0002)
+                except queue.Empty:
+                    item = False
+                if item is None:
+                    encoder_finished = True
+            elif not can_raw:
+                if not chunks_left:
+                    break
+                time.sleep(0.0001)                          # nothing to do until a raw copy in flight has landed
+            if item:                                        # a chunk re-encoded by the host: ship it packed
+                i, hs = item
                 r0, r1, p0, p1 = spans[i]
-                hs = 2 + n_raw % 2
+                slot = device_slot(copy_packed)
+                with torch.cuda.stream(copy_packed):
+                    if trace is not None:
+                        ev0 = torch.cuda.Event(enable_timing=True)
+                        ev0.record(copy_packed)
+                    n_vw = int(L.kmap_valid_words(p1 - p0))
+                    d_packed[slot][:2 * n_vw].copy_(h_packed[hs][:2 * n_vw], non_blocking=True)
+                    d_valid[slot][:n_vw].copy_(h_valid[hs][:n_vw], non_blocking=True)
+                    d_strides[slot][:r1 - r0].copy_(h_strides[hs][:r1 - r0], non_blocking=True)
+                    ev = torch.cuda.Event(enable_timing=trace is not None)
+                    ev.record(copy_packed)
+                if trace is not None:
+                    copy_events.append(("packed", i, ev0, ev))
+                staged_copy_done[hs] = ev
+                staged_free[hs].set()
+                mark("packed copy enqueued", i)
+                to_count.put((i, slot, ev, False))
+                continue
+            if can_raw:                                     # the link has room: ship one chunk as it is
+                i = take("back")
+                if i is None:
+                    continue
+                r0, r1, p0, p1 = spans[i]
+                hs = N_STAGED + n_raw % (max_raw + 1)
                 n_raw += 1
                 strides_of(i, h_strides[hs])
-                slot = device_slot()
+                slot = device_slot(copy)
                 if d_u8[slot] is None:
                     d_u8[slot] = E.empty(max_pos, torch.uint8)
                 with torch.cuda.stream(copy):
+                    if trace is not None:
+                        ev0 = torch.cuda.Event(enable_timing=True)
+                        ev0.record(copy)
                     d_u8[slot][:p1 - p0].copy_(seq_t[p0:p1], non_blocking=True)
                     d_strides[slot][:r1 - r0].copy_(h_strides[hs][:r1 - r0], non_blocking=True)
-                    ev = torch.cuda.Event()
+                    ev = torch.cuda.Event(enable_timing=trace is not None)
                     ev.record(copy)
-                raw_done = ev
-                compute.wait_event(ev)
-                _check(L.kmap_pack2bit(d_u8[slot].data_ptr(), p1 - p0, d_packed[slot].data_ptr(), d_valid[slot].data_ptr(),
-                                       compute.cuda_stream), "kmap_pack2bit")
-                count_chunk(i, slot, ev)
-                continue
-        if encoder_finished and nxt["front"] > nxt["back"]:
-            break
-    if enc is not None:
-        enc.join()
+                if trace is not None:
+                    copy_events.append(("raw", i, ev0, ev))
+                raw_events.append(ev)
+                mark("raw copy enqueued", i)
+                to_count.put((i, slot, ev, True))
+    finally:
+        with lock:                                          # (on an error: no more chunks for the encoder)
+            nxt["front"] = nxt["back"] + 1
+        for e in staged_free:
+            e.set()
+        to_count.put(None)
+        cnt_thread.join()
+        if enc is not None:
+            enc.join()
     if failed:
         raise failed[0]
+    compute.synchronize()
+    mark("all counted")
+    global last_stream_stats
+    h2d = sum((p1 - p0) if i >= n_chunks - n_raw else 12 * int(L.kmap_valid_words(p1 - p0)) for i, (_, _, p0, p1) in enumerate(spans))
+    last_stream_stats = {"chunks": n_chunks, "raw_chunks": n_raw, "stream_ms": round(1e3 * (_time.perf_counter() - t_origin), 1),
+                         "h2d_bytes": int(h2d + 4 * len(b))}
+    if trace is not None:
+        global last_stream_trace
+        first = copy_events[0][2] if copy_events else None
+        for kind, i, e0, e1 in copy_events:
+            trace.append((round(first.elapsed_time(e0), 2), "copy-engine", f"{kind} copy {round(e0.elapsed_time(e1), 2)} ms", i))
+        last_stream_trace = trace
+    counted = len(released)
     assert counted == n_chunks
     return flat, totals, len(seq_np_arr)
 

@@ -8,6 +8,7 @@
 // fallback: no k-mer is hashed or counted here.  No CUDA in this file (plain C++, AVX2 when the CPU has it).
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -31,23 +32,52 @@ inline void pack32_scalar(const uint8_t* p, uint32_t& valid, uint32_t& hi, uint3
     lo = (uint32_t)bits;
 }
 
-__attribute__((target("avx2"))) void pack_range_avx2(const uint8_t* seq, int64_t w0, int64_t w1, uint32_t* packed, uint32_t* valid) {
+// 32 bytes -> validity word + the two packed words (as one 64-bit value, hi word in the low half = packed[2w])
+#define KMAP_PACK32(x, vword, both)                                                                                   \
+    do {                                                                                                              \
+        const __m256i ok_ = _mm256_cmpeq_epi8(_mm256_and_si256(x, fc), zero);          /* 0xFF where the byte is 0..3 */ \
+        vword = (uint32_t)_mm256_movemask_epi8(ok_);                                                                  \
+        const __m256i code_ = _mm256_and_si256(x, _mm256_and_si256(ok_, three));       /* invalid bases packed as 0 */   \
+        const __m256i r_ = _mm256_shuffle_epi8(_mm256_madd_epi16(_mm256_maddubs_epi16(code_, mul1), mul2), pick);     \
+        both = (uint64_t)(uint32_t)_mm256_extract_epi32(r_, 0) | ((uint64_t)(uint32_t)_mm256_extract_epi32(r_, 4) << 32); \
+    } while (0)
+
+// nt: 0 = plain stores, 1 = whole 32-byte vectors of results written with streaming stores (the words are next read by the
+// copy engine, not by this core: no read-for-ownership of the staging lines, no cache pollution)
+__attribute__((target("avx2"))) void pack_range_avx2(const uint8_t* seq, int64_t w0, int64_t w1, uint32_t* packed, uint32_t* valid, int nt) {
     const __m256i fc = _mm256_set1_epi8((char)0xFC), three = _mm256_set1_epi8(3), zero = _mm256_setzero_si256();
     const __m256i mul1 = _mm256_set1_epi16(0x0104);            // maddubs: byte0 * 4 + byte1 (first base higher)
     const __m256i mul2 = _mm256_set1_epi32(0x00010010);        // madd: half0 * 16 + half1
     // byte 0 of the four 32-bit lanes of each 128-bit half, last lane first: the little-endian word then has q0 on top
     const __m256i pick = _mm256_setr_epi8(12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
                                           12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
-    for (int64_t w = w0; w < w1; ++w) {
+    int64_t w = w0;
+    if (nt && ((reinterpret_cast<uintptr_t>(valid) | reinterpret_cast<uintptr_t>(packed)) & 31) == 0) {
+        for (; w < w1 && (w & 7); ++w) {
+            const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(seq + 32 * w));
+            uint64_t both;
+            KMAP_PACK32(x, valid[w], both);
+            memcpy(packed + 2 * w, &both, 8);
+        }
+        alignas(32) uint32_t vb[8];
+        alignas(32) uint64_t pb[8];
+        for (; w + 8 <= w1; w += 8) {
+#pragma GCC unroll 8
+            for (int j = 0; j < 8; ++j) {
+                const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(seq + 32 * (w + j)));
+                KMAP_PACK32(x, vb[j], pb[j]);
+            }
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(valid + w), _mm256_load_si256(reinterpret_cast<const __m256i*>(vb)));
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(packed + 2 * w), _mm256_load_si256(reinterpret_cast<const __m256i*>(pb)));
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(packed + 2 * w + 8), _mm256_load_si256(reinterpret_cast<const __m256i*>(pb + 4)));
+        }
+        _mm_sfence();
+    }
+    for (; w < w1; ++w) {
         const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(seq + 32 * w));
-        const __m256i ok = _mm256_cmpeq_epi8(_mm256_and_si256(x, fc), zero);         // 0xFF where the byte is 0..3
-        valid[w] = (uint32_t)_mm256_movemask_epi8(ok);
-        const __m256i code = _mm256_and_si256(x, _mm256_and_si256(ok, three));       // invalid bases packed as 0 (canonical)
-        const __m256i pair = _mm256_maddubs_epi16(code, mul1);
-        const __m256i quad = _mm256_madd_epi16(pair, mul2);
-        const __m256i r = _mm256_shuffle_epi8(quad, pick);
-        packed[2 * w] = (uint32_t)_mm256_extract_epi32(r, 0);
-        packed[2 * w + 1] = (uint32_t)_mm256_extract_epi32(r, 4);
+        uint64_t both;
+        KMAP_PACK32(x, valid[w], both);
+        memcpy(packed + 2 * w, &both, 8);
     }
 }
 
@@ -71,12 +101,13 @@ int kmap_host_threads(void) {
 
 int kmap_host_pack2bit(const uint8_t* seq, int64_t n, uint32_t* packed, uint32_t* valid, int n_threads) {
     if (n < 0 || !packed || !valid || (!seq && n)) return KMAP_ERR_BAD_ARG;
+    static const int nt = [] { const char* e = getenv("KMAP_HOST_PACK_NT"); return e ? atoi(e) : 1; }();
     const int64_t n_words = (n + 31) / 32 + 4;                 // kmap_valid_words(n): KMAP_PAD_WORDS zero words behind
     const int64_t full = n / 32;                               // words whose 32 bytes are all inside the input
     if (n_threads <= 0) n_threads = kmap_host_threads();
     n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, full / (1 << 15) + 1));
     auto work = [&](int64_t a, int64_t b) {
-        if (have_avx2()) pack_range_avx2(seq, a, b, packed, valid);
+        if (have_avx2()) pack_range_avx2(seq, a, b, packed, valid, nt);
         else pack_range_scalar(seq, a, b, packed, valid);
     };
     if (n_threads == 1) {

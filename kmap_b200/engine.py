@@ -45,10 +45,27 @@ def to_device(a: np.ndarray, dtype=None) -> torch.Tensor:
     return torch.from_numpy(src).to(dev, non_blocking=False)
 
 
-def to_host(t: torch.Tensor, dtype) -> np.ndarray:
-    """device tensor -> host ndarray reinterpreted as `dtype` (same item size)."""
-    a = t.cpu().numpy()
-    return a.view(dtype) if a.dtype != np.dtype(dtype) else a
+PINNED_D2H_MIN_BYTES = 1 << 20
+
+
+def to_host(t: torch.Tensor, dtype=None) -> np.ndarray:
+    """device tensor -> host ndarray [reinterpreted as `dtype` (same item size)].  Results of a megabyte or more land in
+    pinned memory (torch's caching host allocator keeps the blocks between calls): a pageable copy runs at a few GB/s,
+    a pinned one at link speed -- the per-read results of the occurrence scan are ~1 GB per consensus at 1e8 reads."""
+    if t.is_cuda and t.numel() * t.element_size() >= PINNED_D2H_MIN_BYTES:
+        try:
+            host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        except RuntimeError:
+            host = None
+        if host is not None:
+            host.copy_(t, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            a = host.numpy()
+        else:
+            a = t.cpu().numpy()
+    else:
+        a = t.cpu().numpy()
+    return a.view(dtype) if dtype is not None and a.dtype != np.dtype(dtype) else a
 
 
 def empty(n: int, dtype: torch.dtype) -> torch.Tensor:
@@ -473,7 +490,7 @@ def occurrence_scan_device(seq: SeqOnDevice, k: int, conseq_kh: int, d: int, rev
 def occurrence_scan(seq: SeqOnDevice, k: int, conseq_kh: int, d: int, revcom: bool):
     """per read: (min_dist uint8[n_seq] (255 = none), offsets int64[n_seq+1], positions int32[total]) on the host."""
     min_dist, offsets, pos = occurrence_scan_device(seq, k, conseq_kh, d, revcom)
-    return min_dist.cpu().numpy(), offsets.cpu().numpy(), pos.cpu().numpy()
+    return to_host(min_dist), to_host(offsets), to_host(pos)
 
 
 def sum_counts(cnt: torch.Tensor) -> int:
@@ -516,7 +533,7 @@ def co_occurrence_scan(scan_dev):
             reads, diff2 = empty(c, torch.int64), empty(c, torch.int32)
             check(L.kmap_cooc_pair_fill(scan_dev[i][1].data_ptr(), _ptr(scan_dev[i][2]), scan_dev[j][1].data_ptr(), _ptr(scan_dev[j][2]),
                                         _ptr(flags), _ptr(at), n_seq, _ptr(reads), _ptr(diff2), _stream_ptr()), "kmap_cooc_pair_fill")
-            pairs[(i, j)] = (reads.cpu().numpy(), diff2.cpu().numpy())
+            pairs[(i, j)] = (to_host(reads), to_host(diff2))
     return counts, pairs, over
 
 

@@ -336,7 +336,7 @@ def motif_occurence_table(dev: E.SeqOnDevice, conseq_list: Sequence[str], motif_
     for conseq in conseq_list:
         k = len(conseq)
         t = E.occurrence_scan_device(dev, k, int(kmer2hash(conseq)), motif_def_dict[k].max_ham_dist, revcom_mode)
-        out.append(tuple(x.cpu().numpy() for x in t))
+        out.append(tuple(E.to_host(x) for x in t))
         if keep_device:
             out_dev.append(t)
     return (out, out_dev) if keep_device else out
@@ -728,6 +728,28 @@ def hamdist_matrix_u8(kh: np.ndarray, labels: np.ndarray, head_len: Sequence[int
     fn = L.kmap_hamdist_matrix_u32 if hd == np.uint32 else L.kmap_hamdist_matrix_u64
     check(fn(kh_d.data_ptr(), lab_d.data_ptr(), n, kmer_len, None if hl_d is None else hl_d.data_ptr(), len(head_len),
              row0, row1, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "kmap_hamdist_matrix")
+    return out.view(row1 - row0, n)
+
+
+def hamdist_matrix_onehot_mma(kh: np.ndarray, labels: np.ndarray, head_len: Sequence[int], kmer_len: int, row0: int = 0,
+                              row1: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The same rows as hamdist_matrix_u8 (k <= 16), computed as an int8 one-hot GEMM on the tcgen05 tensor cores
+    (csrc/hamdist_mma.cu): the comparator formulation of BASELINE config 5, bit-identical to the XOR/popcount kernel."""
+    L = lib()
+    n = len(kh)
+    row1 = n if row1 is None else row1
+    if kmer_len > 16:
+        raise KmapError("the one-hot GEMM comparator covers k <= 16")
+    kh_d = E.to_device(np.asarray(kh).astype(np.uint32, copy=False))
+    lab_d = E.to_device(np.asarray(labels).astype(np.int32, copy=False))
+    hl_d = E.to_device(np.asarray(list(head_len), dtype=np.int32)) if len(head_len) else None
+    if out is None:
+        out = E.empty((row1 - row0) * n, torch.uint8)
+    nbytes = int(L.kmap_hamdist_mma_scratch_bytes(n))
+    scratch = E.empty(nbytes, torch.uint8)
+    check(L.kmap_hamdist_matrix_onehot_mma(kh_d.data_ptr(), lab_d.data_ptr(), n, kmer_len, None if hl_d is None else hl_d.data_ptr(),
+                                           len(head_len), row0, row1, out.data_ptr(), scratch.data_ptr(), nbytes,
+                                           torch.cuda.current_stream().cuda_stream), "kmap_hamdist_matrix_onehot_mma")
     return out.view(row1 - row0, n)
 
 

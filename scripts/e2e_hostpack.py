@@ -29,11 +29,12 @@ print(json.dumps(out), flush=True)
 del hp, hv
 ref = None
 res = {}
-for name, kw in [("raw_2^29", dict(host_pack=False, chunk_positions=1 << 29)),
-                 ("hybrid_2^29", dict(host_pack=True, chunk_positions=1 << 29)),
-                 ("hybrid_2^28", dict(host_pack=True, chunk_positions=1 << 28)),
-                 ("hybrid_2^27", dict(host_pack=True, chunk_positions=1 << 27)),
-                 ("raw_2^28", dict(host_pack=False, chunk_positions=1 << 28))]:
+for name, kw in [("slots6_raw1", dict(slots=6, max_raw=1)), ("slots6_raw2", dict(slots=6, max_raw=2)), ("slots6_raw1_16thr", dict(slots=6, max_raw=1, threads=16))]:
+    os.environ["KMAP_HOST_THREADS"] = str(kw.pop("threads", 14))
+    os.environ["KMAP_STREAM_SLOTS"] = str(kw.pop("slots"))
+    os.environ["KMAP_STREAM_MAX_RAW"] = str(kw.pop("max_raw"))
+    kw.setdefault("chunk_positions", 1 << 29)
+    kw["host_pack"] = True
     ts = []
     for rep in range(3):
         torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -42,9 +43,17 @@ for name, kw in [("raw_2^29", dict(host_pack=False, chunk_positions=1 << 29)),
     chk = {k: int(np.sum(r[k][1], dtype=np.int64)) ^ int(np.bitwise_xor.reduce(r[k][0])) for k in r}
     if ref is None:
         ref = chk
-    res[name] = {"ms": [round(1e3 * t, 1) for t in ts], "same_lists_digest": chk == ref}
+    res[name] = {"ms": [round(1e3 * t, 1) for t in ts], "same_lists_digest": chk == ref, "last": api.last_stream_stats}
     print(name, res[name], flush=True)
     del r
+os.environ["KMAP_STREAM_TRACE"] = "1"
+os.environ["KMAP_HOST_THREADS"] = "14"
+torch.cuda.synchronize(); t0 = time.perf_counter()
+r = api.count_kmers(seq_np, b_np, range(8, 15), validate=False, host_pack=True, chunk_positions=1 << 29)
+torch.cuda.synchronize(); print("traced call", round(1e3 * (time.perf_counter() - t0), 1), "ms")
+for row in api.last_stream_trace:
+    if row[1] in ("copy-engine", "kmap-host-pack"):
+        print(row)
 out["e2e_ms"] = res
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/e2e_hostpack.json", "w"), indent=1)

@@ -361,6 +361,29 @@ def test_hamdist_row_blocks_and_properties(MD):
         assert np.array_equal(part, full[r0:r1])
 
 
+@pytest.mark.parametrize("k,n", [(14, 1616), (14, 777), (8, 300), (16, 2048), (1, 50), (12, 5000)])
+def test_hamdist_onehot_tcgen05_gemm_equals_popcount_kernel(MD, k, n):
+    """the int8 one-hot GEMM on the tcgen05 tensor cores (csrc/hamdist_mma.cu, the comparator of BASELINE config 5) writes
+    the same bytes as the XOR/popcount kernel and the oracle: head overrides, ragged edges (n not a multiple of the 128 x
+    256 tile or of 16), row blocks"""
+    rng = np.random.default_rng(100 + k + n)
+    kh = rng.integers(0, 4 ** k, n, dtype=np.uint64).astype(np.uint32)
+    labels = rng.integers(0, 4, n)
+    head = [k, max(1, k - 2), max(1, k - 5)]                     # label 3 has no consensus entry: never overrides
+    want = MD.hamdist_matrix_u8(kh, labels, head, k).cpu().numpy()
+    got = MD.hamdist_matrix_onehot_mma(kh, labels, head, k).cpu().numpy()
+    assert np.array_equal(got, want)
+    if n <= 2048 and len(np.unique(kh)) == n:
+        ref = O.cal_samp_kmer_hamdist_mat(kh, np.ones(n, dtype=int), labels, ["A" * h for h in head], k).astype(np.uint8)
+        assert np.array_equal(got, ref)
+    for r0, r1 in ((0, 1), (3, n // 2), (n // 2, n), (n - 1, n), (129, min(n, 400))):
+        if r0 < r1 <= n:
+            part = MD.hamdist_matrix_onehot_mma(kh, labels, head, k, r0, r1).cpu().numpy()
+            assert np.array_equal(part, want[r0:r1]), (r0, r1)
+    plain = MD.hamdist_matrix_onehot_mma(kh, np.full(n, -1), [], k).cpu().numpy()
+    assert np.array_equal(plain, MD.hamdist_matrix_u8(kh, np.full(n, -1), [], k).cpu().numpy())
+
+
 def test_synth_device_matches_numpy(ENG):
     from kmap_b200 import synth
     for spec in (synth.CFG2, synth.CFG2_N, synth.CFG3):
