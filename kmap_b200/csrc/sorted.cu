@@ -17,6 +17,7 @@
 //   merge_revcom                partner = binary search of rc(h) in the sorted list; survivors keep the list order, value
 //                               min(h, rc h), a palindrome is its own partner (count doubled) -- SURVEY Q6
 #include "common.cuh"
+#include <cstdlib>
 #include "tile.cuh"
 
 namespace {
@@ -333,6 +334,151 @@ __global__ void __launch_bounds__(RS_THREADS, 3) radix_scatter_kernel(const u64*
     }
 }
 
+// ---- onesweep: one histogram read for all passes, then ONE kernel per 8-bit digit ----------------------------------------------
+// The three-kernel pass above reads the keys twice per digit (histogram, scatter) and runs two small scans in between.
+// Onesweep (Adinets & Merrill): (a) one kernel reads the keys once and histograms every digit position at the same time;
+// (b) per digit position one kernel does count + inter-tile prefix + scatter: a tile publishes its per-digit counts in a
+// status word (flag | value in one 64-bit word, so the word itself is the message and no fence is needed), then looks back
+// over its predecessors until it meets one that has published an inclusive prefix (decoupled look-back).  Tiles are
+// numbered by an atomic ticket, so every predecessor of a running tile is running or done and the look-back cannot
+// deadlock.  Traffic: 8 B/key once + 16 B/key per digit, against 24 B/key per digit.
+constexpr u64 OS_LOCAL = 1ull << 62, OS_PREFIX = 2ull << 62, OS_VALUE = (1ull << 62) - 1ull;
+constexpr int OS_MAX_PASSES = 8;
+
+__global__ void __launch_bounds__(256) onesweep_hist_kernel(const u64* __restrict__ in, int64_t n, int passes, u64* __restrict__ hist) {
+    __shared__ uint32_t sh[OS_MAX_PASSES][256];
+    for (int p = 0; p < passes; ++p) sh[p][threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        u64 key[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) key[u] = i0 + u * stride < n ? __ldg(in + i0 + u * stride) : KEY_EMPTY;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (key[u] == KEY_EMPTY) continue;
+            for (int p = 0; p < passes; ++p) atomicAdd(&sh[p][(uint32_t)(key[u] >> (8 * p)) & 255u], 1u);
+        }
+    }
+    __syncthreads();
+    for (int p = 0; p < passes; ++p)
+        if (sh[p][threadIdx.x]) atomicAdd(hist + p * 256 + threadIdx.x, (u64)sh[p][threadIdx.x]);
+}
+
+// hist[p][d] -> first output index of digit d in pass p; *n_valid = number of non-empty keys
+__global__ void __launch_bounds__(256) onesweep_bases_kernel(u64* __restrict__ hist, int passes, u64* __restrict__ n_valid) {
+    __shared__ u64 v[256];
+    for (int p = 0; p < passes; ++p) {
+        v[threadIdx.x] = hist[p * 256 + threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u64 run = 0;
+            for (int d = 0; d < 256; ++d) { const u64 t = v[d]; v[d] = run; run += t; }
+            if (p == 0) *n_valid = run;
+        }
+        __syncthreads();
+        hist[p * 256 + threadIdx.x] = v[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS, 3) onesweep_pass_kernel(const u64* __restrict__ in, u64* __restrict__ out, int64_t n_upper,
+                                                                   const u64* __restrict__ n_dev, int shift, int drop_empty,
+                                                                   const u64* __restrict__ digit_base, u64* __restrict__ status,
+                                                                   unsigned int* __restrict__ ticket) {
+    __shared__ u64 skeys[RS_TILE];                         // the tile in digit order
+    __shared__ uint32_t wcnt[RS_THREADS / 32][256];        // per (warp, digit): count, then start inside the tile
+    __shared__ u64 gdelta[256];                            // global index of the digit's run - its start inside the tile
+    __shared__ uint32_t scan_ws[RS_THREADS / 32];
+    __shared__ uint32_t tile_total;
+    __shared__ unsigned int s_tile;
+    const int64_t n = n_dev ? (int64_t)*n_dev : n_upper;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int q = 0; q < RS_THREADS / 32; ++q) wcnt[q][threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t tile = s_tile;
+    if (tile * RS_TILE >= n) return;                       // (block-uniform; nobody looks back at a tile beyond the keys)
+    const int64_t base = tile * RS_TILE + (int64_t)w * RS_WARP_KEYS;
+    u64 key[RS_ITEMS];
+    uint32_t rank[RS_ITEMS];          // while the counters are being filled: count before this round | leader lane << 16 | rank among peers << 21
+    uint32_t live = 0;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const int64_t i = base + r * 32 + lane;
+        key[r] = i < n ? __ldcs(in + i) : KEY_EMPTY;
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const int64_t i = base + r * 32 + lane;
+        const bool ok = i < n && !(drop_empty && key[r] == KEY_EMPTY);
+        const uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, ok ? d : (256u + (uint32_t)lane));
+        const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+        uint32_t old = 0;
+        if (ok && (uint32_t)lane == leader) old = atomicAdd(&wcnt[w][d], (uint32_t)__popc(peers));
+        rank[r] = old | (leader << 16) | ((uint32_t)__popc(peers & ((1u << lane) - 1u)) << 21);
+        if (ok) live |= 1u << r;
+        __syncwarp();
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const uint32_t before = __shfl_sync(0xFFFFFFFFu, rank[r] & 0xFFFFu, (rank[r] >> 16) & 31u);
+        rank[r] = before + (rank[r] >> 21);
+    }
+    __syncthreads();
+    {
+        // thread d: digit d's keys of the warps in order; an exclusive scan over the digits gives the tile layout, the
+        // look-back over the earlier tiles gives the digit's place in the output
+        const uint32_t d = threadIdx.x;
+        uint32_t cnt_w[RS_THREADS / 32];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int q = 0; q < RS_THREADS / 32; ++q) { cnt_w[q] = wcnt[q][d]; mine += cnt_w[q]; }
+        volatile u64* st = status + (size_t)tile * 256 + d;
+        *st = (tile == 0 ? OS_PREFIX : OS_LOCAL) | (u64)mine;
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) scan_ws[w] = incl;
+        __syncthreads();
+        uint32_t pre = 0, all = 0;
+#pragma unroll
+        for (int q = 0; q < RS_THREADS / 32; ++q) { if (q < w) pre += scan_ws[q]; all += scan_ws[q]; }
+        uint32_t start = pre + incl - mine;                 // first slot of digit d in the tile
+        if (threadIdx.x == 0) tile_total = all;
+        u64 before = 0;                                     // keys with digit d in the earlier tiles
+        if (tile > 0) {
+            int64_t t = tile - 1;
+            for (;;) {
+                const volatile u64* ps = status + (size_t)t * 256 + d;
+                u64 sv = *ps;
+                while ((sv >> 62) == 0) sv = *ps;
+                before += sv & OS_VALUE;
+                if ((sv >> 62) == 2 || t == 0) break;
+                --t;
+            }
+            *st = OS_PREFIX | (before + (u64)mine);
+        }
+        gdelta[d] = digit_base[d] + before - start;
+#pragma unroll
+        for (int q = 0; q < RS_THREADS / 32; ++q) { wcnt[q][d] = start; start += cnt_w[q]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r)
+        if ((live >> r) & 1u) skeys[wcnt[w][(uint32_t)(key[r] >> shift) & 255u] + rank[r]] = key[r];
+    __syncthreads();
+    const uint32_t total = tile_total;
+    for (uint32_t i = threadIdx.x; i < total; i += RS_THREADS) {
+        const u64 kk = skeys[i];
+        out[gdelta[(uint32_t)(kk >> shift) & 255u] + i] = kk;
+    }
+}
+
 // ---- run-length encoding of the sorted keys ------------------------------------------------------------------------------------
 constexpr int RL_BLOCK = 256;
 constexpr int RL_ITEMS = 8;
@@ -633,7 +779,9 @@ int kmap_dedup_hash_per_read_u64(uint64_t* hash, int64_t n, const int64_t* borde
 int64_t kmap_sort_scratch_words(int64_t n) {
     if (n < 0) return 0;
     const int64_t t = rs_tiles(n);
-    const int64_t sort_words = 258 + 128 * t + 256 * t;
+    int64_t sort_words = 258 + 128 * t + 256 * t;                   // the three-kernel form
+    const int64_t onesweep_words = OS_MAX_PASSES * 256 + 2 + 256 * t;
+    if (onesweep_words > sort_words) sort_words = onesweep_words;
     const int64_t rl_words = rl_tiles(n) + 2;
     return (sort_words > rl_words ? sort_words : rl_words) + 2;
 }
@@ -653,6 +801,26 @@ int kmap_sort_keys_u64(uint64_t* keys, uint64_t* tmp, int64_t n, int key_bits, u
     u64* a = reinterpret_cast<u64*>(keys);
     u64* b = reinterpret_cast<u64*>(tmp);
     const int passes = (key_bits + 7) / 8;
+    static const bool three_kernel = getenv("KMAP_SORT_THREE_KERNEL") != nullptr;      // (the earlier form, kept for A/B timing)
+    if (!three_kernel) {
+        // scratch: [0..2047] per-pass digit histograms -> bases, [2048] n_valid (n_dev), [2049] ticket, then the status words
+        u64* hist = reinterpret_cast<u64*>(scratch);
+        n_dev = hist + OS_MAX_PASSES * 256;
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(n_dev + 1);
+        u64* status = n_dev + 2;
+        cudaMemsetAsync(hist, 0, (size_t)(OS_MAX_PASSES * 256 + 2) * 8, s);
+        int64_t hb = (n + 1023) / 1024;
+        if (hb > 148 * 8) hb = 148 * 8;
+        onesweep_hist_kernel<<<(unsigned int)hb, 256, 0, s>>>(a, n, passes, hist);
+        onesweep_bases_kernel<<<1, 256, 0, s>>>(hist, passes, n_dev);
+        for (int p = 0; p < passes; ++p) {
+            cudaMemsetAsync(status, 0, (size_t)n_tiles * 256 * 8, s);
+            cudaMemsetAsync(ticket, 0, 4, s);
+            onesweep_pass_kernel<<<(unsigned int)n_tiles, RS_THREADS, 0, s>>>(a, b, n, p == 0 ? nullptr : n_dev, 8 * p, p == 0, hist + p * 256,
+                                                                              status, ticket);
+            u64* t = a; a = b; b = t;
+        }
+    } else
     for (int p = 0; p < passes; ++p) {
         const int drop = p == 0;
         const u64* nd = p == 0 ? nullptr : n_dev;

@@ -21,3 +21,16 @@ for name, labels, heads in (("no override", np.full(n, 2, np.int32), [14, 14]), 
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     print(f"{name}: {ms:.3f} ms  {n*n/ms/1e6:.0f} GB/s written  {n*n/ms*1e3:.3e} pairs/s")
+    # the same matrix as an int8 one-hot GEMM on the tcgen05 tensor cores (csrc/hamdist_mma.cu)
+    nb = int(L.kmap_hamdist_mma_scratch_bytes(n))
+    scr = E.empty(nb, torch.uint8)
+    out2 = E.empty(n * n, torch.uint8)
+    run2 = lambda: check(L.kmap_hamdist_matrix_onehot_mma(kh_d.data_ptr(), lab_d.data_ptr(), n, k, hl_d.data_ptr(), len(heads), 0, n, out2.data_ptr(),
+                                                          scr.data_ptr(), nb, torch.cuda.current_stream().cuda_stream))
+    run2(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps): run2()
+    e1.record(); torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1) / reps
+    print(f"  one-hot tcgen05 GEMM: {ms2:.3f} ms  {n*n/ms2/1e6:.0f} GB/s written  {n*n/ms2*1e3:.3e} pairs/s  identical={bool(torch.equal(out, out2))}")
+    del out2, scr
