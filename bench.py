@@ -325,6 +325,36 @@ def main():
     checks["sum_table_k14"] = tot14
     # per-level position-weighted checksums of the (merged) tables: identical for every number of GPUs iff the tables are
     checks["table_checksums"] = {str(k): table_checksum(tables[k]) for k in range(KMIN, KMAX + 1)}
+    # N > 1: the same step with the merged tables left scattered over the ranks by key range (reduce-scatter instead of
+    # all-reduce: half the exchange volume, kmap_count_all_k_scattered).  Reported beside `value`, which keeps the all-reduce
+    # the north star names.  The owned ranges of all ranks together must give the checksums of the all-reduced tables.
+    scattered = None
+    if args.algo == "allk" and world > 1 and (1 << (2 * KMIN)) % world == 0:
+        rs_comm = api.TableAllReduce(scatter=True)
+        _, rs_tables = E.alloc_tables(KMIN, KMAX, zero=True)
+        for _ in range(max(1, args.warmup)):
+            dev.count_all(KMIN, KMAX, dedup, rs_tables, n_partitions=args.partitions, merge=rs_comm)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            dev.count_all(KMIN, KMAX, dedup, rs_tables, n_partitions=args.partitions, merge=rs_comm)
+        s1.record()
+        barrier()
+        ts = torch.tensor([s0.elapsed_time(s1) / args.steps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        same = True
+        for k in range(KMIN, KMAX + 1):
+            lo, hi = rs_comm.owned_range(k)
+            same = same and bool(torch.equal(rs_tables[k][lo:hi], tables[k][lo:hi]))
+        flag = torch.tensor([int(same)], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        scattered = {"ms_per_step": float(ts.item()), "value": n_total * L * (KMAX - KMIN + 1) / (float(ts.item()) * 1e-3) / 1e9,
+                     "unit": "Gbases/s", "owned_ranges_equal_allreduced_tables": bool(flag.item()),
+                     "note": "reduce-scatter by key range: rank r owns cells [r 4^k / N, (r+1) 4^k / N) of every level"}
+        checks["scattered_merge_equals_allreduce"] = bool(flag.item())
+        rs_comm.close()
+        del rs_tables
     if args.algo == "allk" and world == 1 and not args.no_crosscheck:
         # full-size parity property: the tables the all-k algorithm DERIVES (level 14 -> 13 -> .. -> 8, with the run-end and
         # repeat corrections of every level on the way) equal independent direct counts by the per-k kernels
@@ -553,7 +583,7 @@ def main():
                                    f"counting k={KMIN}..{KMAX}, {args.mode} mode, reads sharded over {n_gpus} GPU(s) with NCCL table merge",
                        "l2": "inputs larger than L2 (packed reads + borders = %.1f GB per GPU)" % ((dev.packed.numel() * 4 + dev.valid.numel() * 4 + n_local * 16) / 1e9),
                        "parallelism": f"reads x{n_gpus}"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (launches_per_step(args, dedup)),
+            "clocks": clocks, "e2e": e2e, "scattered_merge": scattered, "gpu_launches": args.steps * (launches_per_step(args, dedup)),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "hamdist": hamdist, "hamball": piece2, "workflow_cfg2": workflow,
             "checks": checks,
         }

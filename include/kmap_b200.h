@@ -134,6 +134,9 @@ int kmap_comm_destroy(void* comm);
 /* table[i] = sum over the ranks of table[i], in place (uint32, modular): count_uniq_hash of the whole input from the
  * per-shard tables.  Asynchronous on `stream`. */
 int kmap_table_allreduce(uint32_t* table, int64_t n_cells, void* comm, void* stream);
+/* the same exchange as a reduce-scatter by key range, in place: afterwards cells [rank * n_cells / world, (rank + 1) * n_cells /
+ * world) hold the sums over the ranks (the other cells partial sums); n_cells must be a multiple of world */
+int kmap_table_reduce_scatter(uint32_t* table, int64_t n_cells, int rank, int world, void* comm, void* stream);
 /* kmap_count_all_k on this rank's shard of the reads with the tables MERGED over the ranks of `comm` on return (every rank
  * gets the tables of the whole input).  The all-reduces are issued on `comm_stream` as the buffers become final -- the
  * corrections of the small levels during the partition pass, the slices of the level-kmax table while the per-bucket
@@ -144,6 +147,14 @@ int kmap_count_all_k_sharded(const uint32_t* packed, const uint32_t* valid, int6
                              int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
                              uint32_t* bitmap, int n_partitions, int scheme, void* part_scratch, int64_t part_scratch_bytes,
                              void* const* phase_events, void* stream, void* comm, void* comm_stream);
+/* kmap_count_all_k_sharded with the merged tables left scattered over the ranks by key range (reduce-scatter instead of
+ * all-reduce: half the exchange volume): rank r owns cells [r * 4^k / world, (r + 1) * 4^k / world) of every level k, the
+ * reductions to the lower levels run on the owned ranges only.  world must divide 4^kmin.  Compact a range with
+ * kmap_compact_merge_range: the lists of ranks 0, 1, .. concatenate to the reference's list. */
+int kmap_count_all_k_scattered(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
+                               int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
+                               uint32_t* bitmap, int n_partitions, int scheme, void* part_scratch, int64_t part_scratch_bytes,
+                               void* const* phase_events, void* stream, void* comm, void* comm_stream, int rank, int world);
 
 /* kmap_count_dense for tables beyond L2 (9 <= k <= 14) without one global atomic per window: windows are partitioned
  * by the top bits of their key into 4^(k-8) buckets of 16-bit suffixes (scratch), then every bucket is counted in

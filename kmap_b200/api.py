@@ -23,13 +23,31 @@ class TableAllReduce:
     communicator created from a unique id that torch.distributed broadcasts -- the process group is plumbing only); host
     tensors (the gloo tests of the host logic) through torch.distributed."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, scatter: bool = False):
+        """scatter=True: counts merged from inside SeqOnDevice.count_all are left SCATTERED over the ranks by key range
+        (reduce-scatter instead of all-reduce, `kmap_count_all_k_scattered`): rank r owns cells `owned_range(k)` of every level,
+        its other cells hold partial sums.  Half the exchange volume; for consumers that work on key ranges."""
         import torch.distributed as dist
         if not dist.is_initialized():
             raise KmapError("TableAllReduce needs an initialised torch.distributed process group")
         self.dist, self.group = dist, group
+        self.scatter = bool(scatter)
         self._comm = None
         self._stream = None
+
+    def owned_range(self, k: int) -> Tuple[int, int]:
+        """[lo, hi) of the level-k table this rank owns after a scattered merge"""
+        cells = 1 << (2 * k)
+        if cells % self.world:
+            raise KmapError(f"{self.world} ranks do not divide 4^{k} cells")
+        return cells // self.world * self.rank, cells // self.world * (self.rank + 1)
+
+    def reduce_scatter(self, table: torch.Tensor) -> torch.Tensor:
+        """in place: this rank's block of `table` (numel / world cells at block index rank) becomes the sum over the ranks"""
+        comm, _ = self.native()
+        _check(_lib().kmap_table_reduce_scatter(table.data_ptr(), table.numel(), self.rank, self.world, comm,
+                                                torch.cuda.current_stream().cuda_stream), "kmap_table_reduce_scatter")
+        return table
 
     # ---- the native communicator (lazy: the first device tensor creates it; collective over the group) ----------------
     def native(self):

@@ -18,6 +18,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;      // (optional)
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -36,8 +37,9 @@ const NcclApi& nccl_api() {
         api.CommInitRankConfig = reinterpret_cast<decltype(api.CommInitRankConfig)>(dlsym(api.handle, "ncclCommInitRankConfig"));
         api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.handle, "ncclCommDestroy"));
         api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.handle, "ncclAllReduce"));
+        api.ReduceScatter = reinterpret_cast<decltype(api.ReduceScatter)>(dlsym(api.handle, "ncclReduceScatter"));
         api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
-        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.ReduceScatter && api.GetErrorString;
     });
     return api;
 }
@@ -56,6 +58,17 @@ int kmap_allreduce_u32_on(uint32_t* buf, int64_t n, void* comm, cudaStream_t s) 
     if (!api.ok) { kmap_set_error("table_allreduce: no NCCL library in this process"); return KMAP_ERR_COMM; }
     const ncclResult_t r = api.AllReduce(buf, buf, (size_t)n, ncclUint32, ncclSum, reinterpret_cast<ncclComm_t>(comm), s);
     return r == ncclSuccess ? KMAP_OK : nccl_fail("table_allreduce", r);
+}
+
+int kmap_merge_table_on(uint32_t* buf, int64_t n, const KmapMerge* m) {
+    if (n == 0) return KMAP_OK;
+    if (!m->scatter || m->world <= 1 || n % m->world != 0) return kmap_allreduce_u32_on(buf, n, m->comm, m->stream);
+    const NcclApi& api = nccl_api();
+    if (!api.ok) { kmap_set_error("table_reduce_scatter: no NCCL library in this process"); return KMAP_ERR_COMM; }
+    const int64_t block = n / m->world;         // in place: the receive buffer is this rank's block of the send buffer
+    const ncclResult_t r = api.ReduceScatter(buf, buf + (size_t)m->rank * block, (size_t)block, ncclUint32, ncclSum,
+                                             reinterpret_cast<ncclComm_t>(m->comm), m->stream);
+    return r == ncclSuccess ? KMAP_OK : nccl_fail("table_reduce_scatter", r);
 }
 
 extern "C" {
@@ -106,6 +119,13 @@ int kmap_comm_destroy(void* comm) {
 int kmap_table_allreduce(uint32_t* table, int64_t n_cells, void* comm, void* stream) {
     KMAP_REQUIRE(n_cells >= 0 && (table || n_cells == 0) && comm, "bad argument");
     return kmap_allreduce_u32_on(table, n_cells, comm, as_stream(stream));
+}
+
+int kmap_table_reduce_scatter(uint32_t* table, int64_t n_cells, int rank, int world, void* comm, void* stream) {
+    KMAP_REQUIRE(n_cells >= 0 && (table || n_cells == 0) && comm && world >= 1 && rank >= 0 && rank < world, "bad argument");
+    KMAP_REQUIRE(n_cells % world == 0, "the number of cells must be a multiple of the number of ranks");
+    const KmapMerge m = {comm, as_stream(stream), 1, rank, world};
+    return kmap_merge_table_on(table, n_cells, &m);
 }
 
 }  // extern "C"

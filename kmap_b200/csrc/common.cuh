@@ -22,9 +22,15 @@ static inline unsigned int grid_for(int64_t n_threads, int block) {
 }
 
 // the exchange step of a sharded count (comm.cu): NCCL communicator + the stream the all-reduces are issued on
-struct KmapMerge { void* comm; cudaStream_t stream; };
+// scatter: instead of leaving every merged table on every rank (all-reduce), rank r of `world` ends up owning cells
+// [r * n / world, (r + 1) * n / world) of every table (reduce-scatter by key range; the other cells hold partial sums):
+// half the exchange volume, and everything behind the merge (reductions to the lower levels, compaction) runs on 1 / world
+// of the cells.  Needs world | 4^kmin.
+struct KmapMerge { void* comm; cudaStream_t stream; int scatter; int rank; int world; };
 #define KMAP_COMM_CTAS 16         // CTAs the collective may use = SMs the counting kernels leave free while it runs
 int kmap_allreduce_u32_on(uint32_t* buf, int64_t n, void* comm, cudaStream_t s);
+// merge one table the way `m` says: all-reduce, or reduce-scatter in place (rank r's block stays where it is in `buf`)
+int kmap_merge_table_on(uint32_t* buf, int64_t n, const KmapMerge* m);
 
 // dense tables of several levels: t[k] = uint32[4^k] (only the levels a kernel uses are set); passed by value
 struct KmapTableSet { uint32_t* t[16]; };

@@ -582,17 +582,19 @@ int count_all_impl(const uint32_t* packed, const uint32_t* valid, int64_t n, con
         if (rc) return rc;
         if (merge) {               // no early slices on this path: every pre-derive buffer after the count
             if ((rc = OneShotEvent::chain(s, merge->stream))) return rc;
-            for (int k = kmax; k >= kmin && !rc; --k) rc = kmap_allreduce_u32_on(tabs.t[k], (int64_t)1 << (2 * k), merge->comm, merge->stream);
+            for (int k = kmax; k >= kmin && !rc; --k) rc = kmap_merge_table_on(tabs.t[k], (int64_t)1 << (2 * k), merge);
             if (rc) return rc;
         }
     }
     if (merge && (rc = OneShotEvent::chain(merge->stream, s))) return rc;        // the reductions read merged buffers
     mark(2);
+    const bool scattered = merge && merge->scatter && merge->world > 1;      // this rank owns (and reduces) one key range of every level
     for (int k = kmax - 1; k >= kmin; --k) {
-        const int64_t cells = (int64_t)1 << (2 * k);
+        int64_t cells = (int64_t)1 << (2 * k), lo = 0;
+        if (scattered) { cells /= merge->world; lo = cells * merge->rank; }
         int64_t g = (cells + 255) / 256;
         if (g > 148 * 32) g = 148 * 32;
-        derive_table_kernel<<<(unsigned int)g, 256, 0, s>>>(reinterpret_cast<const uint4*>(tabs.t[k + 1]), tabs.t[k], cells);
+        derive_table_kernel<<<(unsigned int)g, 256, 0, s>>>(reinterpret_cast<const uint4*>(tabs.t[k + 1]) + lo, tabs.t[k] + lo, cells);
     }
     rc = kmap_check_launch("count_all_k(derive)");
     if (rc) return rc;
@@ -659,7 +661,23 @@ extern "C" int kmap_count_all_k_sharded(const uint32_t* packed, const uint32_t* 
                                         uint32_t* bitmap, int n_partitions, int scheme, void* part_scratch, int64_t part_scratch_bytes,
                                         void* const* phase_events, void* stream, void* comm, void* comm_stream) {
     KMAP_REQUIRE(comm && comm_stream, "the sharded count needs a communicator and a stream for the exchange");
-    const KmapMerge merge = {comm, as_stream(comm_stream)};
+    const KmapMerge merge = {comm, as_stream(comm_stream), 0, 0, 1};
+    return count_all_impl(packed, valid, n, borders, n_seq, kmin, kmax, dedup, tables_host, dupmask, work, bitmap, n_partitions, scheme,
+                          part_scratch, part_scratch_bytes, phase_events, stream, &merge);
+}
+
+// The same with the merged tables left SCATTERED over the ranks by key range: rank r owns cells [r * 4^k / world,
+// (r + 1) * 4^k / world) of every level k (the other cells of its buffers hold partial sums).  Reduce-scatter instead of
+// all-reduce halves the exchange and the reductions to the lower levels run on the owned ranges only; the compaction of a
+// range is kmap_compact_merge_range, the ranges of ranks 0, 1, .. concatenate to the reference's list.  world must divide 4^kmin.
+extern "C" int kmap_count_all_k_scattered(const uint32_t* packed, const uint32_t* valid, int64_t n, const int64_t* borders, int64_t n_seq,
+                                          int kmin, int kmax, int dedup, uint32_t* const* tables_host, uint32_t* dupmask, uint32_t* work,
+                                          uint32_t* bitmap, int n_partitions, int scheme, void* part_scratch, int64_t part_scratch_bytes,
+                                          void* const* phase_events, void* stream, void* comm, void* comm_stream, int rank, int world) {
+    KMAP_REQUIRE(comm && comm_stream, "the sharded count needs a communicator and a stream for the exchange");
+    KMAP_REQUIRE(world >= 1 && rank >= 0 && rank < world && kmin >= 1 && (((int64_t)1 << (2 * kmin)) % world) == 0,
+                 "the number of ranks must divide 4^kmin");
+    const KmapMerge merge = {comm, as_stream(comm_stream), 1, rank, world};
     return count_all_impl(packed, valid, n, borders, n_seq, kmin, kmax, dedup, tables_host, dupmask, work, bitmap, n_partitions, scheme,
                           part_scratch, part_scratch_bytes, phase_events, stream, &merge);
 }

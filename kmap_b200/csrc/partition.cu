@@ -653,9 +653,9 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
             uint32_t* lo = tt.t[v];
             int64_t cells = (int64_t)1 << (2 * v);
             int u = v - 1;
-            while (u >= kmin && tt.t[u] == lo + cells) { cells += (int64_t)1 << (2 * u); --u; }
+            while (!merge->scatter && u >= kmin && tt.t[u] == lo + cells) { cells += (int64_t)1 << (2 * u); --u; }   // (scattered: table by table)
             if (first) { cudaStreamWaitEvent(merge->stream, ev, 0); first = false; }
-            const int rcm = kmap_allreduce_u32_on(lo, cells, merge->comm, merge->stream);
+            const int rcm = kmap_merge_table_on(lo, cells, merge);
             if (rcm) { cudaEventDestroy(ev); return rcm; }
             v = u;
         }
@@ -717,14 +717,15 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
         cudaStreamWaitEvent(merge->stream, ev, 0);
         cudaEventDestroy(ev);                          // (released once the wait has been satisfied)
         if (trace) { cudaEventCreate(&tc[nt]); cudaEventRecord(tc[nt], s); }
-        rc = kmap_allreduce_u32_on(buf, cells, merge->comm, merge->stream);
+        rc = kmap_merge_table_on(buf, cells, merge);
         if (trace) { cudaEventCreate(&tm[nt]); cudaEventRecord(tm[nt], merge->stream); ++nt; }
     };
     if (route) {
         count_range(n_buckets, n_all);
         merge_after(tt.t[k - 1], (int64_t)1 << (2 * (k - 1)));
     }
-    const int n_chunks = n_buckets >= 1024 ? 4 : 1;
+    // (scattered: a rank's block of the table must stay one contiguous key range, so the table is merged in one piece)
+    const int n_chunks = (n_buckets >= 1024 && !merge->scatter) ? 4 : 1;
     for (int c = 0; c < n_chunks; ++c) {
         const int b_lo = n_buckets * c / n_chunks, b_hi = n_buckets * (c + 1) / n_chunks;
         count_range(b_lo, b_hi);

@@ -304,6 +304,8 @@ class SeqOnDevice:
             if merge is None:
                 return L.kmap_count_all_k(*args)
             comm, comm_stream = merge.native()
+            if getattr(merge, "scatter", False):
+                return L.kmap_count_all_k_scattered(*args, comm, comm_stream.cuda_stream, merge.rank, merge.world)
             return L.kmap_count_all_k_sharded(*args, comm, comm_stream.cuda_stream)
         if merge is not None and dedup:    # (a retry on one rank would leave the others waiting in a collective: give the bitmap upfront)
             bitmap = zeros(max((1 << (2 * kmax)) // 32, 1), torch.int32)

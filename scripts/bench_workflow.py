@@ -1,6 +1,9 @@
 """BASELINE config 2 end to end through the reference-shaped drivers: synthetic HT-SELEX-like reads (1e6 x 40 bp, two planted
 motifs) written as FASTA -> `preproc` -> `scan_motif` (k = 8..14, stock settings otherwise), wall-clock per stage and the
-cProfile top of scan_motif.  Writes gpurun_out/workflow.json."""
+cProfile top of scan_motif.  Writes gpurun_out/workflow[_<spec>].json.
+Usage: python scripts/bench_workflow.py [n_reads] [cfg2|cfg3]   (cfg3 = ChIP-like 100-bp reads, one planted 14-mer: the
+workload of the headline bench; run it at >= 1e7 reads under `ncu --metrics gpu__time_duration.sum` for the launch list that
+shows which counting kernels the CLI path runs)."""
 import cProfile
 import io
 import json
@@ -22,7 +25,8 @@ def main():
     import torch
     from kmap_b200 import kmer_count as K, motif_discovery as MD, synth
     torch.cuda.set_device(0)
-    spec = synth.CFG2
+    spec_name = sys.argv[2] if len(sys.argv) > 2 else "cfg2"
+    spec = {"cfg2": synth.CFG2, "cfg3": synth.CFG3}[spec_name]
     seq, borders = synth.generate_numpy(spec, 0, n_reads)
     L = spec.read_len
     body = np.frombuffer(b"ACGT", dtype=np.uint8)[np.minimum(seq.reshape(-1, L + 1)[:, :L], 3)]
@@ -41,7 +45,7 @@ def main():
     cfg["general"]["res_dir"] = str(res)
     with open(res / "config.toml", "wb") as fh:
         tomli_w.dump(cfg, fh)
-    out = {"reads": n_reads, "read_len": L, "fasta_MB": fa.stat().st_size / 1e6}
+    out = {"spec": spec_name, "reads": n_reads, "read_len": L, "fasta_MB": fa.stat().st_size / 1e6}
     t = time.perf_counter()
     K._preproc(str(fa), str(res))
     torch.cuda.synchronize()
@@ -70,8 +74,9 @@ def main():
     out["final_conseq"] = (res / "final_conseq.txt").read_text().split()
     out["candidate_rows"] = len((res / "candidate_conseq.csv").read_text().splitlines()) - 1
     Path("gpurun_out").mkdir(exist_ok=True)
-    Path("gpurun_out/workflow.json").write_text(json.dumps(out, indent=1))
-    Path("gpurun_out/workflow_profile.txt").write_text(s.getvalue())
+    tag = "" if spec_name == "cfg2" else "_" + spec_name
+    Path(f"gpurun_out/workflow{tag}.json").write_text(json.dumps(out, indent=1))
+    Path(f"gpurun_out/workflow{tag}_profile.txt").write_text(s.getvalue())
     print(json.dumps(out))
     print(s.getvalue()[:6000])
 

@@ -40,9 +40,24 @@ def main():
             ends = np.cumsum(lens)
             return np.concatenate(arrs), np.stack([ends - lens, ends - 1], axis=1).astype(np.int64)
         inputs = [synth.generate_numpy(synth.CFG3, 0, n_reads), synth.generate_numpy(synth.CFG2_N, 0, n_reads), with_long_reads()]
+        from kmap_b200 import engine as E
+        scat = api.TableAllReduce(scatter=True)
         for seq, borders in inputs:
             s, b = api.shard_reads(seq, borders, rank, world)
             for rep_mode in (False, True):
+                # the merge left scattered by key range (kmap_count_all_k_scattered: reduce-scatter + reductions on the owned
+                # ranges only): every rank's owned range of every level equals that range of the all-reduced tables
+                dev = api.upload_reads(s, b)
+                full = dev.count_all(8, 14, dedup=not rep_mode, merge=ctx.table_allreduce)
+                part_t = dev.count_all(8, 14, dedup=not rep_mode, merge=scat)
+                for k in range(8, 15):
+                    lo, hi = scat.owned_range(k)
+                    assert torch.equal(part_t[k][lo:hi], full[k][lo:hi]), (k, rep_mode, "scattered merge")
+                t13 = full[13].clone()
+                scat.reduce_scatter(t13)                       # (x world on the owned block: every rank holds the merged table)
+                lo, hi = scat.owned_range(13)
+                assert torch.equal(t13[lo:hi].to(torch.int64), full[13][lo:hi].to(torch.int64) * world)
+                del dev, full, part_t, t13
                 ks = [8, 11, 13, 14]
                 got = api.count_kmers(s, b, list(range(8, 15)) + [16], rep_mode=rep_mode, table_allreduce=ctx.table_allreduce, lists_on=0)
                 # every rank compacts and returns one key range of every list: the slices concatenate to the whole list
