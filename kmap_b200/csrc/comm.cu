@@ -4,6 +4,7 @@
 // process already carries -- PyTorch's -- else the system one), so the library loads and exports every symbol on a box
 // without NCCL; the calls then fail loudly.  The communicator is created from a 128-byte unique id that the host plumbing
 // (torch.distributed) broadcasts; it is owned by the caller and passed to every call: the library keeps no communicator.
+#include <cstdlib>
 #include <dlfcn.h>
 #include <nccl.h>
 #include <mutex>
@@ -17,6 +18,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;      // (optional)
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommCount)(const ncclComm_t, int*) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -36,6 +38,7 @@ const NcclApi& nccl_api() {
         api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.handle, "ncclCommInitRank"));
         api.CommInitRankConfig = reinterpret_cast<decltype(api.CommInitRankConfig)>(dlsym(api.handle, "ncclCommInitRankConfig"));
         api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.handle, "ncclCommDestroy"));
+        api.CommCount = reinterpret_cast<decltype(api.CommCount)>(dlsym(api.handle, "ncclCommCount"));
         api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.handle, "ncclAllReduce"));
         api.ReduceScatter = reinterpret_cast<decltype(api.ReduceScatter)>(dlsym(api.handle, "ncclReduceScatter"));
         api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
@@ -58,6 +61,21 @@ int kmap_allreduce_u32_on(uint32_t* buf, int64_t n, void* comm, cudaStream_t s) 
     if (!api.ok) { kmap_set_error("table_allreduce: no NCCL library in this process"); return KMAP_ERR_COMM; }
     const ncclResult_t r = api.AllReduce(buf, buf, (size_t)n, ncclUint32, ncclSum, reinterpret_cast<ncclComm_t>(comm), s);
     return r == ncclSuccess ? KMAP_OK : nccl_fail("table_allreduce", r);
+}
+
+int kmap_comm_ctas(int world) {
+    static const int v = [] { const char* e = getenv("KMAP_COMM_CTAS"); const int x = e ? atoi(e) : 0; return x > 0 && x <= 128 ? x : 0; }();
+    return v ? v : (world >= 4 ? 32 : KMAP_COMM_CTAS);
+}
+int kmap_merge_chunks(int world) {
+    static const int v = [] { const char* e = getenv("KMAP_MERGE_CHUNKS"); const int x = e ? atoi(e) : 0; return x > 0 && x <= 8 ? x : 0; }();
+    return v ? v : (world >= 4 ? 2 : 4);
+}
+int kmap_comm_world(void* comm) {
+    const NcclApi& api = nccl_api();
+    int n = 1;
+    if (!api.ok || !api.CommCount || !comm || api.CommCount(reinterpret_cast<ncclComm_t>(comm), &n) != ncclSuccess) return 1;
+    return n;
 }
 
 int kmap_merge_table_on(uint32_t* buf, int64_t n, const KmapMerge* m) {
@@ -98,7 +116,7 @@ int kmap_comm_init(const uint8_t* id_in, int rank, int world, void** comm_out) {
     ncclResult_t r;
     if (api.CommInitRankConfig) {
         ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
-        cfg.maxCTAs = KMAP_COMM_CTAS;
+        cfg.maxCTAs = kmap_comm_ctas(world);
         r = api.CommInitRankConfig(&comm, world, id, rank, &cfg);              // binds to the current CUDA device
     } else {
         r = api.CommInitRank(&comm, world, id, rank);

@@ -28,6 +28,11 @@ static inline unsigned int grid_for(int64_t n_threads, int block) {
 // of the cells.  Needs world | 4^kmin.
 struct KmapMerge { void* comm; cudaStream_t stream; int scatter; int rank; int world; };
 #define KMAP_COMM_CTAS 16         // CTAs the collective may use = SMs the counting kernels leave free while it runs
+// Measured (profiles/r02_merge_sweep_8gpu.txt): with 2 ranks the exchange hides behind the per-bucket count and 16 CTAs are
+// enough; from 4 ranks on a rank's count is shorter than the exchange, which then wants 32 CTAs and fewer, larger calls.
+int kmap_comm_ctas(int world);    // ... KMAP_COMM_CTAS for < 4 ranks, 32 from 4 ranks on, unless the environment says otherwise (KMAP_COMM_CTAS)
+int kmap_merge_chunks(int world); // key ranges the level-kmax table is merged in while it is counted: 4 (< 4 ranks) or 2 (KMAP_MERGE_CHUNKS)
+int kmap_comm_world(void* comm);  // number of ranks of a communicator (1 on failure)
 int kmap_allreduce_u32_on(uint32_t* buf, int64_t n, void* comm, cudaStream_t s);
 // merge one table the way `m` says: all-reduce, or reduce-scatter in place (rank r's block stays where it is in `buf`)
 int kmap_merge_table_on(uint32_t* buf, int64_t n, const KmapMerge* m);

@@ -661,7 +661,7 @@ extern "C" int kmap_count_all_k_sharded(const uint32_t* packed, const uint32_t* 
                                         uint32_t* bitmap, int n_partitions, int scheme, void* part_scratch, int64_t part_scratch_bytes,
                                         void* const* phase_events, void* stream, void* comm, void* comm_stream) {
     KMAP_REQUIRE(comm && comm_stream, "the sharded count needs a communicator and a stream for the exchange");
-    const KmapMerge merge = {comm, as_stream(comm_stream), 0, 0, 1};
+    const KmapMerge merge = {comm, as_stream(comm_stream), 0, 0, kmap_comm_world(comm)};
     return count_all_impl(packed, valid, n, borders, n_seq, kmin, kmax, dedup, tables_host, dupmask, work, bitmap, n_partitions, scheme,
                           part_scratch, part_scratch_bytes, phase_events, stream, &merge);
 }

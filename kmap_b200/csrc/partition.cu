@@ -694,7 +694,7 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
         uint32_t* q = p.queues + (size_t)(n_launch++ % BC_QUEUES) * (2 + n_all);
         bucket_count_kernel<<<(unsigned int)(nb < bc_grid ? nb : bc_grid), BC_THREADS, BC_WORDS * 4, s>>>(p.suffixes, p.base, n_buckets, b_lo, b_hi, table,
                                                                                                         route ? tt.t[k - 1] : nullptr, seg_len, q);
-        bucket_segments_kernel<<<beside ? 148 - KMAP_COMM_CTAS : 148, BC_THREADS, BC_WORDS * 4, s>>>(p.suffixes, p.base, n_buckets, table,
+        bucket_segments_kernel<<<beside ? 148 - kmap_comm_ctas(merge->world) : 148, BC_THREADS, BC_WORDS * 4, s>>>(p.suffixes, p.base, n_buckets, table,
                                                                                                        route ? tt.t[k - 1] : nullptr, seg_len, q);
     };
     if (!merge || !merge->comm) {
@@ -725,7 +725,7 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
         merge_after(tt.t[k - 1], (int64_t)1 << (2 * (k - 1)));
     }
     // (scattered: a rank's block of the table must stay one contiguous key range, so the table is merged in one piece)
-    const int n_chunks = (n_buckets >= 1024 && !merge->scatter) ? 4 : 1;
+    const int n_chunks = (n_buckets >= 1024 && !merge->scatter) ? kmap_merge_chunks(merge->world) : 1;
     for (int c = 0; c < n_chunks; ++c) {
         const int b_lo = n_buckets * c / n_chunks, b_hi = n_buckets * (c + 1) / n_chunks;
         count_range(b_lo, b_hi);
