@@ -441,58 +441,51 @@ def main():
     # partitioned over the ranks in contiguous blocks, no collective (cal_samp_kmer_hamdist_mat, motif_discovery.py:759-808)
     hamdist = None
     if not args.no_hamdist:
-        from kmap_b200.motif_discovery import hamdist_matrix_u8
+        from kmap_b200.motif_discovery import hamdist_formulation, hamdist_matrix_u8
         rng = np.random.default_rng(20240414)
         n_h, k_h = 100_000, 14
         khs = np.unique(rng.integers(0, 4 ** k_h, int(n_h * 1.01), dtype=np.uint64))[:n_h].astype(np.uint32)
         rng.shuffle(khs)
         labels_h = rng.integers(0, 3, n_h).astype(np.int32)
         row0, row1 = api.row_range(n_h, rank, world)
+
+        def time_matrix(impl, out_buf):
+            hamdist_matrix_u8(khs, labels_h, [14, 12], k_h, row0, row1, out=out_buf, impl=impl)         # warm-up
+            barrier()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            for _ in range(5):
+                hamdist_matrix_u8(khs, labels_h, [14, 12], k_h, row0, row1, out=out_buf, impl=impl)
+            h1.record()
+            barrier()
+            th = torch.tensor([h0.elapsed_time(h1) / 5], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(th, op=dist.ReduceOp.MAX)
+            return float(th.item())
+
+        # the product path (hamdist_formulation picks the kernel) and both formulations by name: XOR/popcount (csrc/hamdist.cu)
+        # and the int8 one-hot GEMM on the tcgen05 tensor cores (csrc/hamdist_mma.cu); the outputs must be bit-identical
         out_h = E.empty((row1 - row0) * n_h, torch.uint8)
-        hamdist_matrix_u8(khs, labels_h, [14, 12], k_h, row0, row1, out=out_h)             # warm-up
-        barrier()
-        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        h0.record()
-        for _ in range(5):
-            hamdist_matrix_u8(khs, labels_h, [14, 12], k_h, row0, row1, out=out_h)
-        h1.record()
-        barrier()
-        th = torch.tensor([h0.elapsed_time(h1) / 5], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(th, op=dist.ReduceOp.MAX)
-        ms_h = float(th.item())
+        out_g = E.empty((row1 - row0) * n_h, torch.uint8)
+        chosen = hamdist_formulation(n_h, k_h, [14, 12])
+        ms_h = time_matrix(None, out_h)
+        ms_pop = time_matrix("popcount", out_g)
+        same = bool(torch.equal(out_g, out_h))
+        ms_mma = time_matrix("onehot_mma", out_g)
+        same = same and bool(torch.equal(out_g, out_h))
+        checks["hamdist_onehot_gemm_equals_popcount"] = same
         diag = out_h.view(row1 - row0, n_h)[torch.arange(min(row1 - row0, 1000), device="cuda"), torch.arange(row0, row0 + min(row1 - row0, 1000), device="cuda")]
         checks["hamdist_diag_zero"] = bool((diag == 0).all().item())
         hamdist = {"metric": "hamdist_pairs_per_s", "value": n_h * n_h / ms_h * 1e3, "unit": "pairs/s", "ms": ms_h, "pairs": n_h * n_h,
                    "n_kmers": n_h, "k": k_h, "rows_per_gpu": row1 - row0, "partition": "contiguous row blocks, no collective",
-                   "bytes_written_per_gpu": (row1 - row0) * n_h, "write_GBs_per_gpu": (row1 - row0) * n_h / ms_h / 1e6,
+                   "formulation": chosen, "bytes_written_per_gpu": (row1 - row0) * n_h, "write_GBs_per_gpu": (row1 - row0) * n_h / ms_h / 1e6,
                    "frac_of_hbm_copy_peak": (row1 - row0) * n_h / ms_h / 1e6 / peak,
-                   "note": "uint8 output, 1 B per pair; same-label pairs of the 12-base consensus use the head distance; includes the "
-                           "H2D of the keys and labels; a B200 writes at most ~3.9 TB/s (the copy peak counts a read and a write)"}
-        # the comparator BASELINE config 5 names: the same rows as an int8 one-hot GEMM on the tcgen05 tensor cores
-        # (csrc/hamdist_mma.cu, hand-written tcgen05.mma.kind::i8 + TMEM epilogue); the output must be bit-identical
-        from kmap_b200.motif_discovery import hamdist_matrix_onehot_mma
-        out_g = E.empty((row1 - row0) * n_h, torch.uint8)
-        hamdist_matrix_onehot_mma(khs, labels_h, [14, 12], k_h, row0, row1, out=out_g)     # warm-up
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(5):
-            hamdist_matrix_onehot_mma(khs, labels_h, [14, 12], k_h, row0, row1, out=out_g)
-        g1.record()
-        barrier()
-        tg = torch.tensor([g0.elapsed_time(g1) / 5], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        ms_g = float(tg.item())
-        same = bool(torch.equal(out_g, out_h))
-        checks["hamdist_onehot_gemm_equals_popcount"] = same
-        hamdist["onehot_tcgen05_gemm"] = {
-            "ms": ms_g, "pairs_per_s": n_h * n_h / ms_g * 1e3, "identical_output": same, "popcount_over_gemm_time": ms_h / ms_g,
-            "mma": "tcgen05.mma.cta_group::1.kind::i8, M=128 N=256 K=2x32 per 128x256 tile, S32 accumulators in TMEM (2 x 256 columns)",
-            "note": "one-hot A x complement-one-hot B^T gives the distance itself; 2 x 56 int8 MACs per pair = 1.1e12 MACs = under 0.3 ms "
-                    "of tensor time: both formulations are bound by the 1 B/pair store, so the simpler popcount kernel is kept "
-                    "(DESIGN.md section 4.7)"}
+                   "formulations_ms": {"popcount": ms_pop, "onehot_tcgen05_gemm": ms_mma, "identical_output": same},
+                   "mma": "tcgen05.mma.cta_group::1.kind::i8, M=128 N=256 K=64..128, S32 accumulators in TMEM (2 x 256 columns), "
+                          "cp.async.bulk operand tiles, TMA tensor stores",
+                   "note": "uint8 output, 1 B per pair; same-label pairs of the 12-base consensus use the head distance (extra K columns "
+                           "in the GEMM, masked flags in the popcount kernel); every figure includes the H2D of the keys and labels and, "
+                           "for the GEMM, the operand preparation; the write-only fill rate of this GPU is in fill_rate_GBs"}
         del out_h, out_g
 
     # ---- end-to-end through the public API with host buffers -------------------------------------------------------------

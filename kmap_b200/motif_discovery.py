@@ -713,12 +713,36 @@ def _convert_to_block_arr(arr: np.ndarray, block_size_arr: np.ndarray) -> np.nda
     return np.repeat(arr, block_size_arr)
 
 
+HAMDIST_MMA_MIN_N = 2048            # below this the matrix is a few hundred tiles: the XOR/popcount kernel, no operand preparation
+HAMDIST_MMA_MAX_SLOTS = 32          # K = 128 int8 = 32 slots of one base: k bases + the tail bases of every shorter consensus
+
+
+def hamdist_formulation(n: int, kmer_len: int, head_len: Sequence[int]) -> str:
+    """which kernel hamdist_matrix_u8 uses.  Measured on B200 (profiles/r02_ncu_hamdist_*.txt, 1e10 pairs): the int8 one-hot
+    GEMM on the tcgen05 tensor cores writes the matrix in 2.12 ms with or without head overrides (they are extra K columns),
+    the XOR/popcount kernel in 2.63 / 2.89 ms (bound by the POPC pipe: 16 per clock and SM) -- so the tensor cores are kept
+    wherever the formulation applies: 32-bit hashes (k <= 16), override columns that fit into K = 128, a matrix large enough
+    to fill the machine.  Everything else (uint64 hashes, many short consensus sequences, small samples) stays on popcount."""
+    slots = kmer_len + sum(kmer_len - max(int(h), 0) for h in head_len if int(h) < kmer_len)
+    if kmer_len <= 16 and n >= HAMDIST_MMA_MIN_N and slots <= HAMDIST_MMA_MAX_SLOTS and len(head_len) <= 127:
+        return "onehot_mma"
+    return "popcount"
+
+
 def hamdist_matrix_u8(kh: np.ndarray, labels: np.ndarray, head_len: Sequence[int], kmer_len: int, row0: int = 0,
-                      row1: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """rows [row0,row1) of the pairwise distance matrix as a uint8 device tensor [(row1-row0), n]"""
+                      row1: Optional[int] = None, out: Optional[torch.Tensor] = None, impl: Optional[str] = None) -> torch.Tensor:
+    """rows [row0,row1) of the pairwise distance matrix as a uint8 device tensor [(row1-row0), n] (md:759-808).
+    impl: None = hamdist_formulation(); "popcount" (csrc/hamdist.cu) or "onehot_mma" (csrc/hamdist_mma.cu) force one; both
+    write the same bytes."""
     L = lib()
     n = len(kh)
     row1 = n if row1 is None else row1
+    if impl is None:
+        impl = hamdist_formulation(n, kmer_len, head_len)
+    if impl == "onehot_mma":
+        return hamdist_matrix_onehot_mma(kh, labels, head_len, kmer_len, row0, row1, out)
+    if impl != "popcount":
+        raise KmapError(f"unknown distance-matrix formulation {impl!r}")
     hd = get_hash_dtype(kmer_len)
     kh_d = E.to_device(np.asarray(kh).astype(hd, copy=False))
     lab_d = E.to_device(np.asarray(labels).astype(np.int32, copy=False))
@@ -733,13 +757,14 @@ def hamdist_matrix_u8(kh: np.ndarray, labels: np.ndarray, head_len: Sequence[int
 
 def hamdist_matrix_onehot_mma(kh: np.ndarray, labels: np.ndarray, head_len: Sequence[int], kmer_len: int, row0: int = 0,
                               row1: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """The same rows as hamdist_matrix_u8 (k <= 16), computed as an int8 one-hot GEMM on the tcgen05 tensor cores
-    (csrc/hamdist_mma.cu): the comparator formulation of BASELINE config 5, bit-identical to the XOR/popcount kernel."""
+    """The rows of hamdist_matrix_u8 (k <= 16) computed as an int8 one-hot GEMM on the tcgen05 tensor cores
+    (csrc/hamdist_mma.cu): one-hot A x complement-one-hot B^T is the distance itself, the head override of same-label pairs
+    is a few extra K columns, the tiles leave through TMA stores.  Bit-identical to the XOR/popcount kernel."""
     L = lib()
     n = len(kh)
     row1 = n if row1 is None else row1
     if kmer_len > 16:
-        raise KmapError("the one-hot GEMM comparator covers k <= 16")
+        raise KmapError("the one-hot GEMM formulation covers k <= 16 (32-bit hashes)")
     kh_d = E.to_device(np.asarray(kh).astype(np.uint32, copy=False))
     lab_d = E.to_device(np.asarray(labels).astype(np.int32, copy=False))
     hl_d = E.to_device(np.asarray(list(head_len), dtype=np.int32)) if len(head_len) else None

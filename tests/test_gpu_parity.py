@@ -363,14 +363,15 @@ def test_hamdist_row_blocks_and_properties(MD):
 
 @pytest.mark.parametrize("k,n", [(14, 1616), (14, 777), (8, 300), (16, 2048), (1, 50), (12, 5000)])
 def test_hamdist_onehot_tcgen05_gemm_equals_popcount_kernel(MD, k, n):
-    """the int8 one-hot GEMM on the tcgen05 tensor cores (csrc/hamdist_mma.cu, the comparator of BASELINE config 5) writes
-    the same bytes as the XOR/popcount kernel and the oracle: head overrides, ragged edges (n not a multiple of the 128 x
-    256 tile or of 16), row blocks"""
+    """the int8 one-hot GEMM on the tcgen05 tensor cores (csrc/hamdist_mma.cu, the formulation BASELINE config 5 asks to be
+    measured against XOR/popcount) writes the same bytes as the XOR/popcount kernel and the oracle: head overrides as extra
+    K columns (K = 64, 96, 128) and recomputed in the epilogue when they do not fit, ragged edges (n not a multiple of the
+    128 x 256 tile or of 16: TMA clipping / the warps' own stores), row blocks that do not start at a tile boundary"""
     rng = np.random.default_rng(100 + k + n)
     kh = rng.integers(0, 4 ** k, n, dtype=np.uint64).astype(np.uint32)
     labels = rng.integers(0, 4, n)
     head = [k, max(1, k - 2), max(1, k - 5)]                     # label 3 has no consensus entry: never overrides
-    want = MD.hamdist_matrix_u8(kh, labels, head, k).cpu().numpy()
+    want = MD.hamdist_matrix_u8(kh, labels, head, k, impl="popcount").cpu().numpy()
     got = MD.hamdist_matrix_onehot_mma(kh, labels, head, k).cpu().numpy()
     assert np.array_equal(got, want)
     if n <= 2048 and len(np.unique(kh)) == n:
@@ -380,8 +381,20 @@ def test_hamdist_onehot_tcgen05_gemm_equals_popcount_kernel(MD, k, n):
         if r0 < r1 <= n:
             part = MD.hamdist_matrix_onehot_mma(kh, labels, head, k, r0, r1).cpu().numpy()
             assert np.array_equal(part, want[r0:r1]), (r0, r1)
+    # what the product picks: the GEMM where it applies and pays (k <= 16, override columns within K = 128, n >= 2048)
+    assert MD.hamdist_formulation(n, k, head) == ("onehot_mma" if n >= 2048 else "popcount")
+    assert MD.hamdist_formulation(100000, 17, []) == "popcount" and MD.hamdist_formulation(100000, 14, [14, 2, 3]) == "popcount"
+    assert np.array_equal(MD.hamdist_matrix_u8(kh, labels, head, k).cpu().numpy(), want)
     plain = MD.hamdist_matrix_onehot_mma(kh, np.full(n, -1), [], k).cpu().numpy()
-    assert np.array_equal(plain, MD.hamdist_matrix_u8(kh, np.full(n, -1), [], k).cpu().numpy())
+    assert np.array_equal(plain, MD.hamdist_matrix_u8(kh, np.full(n, -1), [], k, impl="popcount").cpu().numpy())
+    if k >= 12:       # so many tail bases that the override columns do not fit into K = 128: the epilogue recomputes those pairs
+        many = [k, 2, 3, k - 2]
+        assert np.array_equal(MD.hamdist_matrix_onehot_mma(kh, labels, many, k).cpu().numpy(),
+                              MD.hamdist_matrix_u8(kh, labels, many, k, impl="popcount").cpu().numpy())
+        # K = 128 exactly used / one label only
+        for heads in ([k, k - 4, k - 4, k - 4][:4], [k - 1]):
+            assert np.array_equal(MD.hamdist_matrix_onehot_mma(kh, labels, heads, k).cpu().numpy(),
+                                  MD.hamdist_matrix_u8(kh, labels, heads, k, impl="popcount").cpu().numpy()), heads
 
 
 def test_synth_device_matches_numpy(ENG):

@@ -158,3 +158,15 @@ def test_consumers_from_scan_merge_logic(tmp_path):
         a = MD.get_motif_pos_density(tmp_path / "o.csv", i, len(c))
         b = MD.pos_density_from_scan(info, i, len(c))
         assert a[:2] == b[:2] and np.array_equal(a[2], b[2])
+
+
+def test_hamdist_formulation_choice():
+    """which distance-matrix kernel the product picks (motif_discovery.hamdist_formulation): the tcgen05 GEMM for 32-bit hashes
+    when the override columns fit into K = 128 and the sample is large, the XOR/popcount kernel otherwise"""
+    from kmap_b200 import motif_discovery as MD
+    assert MD.hamdist_formulation(100_000, 14, [14, 12]) == "onehot_mma"          # BASELINE config 5
+    assert MD.hamdist_formulation(100_000, 14, []) == "onehot_mma"
+    assert MD.hamdist_formulation(100_000, 16, [16, 12, 12, 12, 12]) == "onehot_mma"   # 16 + 4 * 4 = 32 slots: K = 128 exactly
+    assert MD.hamdist_formulation(100_000, 16, [16, 12, 12, 12, 11]) == "popcount"     # 33 slots
+    assert MD.hamdist_formulation(100_000, 17, [17]) == "popcount"                # uint64 hashes
+    assert MD.hamdist_formulation(2047, 14, [14]) == "popcount" and MD.hamdist_formulation(2048, 14, [14]) == "onehot_mma"
