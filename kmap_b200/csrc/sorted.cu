@@ -452,14 +452,26 @@ __global__ void __launch_bounds__(RS_THREADS, 3) onesweep_pass_kernel(const u64*
         if (threadIdx.x == 0) tile_total = all;
         u64 before = 0;                                     // keys with digit d in the earlier tiles
         if (tile > 0) {
+            // Look-back, eight predecessors per step with their status words requested together: the walk is a chain of
+            // dependent L2 round trips otherwise, and the time a tile spends in it sets how far back the next tiles must walk.
             int64_t t = tile - 1;
-            for (;;) {
-                const volatile u64* ps = status + (size_t)t * 256 + d;
-                u64 sv = *ps;
-                while ((sv >> 62) == 0) sv = *ps;
-                before += sv & OS_VALUE;
-                if ((sv >> 62) == 2 || t == 0) break;
-                --t;
+            bool done = false;
+            while (!done) {
+                u64 sv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int64_t tt = t - u;
+                    sv[u] = tt >= 0 ? *(const volatile u64*)(status + (size_t)tt * 256 + d) : OS_PREFIX;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (done) break;
+                    u64 x = sv[u];
+                    while ((x >> 62) == 0) x = *(const volatile u64*)(status + (size_t)(t - u) * 256 + d);    // not published yet
+                    before += x & OS_VALUE;
+                    if ((x >> 62) == 2) done = true;
+                }
+                t -= 8;
             }
             *st = OS_PREFIX | (before + (u64)mine);
         }

@@ -33,5 +33,20 @@ val, idx = E.topk_candidates(cnt, 6)
 mdd = K.init_motif_def_dict(ROOT / "kmap_b200" / "default_motif_def_table.csv")
 khh = E.to_host(kh, np.uint32)
 lab = MD.label_kmers(khh, ["AATCGATAGC"], 14, mdd, True)
+# round 2: consumers of the occurrence scan, host encoders + border strides, streamed count, both distance-matrix formulations
+from kmap_b200 import api  # noqa: E402
+conseqs = ["AATCGATAGC", "AGGACCTACGTAC"]
+scan = [E.occurrence_scan_device(dev, len(c), int(K.kmer2hash(c)), mdd[len(c)].max_ham_dist, True) for c in conseqs]
+counts, pairs, over = E.co_occurrence_scan(scan)
+print("co-occurrence:", counts.tolist(), len(over), E.sum_counts(cnt))
+res = api.count_kmers(seq, borders, range(8, 15), chunk_positions=len(seq) // 5 + 1)
+print("streamed:", {k_: len(v[0]) for k_, v in res.items()})
+rng = np.random.default_rng(0)
+kk = rng.integers(0, 4 ** 14, 3000, dtype=np.uint64).astype(np.uint32)
+lb = rng.integers(0, 3, 3000)
+a1 = MD.hamdist_matrix_u8(kk, lb, [14, 12], 14, 5, 2900, impl="popcount")
+a2 = MD.hamdist_matrix_u8(kk, lb, [14, 12], 14, 5, 2900, impl="onehot_mma")
+a3 = MD.hamdist_matrix_u8(kk, lb, [14, 2, 3], 14, impl="onehot_mma")
+print("hamdist equal:", bool(torch.equal(a1, a2)), tuple(a3.shape))
 torch.cuda.synchronize()
 print("done")
