@@ -271,8 +271,8 @@ def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterabl
     flat = None
     merged_inside = False
     if bounds is not None and len(bounds) > 2:
-        if validate:
-            E.check_borders_tile(np.asarray(boarder_mat).reshape(-1, 2), len(seq_np_arr))
+        # (the layout check of `validate` is inherent here: _chunk_bounds verified the ends and the cuts, and the stride encoder
+        #  verifies every row inside a chunk, kmap_host_border_strides)
         world_local = table_allreduce.world if table_allreduce is not None else 1
         flat, tables, n_total = count_tables_streamed(seq_np_arr, boarder_mat, ks[0], ks[-1], rep_mode, bounds, host_pack,
                                                       host_pack_threads(world_local))
