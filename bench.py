@@ -104,8 +104,8 @@ def launches_per_step(args, dedup):
     if args.algo != "allk":
         return KMAX - KMIN + 1
     derive = KMAX - KMIN
-    if args.partitions <= 0:                     # dedup_scan + hist + 3 scan kernels + partition + bucket_count + derive
-        return (1 if dedup else 0) + 6 + derive
+    if args.partitions <= 0:     # dedup_scan + hist + 3 scan kernels + partition + bucket_count + bucket_segments + derive
+        return (1 if dedup else 0) + 7 + derive
     return (1 if dedup else 0) + 5 + max(1, args.partitions) + derive      # + terminal-correction launches + prefix passes
 
 
