@@ -188,160 +188,18 @@ constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;        // 4096 keys per tile
 constexpr int RS_WARP_KEYS = RS_TILE / (RS_THREADS / 32);   // 512 consecutive keys per warp
 
-// counts[d * n_tiles + tile] = keys of the tile whose digit is d (invalid keys are not counted when drop_empty)
-__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const u64* __restrict__ in, int64_t n_upper, const u64* __restrict__ n_dev,
-                                                                int shift, int drop_empty, int64_t n_tiles, uint32_t* __restrict__ counts) {
-    __shared__ uint32_t hist[256];
-    const int64_t n = n_dev ? (int64_t)*n_dev : n_upper;
-    hist[threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
-#pragma unroll 4
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        const int64_t i = base + j * RS_THREADS + threadIdx.x;
-        if (i < n) {
-            const u64 key = __ldg(in + i);
-            if (!(drop_empty && key == KEY_EMPTY)) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
-        }
-    }
-    __syncthreads();
-    counts[(size_t)threadIdx.x * n_tiles + blockIdx.x] = hist[threadIdx.x];
-}
-
-// totals[d] = keys with digit d
-__global__ void __launch_bounds__(256) radix_digit_total_kernel(const uint32_t* __restrict__ counts, int64_t n_tiles, u64* __restrict__ totals) {
-    __shared__ u64 ws[8];
-    const uint32_t* row = counts + (size_t)blockIdx.x * n_tiles;
-    u64 s = 0;
-    for (int64_t t = threadIdx.x; t < n_tiles; t += 256) s += row[t];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, o);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) { u64 t = 0; for (int q = 0; q < 8; ++q) t += ws[q]; totals[blockIdx.x] = t; }
-}
-
-// offsets[d * n_tiles + tile] = first output index of the tile's keys with digit d; block d scans its row.
-// Block 0 also writes *n_out = number of keys that take part (the sum of the totals).
-__global__ void __launch_bounds__(1024) radix_offsets_kernel(const uint32_t* __restrict__ counts, int64_t n_tiles, const u64* __restrict__ totals,
-                                                             u64* __restrict__ offsets, u64* __restrict__ n_out) {
-    __shared__ u64 partial[1024];
-    __shared__ u64 digit_base;
-    const int d = blockIdx.x;
-    if (threadIdx.x == 0) {
-        u64 b = 0, all = 0;
-        for (int q = 0; q < 256; ++q) { if (q < d) b += totals[q]; all += totals[q]; }
-        digit_base = b;
-        if (d == 0 && n_out) *n_out = all;
-    }
-    const uint32_t* row = counts + (size_t)d * n_tiles;
-    u64* orow = offsets + (size_t)d * n_tiles;
-    const int64_t chunk = (n_tiles + 1023) / 1024;
-    const int64_t lo = (int64_t)threadIdx.x * chunk, hi = lo + chunk < n_tiles ? lo + chunk : n_tiles;
-    u64 s = 0;
-    for (int64_t t = lo; t < hi; ++t) s += row[t];
-    partial[threadIdx.x] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        u64 run = digit_base;
-        for (int i = 0; i < 1024; ++i) { const u64 t = partial[i]; partial[i] = run; run += t; }
-    }
-    __syncthreads();
-    u64 run = partial[threadIdx.x];
-    for (int64_t t = lo; t < hi; ++t) { orow[t] = run; run += row[t]; }
-}
-
-// stable scatter: warp w of the tile owns keys [w * 512, (w + 1) * 512) in 16 rounds of 32 consecutive keys; inside a
-// round the rank among equal digits comes from __match_any_sync, across rounds from a per-warp counter, across warps and
-// tiles from the scanned histograms.  The keys are first put in digit order in shared memory, so that the write-out stores
-// runs of consecutive addresses (one run per digit present in the tile) instead of one scattered 8-byte store per key.
-__global__ void __launch_bounds__(RS_THREADS, 3) radix_scatter_kernel(const u64* __restrict__ in, u64* __restrict__ out, int64_t n_upper,
-                                                                   const u64* __restrict__ n_dev, int shift, int drop_empty,
-                                                                   int64_t n_tiles, const u64* __restrict__ offsets) {
-    __shared__ u64 skeys[RS_TILE];                         // the tile in digit order
-    __shared__ uint32_t wcnt[RS_THREADS / 32][256];        // per (warp, digit): count, then start inside the tile
-    __shared__ u64 gdelta[256];                            // global index of the digit's run - its start inside the tile
-    __shared__ uint32_t scan_ws[RS_THREADS / 32];
-    __shared__ uint32_t tile_total;
-    const int64_t n = n_dev ? (int64_t)*n_dev : n_upper;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int q = 0; q < RS_THREADS / 32; ++q) wcnt[q][threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * RS_WARP_KEYS;
-    u64 key[RS_ITEMS];
-    uint32_t rank[RS_ITEMS];          // while the counters are being filled: count before this round | leader lane << 16 | rank among peers << 21
-    uint32_t live = 0;
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; ++r) {
-        const int64_t i = base + r * 32 + lane;
-        key[r] = i < n ? __ldcs(in + i) : KEY_EMPTY;
-    }
-    // The leader of every group of equal digits adds the group's size to the warp's counter of that digit.  The rounds are
-    // issued back to back (the returned values are only looked at after the loop), and __syncwarp orders the updates of
-    // successive rounds, so earlier rounds get the lower ranks: the scatter is stable.
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; ++r) {
-        const int64_t i = base + r * 32 + lane;
-        const bool ok = i < n && !(drop_empty && key[r] == KEY_EMPTY);
-        const uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, ok ? d : (256u + (uint32_t)lane));
-        const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
-        uint32_t old = 0;
-        if (ok && (uint32_t)lane == leader) old = atomicAdd(&wcnt[w][d], (uint32_t)__popc(peers));
-        rank[r] = old | (leader << 16) | ((uint32_t)__popc(peers & ((1u << lane) - 1u)) << 21);
-        if (ok) live |= 1u << r;
-        __syncwarp();
-    }
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; ++r) {
-        const uint32_t before = __shfl_sync(0xFFFFFFFFu, rank[r] & 0xFFFFu, (rank[r] >> 16) & 31u);
-        rank[r] = before + (rank[r] >> 21);
-    }
-    __syncthreads();
-    {
-        // thread d: digit d's keys of the warps in order; then an exclusive scan over the digits gives the tile layout
-        const uint32_t d = threadIdx.x;
-        uint32_t cnt_w[RS_THREADS / 32];
-        uint32_t mine = 0;
-#pragma unroll
-        for (int q = 0; q < RS_THREADS / 32; ++q) { cnt_w[q] = wcnt[q][d]; mine += cnt_w[q]; }
-        uint32_t incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += y;
-        }
-        if (lane == 31) scan_ws[w] = incl;
-        __syncthreads();
-        uint32_t pre = 0, all = 0;
-#pragma unroll
-        for (int q = 0; q < RS_THREADS / 32; ++q) { if (q < w) pre += scan_ws[q]; all += scan_ws[q]; }
-        uint32_t start = pre + incl - mine;                 // first slot of digit d in the tile
-        if (threadIdx.x == 0) tile_total = all;
-        gdelta[d] = offsets[(size_t)d * n_tiles + blockIdx.x] - start;
-#pragma unroll
-        for (int q = 0; q < RS_THREADS / 32; ++q) { wcnt[q][d] = start; start += cnt_w[q]; }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; ++r)
-        if ((live >> r) & 1u) skeys[wcnt[w][(uint32_t)(key[r] >> shift) & 255u] + rank[r]] = key[r];
-    __syncthreads();
-    const uint32_t total = tile_total;
-    for (uint32_t i = threadIdx.x; i < total; i += RS_THREADS) {
-        const u64 kk = skeys[i];
-        out[gdelta[(uint32_t)(kk >> shift) & 255u] + i] = kk;
-    }
-}
-
 // ---- onesweep: one histogram read for all passes, then ONE kernel per 8-bit digit ----------------------------------------------
-// The three-kernel pass above reads the keys twice per digit (histogram, scatter) and runs two small scans in between.
-// Onesweep (Adinets & Merrill): (a) one kernel reads the keys once and histograms every digit position at the same time;
+// A histogram -> scan -> scatter pass reads the keys twice per digit and runs two small scans in between (that was round 1's
+// form: 2.72 ms for the 4.1e7 keys that take 2.15 ms here).  Onesweep (Adinets & Merrill): (a) one kernel reads the keys once and histograms every digit position at the same time;
 // (b) per digit position one kernel does count + inter-tile prefix + scatter: a tile publishes its per-digit counts in a
 // status word (flag | value in one 64-bit word, so the word itself is the message and no fence is needed), then looks back
 // over its predecessors until it meets one that has published an inclusive prefix (decoupled look-back).  Tiles are
 // numbered by an atomic ticket, so every predecessor of a running tile is running or done and the look-back cannot
 // deadlock.  Traffic: 8 B/key once + 16 B/key per digit, against 24 B/key per digit.
+// Stable scatter inside a tile: warp w owns keys [w * 512, (w + 1) * 512) in 16 rounds of 32 consecutive keys; inside a round
+// the rank among equal digits comes from __match_any_sync, across rounds from a per-warp counter, across warps from the tile's
+// digit scan.  The keys are first put in digit order in shared memory, so that the write-out stores runs of consecutive
+// addresses (one run per digit present in the tile) instead of one scattered 8-byte store per key.
 constexpr u64 OS_LOCAL = 1ull << 62, OS_PREFIX = 2ull << 62, OS_VALUE = (1ull << 62) - 1ull;
 constexpr int OS_MAX_PASSES = 8;
 
@@ -786,14 +644,12 @@ int kmap_dedup_hash_per_read_u64(uint64_t* hash, int64_t n, const int64_t* borde
     return dedup_keys<u64>(reinterpret_cast<u64*>(hash), n, borders, n_seq, work, as_stream(stream));
 }
 
-// scratch (uint64 words): [0..255] digit totals, [256] n after the first pass, [257] spare, then the per-tile digit counts
-// (uint32) and offsets (uint64) of one pass; the run-length step re-uses the front of it for its tile counts
+// scratch (uint64 words): the sort's histograms / counters / status words (see kmap_sort_keys_u64); the run-length step
+// re-uses the front of it for its tile counts
 int64_t kmap_sort_scratch_words(int64_t n) {
     if (n < 0) return 0;
     const int64_t t = rs_tiles(n);
-    int64_t sort_words = 258 + 128 * t + 256 * t;                   // the three-kernel form
-    const int64_t onesweep_words = OS_MAX_PASSES * 256 + 2 + 256 * t;
-    if (onesweep_words > sort_words) sort_words = onesweep_words;
+    const int64_t sort_words = OS_MAX_PASSES * 256 + 2 + 256 * t;   // digit histograms, two counters, one status word per (tile, digit)
     const int64_t rl_words = rl_tiles(n) + 2;
     return (sort_words > rl_words ? sort_words : rl_words) + 2;
 }
@@ -806,15 +662,11 @@ int kmap_sort_keys_u64(uint64_t* keys, uint64_t* tmp, int64_t n, int key_bits, u
     KMAP_REQUIRE(keys && tmp && scratch, "null pointer");
     cudaStream_t s = as_stream(stream);
     const int64_t n_tiles = rs_tiles(n);
-    u64* totals = reinterpret_cast<u64*>(scratch);
-    u64* n_dev = totals + 256;
-    uint32_t* counts = reinterpret_cast<uint32_t*>(scratch + 258);
-    u64* offsets = reinterpret_cast<u64*>(scratch + 258 + 128 * n_tiles);
+    u64* n_dev = nullptr;
     u64* a = reinterpret_cast<u64*>(keys);
     u64* b = reinterpret_cast<u64*>(tmp);
     const int passes = (key_bits + 7) / 8;
-    static const bool three_kernel = getenv("KMAP_SORT_THREE_KERNEL") != nullptr;      // (the earlier form, kept for A/B timing)
-    if (!three_kernel) {
+    {
         // scratch: [0..2047] per-pass digit histograms -> bases, [2048] n_valid (n_dev), [2049] ticket, then the status words
         u64* hist = reinterpret_cast<u64*>(scratch);
         n_dev = hist + OS_MAX_PASSES * 256;
@@ -832,15 +684,6 @@ int kmap_sort_keys_u64(uint64_t* keys, uint64_t* tmp, int64_t n, int key_bits, u
                                                                               status, ticket);
             u64* t = a; a = b; b = t;
         }
-    } else
-    for (int p = 0; p < passes; ++p) {
-        const int drop = p == 0;
-        const u64* nd = p == 0 ? nullptr : n_dev;
-        radix_hist_kernel<<<(unsigned int)n_tiles, RS_THREADS, 0, s>>>(a, n, nd, 8 * p, drop, n_tiles, counts);
-        radix_digit_total_kernel<<<256, 256, 0, s>>>(counts, n_tiles, totals);
-        radix_offsets_kernel<<<256, 1024, 0, s>>>(counts, n_tiles, totals, offsets, p == 0 ? n_dev : nullptr);
-        radix_scatter_kernel<<<(unsigned int)n_tiles, RS_THREADS, 0, s>>>(a, b, n, nd, 8 * p, drop, n_tiles, offsets);
-        u64* t = a; a = b; b = t;
     }
     int rc = kmap_check_launch("sort_keys");
     if (rc) return rc;

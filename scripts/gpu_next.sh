@@ -9,7 +9,7 @@ tail -30 gpurun_out/pytest_gpu.log
 if [ "$1" = "prof" ]; then
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fasta_tile|fasta_emit" -c 3 \
     -o gpurun_out/prof_fasta -f python scripts/bench_next.py 1e6 5e5 prof > gpurun_out/prof_fasta.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"radix_|dedup_keys|window_keys|head_|merge_plan|merge_write|run_length" -c 45 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"onesweep_|dedup_keys|window_keys|head_|merge_plan|merge_write|run_length" -c 45 \
     -o gpurun_out/prof_next -f python scripts/bench_next.py 1e6 5e5 prof > gpurun_out/prof_next.log 2>&1
 tail -2 gpurun_out/prof_next.log
 fi
