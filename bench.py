@@ -252,12 +252,14 @@ def main():
     # ---- device-resident input (generated on the device by the counter-based generator) -----------------------------
     seq_d, borders_d = synth.generate_device(spec, r0, n_local)
     dev = E.SeqOnDevice.from_device_u8(seq_d, borders_d)
-    flat_tables, tables = E.alloc_tables(KMIN, KMAX, zero=True)      # one buffer: the NCCL merge is one all-reduce
+    # N > 1: the tables live in this rank's peer region, so the merge is the one-byte-per-cell exchange over NVLink peer
+    # memory (csrc/peer.cu); the NCCL all-reduce of the same step is timed beside it further down
+    merge_comm = api.TableAllReduce() if world > 1 else None
+    flat_tables, tables = merge_comm.alloc_tables(KMIN, KMAX, zero=True) if world > 1 else E.alloc_tables(KMIN, KMAX, zero=True)
     torch.cuda.synchronize()
 
     count_events = []
     phase_events = []
-    merge_comm = api.TableAllReduce() if world > 1 else None
 
     def step(record=False):
         if args.algo == "allk":
@@ -328,10 +330,37 @@ def main():
     # N > 1: the same step with the merged tables left scattered over the ranks by key range (reduce-scatter instead of
     # all-reduce: half the exchange volume, kmap_count_all_k_scattered).  Reported beside `value`, which keeps the all-reduce
     # the north star names.  The owned ranges of all ranks together must give the checksums of the all-reduced tables.
+    exchange = None
+    if world > 1:
+        merge_comm.check()
+        exchange = {"product": "peer memory, one byte per cell (csrc/peer.cu)" if merge_comm.peer_exchange else "NCCL all-reduce",
+                    "peer_exchange_refused": merge_comm._peer_refused}
+    if args.algo == "allk" and world > 1 and merge_comm.peer_exchange:
+        # the same step with the tables outside the peer region: the NCCL all-reduce of round 1 / the first half of round 2
+        _, nc_tables = E.alloc_tables(KMIN, KMAX, zero=True)
+        for _ in range(max(1, args.warmup)):
+            dev.count_all(KMIN, KMAX, dedup, nc_tables, n_partitions=args.partitions, merge=merge_comm)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            dev.count_all(KMIN, KMAX, dedup, nc_tables, n_partitions=args.partitions, merge=merge_comm)
+        s1.record()
+        barrier()
+        ts = torch.tensor([s0.elapsed_time(s1) / args.steps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        same = all(bool(torch.equal(nc_tables[k], tables[k])) for k in range(KMIN, KMAX + 1))
+        flag = torch.tensor([int(same)], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        exchange["nccl_allreduce_ms_per_step"] = float(ts.item())
+        exchange["nccl_allreduce_value"] = n_total * L * (KMAX - KMIN + 1) / (float(ts.item()) * 1e-3) / 1e9
+        exchange["tables_identical"] = bool(flag.item())
+        checks["peer_exchange_equals_nccl_allreduce"] = bool(flag.item())
+        del nc_tables
     scattered = None
     if args.algo == "allk" and world > 1 and (1 << (2 * KMIN)) % world == 0:
         rs_comm = api.TableAllReduce(scatter=True)
-        _, rs_tables = E.alloc_tables(KMIN, KMAX, zero=True)
+        _, rs_tables = rs_comm.alloc_tables(KMIN, KMAX, zero=True)
         for _ in range(max(1, args.warmup)):
             dev.count_all(KMIN, KMAX, dedup, rs_tables, n_partitions=args.partitions, merge=rs_comm)
         barrier()
@@ -576,7 +605,7 @@ def main():
                                    f"counting k={KMIN}..{KMAX}, {args.mode} mode, reads sharded over {n_gpus} GPU(s) with NCCL table merge",
                        "l2": "inputs larger than L2 (packed reads + borders = %.1f GB per GPU)" % ((dev.packed.numel() * 4 + dev.valid.numel() * 4 + n_local * 16) / 1e9),
                        "parallelism": f"reads x{n_gpus}"},
-            "clocks": clocks, "e2e": e2e, "scattered_merge": scattered, "gpu_launches": args.steps * (launches_per_step(args, dedup)),
+            "clocks": clocks, "e2e": e2e, "exchange": exchange, "scattered_merge": scattered, "gpu_launches": args.steps * (launches_per_step(args, dedup)),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "hamdist": hamdist, "hamball": piece2, "workflow_cfg2": workflow,
             "checks": checks,
         }

@@ -137,6 +137,22 @@ int kmap_table_allreduce(uint32_t* table, int64_t n_cells, void* comm, void* str
 /* the same exchange as a reduce-scatter by key range, in place: afterwards cells [rank * n_cells / world, (rank + 1) * n_cells /
  * world) hold the sums over the ranks (the other cells partial sums); n_cells must be a multiple of world */
 int kmap_table_reduce_scatter(uint32_t* table, int64_t n_cells, int rank, int world, void* comm, void* stream);
+/* The same exchange over NVLink PEER MEMORY, one byte per cell (csrc/peer.cu): a rank's table of a sharded input holds small
+ * counts, so the cells travel as signed bytes -- the owner of a key range loads the bytes of every rank over NVLink, sums,
+ * and stores the narrowed sums into every rank's memory -- and a cell that does not fit a byte is marked and fetched as a
+ * word from the owner's table: bit-identical to the all-reduce for any input at 1/8 of its link traffic.  Every rank
+ * allocates a region (kmap_peer_region_alloc: [table area: table_cells uint32][2 bytes per cell][flags], returns the
+ * 64-byte IPC handle), the host plumbing gathers the handles of all ranks, and kmap_comm_attach_peers maps the peers'
+ * regions.  From then on kmap_table_allreduce / kmap_table_reduce_scatter / kmap_count_all_k_sharded / _scattered take
+ * this path for every table (a multiple of 16 x world cells at a multiple of 16 cells) that lies INSIDE the table area of the
+ * region, the same cells on every rank, and the NCCL path for any other buffer.  At most 8 ranks, one node.  A rank that
+ * does not show up at a barrier for 120 s is reported by kmap_comm_peer_status (collective calls do not hang the GPU). */
+int64_t kmap_peer_region_bytes(int64_t table_cells);
+int kmap_peer_region_alloc(int64_t table_cells, void** region_out_host, uint8_t* handle_out_host);   /* 64 bytes, HOST */
+int kmap_peer_region_free(void* region);
+int kmap_comm_attach_peers(void* comm, int rank, int world, void* my_region, int64_t table_cells, const uint8_t* handles_host);
+int kmap_comm_detach_peers(void* comm);
+int kmap_comm_peer_status(void* comm, int* status_out_host, void* stream);
 /* kmap_count_all_k on this rank's shard of the reads with the tables MERGED over the ranks of `comm` on return (every rank
  * gets the tables of the whole input).  The all-reduces are issued on `comm_stream` as the buffers become final -- the
  * corrections of the small levels during the partition pass, the slices of the level-kmax table while the per-bucket

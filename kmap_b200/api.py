@@ -16,6 +16,13 @@ from . import engine as E
 from ._lib import KmapError, check as _check, lib as _lib
 
 
+class _DeviceBlob:
+    """n int32 cells at a raw device pointer (memory owned by libkmap_b200), for torch.as_tensor"""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
+
+
 class TableAllReduce:
     """In-place sum of a dense count table over all ranks.  uint32 counts travel as their int32 bit patterns: two's
     complement addition is the same modular sum, so the merged table is bit-identical for any number of ranks.
@@ -34,6 +41,8 @@ class TableAllReduce:
         self.scatter = bool(scatter)
         self._comm = None
         self._stream = None
+        self._region = None            # peer-memory exchange (csrc/peer.cu): (device pointer, table cells) of this rank's region
+        self._peer_refused = None      # why the peer-memory exchange is not in use (None: not tried yet / in use)
 
     def owned_range(self, k: int) -> Tuple[int, int]:
         """[lo, hi) of the level-k table this rank owns after a scattered merge"""
@@ -69,9 +78,105 @@ class TableAllReduce:
             self._stream = torch.cuda.Stream()
         return self._comm, self._stream
 
+    # ---- the peer-memory exchange: tables that live in a region every rank of the node has mapped ---------------------
+    def alloc_tables(self, kmin: int, kmax: int, zero: bool = False):
+        """(flat, {k: view}) like engine.alloc_tables, for counts merged through this object.  On one NVLink node (2..8 ranks)
+        the tables are views of this rank's PEER REGION, and every merge of them -- `count_all(merge=self)`, `self(table)` --
+        takes the one-byte-per-cell exchange over peer memory (csrc/peer.cu, kmap_comm_attach_peers) instead of the NCCL
+        all-reduce; bit-identical.  The region holds ONE set of tables: a second call hands out the same memory.  Collective
+        on first use (every rank must call it with the same levels).  KMAP_PEER_EXCHANGE=0 keeps NCCL."""
+        total = sum(1 << (2 * k) for k in range(kmin, kmax + 1))
+        if not self._ensure_region(total):
+            return E.alloc_tables(kmin, kmax, zero)
+        ptr, _ = self._region
+        flat = torch.as_tensor(_DeviceBlob(ptr, total), device=E.require_cuda())
+        if flat.data_ptr() != ptr:
+            raise KmapError("torch copied the peer region instead of wrapping it")
+        if zero:
+            flat.zero_()
+        views, o = {}, 0
+        for k in range(kmax, kmin - 1, -1):
+            views[k] = flat[o:o + (1 << (2 * k))]
+            o += 1 << (2 * k)
+        return flat, views
+
+    @property
+    def peer_exchange(self) -> bool:
+        return self._region is not None
+
+    def _ensure_region(self, cells: int) -> bool:
+        import ctypes
+        import os
+        import socket
+        cells = (int(cells) + 15) // 16 * 16
+        if self._region is not None and self._region[1] >= cells:
+            return True
+        if self._peer_refused is not None:
+            return False
+        L = _lib()
+        comm, _ = self.native()
+        rank, world = self.rank, self.world
+        why = None
+        if os.environ.get("KMAP_PEER_EXCHANGE", "1") == "0":
+            why = "KMAP_PEER_EXCHANGE=0"
+        elif not 2 <= world <= 8:
+            why = f"{world} ranks (the peer-memory exchange takes 2..8 ranks of one node)"
+        else:
+            hosts = [None] * world
+            self.dist.all_gather_object(hosts, (socket.gethostname(), torch.cuda.current_device()), group=self.group)
+            if len({h for h, _ in hosts}) != 1:
+                why = "the ranks are on more than one node"
+            elif len({d for _, d in hosts}) != world:
+                why = "two ranks share a device"
+            elif not all(torch.cuda.can_device_access_peer(torch.cuda.current_device(), d) for _, d in hosts
+                         if d != torch.cuda.current_device()):
+                why = "no peer access between the devices"
+        if why is None:
+            if self._region is not None:                      # (grown: every rank drops its mapping before any region is freed)
+                torch.cuda.synchronize()
+                _check(L.kmap_comm_detach_peers(comm), "kmap_comm_detach_peers")
+                self.dist.barrier(group=self.group)
+                _check(L.kmap_peer_region_free(self._region[0]), "kmap_peer_region_free")
+                self._region = None
+            region, handle = ctypes.c_void_p(), (ctypes.c_uint8 * 64)()
+            ok = L.kmap_peer_region_alloc(cells, ctypes.byref(region), handle) == 0
+            box = [None] * world
+            self.dist.all_gather_object(box, bytes(handle) if ok else None, group=self.group)
+            if any(b is None for b in box):
+                why = "a rank could not allocate its region: " + L.kmap_last_error().decode(errors="replace")
+            else:
+                handles = (ctypes.c_uint8 * (64 * world)).from_buffer_copy(b"".join(box))
+                ok = L.kmap_comm_attach_peers(comm, rank, world, region, cells, handles) == 0
+                oks = [None] * world
+                self.dist.all_gather_object(oks, ok, group=self.group)
+                if all(oks):
+                    self._region = (region.value, cells)
+                    return True
+                why = "a rank could not map its peers: " + L.kmap_last_error().decode(errors="replace")
+                if ok:
+                    L.kmap_comm_detach_peers(comm)
+                self.dist.barrier(group=self.group)
+            if ok or region.value:
+                L.kmap_peer_region_free(region)
+        self._peer_refused = why
+        return False
+
+    def check(self):
+        """raises if a rank failed to reach a barrier of the peer-memory exchange (synchronises the exchange stream)"""
+        if self._comm is not None and self._region is not None:
+            import ctypes
+            status = ctypes.c_int(0)
+            _check(_lib().kmap_comm_peer_status(self._comm, ctypes.byref(status), self._stream.cuda_stream), "kmap_comm_peer_status")
+
     def close(self):
         if self._comm is not None:
             torch.cuda.synchronize()
+            region = self._region
+            self._region = None
+            if region is not None:
+                _check(_lib().kmap_comm_detach_peers(self._comm), "kmap_comm_detach_peers")
+                self.dist.barrier(group=self.group)          # nobody frees a region a peer still has mapped
+                _check(_lib().kmap_peer_region_free(region[0]), "kmap_peer_region_free")
             _check(_lib().kmap_comm_destroy(self._comm), "kmap_comm_destroy")
             self._comm = None
 
@@ -275,12 +380,14 @@ def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterabl
         #  verifies every row inside a chunk, kmap_host_border_strides)
         world_local = table_allreduce.world if table_allreduce is not None else 1
         flat, tables, n_total = count_tables_streamed(seq_np_arr, boarder_mat, ks[0], ks[-1], rep_mode, bounds, host_pack,
-                                                      host_pack_threads(world_local))
+                                                      host_pack_threads(world_local),
+                                                      alloc_totals=table_allreduce.alloc_tables if table_allreduce is not None else None)
     else:
         dev = upload_reads(seq_np_arr, boarder_mat, validate)
         n_total = dev.n
         if contiguous:
-            flat, tables = E.alloc_tables(ks[0], ks[-1])
+            # (sharded: the tables live in the peer region of the exchange, so the merge takes the peer-memory path)
+            flat, tables = (table_allreduce.alloc_tables if table_allreduce is not None else E.alloc_tables)(ks[0], ks[-1])
             # one update per window at kmax, the rest derived; sharded: merged over the ranks from inside the count
             dev.count_all(ks[0], ks[-1], dedup=not rep_mode, tables=tables, merge=table_allreduce)
             merged_inside = table_allreduce is not None
@@ -400,7 +507,7 @@ def host_pack_threads(world_local: int = 1) -> int:
 
 
 def count_tables_streamed(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, kmin: int, kmax: int, rep_mode: bool, cuts,
-                          host_pack: Optional[bool] = None, n_threads: int = 0):
+                          host_pack: Optional[bool] = None, n_threads: int = 0, alloc_totals=None):
     """Dense forward tables of every k in [kmin, kmax] with the reads streamed through the device chunk by chunk.
     Reads are independent units (per-read de-duplication never crosses a read, kmer_count.py:755-759), so the table of the
     whole input is the sum of the chunk tables (SeqOnDevice.count_all per chunk + kmap_add_u32).
@@ -453,7 +560,7 @@ def count_tables_streamed(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, kmin:
     copy_packed = _copy_stream(1)
     copy.wait_stream(compute)
     copy_packed.wait_stream(compute)
-    flat, totals = E.alloc_tables(kmin, kmax)
+    flat, totals = (alloc_totals or E.alloc_tables)(kmin, kmax)
     part_flat, part = E.alloc_tables(kmin, kmax)
 
     lock = threading.Lock()

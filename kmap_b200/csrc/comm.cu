@@ -47,6 +47,11 @@ const NcclApi& nccl_api() {
     return api;
 }
 
+// what kmap_comm_init hands out: the NCCL communicator and, once kmap_comm_attach_peers has been called, the peer-memory
+// exchange of peer.cu that takes over the tables living in its region
+struct KmapComm { ncclComm_t nccl; void* peer; };
+inline KmapComm* as_comm(void* c) { return static_cast<KmapComm*>(c); }
+
 int nccl_fail(const char* what, ncclResult_t r) {
     kmap_set_error("%s: %s", what, nccl_api().GetErrorString ? nccl_api().GetErrorString(r) : "NCCL error");
     return KMAP_ERR_COMM;
@@ -54,12 +59,20 @@ int nccl_fail(const char* what, ncclResult_t r) {
 
 }  // namespace
 
+// implemented in peer.cu
+void* kmap_peer_new(int rank, int world, void* my_region, int64_t table_cells, const uint8_t* handles);
+void kmap_peer_delete(void* peer);
+bool kmap_peer_covers(const void* peer, const uint32_t* buf, int64_t n, int scatter);
+int kmap_peer_exchange(void* peer, uint32_t* buf, int64_t n, int scatter, cudaStream_t s);
+int kmap_peer_status_of(void* peer, int* status_out, cudaStream_t s);
+
 // used by count_all.cu / partition.cu for the merges they overlap with counting
 int kmap_allreduce_u32_on(uint32_t* buf, int64_t n, void* comm, cudaStream_t s) {
     if (n == 0) return KMAP_OK;
+    if (as_comm(comm)->peer && kmap_peer_covers(as_comm(comm)->peer, buf, n, 0)) return kmap_peer_exchange(as_comm(comm)->peer, buf, n, 0, s);
     const NcclApi& api = nccl_api();
     if (!api.ok) { kmap_set_error("table_allreduce: no NCCL library in this process"); return KMAP_ERR_COMM; }
-    const ncclResult_t r = api.AllReduce(buf, buf, (size_t)n, ncclUint32, ncclSum, reinterpret_cast<ncclComm_t>(comm), s);
+    const ncclResult_t r = api.AllReduce(buf, buf, (size_t)n, ncclUint32, ncclSum, as_comm(comm)->nccl, s);
     return r == ncclSuccess ? KMAP_OK : nccl_fail("table_allreduce", r);
 }
 
@@ -74,18 +87,23 @@ int kmap_merge_chunks(int world) {
 int kmap_comm_world(void* comm) {
     const NcclApi& api = nccl_api();
     int n = 1;
-    if (!api.ok || !api.CommCount || !comm || api.CommCount(reinterpret_cast<ncclComm_t>(comm), &n) != ncclSuccess) return 1;
+    if (!api.ok || !api.CommCount || !comm || api.CommCount(as_comm(comm)->nccl, &n) != ncclSuccess) return 1;
     return n;
+}
+
+bool kmap_merge_on_peer_memory(const uint32_t* buf, int64_t n, const KmapMerge* m) {
+    return m && m->comm && n > 0 && as_comm(m->comm)->peer && kmap_peer_covers(as_comm(m->comm)->peer, buf, n, m->scatter);
 }
 
 int kmap_merge_table_on(uint32_t* buf, int64_t n, const KmapMerge* m) {
     if (n == 0) return KMAP_OK;
     if (!m->scatter || m->world <= 1 || n % m->world != 0) return kmap_allreduce_u32_on(buf, n, m->comm, m->stream);
+    if (as_comm(m->comm)->peer && kmap_peer_covers(as_comm(m->comm)->peer, buf, n, 1)) return kmap_peer_exchange(as_comm(m->comm)->peer, buf, n, 1, m->stream);
     const NcclApi& api = nccl_api();
     if (!api.ok) { kmap_set_error("table_reduce_scatter: no NCCL library in this process"); return KMAP_ERR_COMM; }
     const int64_t block = n / m->world;         // in place: the receive buffer is this rank's block of the send buffer
     const ncclResult_t r = api.ReduceScatter(buf, buf + (size_t)m->rank * block, (size_t)block, ncclUint32, ncclSum,
-                                             reinterpret_cast<ncclComm_t>(m->comm), m->stream);
+                                             as_comm(m->comm)->nccl, m->stream);
     return r == ncclSuccess ? KMAP_OK : nccl_fail("table_reduce_scatter", r);
 }
 
@@ -122,16 +140,46 @@ int kmap_comm_init(const uint8_t* id_in, int rank, int world, void** comm_out) {
         r = api.CommInitRank(&comm, world, id, rank);
     }
     if (r != ncclSuccess) return nccl_fail("comm_init", r);
-    *comm_out = comm;
+    *comm_out = new KmapComm{comm, nullptr};
     return KMAP_OK;
 }
 
 int kmap_comm_destroy(void* comm) {
     if (!comm) return KMAP_OK;
+    KmapComm* c = as_comm(comm);
+    kmap_peer_delete(c->peer);
     const NcclApi& api = nccl_api();
-    if (!api.ok) return KMAP_OK;
-    const ncclResult_t r = api.CommDestroy(reinterpret_cast<ncclComm_t>(comm));
+    const ncclResult_t r = api.ok ? api.CommDestroy(c->nccl) : ncclSuccess;
+    delete c;
     return r == ncclSuccess ? KMAP_OK : nccl_fail("comm_destroy", r);
+}
+
+int kmap_comm_attach_peers(void* comm, int rank, int world, void* my_region, int64_t table_cells, const uint8_t* handles_host) {
+    KMAP_REQUIRE(comm && my_region && handles_host, "null pointer");
+    KmapComm* c = as_comm(comm);
+    KMAP_REQUIRE(!c->peer, "peers are attached already");
+    KMAP_REQUIRE(world == kmap_comm_world(comm), "world differs from the communicator's");
+    c->peer = kmap_peer_new(rank, world, my_region, table_cells, handles_host);
+    return c->peer ? KMAP_OK : KMAP_ERR_COMM;
+}
+
+int kmap_comm_detach_peers(void* comm) {
+    if (!comm) return KMAP_OK;
+    kmap_peer_delete(as_comm(comm)->peer);
+    as_comm(comm)->peer = nullptr;
+    return KMAP_OK;
+}
+
+int kmap_comm_peer_status(void* comm, int* status_out_host, void* stream) {
+    KMAP_REQUIRE(comm && status_out_host, "null pointer");
+    *status_out_host = 0;
+    if (!as_comm(comm)->peer) return KMAP_OK;
+    const int rc = kmap_peer_status_of(as_comm(comm)->peer, status_out_host, as_stream(stream));
+    if (rc == KMAP_OK && *status_out_host) {
+        kmap_set_error("peer-memory exchange: rank %d never reached a barrier (waited 120 s)", *status_out_host - 1);
+        return KMAP_ERR_COMM;
+    }
+    return rc;
 }
 
 int kmap_table_allreduce(uint32_t* table, int64_t n_cells, void* comm, void* stream) {

@@ -36,6 +36,8 @@ int kmap_comm_world(void* comm);  // number of ranks of a communicator (1 on fai
 int kmap_allreduce_u32_on(uint32_t* buf, int64_t n, void* comm, cudaStream_t s);
 // merge one table the way `m` says: all-reduce, or reduce-scatter in place (rank r's block stays where it is in `buf`)
 int kmap_merge_table_on(uint32_t* buf, int64_t n, const KmapMerge* m);
+// would that merge take the peer-memory exchange (peer.cu: the buffer lies in the table area of the rank's peer region)?
+bool kmap_merge_on_peer_memory(const uint32_t* buf, int64_t n, const KmapMerge* m);
 
 // dense tables of several levels: t[k] = uint32[4^k] (only the levels a kernel uses are set); passed by value
 struct KmapTableSet { uint32_t* t[16]; };

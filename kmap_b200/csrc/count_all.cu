@@ -491,10 +491,21 @@ int count_all_impl(const uint32_t* packed, const uint32_t* valid, int64_t n, con
     cudaStream_t s = as_stream(stream);
     TableSet tabs;
     for (int k = 0; k < 16; ++k) tabs.t[k] = nullptr;
+    // The level-kmax table of the partitioned count is first touched by the per-bucket count, long after the per-read scan:
+    // with an exchange stream at hand its zero fill (1 GiB at k = 14) runs there, beside the scan, which leaves HBM idle.
+    const bool zero_aside = merge && merge->stream && merge->stream != s && dedup && scheme != KMAP_KMAX_PREFIX_PASSES && part_scratch &&
+                            kmax >= 12 && kmax <= 14;
     for (int k = kmin; k <= kmax; ++k) {
         tabs.t[k] = tables_host[k - kmin];
         KMAP_REQUIRE(tabs.t[k], "null table");
-        cudaError_t e = cudaMemsetAsync(tabs.t[k], 0, ((size_t)1 << (2 * k)) * 4, s);
+        cudaError_t e = cudaSuccess;
+        if (k == kmax && zero_aside) {
+            int rcz = OneShotEvent::chain(s, merge->stream);              // (whatever the caller did with the table before is done)
+            if (rcz) return rcz;
+            e = cudaMemsetAsync(tabs.t[k], 0, ((size_t)1 << (2 * k)) * 4, merge->stream);
+        } else {
+            e = cudaMemsetAsync(tabs.t[k], 0, ((size_t)1 << (2 * k)) * 4, s);
+        }
         if (e != cudaSuccess) { kmap_set_error("count_all_k: %s", cudaGetErrorString(e)); return (int)e; }
     }
     // an empty shard launches nothing of its own but still takes part in every collective of the sharded form
@@ -555,6 +566,7 @@ int count_all_impl(const uint32_t* packed, const uint32_t* valid, int64_t n, con
     if (rc) return rc;
     mark(1);
     const uint32_t* hide = dedup ? dupmask : nullptr;
+    if (zero_aside && (rc = OneShotEvent::chain(merge->stream, s))) return rc;         // the zero fill of the level-kmax table
     if (use_partition) {
         // level kmax through key partitioning + shared-memory counters (partition.cu).  Run-end corrections: fused into the
         // histogram pass, except that a level whose table is beyond L2 -- level 13 under k = 14 -- travels through the

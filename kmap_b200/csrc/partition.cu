@@ -640,7 +640,17 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
         chunk_base_kernel<<<(n_all + 255) / 256, 256, 0, s>>>(p.chunk_total, n_all, p.base, p.chunk_base);
         if (step_events && step_events[0]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(step_events[0]), s);
     }
-    if (merge && merge->comm && terminal_tabs) {
+    // Peer-memory exchange (peer.cu) with every level in one buffer, largest first (engine.alloc_tables): ONE exchange of the
+    // whole buffer after the count -- 7 % more cells than levels k and k-1 alone, and no exchange kernels waiting for SMs
+    // while the partition pass holds them all.
+    int64_t span_all = (int64_t)n_buckets * 65536;
+    bool one_exchange = false;
+    if (merge && merge->comm && !merge->scatter && terminal_tabs && kmap_merge_on_peer_memory(table, span_all, merge)) {
+        int u = k - 1;
+        while (u >= kmin && tt.t[u] == table + span_all) { span_all += (int64_t)1 << (2 * u); --u; }
+        one_exchange = u < kmin && kmap_merge_on_peer_memory(table, span_all, merge);
+    }
+    if (merge && merge->comm && terminal_tabs && !one_exchange) {
         // the corrections of levels kmin .. kcorr-1 are complete (per-read scan + the REDs of the histogram pass): merge them
         // over the ranks while the partition pass runs.  Neighbouring tables (engine.alloc_tables lays them out largest first
         // in one buffer, identically on every rank) go in one call.
@@ -681,7 +691,9 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
     // collective's kernels (comm.cu caps them at that many CTAs) and the grid is one CTA per bucket instead of one persistent
     // CTA per SM, so that SMs change hands at bucket granularity (measured at 2 GPUs with persistent CTAs: the collective got
     // its SMs only between launches and the counting launches lost theirs to it: 6.9 ms instead of 4.4).
-    const bool beside = merge && merge->comm;
+    const int64_t cells_k = (int64_t)n_buckets * BC_CELLS;
+    const bool peer_path = kmap_merge_on_peer_memory(table, cells_k, merge);     // exchange AFTER the count (see below): nothing runs beside it
+    const bool beside = merge && merge->comm && !peer_path;
     const int bc_grid = beside ? n_all : 148;
     // segments: 1.25 x the average bucket (no bucket of a uniform input is cut), at least 2^17 suffixes, a multiple of 8
     unsigned long long seg_len = (unsigned long long)(n / n_buckets + 1) * 5 / 4;
@@ -720,16 +732,33 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
         rc = kmap_merge_table_on(buf, cells, merge);
         if (trace) { cudaEventCreate(&tm[nt]); cudaEventRecord(tm[nt], merge->stream); ++nt; }
     };
-    if (route) {
-        count_range(n_buckets, n_all);
-        merge_after(tt.t[k - 1], (int64_t)1 << (2 * (k - 1)));
-    }
-    // (scattered: a rank's block of the table must stay one contiguous key range, so the table is merged in one piece)
-    const int n_chunks = (n_buckets >= 1024 && !merge->scatter) ? kmap_merge_chunks(merge->world) : 1;
-    for (int c = 0; c < n_chunks; ++c) {
-        const int b_lo = n_buckets * c / n_chunks, b_hi = n_buckets * (c + 1) / n_chunks;
-        count_range(b_lo, b_hi);
-        merge_after(table + (size_t)b_lo * BC_CELLS, (int64_t)(b_hi - b_lo) * BC_CELLS);
+    if (peer_path) {
+        // The peer-memory exchange (peer.cu) is short next to the count and its kernels want the SMs the count fills (a CTA of
+        // the per-bucket count leaves room for one small CTA beside it: an exchange issued range by range while the count runs
+        // took 3 x as long as alone, 2 GPUs: 5.5 ms for this phase against 3.7 + 0.9 back to back).  So: count everything, then
+        // ONE exchange -- of the level-k table and the routed level k-1 together when they are neighbours in memory.
+        count_range(0, n_all);
+        const int64_t cells_r = route ? (int64_t)1 << (2 * (k - 1)) : 0;
+        if (one_exchange) {
+            merge_after(table, span_all);
+        } else if (route && !merge->scatter && tt.t[k - 1] == table + cells_k && kmap_merge_on_peer_memory(table, cells_k + cells_r, merge)) {
+            merge_after(table, cells_k + cells_r);
+        } else {
+            if (route) merge_after(tt.t[k - 1], cells_r);
+            merge_after(table, cells_k);
+        }
+    } else {
+        if (route) {
+            count_range(n_buckets, n_all);
+            merge_after(tt.t[k - 1], (int64_t)1 << (2 * (k - 1)));
+        }
+        // (scattered: a rank's block of the table must stay one contiguous key range, so the table is merged in one piece)
+        const int n_chunks = (n_buckets >= 1024 && !merge->scatter) ? kmap_merge_chunks(merge->world) : 1;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int b_lo = n_buckets * c / n_chunks, b_hi = n_buckets * (c + 1) / n_chunks;
+            count_range(b_lo, b_hi);
+            merge_after(table + (size_t)b_lo * BC_CELLS, (int64_t)(b_hi - b_lo) * BC_CELLS);
+        }
     }
     if (trace) {
         cudaStreamSynchronize(s); cudaStreamSynchronize(merge->stream);

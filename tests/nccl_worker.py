@@ -42,6 +42,39 @@ def main():
         inputs = [synth.generate_numpy(synth.CFG3, 0, n_reads), synth.generate_numpy(synth.CFG2_N, 0, n_reads), with_long_reads()]
         from kmap_b200 import engine as E
         scat = api.TableAllReduce(scatter=True)
+        # the peer-memory exchange (csrc/peer.cu) on a table of every kind of cell: bytes that fit, the escape value itself,
+        # words far outside a byte, sums that wrap -- against the modular sum computed from the gathered tables
+        ar = ctx.table_allreduce
+        flat, _ = ar.alloc_tables(8, 9)
+        assert ar.peer_exchange, ar._peer_refused
+        g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+        n_cells = flat.numel()
+        vals = torch.randint(-130, 131, (n_cells,), device="cuda", generator=g, dtype=torch.int64)
+        big = torch.randint(0, 1 << 32, (n_cells,), device="cuda", generator=g, dtype=torch.int64)
+        pick = torch.randint(0, 50, (n_cells,), device="cuda", generator=g)
+        vals = torch.where(pick == 0, big, vals)
+        vals[:4096] = big[:4096]                               # a run of nothing but escapes
+        vals[4096:8192] = -128
+        mine = (vals & 0xFFFFFFFF)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        want = (sum(every) & 0xFFFFFFFF)
+        for lo, hi in ((0, n_cells), (1 << 16, (1 << 16) + 4096 * world), (16, n_cells - 16)):
+            flat.copy_(torch.where(mine >= (1 << 31), mine - (1 << 32), mine).to(torch.int32))
+            ar(flat[lo:hi])
+            torch.cuda.synchronize()
+            got = flat.to(torch.int64) & 0xFFFFFFFF
+            assert torch.equal(got[lo:hi], want[lo:hi]), ("peer exchange", lo, hi)
+            assert torch.equal(got[:lo], mine[:lo]) and torch.equal(got[hi:], mine[hi:]), ("cells outside the exchanged range", lo, hi)
+        sflat, _ = scat.alloc_tables(8, 9)
+        sflat.copy_(torch.where(mine >= (1 << 31), mine - (1 << 32), mine).to(torch.int32))
+        scat.reduce_scatter(sflat)
+        torch.cuda.synchronize()
+        blk = n_cells // world
+        got = sflat.to(torch.int64) & 0xFFFFFFFF
+        assert torch.equal(got[rank * blk:(rank + 1) * blk], want[rank * blk:(rank + 1) * blk]), "peer reduce-scatter"
+        ar.check()
+        scat.check()
         for seq, borders in inputs:
             s, b = api.shard_reads(seq, borders, rank, world)
             for rep_mode in (False, True):
@@ -53,6 +86,15 @@ def main():
                 for k in range(8, 15):
                     lo, hi = scat.owned_range(k)
                     assert torch.equal(part_t[k][lo:hi], full[k][lo:hi]), (k, rep_mode, "scattered merge")
+                # the same two merges with the tables in the peer regions: one byte per cell over NVLink peer memory
+                peer_t = dev.count_all(8, 14, dedup=not rep_mode, tables=ar.alloc_tables(8, 14)[1], merge=ar)
+                peer_s = dev.count_all(8, 14, dedup=not rep_mode, tables=scat.alloc_tables(8, 14)[1], merge=scat)
+                for k in range(8, 15):
+                    lo, hi = scat.owned_range(k)
+                    assert torch.equal(peer_t[k], full[k]), (k, rep_mode, "peer-memory exchange vs NCCL all-reduce")
+                    assert torch.equal(peer_s[k][lo:hi], full[k][lo:hi]), (k, rep_mode, "peer-memory scattered merge")
+                ar.check()
+                del peer_t, peer_s
                 t13 = full[13].clone()
                 scat.reduce_scatter(t13)                       # (x world on the owned block: every rank holds the merged table)
                 lo, hi = scat.owned_range(13)
