@@ -99,13 +99,17 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+FOLD_RUN_ENDS_DEFAULT = "0"      # the library's default of KMAP_FOLD_RUN_ENDS (csrc/partition.cu: kmap_fold_run_ends)
+
+
 def launches_per_step(args, dedup):
     """kernels of libkmap_b200 launched per step (memsets not counted)"""
     if args.algo != "allk":
         return KMAX - KMIN + 1
     derive = KMAX - KMIN
     if args.partitions <= 0:     # dedup_scan + hist + 3 scan kernels + partition + bucket_count + bucket_segments + derive
-        return (1 if dedup else 0) + 7 + derive
+        fold = derive if int(os.environ.get("KMAP_FOLD_RUN_ENDS", FOLD_RUN_ENDS_DEFAULT)) >= 1 else 0    # + one fold_corrections_kernel per lower level
+        return (1 if dedup else 0) + 7 + derive + fold
     return (1 if dedup else 0) + 5 + max(1, args.partitions) + derive      # + terminal-correction launches + prefix passes
 
 

@@ -469,6 +469,13 @@ __global__ void __launch_bounds__(256) add_tables_kernel(uint32_t* __restrict__ 
 }
 
 struct OneShotEvent {       // record on one stream, make another wait, release
+    // keep != NULL: only record on `from` and hand the event over (the caller makes `to` wait later and destroys it)
+    static int chain(cudaStream_t from, cudaStream_t to, cudaEvent_t* keep) {
+        (void)to;
+        if (cudaEventCreateWithFlags(keep, cudaEventDisableTiming) != cudaSuccess) { *keep = nullptr; return kmap_check_launch("count_all_k(event)"); }
+        cudaEventRecord(*keep, from);
+        return KMAP_OK;
+    }
     static int chain(cudaStream_t from, cudaStream_t to) {
         cudaEvent_t ev;
         if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return kmap_check_launch("count_all_k(event)");
@@ -489,20 +496,26 @@ int count_all_impl(const uint32_t* packed, const uint32_t* valid, int64_t n, con
     KMAP_REQUIRE(tables_host, "null pointer");
     KMAP_REQUIRE(scheme >= KMAP_KMAX_PREFIX_PASSES && scheme <= KMAP_KMAX_SORTED, "unknown scheme");
     cudaStream_t s = as_stream(stream);
+    cudaEvent_t zeroed = nullptr;
     TableSet tabs;
     for (int k = 0; k < 16; ++k) tabs.t[k] = nullptr;
     // The level-kmax table of the partitioned count is first touched by the per-bucket count, long after the per-read scan:
     // with an exchange stream at hand its zero fill (1 GiB at k = 14) runs there, beside the scan, which leaves HBM idle.
-    const bool zero_aside = merge && merge->stream && merge->stream != s && dedup && scheme != KMAP_KMAX_PREFIX_PASSES && part_scratch &&
-                            kmax >= 12 && kmax <= 14;
+    // (single GPU: a stream created for the call and released when its fill is done)
+    bool zero_aside = dedup && scheme != KMAP_KMAX_PREFIX_PASSES && part_scratch && kmax >= 12 && kmax <= 14 && n > 0 && n_seq > 0;
+    cudaStream_t aside = merge && merge->stream && merge->stream != s ? merge->stream : nullptr;
+    const bool own_aside = zero_aside && !aside;
+    if (own_aside && cudaStreamCreateWithFlags(&aside, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); zero_aside = false; }
     for (int k = kmin; k <= kmax; ++k) {
         tabs.t[k] = tables_host[k - kmin];
         KMAP_REQUIRE(tabs.t[k], "null table");
         cudaError_t e = cudaSuccess;
         if (k == kmax && zero_aside) {
-            int rcz = OneShotEvent::chain(s, merge->stream);              // (whatever the caller did with the table before is done)
+            int rcz = OneShotEvent::chain(s, aside);                      // (whatever the caller did with the table before is done)
+            if (!rcz) e = cudaMemsetAsync(tabs.t[k], 0, ((size_t)1 << (2 * k)) * 4, aside);
+            if (!rcz) rcz = OneShotEvent::chain(aside, s, &zeroed);       // (waited for in front of the level-kmax count)
+            if (own_aside) cudaStreamDestroy(aside);                      // (the stream goes away when the fill has completed)
             if (rcz) return rcz;
-            e = cudaMemsetAsync(tabs.t[k], 0, ((size_t)1 << (2 * k)) * 4, merge->stream);
         } else {
             e = cudaMemsetAsync(tabs.t[k], 0, ((size_t)1 << (2 * k)) * 4, s);
         }
@@ -566,7 +579,11 @@ int count_all_impl(const uint32_t* packed, const uint32_t* valid, int64_t n, con
     if (rc) return rc;
     mark(1);
     const uint32_t* hide = dedup ? dupmask : nullptr;
-    if (zero_aside && (rc = OneShotEvent::chain(merge->stream, s))) return rc;         // the zero fill of the level-kmax table
+    if (zeroed) {                                                                      // the zero fill of the level-kmax table
+        cudaStreamWaitEvent(s, zeroed, 0);
+        cudaEventDestroy(zeroed);
+        zeroed = nullptr;
+    }
     if (use_partition) {
         // level kmax through key partitioning + shared-memory counters (partition.cu).  Run-end corrections: fused into the
         // histogram pass, except that a level whose table is beyond L2 -- level 13 under k = 14 -- travels through the

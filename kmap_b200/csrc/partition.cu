@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(PT_THREADS) bucket_hist_kernel(const uint32_t*
                                                                  const uint32_t* __restrict__ hide, int64_t n_words, int64_t n_tiles,
                                                                  int k, int n_buckets, int n_extra, uint16_t* __restrict__ counts,
                                                                  uint32_t* __restrict__ off, uint32_t* __restrict__ chunk_total,
-                                                                 KmapTableSet tabs, int kmin, int kcorr) {
+                                                                 KmapTableSet tabs, int kmin, int kcorr, int single_from) {
     __shared__ __align__(16) uint32_t cnt2[2][PT_MAX_ALL];          // double buffer: one barrier per tile
     __shared__ uint32_t* stab[16];
     if (TERMINAL && threadIdx.x < 16) stab[threadIdx.x] = tabs.t[threadIdx.x];
@@ -107,10 +107,10 @@ __global__ void __launch_bounds__(PT_THREADS) bucket_hist_kernel(const uint32_t*
         tile_hist(cook(ra, k, route), sh, cnt, n_buckets);
         tile_hist(cook(rb, k, route), sh, cnt, n_buckets);
         if (TERMINAL) {                                             // levels kmin .. kcorr-1
-            run_end_corrections(ra, rp, kmin, kcorr, stab);
+            run_end_corrections(ra, rp, kmin, kcorr, stab, single_from);
             RawPrev rq;
             rq.vp = r.v0; rq.hp = r.h0; rq.wp = r.w1;
-            run_end_corrections(rb, rq, kmin, kcorr, stab);
+            run_end_corrections(rb, rq, kmin, kcorr, stab, single_from);
         }
         __syncthreads();       // this tile's counts are complete; the other buffer was zeroed before the previous barrier
         if (b0 < n_buckets) {
@@ -552,6 +552,44 @@ __global__ void __launch_bounds__(BC_THREADS, 1) bucket_segments_kernel(const ui
     }
 }
 
+// One level of the folded run-end corrections: T_v += C_v and, unless v is the lowest level, C_(v-1) += the 4:1 reduction of C_v
+// over the FIRST base (cells h, q + h, 2q + h, 3q + h with q = 4^(v-1)).  One thread = 4 consecutive cells of every quarter.
+__global__ void __launch_bounds__(256) fold_corrections_kernel(const uint32_t* __restrict__ cv, uint32_t* __restrict__ tv,
+                                                               uint32_t* __restrict__ clow, int v) {
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    auto add4 = [](uint4 a, const uint4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; return a; };
+    if (!clow) {
+        const int64_t n4 = (((int64_t)1 << (2 * v)) + 3) / 4;             // (4^v >= 4 for v >= 1)
+        for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) {
+            if (((int64_t)1 << (2 * v)) < 4) { if (i == 0) tv[0] += cv[0]; continue; }
+            reinterpret_cast<uint4*>(tv)[i] = add4(reinterpret_cast<const uint4*>(tv)[i], reinterpret_cast<const uint4*>(cv)[i]);
+        }
+        return;
+    }
+    const int64_t q = (int64_t)1 << (2 * (v - 1));
+    if (q < 4) {                                                          // v = 1: four cells
+        if (blockIdx.x == 0 && threadIdx.x == 0) { uint32_t sum = 0; for (int b = 0; b < 4; ++b) { tv[b] += cv[b]; sum += cv[b]; } clow[0] += sum; }
+        return;
+    }
+    const int64_t q4 = q / 4;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < q4; i += stride) {
+        uint4 sum = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint4 c = reinterpret_cast<const uint4*>(cv)[b * q4 + i];
+            reinterpret_cast<uint4*>(tv)[b * q4 + i] = add4(reinterpret_cast<const uint4*>(tv)[b * q4 + i], c);
+            sum = add4(sum, c);
+        }
+        reinterpret_cast<uint4*>(clow)[i] = add4(reinterpret_cast<const uint4*>(clow)[i], sum);
+    }
+}
+
+// KMAP_FOLD_RUN_ENDS=0/1 (read once): the folded run-end corrections of kmap_count_partitioned
+static int kmap_fold_run_ends() {
+    static const int mode = [] { const char* e = getenv("KMAP_FOLD_RUN_ENDS"); return e ? atoi(e) : 0; }();
+    return mode;
+}
+
 struct PartScratch {
     uint32_t* chunk_total;            // [PT_HGRID][n_all]
     unsigned long long* base;         // [n_all + 1]
@@ -562,7 +600,10 @@ struct PartScratch {
     unsigned long long* ticket;       // tile dispenser of the partition pass
     unsigned long long* total;        // [n_all]
     uint32_t* queues;                 // BC_QUEUES x (2 + n_all) words: segment queues of the per-bucket count launches
+    uint32_t* corr;                   // folded run-end corrections: level v (< k) at cell offset corr_offset(v)
 };
+// (levels back to back, every one starting at a multiple of 4 cells: 128-bit accesses)
+static int64_t corr_offset(int v) { return ((((int64_t)1 << (2 * v)) - 1) / 3 + 4 * v + 3) & ~(int64_t)3; }
 
 static int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
@@ -583,7 +624,9 @@ static int64_t carve(void* scratch, int n_buckets, int64_t n, PartScratch* p) {
     uint8_t* a6 = take(8);
     uint8_t* a7 = take((int64_t)n_all * 8);
     uint8_t* a8 = take((int64_t)BC_QUEUES * (2 + n_all) * 4);
+    uint8_t* a9 = take((((int64_t)n_buckets << 16) / 3 + 128) * 4);
     if (p) {
+        p->corr = reinterpret_cast<uint32_t*>(a9);
         p->chunk_total = reinterpret_cast<uint32_t*>(a0);
         p->base = reinterpret_cast<unsigned long long*>(a1);
         p->chunk_base = reinterpret_cast<unsigned long long*>(a2);
@@ -627,19 +670,6 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
     const KmapTableSet& tt = terminal_tabs ? *terminal_tabs : none;
     const int km = terminal_tabs ? kmin : k;
     const bool local = n > 0;                           // (an empty shard of a sharded count: collectives only)
-    if (local) {
-        if (n_buckets <= PT_THREADS) {
-            if (terminal_tabs) bucket_hist_kernel<true, 1><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, tt, km, kcorr);
-            else bucket_hist_kernel<false, 1><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, tt, km, kcorr);
-        } else {
-            if (terminal_tabs) bucket_hist_kernel<true, PT_MAX_PER><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, tt, km, kcorr);
-            else bucket_hist_kernel<false, PT_MAX_PER><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, tt, km, kcorr);
-        }
-        bucket_total_kernel<<<(n_all + 255) / 256, 256, 0, s>>>(p.chunk_total, n_all, p.total);
-        bucket_scan_kernel<<<1, PT_THREADS, 0, s>>>(p.total, n_all, p.base);
-        chunk_base_kernel<<<(n_all + 255) / 256, 256, 0, s>>>(p.chunk_total, n_all, p.base, p.chunk_base);
-        if (step_events && step_events[0]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(step_events[0]), s);
-    }
     // Peer-memory exchange (peer.cu) with every level in one buffer, largest first (engine.alloc_tables): ONE exchange of the
     // whole buffer after the count -- 7 % more cells than levels k and k-1 alone, and no exchange kernels waiting for SMs
     // while the partition pass holds them all.
@@ -649,6 +679,35 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
         int u = k - 1;
         while (u >= kmin && tt.t[u] == table + span_all) { span_all += (int64_t)1 << (2 * u); --u; }
         one_exchange = u < kmin && kmap_merge_on_peer_memory(table, span_all, merge);
+    }
+    // Folded run-end corrections (single GPU): a run of r valid bases owes "+1 at level v" to the v-mer in front of its end for
+    // every v <= min(r, k-1): five scattered REDs per read for k = 8..14.  The v-mer is the (v+1)-mer minus its FIRST base, so
+    // C_v = (4:1 reduction of C_(v+1) over the first base) + the runs of exactly v bases: each run is entered ONCE, at the level
+    // of its length (the routed level k-1 entries are exactly the runs of k-1 or more bases), into correction tables of their
+    // own, and fold_corrections_kernel brings them down level by level and adds them to the count tables: streaming passes
+    // over 4^(k-1) cells instead of (k-1-kmin) REDs per read.
+    // (KMAP_FOLD_RUN_ENDS: 1 = single GPU, 2 = also the sharded count whose tables are merged by ONE exchange after the count --
+    //  the corrections must be complete before they are exchanged, which the early merges of the NCCL path do not wait for)
+    const bool fold = terminal_tabs && local && k - 1 >= kmin && ((!merge || !merge->comm) ? kmap_fold_run_ends() >= 1 : (kmap_fold_run_ends() >= 2 && one_exchange));
+    KmapTableSet ctabs = KmapTableSet();
+    if (fold) {
+        for (int v = kmin; v < k; ++v) ctabs.t[v] = p.corr + corr_offset(v);
+        cudaMemsetAsync(ctabs.t[kmin], 0, (size_t)(corr_offset(k) - corr_offset(kmin)) * 4, s);
+    }
+    const KmapTableSet& ht = fold ? ctabs : tt;        // where the histogram pass sends its run-end updates
+    const int single_from = fold ? (route ? k - 1 : 64) : 0;
+    if (local) {
+        if (n_buckets <= PT_THREADS) {
+            if (terminal_tabs) bucket_hist_kernel<true, 1><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, ht, km, kcorr, single_from);
+            else bucket_hist_kernel<false, 1><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, ht, km, kcorr, single_from);
+        } else {
+            if (terminal_tabs) bucket_hist_kernel<true, PT_MAX_PER><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, ht, km, kcorr, single_from);
+            else bucket_hist_kernel<false, PT_MAX_PER><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, ht, km, kcorr, single_from);
+        }
+        bucket_total_kernel<<<(n_all + 255) / 256, 256, 0, s>>>(p.chunk_total, n_all, p.total);
+        bucket_scan_kernel<<<1, PT_THREADS, 0, s>>>(p.total, n_all, p.base);
+        chunk_base_kernel<<<(n_all + 255) / 256, 256, 0, s>>>(p.chunk_total, n_all, p.base, p.chunk_base);
+        if (step_events && step_events[0]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(step_events[0]), s);
     }
     if (merge && merge->comm && terminal_tabs && !one_exchange) {
         // the corrections of levels kmin .. kcorr-1 are complete (per-read scan + the REDs of the histogram pass): merge them
@@ -705,12 +764,21 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
         if (nb <= 0 || !local) return;
         uint32_t* q = p.queues + (size_t)(n_launch++ % BC_QUEUES) * (2 + n_all);
         bucket_count_kernel<<<(unsigned int)(nb < bc_grid ? nb : bc_grid), BC_THREADS, BC_WORDS * 4, s>>>(p.suffixes, p.base, n_buckets, b_lo, b_hi, table,
-                                                                                                        route ? tt.t[k - 1] : nullptr, seg_len, q);
+                                                                                                        route ? ht.t[k - 1] : nullptr, seg_len, q);
         bucket_segments_kernel<<<beside ? 148 - kmap_comm_ctas(merge->world) : 148, BC_THREADS, BC_WORDS * 4, s>>>(p.suffixes, p.base, n_buckets, table,
-                                                                                                       route ? tt.t[k - 1] : nullptr, seg_len, q);
+                                                                                                       route ? ht.t[k - 1] : nullptr, seg_len, q);
+    };
+    auto fold_chain = [&]() {                           // brings the folded run-end corrections down the levels and into the tables
+        for (int v = k - 1; fold && v >= kmin; --v) {
+            const int64_t q4 = v > kmin ? ((int64_t)1 << (2 * (v - 1))) / 4 : ((int64_t)1 << (2 * v)) / 4;      // uint4 groups per launch
+            int64_t g = (q4 + 255) / 256;
+            if (g > 148 * 16) g = 148 * 16;
+            fold_corrections_kernel<<<(unsigned int)(g < 1 ? 1 : g), 256, 0, s>>>(ctabs.t[v], tt.t[v], v > kmin ? ctabs.t[v - 1] : nullptr, v);
+        }
     };
     if (!merge || !merge->comm) {
         count_range(0, n_all);
+        fold_chain();
         return kmap_check_launch("count_partitioned");
     }
     // Sharded input: the slices of the table are final as soon as their buckets are counted, so the all-reduce over the
@@ -738,6 +806,7 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
         // took 3 x as long as alone, 2 GPUs: 5.5 ms for this phase against 3.7 + 0.9 back to back).  So: count everything, then
         // ONE exchange -- of the level-k table and the routed level k-1 together when they are neighbours in memory.
         count_range(0, n_all);
+        fold_chain();
         const int64_t cells_r = route ? (int64_t)1 << (2 * (k - 1)) : 0;
         if (one_exchange) {
             merge_after(table, span_all);

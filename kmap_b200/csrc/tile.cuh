@@ -107,7 +107,11 @@ __device__ __forceinline__ RawPrev load_raw_prev(const uint32_t* __restrict__ pa
 // (count_all.cu) do not bring it down from the level above.  Windows hidden in `hide` belong to reads that are counted
 // by the direct per-k kernels.  stab[v] = table of level v.  Everything comes from registers: the only memory operations
 // are the REDs.
-__device__ __forceinline__ void run_end_corrections(const RawWords& r, const RawPrev& q, int kmin, int k, uint32_t* const* stab) {
+// single_from > 0 (the folded form, partition.cu): a run contributes ONE update, at the level of its length capped at k-1 --
+// the levels below are brought down by 4:1 reductions over the FIRST base of the correction tables -- and a run of
+// single_from or more bases contributes none here (it travels through the partition as a routed entry).
+__device__ __forceinline__ void run_end_corrections(const RawWords& r, const RawPrev& q, int kmin, int k, uint32_t* const* stab,
+                                                    int single_from = 0) {
     uint32_t ends = r.v0 & ~((r.v0 >> 1) | (r.v1 << 31));                  // bit j: position j valid, j+1 not
     if (ends == 0) return;
     const uint64_t W = ((uint64_t)r.v0 << 32) | q.vp;                      // position j of this word = bit 32 + j
@@ -119,6 +123,7 @@ __device__ __forceinline__ void run_end_corrections(const RawWords& r, const Raw
         const int back = inv ? __clzll(inv) : 64;                          // valid bases ending at position j (>= 1)
         const int vmax = min(back, k - 1);
         if (vmax < kmin) continue;
+        if (single_from > 0 && back >= single_from) continue;
         // the windows of kmin..vmax bases that end at j start at j-v+1 >= -14: 32 bases from offset o = 16 + j - vmax + 1 of
         // the 64 bases [wp w0 w1 w2] cover them all
         const int o = 17 + j - vmax;                                       // 2 .. 48
@@ -126,7 +131,8 @@ __device__ __forceinline__ void run_end_corrections(const RawWords& r, const Raw
         const uint32_t b = o < 16 ? r.w0 : (o < 32 ? r.w1 : r.w2);
         const uint32_t c = o < 16 ? r.w1 : (o < 32 ? r.w2 : 0u);
         const uint32_t hi = __funnelshift_l(b, a, 2 * (o & 15)), lo = __funnelshift_l(c, b, 2 * (o & 15));
-        for (int v = vmax; v >= kmin; --v) {
+        const int vlow = single_from > 0 ? vmax : kmin;
+        for (int v = vmax; v >= vlow; --v) {
             if ((H >> (33 + j - v)) & 1ull) continue;
             const uint32_t x = __funnelshift_l(lo, hi, 2 * (vmax - v));
             atomicAdd(stab[v] + (x >> (32 - 2 * v)), 1u);
