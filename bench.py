@@ -99,7 +99,7 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-FOLD_RUN_ENDS_DEFAULT = "0"      # the library's default of KMAP_FOLD_RUN_ENDS (csrc/partition.cu: kmap_fold_run_ends)
+FOLD_RUN_ENDS_DEFAULT = "2"      # the library's default of KMAP_FOLD_RUN_ENDS (csrc/partition.cu: kmap_fold_run_ends)
 
 
 def launches_per_step(args, dedup):

@@ -584,9 +584,10 @@ __global__ void __launch_bounds__(256) fold_corrections_kernel(const uint32_t* _
     }
 }
 
-// KMAP_FOLD_RUN_ENDS=0/1 (read once): the folded run-end corrections of kmap_count_partitioned
+// KMAP_FOLD_RUN_ENDS (read once): the folded run-end corrections of kmap_count_partitioned -- 0 = scattered REDs per level from
+// the histogram pass (round 1), 1 = folded on a single GPU, 2 (default) = also under the one-exchange sharded count
 static int kmap_fold_run_ends() {
-    static const int mode = [] { const char* e = getenv("KMAP_FOLD_RUN_ENDS"); return e ? atoi(e) : 0; }();
+    static const int mode = [] { const char* e = getenv("KMAP_FOLD_RUN_ENDS"); return e ? atoi(e) : 2; }();
     return mode;
 }
 
@@ -695,7 +696,7 @@ int kmap_count_partitioned(const uint32_t* packed, const uint32_t* valid, const 
         cudaMemsetAsync(ctabs.t[kmin], 0, (size_t)(corr_offset(k) - corr_offset(kmin)) * 4, s);
     }
     const KmapTableSet& ht = fold ? ctabs : tt;        // where the histogram pass sends its run-end updates
-    const int single_from = fold ? (route ? k - 1 : 64) : 0;
+    const int single_from = fold ? (route ? k - 1 : (1 << 20)) : 0;   // (not routed: no run is long enough to be skipped)
     if (local) {
         if (n_buckets <= PT_THREADS) {
             if (terminal_tabs) bucket_hist_kernel<true, 1><<<PT_HGRID, PT_THREADS, 0, s>>>(packed, valid, hide, n_words, n_tiles, k, n_buckets, n_extra, p.counts, p.off, p.chunk_total, ht, km, kcorr, single_from);
