@@ -609,7 +609,9 @@ def main():
                                    f"counting k={KMIN}..{KMAX}, {args.mode} mode, reads sharded over {n_gpus} GPU(s) with NCCL table merge",
                        "l2": "inputs larger than L2 (packed reads + borders = %.1f GB per GPU)" % ((dev.packed.numel() * 4 + dev.valid.numel() * 4 + n_local * 16) / 1e9),
                        "parallelism": f"reads x{n_gpus}"},
-            "clocks": clocks, "e2e": e2e, "exchange": exchange, "scattered_merge": scattered, "gpu_launches": args.steps * (launches_per_step(args, dedup)),
+            "clocks": clocks, "e2e": e2e, "exchange": exchange, "scattered_merge": scattered, "gpu_launches": args.steps * (launches_per_step(args, dedup)
+                                          # + the exchange over peer memory: narrow / reduce / widen and the three barriers between them
+                                          + (6 if world > 1 and args.algo == "allk" and merge_comm.peer_exchange else 0)),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "hamdist": hamdist, "hamball": piece2, "workflow_cfg2": workflow,
             "checks": checks,
         }

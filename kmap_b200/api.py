@@ -166,7 +166,9 @@ class TableAllReduce:
         if self._comm is not None and self._region is not None:
             import ctypes
             status = ctypes.c_int(0)
-            _check(_lib().kmap_comm_peer_status(self._comm, ctypes.byref(status), self._stream.cuda_stream), "kmap_comm_peer_status")
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(self._stream)               # (exchanges run on the exchange stream or, for self(table), on the current one)
+            _check(_lib().kmap_comm_peer_status(self._comm, ctypes.byref(status), cur.cuda_stream), "kmap_comm_peer_status")
 
     def close(self):
         if self._comm is not None:
@@ -403,6 +405,7 @@ def count_kmers(seq_np_arr: np.ndarray, boarder_mat: np.ndarray, k_list: Iterabl
                 table_allreduce(tables[k])
         # the merged table holds the distinct k-mers of EVERY shard: the capacity bound is the total window count
         n_total = table_allreduce.sum_int(n_total, device=tables[ks[0]].device)
+        table_allreduce.check()                                    # (peer-memory exchange: every rank reached every barrier)
         if lists_on is not None and lists_on != "sharded" and table_allreduce.rank != lists_on:
             return out
     sharded_lists = table_allreduce is not None and lists_on == "sharded"

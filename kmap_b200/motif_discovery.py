@@ -978,6 +978,8 @@ def _scan_motif(res_dir: str, debug=False):
             alloc = ctx.table_allreduce.alloc_tables if ctx.table_allreduce is not None else E.alloc_tables
             flat, first_tables = alloc(ks_first[0], ks_first[-1])      # (sharded: in the peer region of the exchange, csrc/peer.cu)
             dev.count_all(ks_first[0], ks_first[-1], dedup=not rep_mode, tables=first_tables, merge=ctx.table_allreduce)
+            if ctx.table_allreduce is not None:
+                ctx.table_allreduce.check()
         k_single = [k for k in range(min_k, min(max_k, 15) + 1) if k not in first_tables]
         table_buffer = E.empty(1 << (2 * max(k_single)), torch.int32) if k_single else None   # one allocation for those k
         for kmer_len in range(min_k, max_k + 1):
