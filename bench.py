@@ -453,7 +453,11 @@ def main():
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "kernel": kernel, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": b_launch, "avg_launch_ms": t_launch * 1e3,
-                    "share_of_step": t_launch * 1e3 / (kern_s * 1e3), "phases_ms": ph_ms, "k14_count_pipeline": pipeline,
+                    "share_of_step": t_launch * 1e3 / (kern_s * 1e3), "phases_ms": ph_ms,
+                    "phases_note": "bucket_hist = histogram pass + run-end detection; bucket_count = per-bucket count + the reductions of "
+                                   "the folded run-end corrections" + (" + the exchange of the tables over the ranks" if world > 1 else "")
+                                   + "; zero = fills on the counting stream (the level-14 table is filled beside the per-read scan)",
+                    "k14_count_pipeline": pipeline,
                     "step_model": {"note": "SURVEY 8d model for 7 independent per-k passes (0.375 B/base + 8 B/k-mer each) over the "
                                            "measured step time; the all-k algorithm updates the k=14 table only and derives the "
                                            "smaller tables by 4:1 reductions, so this can exceed what 7 passes could reach",
